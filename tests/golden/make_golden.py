@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""Extract the reference's own golden vectors for the scalar-mult / MSM path into small fixtures.
+
+Run in the build container (where /root/reference exists):
+    python tests/golden/make_golden.py
+The GPU box has no /root/reference; tests read only the JSON files written here.
+
+Sources (all under /root/reference/test/vectors, used by the reference tests cited):
+  secp256k1/privates-2.txt      test/secp256k1.test.ts:59-76     k:x:y = k*G
+  secp256k1/points.json         test/secp256k1.test.ts:96-127    pointMultiply / pointFromScalar / pointAdd
+  secp256k1/endomorphism.json   test/nist.test.ts:551            GLV sign cases
+  bls12-381/zkcrypto/converted.json  test/bls12-381.test.ts:1463-1533   i*G, i<1000, G1+G2 uncompressed
+  bn254/eth-dump.js             test/bn254.test.ts:750-778       EIP-196 ECADD/ECMUL dumps
+  bn254/seda.js                 test/bn254.test.ts:859-887       add / mul
+  ed25519/vectors.txt           test/ed25519.test.ts:50-78       sk:pk:msg:sig (RFC 8032 / cr.yp.to)
+"""
+import json
+import os
+import re
+
+REF = "/root/reference/test/vectors"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def dump(name, obj):
+    path = os.path.join(OUT, name)
+    with open(path, "w") as f:
+        json.dump(obj, f, separators=(",", ":"))
+    print(name, os.path.getsize(path), "bytes")
+
+
+def secp256k1():
+    rows = []
+    for line in open(f"{REF}/secp256k1/privates-2.txt"):
+        line = line.strip()
+        if not line:
+            continue
+        k, x, y = line.split(":")
+        rows.append([k, x, y])
+    pts = json.load(open(f"{REF}/secp256k1/points.json"))["valid"]
+    out = {
+        "privates2": rows,  # decimal k, hex x, hex y
+        "pointMultiply": [[v["P"], v["d"], v["expected"]] for v in pts["pointMultiply"]],
+        "pointFromScalar": [[v["d"], v["expected"]] for v in pts["pointFromScalar"]],
+        "pointAdd": [[v["P"], v["Q"], v["expected"]] for v in pts["pointAdd"]],
+        "endomorphism": json.load(open(f"{REF}/secp256k1/endomorphism.json")),
+    }
+    dump("secp256k1.json", out)
+
+
+def bls():
+    d = json.load(open(f"{REF}/bls12-381/zkcrypto/converted.json"))
+    out = {
+        # index i holds i*G (i = 0 is the point at infinity, Zcash flag encoding)
+        "G1_Uncompressed": d["G1_Uncompressed"][:1000],
+        "G2_Uncompressed": d["G2_Uncompressed"][:256],
+    }
+    dump("bls12_381.json", out)
+
+
+def bn254():
+    src = open(f"{REF}/bn254/eth-dump.js").read()
+    adds, muls = [], []
+    for m in re.finditer(r"^NOBLE_DUMP_EC_(ADD|MUL) (\S*) (\S+)$", src, re.M):
+        kind, inp, outp = m.group(1), m.group(2), m.group(3)
+        (adds if kind == "ADD" else muls).append([inp, outp])
+    seda_src = open(f"{REF}/bn254/seda.js").read()
+    # seda.js is `const vectors = {...}; export default vectors` with JS object-literal syntax
+    body = seda_src[seda_src.index("{"): seda_src.rindex("}") + 1]
+    body = re.sub(r"(\w+):", r'"\1":', body)
+    body = body.replace("'", '"')
+    body = re.sub(r",\s*([}\]])", r"\1", body)
+    seda = json.loads(body)
+    dump("bn254.json", {"eth_add": adds, "eth_mul": muls, "seda_add": seda["add"], "seda_mul": seda["mul"]})
+
+
+def ed25519():
+    rows = []
+    for i, line in enumerate(open(f"{REF}/ed25519/vectors.txt")):
+        if i >= 128:
+            break
+        parts = line.strip().split(":")
+        sk_pk, pk, msg, sig_msg = parts[0], parts[1], parts[2], parts[3]
+        rows.append({"sk": sk_pk[:64], "pk": pk, "msg": msg, "sig": sig_msg[:128]})
+    dump("ed25519.json", {"vectors": rows})
+
+
+if __name__ == "__main__":
+    secp256k1()
+    bls()
+    bn254()
+    ed25519()
