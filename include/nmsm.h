@@ -1,0 +1,114 @@
+/* nmsm — C ABI of the B200-native scalar-multiplication / MSM engine.
+ *
+ * This is the drop-in boundary for noble-curves' hot path.  noble has no FFI of its
+ * own; these entry points are what an N-API addon binds behind the reference's
+ * public functions:
+ *
+ *   nmsm_msm            <- pippenger(c, points, scalars)          /root/reference/src/abstract/curve.ts:863-905
+ *   nmsm_mul_batch      <- Point.multiply / Point.multiplyUnsafe  src/abstract/weierstrass.ts:900-928,
+ *                                                                 src/abstract/edwards.ts:555-577
+ *   nmsm_msm_partial_device / nmsm_fold_partials_device           (multi-GPU split of the same MSM; MSM is
+ *                                                                 linear in its term set, curve.ts:863)
+ *   nmsm_last_error     <- the thrown Error messages              curve.ts:390-404,875
+ *
+ * Data formats (all little-endian, plain bytes, caller-owned):
+ *   point   : canonical affine (x, y); each base-field coordinate is FpBytes little-endian bytes
+ *             (32 for secp256k1 / ed25519 / bn254, 48 for BLS12-381); Fp2 coordinates are c0 then c1.
+ *             Weierstrass infinity is (0, 0) (weierstrass.ts:716,966); Edwards identity is (0, 1).
+ *   scalar  : 32 bytes little-endian, 0 <= s < n (curve order).
+ *   result  : same point format + `is_inf` flag (1 = identity).
+ * Coordinates are NOT Montgomery form at this boundary.
+ *
+ * Error convention: 0 = ok; negative = error (see NMSM_ERR_*), message via nmsm_last_error().
+ * Threading: one context per process (per GPU); calls are serialised by an internal mutex.
+ * No CPU fallback exists: every entry point fails with NMSM_ERR_CUDA when no device is usable.
+ */
+#ifndef NMSM_H
+#define NMSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  NMSM_SECP256K1 = 0,
+  NMSM_ED25519 = 1,
+  NMSM_BN254_G1 = 2,
+  NMSM_BN254_G2 = 3,
+  NMSM_BLS12_381_G1 = 4,
+  NMSM_BLS12_381_G2 = 5
+};
+
+enum {
+  NMSM_OK = 0,
+  NMSM_ERR_ARG = -1,            /* bad curve id / null pointer / size                                   */
+  NMSM_ERR_SCALAR = -2,         /* 'invalid scalar at index i' (curve.ts:402); i = nmsm_last_error_index */
+  NMSM_ERR_POINT = -3,          /* 'invalid point at index i'  (curve.ts:393)                            */
+  NMSM_ERR_LENGTH = -4,         /* 'arrays of points and scalars must have equal length' (curve.ts:875)  */
+  NMSM_ERR_CUDA = -5            /* CUDA failure or no device                                             */
+};
+
+/* Bind this process to CUDA device `device` and create the context (stream, workspace). Idempotent. */
+int nmsm_init(int device);
+void nmsm_shutdown(void);
+const char* nmsm_last_error(void);
+long long nmsm_last_error_index(void);
+
+/* Bytes per point (x||y) and per raw accumulator for a curve; negative on bad id. */
+int nmsm_point_bytes(int curve);
+int nmsm_acc_bytes(int curve);
+
+/* sum_i scalars[i] * pts[i]; host buffers (copied H2D inside the call).  n == 0 -> identity. */
+int nmsm_msm(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t* out_xy,
+             int* out_is_inf);
+
+/* Same with inputs already resident in device memory (16-byte aligned device pointers). */
+int nmsm_msm_device(int curve, const void* d_pts, const void* d_scalars, uint64_t n, uint8_t* out_xy,
+                    int* out_is_inf);
+
+/* Multi-GPU building blocks: the un-normalised accumulator of a shard is written to device memory
+ * (nmsm_acc_bytes bytes, opaque Montgomery-form words), exchanged by the caller (NCCL all-gather),
+ * and folded + normalised by nmsm_fold_partials_device. */
+int nmsm_msm_partial_device(int curve, const void* d_pts, const void* d_scalars, uint64_t n, void* d_out_acc);
+int nmsm_fold_partials_device(int curve, const void* d_accs, int count, uint8_t* out_xy, int* out_is_inf);
+
+/* out[i] = scalars[i] * pts[i] for i < n (host buffers).  allow_zero = 0: Point.multiply range
+ * (1 <= k < n); allow_zero = 1: Point.multiplyUnsafe range (0 <= k < n).  out_is_inf: n bytes. */
+int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero,
+                   uint8_t* out_xy, uint8_t* out_is_inf);
+
+/* Tuning / introspection ------------------------------------------------------------------- */
+/* Force the window size c (0 = automatic cost model).  Returns the previous value. */
+int nmsm_set_window_bits(int c);
+
+/* Plan + per-kernel device times (ms, CUDA events on the library stream) of the last MSM call.
+ * `ms` receives NMSM_TIMING_SLOTS floats; see the NMSM_T_* indices. */
+enum {
+  NMSM_T_PREPARE = 0, NMSM_T_COUNT, NMSM_T_SCAN, NMSM_T_SCATTER, NMSM_T_ACCUMULATE, NMSM_T_FIXUP,
+  NMSM_T_REDUCE, NMSM_T_WINDOW_SUM, NMSM_T_FINAL, NMSM_T_TOTAL, NMSM_TIMING_SLOTS
+};
+typedef struct {
+  int c, windows, buckets_per_window, entries_per_thread, reduce_chunk;
+  uint64_t sorted_entries;      /* non-zero digits = mixed additions issued + bucket starts       */
+  uint64_t modmul_equiv;        /* field multiplications executed by the plan (SURVEY §8d formula) */
+  int launches;                 /* kernels launched by the call                                   */
+} nmsm_plan_info;
+int nmsm_set_profiling(int enabled);
+int nmsm_last_timing(float* ms, nmsm_plan_info* info);
+
+/* Register-resident Montgomery-multiplication throughput (the roofline denominator).
+ * field: 0 = 256-bit (bn254 Fp, 8 limbs), 1 = 381-bit (BLS12-381 Fp, 12 limbs).
+ * Returns modmul/s measured with CUDA events; <= 0 on error. */
+double nmsm_bench_modmul(int field, int blocks_per_sm, int threads, int iters, int ilp);
+
+/* Pinned host memory helpers for the end-to-end path. */
+void* nmsm_host_alloc(size_t bytes);
+void nmsm_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMSM_H */

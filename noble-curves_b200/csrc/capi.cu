@@ -1,0 +1,225 @@
+// libnmsm.so — C ABI (include/nmsm.h) over the sm_100a kernels in msm.cuh.
+// The per-curve engines are instantiated in inst_*.cu (compiled in parallel); this file holds the
+// process-wide context, the Montgomery-multiplication microbenchmark and the extern "C" surface.
+// There is deliberately no CPU path: every entry point needs a CUDA device.
+#include "context.h"
+#include "curve_consts.cuh"
+#include "field.cuh"
+
+namespace nmsm {
+
+Context g_ctx;
+std::mutex g_mu;
+
+static const EngineVTable* engine_for(int curve) {
+  switch (curve) {
+    case NMSM_SECP256K1: return engine_secp256k1();
+    case NMSM_ED25519: return engine_ed25519();
+    case NMSM_BN254_G1: return engine_bn254g1();
+    case NMSM_BN254_G2: return engine_bn254g2();
+    case NMSM_BLS12_381_G1: return engine_bls381g1();
+    case NMSM_BLS12_381_G2: return engine_bls381g2();
+    default: return nullptr;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Montgomery-multiplication throughput microbenchmark (roofline denominator)
+// ---------------------------------------------------------------------------------------------
+template <class P, int ILP>
+__global__ void k_modmul_bench(uint32_t* io, int iters) {
+  Fp<P> x[ILP], y;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < P::N; k++) {
+    y.v[k] = P::R2(k) ^ (t * 2654435761u >> 7 & 0xffff);
+#pragma unroll
+    for (int q = 0; q < ILP; q++) x[q].v[k] = P::R1(k) + q + (k == 0 ? t : 0);
+  }
+  // make operands < p so the reduced-input invariant holds
+  y.v[P::N - 1] &= 0x0fffffffu;
+#pragma unroll
+  for (int q = 0; q < ILP; q++) x[q].v[P::N - 1] &= 0x0fffffffu;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int q = 0; q < ILP; q++) x[q] = x[q] * y;
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int q = 0; q < ILP; q++)
+#pragma unroll
+    for (int k = 0; k < P::N; k++) acc ^= x[q].v[k];
+  if (acc == 0x12345678u) io[t] = acc;  // keep the chain alive without measurable traffic
+}
+
+template <class P>
+static double bench_modmul(int blocks_per_sm, int threads, int iters, int ilp) {
+  Context& C = g_ctx;
+  uint32_t* d = nullptr;
+  int blocks = blocks_per_sm * C.sm_count;
+  if (cudaMalloc(&d, (size_t)blocks * threads * 4) != cudaSuccess) return -1;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(a, C.stream);
+    if (ilp == 1) k_modmul_bench<P, 1><<<blocks, threads, 0, C.stream>>>(d, iters);
+    else if (ilp == 2) k_modmul_bench<P, 2><<<blocks, threads, 0, C.stream>>>(d, iters);
+    else k_modmul_bench<P, 4><<<blocks, threads, 0, C.stream>>>(d, iters);
+    cudaEventRecord(b, C.stream);
+    if (cudaEventSynchronize(b) != cudaSuccess) { best = -1; break; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  if (best <= 0) return -1;
+  int eff_ilp = ilp == 1 ? 1 : (ilp == 2 ? 2 : 4);
+  return (double)blocks * threads * (double)iters * eff_ilp / (best * 1e-3);
+}
+
+}  // namespace nmsm
+
+using namespace nmsm;
+
+// ---------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------
+#define ENGINE(curve)                                      \
+  const EngineVTable* E = engine_for(curve);               \
+  if (!E) return fail(NMSM_ERR_ARG, "unknown curve id")
+
+extern "C" {
+
+int nmsm_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Context& C = g_ctx;
+  if (C.ready && C.device == device) return NMSM_OK;
+  if (C.ready) return fail(NMSM_ERR_ARG, "nmsm_init: context already bound to another device");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(NMSM_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                   cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(NMSM_ERR_ARG, "nmsm_init: bad device ordinal");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  C.sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking));
+  CK(cudaMallocHost((void**)&C.h_result, 1024));
+  for (auto& ev : C.ev) CK(cudaEventCreate(&ev));
+  C.device = device;
+  C.ready = true;
+  return NMSM_OK;
+}
+
+void nmsm_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Context& C = g_ctx;
+  if (!C.ready) return;
+  cudaStreamSynchronize(C.stream);
+  for (Buf* b : {&C.in_pts, &C.in_scalars, &C.aff, &C.counts, &C.offsets, &C.cursor, &C.sorted, &C.buckets,
+                 &C.heads, &C.tails, &C.chunk_out, &C.window_out, &C.result, &C.mul_out})
+    b->release();
+  for (auto& ev : C.ev) cudaEventDestroy(ev);
+  cudaFreeHost(C.h_result);
+  cudaStreamDestroy(C.stream);
+  C.ready = false;
+  C.device = -1;
+}
+
+const char* nmsm_last_error(void) { return g_ctx.last_error.c_str(); }
+long long nmsm_last_error_index(void) { return g_ctx.last_error_index; }
+
+int nmsm_point_bytes(int curve) {
+  ENGINE(curve);
+  return E->point_bytes;
+}
+int nmsm_acc_bytes(int curve) {
+  ENGINE(curve);
+  return E->acc_bytes;
+}
+
+int nmsm_msm(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (!out_xy || !out_is_inf || (n && (!pts || !scalars))) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  return E->msm_host(pts, scalars, n, out_xy, out_is_inf);
+}
+
+int nmsm_msm_device(int curve, const void* d_pts, const void* d_scalars, uint64_t n, uint8_t* out_xy,
+                    int* out_is_inf) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (!out_xy || !out_is_inf || (n && (!d_pts || !d_scalars))) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  return E->msm_device((const uint32_t*)d_pts, (const uint32_t*)d_scalars, n, nullptr, out_xy, out_is_inf);
+}
+
+int nmsm_msm_partial_device(int curve, const void* d_pts, const void* d_scalars, uint64_t n, void* d_out_acc) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (!d_out_acc || (n && (!d_pts || !d_scalars))) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  return E->msm_device((const uint32_t*)d_pts, (const uint32_t*)d_scalars, n, (uint32_t*)d_out_acc, nullptr, nullptr);
+}
+
+int nmsm_fold_partials_device(int curve, const void* d_accs, int count, uint8_t* out_xy, int* out_is_inf) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (!d_accs || count < 0 || !out_xy || !out_is_inf) return fail(NMSM_ERR_ARG, "bad argument");
+  ENGINE(curve);
+  return E->fold((const uint32_t*)d_accs, count, out_xy, out_is_inf);
+}
+
+int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero,
+                   uint8_t* out_xy, uint8_t* out_is_inf) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (n && (!pts || !scalars || !out_xy || !out_is_inf)) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  return E->mul_batch(pts, scalars, n, allow_zero, out_xy, out_is_inf);
+}
+
+int nmsm_set_window_bits(int c) {
+  int prev = g_ctx.forced_c;
+  g_ctx.forced_c = (c >= 1 && c <= 16) ? c : 0;
+  return prev;
+}
+
+int nmsm_set_profiling(int enabled) {
+  int prev = g_ctx.profiling ? 1 : 0;
+  g_ctx.profiling = enabled != 0;
+  return prev;
+}
+
+int nmsm_last_timing(float* ms, nmsm_plan_info* info) {
+  if (ms) memcpy(ms, g_ctx.last_ms, sizeof(g_ctx.last_ms));
+  if (info) *info = g_ctx.last_info;
+  return NMSM_OK;
+}
+
+double nmsm_bench_modmul(int field, int blocks_per_sm, int threads, int iters, int ilp) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (ensure_init()) return -1;
+  if (blocks_per_sm < 1 || threads < 32 || threads > 1024 || iters < 1) return -1;
+  if (field == 0) return bench_modmul<FpBn254>(blocks_per_sm, threads, iters, ilp);
+  if (field == 1) return bench_modmul<FpBls381>(blocks_per_sm, threads, iters, ilp);
+  return -1;
+}
+
+void* nmsm_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void nmsm_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

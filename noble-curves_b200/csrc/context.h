@@ -1,0 +1,99 @@
+// Process-wide context, error mapping and the per-curve dispatch table shared by capi.cu and the
+// per-curve translation units (inst_*.cu).  No kernels are visible from here, so capi.cu does not
+// re-instantiate the curve templates.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/nmsm.h"
+
+namespace nmsm {
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Context {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  Buf in_pts, in_scalars, aff, counts, offsets, cursor, sorted, buckets, heads, tails, chunk_out, window_out,
+      result, mul_out;
+  uint32_t* h_result = nullptr;  // pinned staging for (xy | inf | err0 | err1)
+  cudaEvent_t ev[NMSM_TIMING_SLOTS + 2] = {};
+  bool profiling = false;
+  int forced_c = 0;
+  float last_ms[NMSM_TIMING_SLOTS] = {};
+  nmsm_plan_info last_info = {};
+  std::string last_error;
+  long long last_error_index = -1;
+};
+
+extern Context g_ctx;
+extern std::mutex g_mu;
+
+inline int fail(int code, const std::string& msg, long long idx = -1) {
+  g_ctx.last_error = msg;
+  g_ctx.last_error_index = idx;
+  return code;
+}
+inline int cuda_fail(cudaError_t e, const char* what) {
+  return fail(NMSM_ERR_CUDA, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                         \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+inline int ensure_init() {
+  if (g_ctx.ready) return NMSM_OK;
+  return fail(NMSM_ERR_CUDA, "nmsm_init() has not been called (no CUDA context; there is no CPU fallback)");
+}
+
+
+// One table per curve, defined in inst_<curve>.cu
+struct EngineVTable {
+  int point_bytes;
+  int acc_bytes;
+  int (*msm_host)(const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf);
+  int (*msm_device)(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
+                    uint8_t* out_xy, int* out_is_inf);
+  int (*fold)(const uint32_t* d_accs, int count, uint8_t* out_xy, int* out_is_inf);
+  int (*mul_batch)(const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
+                   uint8_t* out_is_inf);
+};
+const EngineVTable* engine_secp256k1();
+const EngineVTable* engine_ed25519();
+const EngineVTable* engine_bn254g1();
+const EngineVTable* engine_bn254g2();
+const EngineVTable* engine_bls381g1();
+const EngineVTable* engine_bls381g2();
+
+}  // namespace nmsm

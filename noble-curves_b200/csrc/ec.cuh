@@ -1,0 +1,307 @@
+// Group law policies used by every kernel (MSM buckets, batched scalar multiplication, folds).
+//
+// The reference uses complete formulas on homogeneous projective / extended
+// coordinates (weierstrass.ts:793-880 RCB, edwards.ts:505-545 hwcd).  Results are only defined up
+// to the projective representative, so parity is on canonical affine (x, y) (test/point.test.ts:36-44).
+// Here:
+//   * short Weierstrass a = 0 (secp256k1, bn254 G1/G2, BLS12-381 G1/G2): XYZZ accumulators
+//     (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; identity <=> ZZ == 0) with affine mixed addition
+//     madd-2008-s (8M+2S), add-2008-s (12M+2S), dbl-2008-s-1 (6M+3S for a=0), mdbl-2008-s-1.
+//     The incomplete formulas are completed by explicit branches for P+P, P+(-P), O+P, P+O — all
+//     of which occur in the reference's own tests (point.test.ts:269,842-853).
+//   * twisted Edwards a = -1 (ed25519): extended coordinates with the unified, complete
+//     add-2008-hwcd-3 on prepared affine inputs (y-x, y+x, 2dxy) (7M) and dbl-2008-hwcd (4M+4S).
+#pragma once
+#include "curve_consts.cuh"
+#include "field.cuh"
+#include "fp2.cuh"
+
+namespace nmsm {
+
+// ------------------------------------------------------------------------------------------
+// Short Weierstrass, a = 0
+// ------------------------------------------------------------------------------------------
+template <class F>
+struct SwXyzz {
+  using Field = F;
+  static constexpr int COORD_WORDS = F::LIMBS;
+  static constexpr int IN_WORDS = 2 * F::LIMBS;   // canonical affine input (x, y)
+  static constexpr int AFF_WORDS = 2 * F::LIMBS;  // prepared affine
+  static constexpr int ACC_WORDS = 4 * F::LIMBS;
+  // multiplication counts in field-mul equivalents (1S = 1M), SURVEY §8(d)
+  static constexpr int COST_MADD = 10, COST_ADD = 14, COST_DBL = 9;
+  static constexpr bool IS_EDWARDS = false;
+
+  struct Affine {
+    F x, y;
+  };
+  struct Acc {
+    F X, Y, ZZ, ZZZ;
+  };
+
+  NMSM_HD static Acc identity() { return Acc{F::zero(), F::one(), F::zero(), F::zero()}; }
+  NMSM_HD static bool is_identity(const Acc& p) { return p.ZZ.is_zero(); }
+  NMSM_HD static bool affine_is_identity(const Affine& a) { return a.x.is_zero() && a.y.is_zero(); }
+  // weierstrass.ts:716 — affine (0,0) encodes the point at infinity
+  NMSM_HD static Affine prepare(const uint32_t* xy) {
+    return Affine{F::from_canonical(xy), F::from_canonical(xy + F::LIMBS)};
+  }
+  NMSM_HD static bool input_in_range(const uint32_t* xy) {
+    return F::canonical_in_range(xy) && F::canonical_in_range(xy + F::LIMBS);
+  }
+  NMSM_HD static Affine neg(const Affine& a) { return Affine{a.x, -a.y}; }
+  NMSM_HD static Affine cneg(const Affine& a, bool n) {
+    F ny = -a.y;
+    return Affine{a.x, n ? ny : a.y};
+  }
+  NMSM_HD static Acc from_affine(const Affine& a) {
+    if (affine_is_identity(a)) return identity();
+    return Acc{a.x, a.y, F::one(), F::one()};
+  }
+  NMSM_HD static Acc neg(const Acc& p) { return Acc{p.X, -p.Y, p.ZZ, p.ZZZ}; }
+
+  // 2*(x, y) for an affine point: mdbl-2008-s-1
+  NMSM_HD static Acc dbl_affine(const Affine& a) {
+    F U = nmsm::dbl(a.y);
+    F V = sqr(U);
+    F W = U * V;
+    F S = a.x * V;
+    F xx = sqr(a.x);
+    F M = nmsm::dbl(xx) + xx;
+    F X3 = sqr(M) - nmsm::dbl(S);
+    F Y3 = M * (S - X3) - W * a.y;
+    return Acc{X3, Y3, V, W};  // y == 0 gives ZZ = 0 (identity), as it must for a 2-torsion point
+  }
+  // dbl-2008-s-1, a = 0
+  NMSM_HD static void dbl(Acc& p) {
+    if (is_identity(p)) return;
+    F U = nmsm::dbl(p.Y);
+    F V = sqr(U);
+    F W = U * V;
+    F S = p.X * V;
+    F xx = sqr(p.X);
+    F M = nmsm::dbl(xx) + xx;
+    F X3 = sqr(M) - nmsm::dbl(S);
+    F Y3 = M * (S - X3) - W * p.Y;
+    p.ZZ = V * p.ZZ;
+    p.ZZZ = W * p.ZZZ;
+    p.X = X3;
+    p.Y = Y3;
+  }
+  // p += a (affine): madd-2008-s with the exceptional cases handled explicitly
+  NMSM_HD static void madd(Acc& p, const Affine& a) {
+    if (affine_is_identity(a)) return;
+    if (is_identity(p)) {
+      p = Acc{a.x, a.y, F::one(), F::one()};
+      return;
+    }
+    F U2 = a.x * p.ZZ;
+    F S2 = a.y * p.ZZZ;
+    F P = U2 - p.X;
+    F R = S2 - p.Y;
+    if (P.is_zero()) {
+      if (R.is_zero())
+        p = dbl_affine(a);
+      else
+        p = identity();
+      return;
+    }
+    F PP = sqr(P);
+    F PPP = P * PP;
+    F Q = p.X * PP;
+    F X3 = sqr(R) - PPP - nmsm::dbl(Q);
+    F Y3 = R * (Q - X3) - p.Y * PPP;
+    p.ZZ = p.ZZ * PP;
+    p.ZZZ = p.ZZZ * PPP;
+    p.X = X3;
+    p.Y = Y3;
+  }
+  // p += q: add-2008-s with exceptional cases
+  NMSM_HD static void add(Acc& p, const Acc& q) {
+    if (is_identity(q)) return;
+    if (is_identity(p)) {
+      p = q;
+      return;
+    }
+    F U1 = p.X * q.ZZ;
+    F U2 = q.X * p.ZZ;
+    F S1 = p.Y * q.ZZZ;
+    F S2 = q.Y * p.ZZZ;
+    F P = U2 - U1;
+    F R = S2 - S1;
+    if (P.is_zero()) {
+      if (R.is_zero())
+        dbl(p);
+      else
+        p = identity();
+      return;
+    }
+    F PP = sqr(P);
+    F PPP = P * PP;
+    F Q = U1 * PP;
+    F X3 = sqr(R) - PPP - nmsm::dbl(Q);
+    F Y3 = R * (Q - X3) - S1 * PPP;
+    p.ZZ = p.ZZ * q.ZZ * PP;
+    p.ZZZ = p.ZZZ * q.ZZZ * PPP;
+    p.X = X3;
+    p.Y = Y3;
+  }
+  // canonical affine output; identity -> (0, 0), flag 1 (weierstrass.ts:966)
+  NMSM_HD static void to_affine_canonical(const Acc& p, uint32_t* xy, uint32_t* is_inf) {
+    if (is_identity(p)) {
+      for (int k = 0; k < 2 * F::LIMBS; k++) xy[k] = 0;
+      *is_inf = 1;
+      return;
+    }
+    F i3 = inv(p.ZZZ);       // 1/Z^3
+    F t = p.ZZ * i3;         // 1/Z
+    F x = p.X * sqr(t);      // X / Z^2
+    F y = p.Y * i3;          // Y / Z^3
+    x.to_canonical(xy);
+    y.to_canonical(xy + F::LIMBS);
+    *is_inf = 0;
+  }
+  NMSM_HD static void store_acc(uint32_t* dst, const Acc& p) {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
+    for (int k = 0; k < ACC_WORDS; k++) dst[k] = s[k];
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// Twisted Edwards, a = -1 (ed25519)
+// ------------------------------------------------------------------------------------------
+template <class F, class K>
+struct EdExt {
+  using Field = F;
+  static constexpr int COORD_WORDS = F::LIMBS;
+  static constexpr int IN_WORDS = 2 * F::LIMBS;
+  static constexpr int AFF_WORDS = 3 * F::LIMBS;
+  static constexpr int ACC_WORDS = 4 * F::LIMBS;
+  static constexpr int COST_MADD = 7, COST_ADD = 9, COST_DBL = 8;
+  static constexpr bool IS_EDWARDS = true;
+
+  struct Affine {
+    F ymx, ypx, t2d;  // y-x, y+x, 2d*x*y
+  };
+  struct Acc {
+    F X, Y, Z, T;
+  };
+
+  NMSM_HD static F d2() {
+    F r;
+    for (int k = 0; k < F::N; k++) r.v[k] = K::D2_MONT(k);
+    return r;
+  }
+  NMSM_HD static Acc identity() { return Acc{F::zero(), F::one(), F::one(), F::zero()}; }
+  NMSM_HD static bool is_identity(const Acc& p) { return p.X.is_zero() && p.Y == p.Z; }
+  NMSM_HD static bool affine_is_identity(const Affine& a) { return a.t2d.is_zero() && a.ymx == a.ypx; }
+  NMSM_HD static Affine prepare(const uint32_t* xy) {
+    F x = F::from_canonical(xy), y = F::from_canonical(xy + F::LIMBS);
+    return Affine{y - x, y + x, x * y * d2()};
+  }
+  NMSM_HD static bool input_in_range(const uint32_t* xy) {
+    return F::canonical_in_range(xy) && F::canonical_in_range(xy + F::LIMBS);
+  }
+  // -(x, y) = (-x, y)
+  NMSM_HD static Affine neg(const Affine& a) { return Affine{a.ypx, a.ymx, -a.t2d}; }
+  NMSM_HD static Affine cneg(const Affine& a, bool n) {
+    F nt = -a.t2d;
+    return Affine{n ? a.ypx : a.ymx, n ? a.ymx : a.ypx, n ? nt : a.t2d};
+  }
+  NMSM_HD static Acc neg(const Acc& p) { return Acc{-p.X, p.Y, p.Z, -p.T}; }
+  NMSM_HD static Acc from_affine(const Affine& a) {
+    Acc r = identity();
+    madd(r, a);
+    return r;
+  }
+  // dbl-2008-hwcd, a = -1 (edwards.ts:505-521)
+  NMSM_HD static void dbl(Acc& p) {
+    F A = sqr(p.X);
+    F B = sqr(p.Y);
+    F C = nmsm::dbl(sqr(p.Z));
+    F D = -A;
+    F E = sqr(p.X + p.Y) - A - B;
+    F G = D + B;
+    F Fv = G - C;
+    F H = D - B;
+    p.X = E * Fv;
+    p.Y = G * H;
+    p.T = E * H;
+    p.Z = Fv * G;
+  }
+  // add-2008-hwcd-3 with Z2 = 1 and precomputed (y2-x2, y2+x2, 2d*x2*y2): complete for a=-1, d non-square
+  NMSM_HD static void madd(Acc& p, const Affine& a) {
+    F A = (p.Y - p.X) * a.ymx;
+    F B = (p.Y + p.X) * a.ypx;
+    F C = p.T * a.t2d;
+    F D = nmsm::dbl(p.Z);
+    F E = B - A;
+    F Fv = D - C;
+    F G = D + C;
+    F H = B + A;
+    p.X = E * Fv;
+    p.Y = G * H;
+    p.T = E * H;
+    p.Z = Fv * G;
+  }
+  NMSM_HD static void add(Acc& p, const Acc& q) {
+    F A = (p.Y - p.X) * (q.Y - q.X);
+    F B = (p.Y + p.X) * (q.Y + q.X);
+    F C = p.T * d2() * q.T;
+    F D = nmsm::dbl(p.Z * q.Z);
+    F E = B - A;
+    F Fv = D - C;
+    F G = D + C;
+    F H = B + A;
+    p.X = E * Fv;
+    p.Y = G * H;
+    p.T = E * H;
+    p.Z = Fv * G;
+  }
+  // canonical affine output; identity -> (0, 1), flag 1 (edwards.ts:606)
+  NMSM_HD static void to_affine_canonical(const Acc& p, uint32_t* xy, uint32_t* is_inf) {
+    F iz = inv(p.Z);
+    F x = p.X * iz, y = p.Y * iz;
+    x.to_canonical(xy);
+    y.to_canonical(xy + F::LIMBS);
+    *is_inf = (x.is_zero() && y == F::one()) ? 1u : 0u;
+  }
+  NMSM_HD static void store_acc(uint32_t* dst, const Acc& p) {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
+    for (int k = 0; k < ACC_WORDS; k++) dst[k] = s[k];
+  }
+};
+
+// Curve policies; ID values are the curve ids of the C ABI (include/nmsm.h)
+struct CurveSecp256k1 {
+  using G = SwXyzz<Fp<FpSecp256k1>>;
+  using Fn = Fn_secp256k1;
+  static constexpr int ID = 0;
+};
+struct CurveEd25519 {
+  using G = EdExt<Fp<FpEd25519>, Ed25519Consts>;
+  using Fn = Fn_ed25519;
+  static constexpr int ID = 1;
+};
+struct CurveBn254G1 {
+  using G = SwXyzz<Fp<FpBn254>>;
+  using Fn = Fn_bn254;
+  static constexpr int ID = 2;
+};
+struct CurveBn254G2 {
+  using G = SwXyzz<Fp2<FpBn254>>;
+  using Fn = Fn_bn254;
+  static constexpr int ID = 3;
+};
+struct CurveBls381G1 {
+  using G = SwXyzz<Fp<FpBls381>>;
+  using Fn = Fn_bls12_381;
+  static constexpr int ID = 4;
+};
+struct CurveBls381G2 {
+  using G = SwXyzz<Fp2<FpBls381>>;
+  using Fn = Fn_bls12_381;
+  static constexpr int ID = 5;
+};
+
+}  // namespace nmsm

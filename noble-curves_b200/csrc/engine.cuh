@@ -1,0 +1,198 @@
+// Host-side engine template instantiated once per curve (inst_*.cu): workspace management, plan
+// selection, launches, error mapping.  No CPU compute path exists.
+#pragma once
+#include "context.h"
+#include "msm.cuh"
+
+namespace nmsm {
+
+// ---------------------------------------------------------------------------------------------
+// MSM driver
+// ---------------------------------------------------------------------------------------------
+inline unsigned int cdiv(uint64_t a, unsigned int b) { return (unsigned int)((a + b - 1) / b); }
+
+#define EV(slot)                                                         \
+  do {                                                                   \
+    if (C.profiling) cudaEventRecord(C.ev[slot], C.stream);              \
+  } while (0)
+
+template <class Cv>
+struct Engine {
+  using G = typename Cv::G;
+
+// Runs the pipeline on device-resident canonical inputs.  If d_out_acc != nullptr the raw
+// accumulator is written there and no affine result is produced.
+static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
+                   uint8_t* out_xy, int* out_is_inf) {
+  Context& C = g_ctx;
+  if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
+  const int RES_WORDS = G::IN_WORDS + 4;  // xy | inf | err_pt | err_sc | pad
+  CK(C.result.ensure(RES_WORDS * 4));
+  uint32_t* d_res = (uint32_t*)C.result.p;
+  unsigned int* d_err = (unsigned int*)(d_res + G::IN_WORDS + 1);
+
+  if (n == 0) {  // curve.ts:878 — empty input returns the identity
+    if (d_out_acc) {
+      typename G::Acc id = G::identity();
+      CK(cudaMemcpyAsync(d_out_acc, &id, sizeof(id), cudaMemcpyHostToDevice, C.stream));
+      CK(cudaStreamSynchronize(C.stream));
+      return NMSM_OK;
+    }
+    memset(out_xy, 0, G::IN_WORDS * 4);
+    if (G::IS_EDWARDS) out_xy[G::COORD_WORDS * 4] = 1;  // (0, 1)
+    *out_is_inf = 1;
+    return NMSM_OK;
+  }
+
+  MsmPlan plan = make_plan<Cv>(n, C.forced_c, C.sm_count);
+  const uint64_t max_entries = n * (uint64_t)plan.W;
+  if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
+  const uint64_t max_threads = (max_entries + plan.L - 1) / plan.L;
+
+  CK(C.aff.ensure(n * G::AFF_WORDS * 4));
+  CK(C.counts.ensure((size_t)(plan.G + 1) * 4));
+  CK(C.offsets.ensure((size_t)(plan.G + 1) * 4));
+  CK(C.cursor.ensure((size_t)(plan.G + 1) * 4));
+  CK(C.sorted.ensure(max_entries * 4));
+  CK(C.buckets.ensure((size_t)plan.G * G::ACC_WORDS * 4));
+  CK(C.heads.ensure(max_threads * G::ACC_WORDS * 4));
+  CK(C.tails.ensure(max_threads * G::ACC_WORDS * 4));
+  CK(C.chunk_out.ensure((size_t)plan.W * plan.chunks * G::ACC_WORDS * 4));
+  CK(C.window_out.ensure((size_t)plan.W * G::ACC_WORDS * 4));
+
+  uint32_t* aff = (uint32_t*)C.aff.p;
+  unsigned int* counts = (unsigned int*)C.counts.p;
+  uint32_t* offsets = (uint32_t*)C.offsets.p;
+  unsigned int* cursor = (unsigned int*)C.cursor.p;
+  uint32_t* sorted = (uint32_t*)C.sorted.p;
+  uint32_t* buckets = (uint32_t*)C.buckets.p;
+  uint32_t* heads = (uint32_t*)C.heads.p;
+  uint32_t* tails = (uint32_t*)C.tails.p;
+  uint32_t* chunk_out = (uint32_t*)C.chunk_out.p;
+  uint32_t* window_out = (uint32_t*)C.window_out.p;
+  cudaStream_t st = C.stream;
+  const uint32_t n32 = (uint32_t)n;
+
+  EV(0);
+  CK(cudaMemsetAsync(d_err, 0xff, 8, st));
+  CK(cudaMemsetAsync(counts, 0, (size_t)(plan.G + 1) * 4, st));
+  k_prepare<Cv><<<cdiv(n, 128), 128, 0, st>>>(d_pts, n32, aff, d_err);
+  EV(1);
+  k_digits<Cv, false><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, counts, nullptr, d_err);
+  EV(2);
+  k_scan<<<1, 1024, 0, st>>>(counts, (uint32_t)plan.G, offsets, cursor);
+  EV(3);
+  k_digits<Cv, true><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, cursor, sorted, d_err);
+  EV(4);
+  k_accumulate<Cv><<<cdiv(max_threads, 128), 128, 0, st>>>(aff, sorted, offsets, plan, buckets, heads, tails);
+  EV(5);
+  k_fixup<Cv><<<cdiv(plan.G, 128), 128, 0, st>>>(offsets, plan, buckets, heads, tails);
+  EV(6);
+  k_reduce<Cv><<<cdiv((uint64_t)plan.W * plan.chunks, 128), 128, 0, st>>>(buckets, plan, chunk_out);
+  EV(7);
+  k_window_sum<Cv><<<plan.W, 128, 4 * G::ACC_WORDS * 4, st>>>(chunk_out, plan, window_out);
+  EV(8);
+  if (d_out_acc)
+    k_final<Cv, false><<<1, 32, 0, st>>>(window_out, plan, d_out_acc, nullptr);
+  else
+    k_final<Cv, true><<<1, 32, 0, st>>>(window_out, plan, d_res, d_res + G::IN_WORDS);
+  EV(9);
+  CK(cudaGetLastError());
+  // one small D2H: result + error slots (+ entry count for accounting)
+  CK(cudaMemcpyAsync(C.h_result, d_res, RES_WORDS * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(C.h_result + RES_WORDS, offsets + plan.G, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+
+  const uint32_t err_pt = C.h_result[G::IN_WORDS + 1], err_sc = C.h_result[G::IN_WORDS + 2];
+  // the reference validates all points before any scalar (curve.ts:871-872)
+  if (err_pt != 0xffffffffu) return fail(NMSM_ERR_POINT, "invalid point at index " + std::to_string(err_pt), err_pt);
+  if (err_sc != 0xffffffffu) return fail(NMSM_ERR_SCALAR, "invalid scalar at index " + std::to_string(err_sc), err_sc);
+
+  const uint64_t entries = C.h_result[RES_WORDS];
+  C.last_info.c = plan.c;
+  C.last_info.windows = plan.W;
+  C.last_info.buckets_per_window = plan.B;
+  C.last_info.entries_per_thread = plan.L;
+  C.last_info.reduce_chunk = plan.K;
+  C.last_info.sorted_entries = entries;
+  C.last_info.modmul_equiv = plan_modmuls<Cv>(plan, entries);
+  C.last_info.launches = 9;
+  if (C.profiling) {
+    for (int k = 0; k < 9; k++) cudaEventElapsedTime(&C.last_ms[k], C.ev[k], C.ev[k + 1]);
+    cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev[0], C.ev[9]);
+  }
+  if (!d_out_acc) {
+    memcpy(out_xy, C.h_result, G::IN_WORDS * 4);
+    *out_is_inf = (int)C.h_result[G::IN_WORDS];
+  }
+  return NMSM_OK;
+}
+
+static int run_msm_host(const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf) {
+  Context& C = g_ctx;
+  if (n) {
+    CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
+    CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
+    CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
+    CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
+  }
+  return run_msm((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p, n, nullptr, out_xy, out_is_inf);
+}
+
+static int run_fold(const uint32_t* d_accs, int count, uint8_t* out_xy, int* out_is_inf) {
+  Context& C = g_ctx;
+  const int RES_WORDS = G::IN_WORDS + 4;
+  CK(C.result.ensure(RES_WORDS * 4));
+  uint32_t* d_res = (uint32_t*)C.result.p;
+  k_fold<Cv><<<1, 32, 0, C.stream>>>(d_accs, count, d_res, d_res + G::IN_WORDS);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(C.h_result, d_res, RES_WORDS * 4, cudaMemcpyDeviceToHost, C.stream));
+  CK(cudaStreamSynchronize(C.stream));
+  memcpy(out_xy, C.h_result, G::IN_WORDS * 4);
+  *out_is_inf = (int)C.h_result[G::IN_WORDS];
+  return NMSM_OK;
+}
+
+static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
+                         uint8_t* out_is_inf) {
+  Context& C = g_ctx;
+  if (n == 0) return NMSM_OK;
+  if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
+  CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
+  CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
+  CK(C.mul_out.ensure(n * (G::IN_WORDS + 1) * 4 + 16));
+  CK(C.result.ensure(64));
+  unsigned int* d_err = (unsigned int*)C.result.p;
+  uint32_t* d_xy = (uint32_t*)C.mul_out.p;
+  uint32_t* d_inf = d_xy + n * G::IN_WORDS;
+  cudaStream_t st = C.stream;
+  CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(d_err, 0xff, 8, st));
+  k_mul_batch<Cv><<<cdiv(n, 128), 128, 0, st>>>((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p,
+                                                   (uint32_t)n, allow_zero, d_xy, d_inf, d_err);
+  CK(cudaGetLastError());
+  std::vector<uint32_t> inf(n);
+  unsigned int err[2];
+  CK(cudaMemcpyAsync(err, d_err, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_xy, d_xy, n * G::IN_WORDS * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(inf.data(), d_inf, n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (err[0] != 0xffffffffu) return fail(NMSM_ERR_POINT, "invalid point at index " + std::to_string(err[0]), err[0]);
+  if (err[1] != 0xffffffffu)
+    return fail(NMSM_ERR_SCALAR, "invalid scalar: out of range (index " + std::to_string(err[1]) + ")", err[1]);
+  for (uint64_t i = 0; i < n; i++) out_is_inf[i] = (uint8_t)inf[i];
+  return NMSM_OK;
+}
+};
+
+
+#define NMSM_DEFINE_ENGINE(FN, CURVE)                                                          \
+  const EngineVTable* FN() {                                                                   \
+    static const EngineVTable vt = {CURVE::G::IN_WORDS * 4,         CURVE::G::ACC_WORDS * 4,   \
+                                    &Engine<CURVE>::run_msm_host,   &Engine<CURVE>::run_msm,   \
+                                    &Engine<CURVE>::run_fold,       &Engine<CURVE>::run_mul_batch}; \
+    return &vt;                                                                                \
+  }
+
+}  // namespace nmsm

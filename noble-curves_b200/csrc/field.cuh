@@ -1,0 +1,207 @@
+// Prime-field arithmetic in Montgomery form on 32-bit register limbs (N = 8 for the 254/255/256-bit
+// primes, N = 12 for the 381-bit BLS12-381 base field).
+//
+// Replaces (results identical after from-Montgomery) the reference's bigint field:
+//   /root/reference/src/abstract/modular.ts:888-1038  `_Field` add/sub/neg/mul/sqr/inv/is0/eql
+//   /root/reference/src/abstract/modular.ts:50-54     mod()
+// The reference computes (a*b) % p on BigInt; here elements live as a*R mod p, R = 2^(32N), and
+// every value handed to callers is fully reduced to [0, p) so equality is limb equality.
+//
+// mont_mul layout ("absolute even/odd columns"): two accumulator arrays indexed by absolute limb
+// position.  A partial product x_j*w at position q goes to the array whose 64-bit slots are aligned
+// to q's parity, so each row is one carry chain of (mad.lo.cc, madc.hi.cc) pairs = IMAD.WIDE.U32.X,
+// with no per-product carry fix-up.  After step i the low limb of the slot array is zero and the
+// high half is folded into the other array with an add.cc whose carry feeds that array's next
+// chain.  Because indices are compile-time after unrolling, the "shift right by one limb per step"
+// of CIOS is pure register renaming.  Cost: 2N^2 + N IMAD.WIDE-equivalents (N=12: 300, N=8: 136).
+#pragma once
+#include "bigint.cuh"
+
+namespace nmsm {
+
+// r = (top:r) - p if (top:r) >= p.  Requires (top:r) < 2p.
+template <class C>
+NMSM_HD void reduce_once(uint32_t* r, uint32_t top) {
+  constexpr int N = C::N;
+  uint32_t d[N];
+  d[0] = sub_cc(r[0], C::P(0));
+#pragma unroll
+  for (int k = 1; k < N; k++) d[k] = subc_cc(r[k], C::P(k));
+  uint32_t t = subc(top, 0);  // 0xffffffff iff (top:r) < p
+  bool keep = (t >> 31) != 0;
+#pragma unroll
+  for (int k = 0; k < N; k++) r[k] = keep ? r[k] : d[k];
+}
+
+template <class C>
+NMSM_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = C::N;
+  static_assert(N % 2 == 0, "even limb count expected");
+  uint32_t E[2 * N + 2], O[2 * N + 2];
+#pragma unroll
+  for (int k = 0; k < 2 * N + 2; k++) {
+    E[k] = 0;
+    O[k] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t* P1 = (i & 1) ? O : E;  // slots aligned at position i
+    uint32_t* P2 = (i & 1) ? E : O;  // slots aligned at position i+1; P2[i] = leftover high half
+    const uint32_t w = b[i];
+    // fold the leftover high half into limb i; carry continues into P2's chain at position i+1
+    if (i > 0) P1[i] = add_cc(P1[i], P2[i]);
+#pragma unroll
+    for (int j = 1; j < N; j += 2) {
+      P2[i + j] = (i == 0 && j == 1) ? mad_lo_cc(a[j], w, P2[i + j]) : madc_lo_cc(a[j], w, P2[i + j]);
+      P2[i + j + 1] = madc_hi_cc(a[j], w, P2[i + j + 1]);
+    }
+    P2[i + N + 1] = addc(P2[i + N + 1], 0);
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      P1[i + j] = (j == 0) ? mad_lo_cc(a[j], w, P1[i + j]) : madc_lo_cc(a[j], w, P1[i + j]);
+      P1[i + j + 1] = madc_hi_cc(a[j], w, P1[i + j + 1]);
+    }
+    P1[i + N] = addc(P1[i + N], 0);
+    // Montgomery quotient digit: makes limb i vanish
+    const uint32_t m = P1[i] * C::INV;
+#pragma unroll
+    for (int j = 1; j < N; j += 2) {
+      P2[i + j] = (j == 1) ? mad_lo_cc(m, C::P(j), P2[i + j]) : madc_lo_cc(m, C::P(j), P2[i + j]);
+      P2[i + j + 1] = madc_hi_cc(m, C::P(j), P2[i + j + 1]);
+    }
+    P2[i + N + 1] = addc(P2[i + N + 1], 0);
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      P1[i + j] = (j == 0) ? mad_lo_cc(m, C::P(j), P1[i + j]) : madc_lo_cc(m, C::P(j), P1[i + j]);
+      P1[i + j + 1] = madc_hi_cc(m, C::P(j), P1[i + j + 1]);
+    }
+    P1[i + N] = addc(P1[i + N], 0);
+  }
+  // merge the two column arrays: limbs N..2N
+  r[0] = add_cc(E[N], O[N]);
+#pragma unroll
+  for (int k = 1; k < N; k++) r[k] = addc_cc(E[N + k], O[N + k]);
+  uint32_t top = addc(E[2 * N], O[2 * N]);
+  reduce_once<C>(r, top);
+}
+
+template <class C>
+struct Fp {
+  static constexpr int N = C::N;
+  static constexpr int LIMBS = C::N;    // 32-bit words per element
+  static constexpr int BASE_MULS = 1;   // base-field multiplications per mul (accounting)
+  static constexpr int BASE_SQRS = 1;
+  using Params = C;
+  uint32_t v[N];
+
+  NMSM_HD static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int k = 0; k < N; k++) r.v[k] = 0;
+    return r;
+  }
+  NMSM_HD static Fp one() {  // Montgomery form of 1
+    Fp r;
+#pragma unroll
+    for (int k = 0; k < N; k++) r.v[k] = C::R1(k);
+    return r;
+  }
+  NMSM_HD bool is_zero() const {
+    uint32_t t = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) t |= v[k];
+    return t == 0;
+  }
+  NMSM_HD bool operator==(const Fp& o) const {
+    uint32_t t = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) t |= v[k] ^ o.v[k];
+    return t == 0;
+  }
+  NMSM_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+
+  NMSM_HD friend Fp operator*(const Fp& a, const Fp& b) {
+    Fp r;
+    mont_mul<C>(r.v, a.v, b.v);
+    return r;
+  }
+  NMSM_HD friend Fp operator+(const Fp& a, const Fp& b) {
+    Fp r;
+    r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int k = 1; k < N; k++) r.v[k] = addc_cc(a.v[k], b.v[k]);
+    uint32_t top = addc(0, 0);
+    reduce_once<C>(r.v, top);
+    return r;
+  }
+  NMSM_HD friend Fp operator-(const Fp& a, const Fp& b) {
+    Fp r;
+    r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int k = 1; k < N; k++) r.v[k] = subc_cc(a.v[k], b.v[k]);
+    uint32_t mask = subc(0, 0);  // all ones iff a < b
+    r.v[0] = add_cc(r.v[0], C::P(0) & mask);
+#pragma unroll
+    for (int k = 1; k < N; k++) r.v[k] = addc_cc(r.v[k], C::P(k) & mask);
+    return r;
+  }
+  NMSM_HD Fp operator-() const { return zero() - *this; }
+
+  // canonical little-endian limbs <-> Montgomery
+  NMSM_HD static Fp from_canonical(const uint32_t* x) {
+    Fp a, r2;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      a.v[k] = x[k];
+      r2.v[k] = C::R2(k);
+    }
+    return a * r2;
+  }
+  NMSM_HD void to_canonical(uint32_t* x) const {
+    Fp o;
+#pragma unroll
+    for (int k = 0; k < N; k++) o.v[k] = (k == 0) ? 1u : 0u;
+    Fp r = (*this) * o;
+#pragma unroll
+    for (int k = 0; k < N; k++) x[k] = r.v[k];
+  }
+  // x < p as canonical integer?
+  NMSM_HD static bool canonical_in_range(const uint32_t* x) {
+    uint32_t t = sub_cc(x[0], C::P(0));
+#pragma unroll
+    for (int k = 1; k < N; k++) t = subc_cc(x[k], C::P(k));
+    (void)t;
+    return subc(0, 0) != 0;  // borrow => x < p
+  }
+};
+
+template <class C>
+NMSM_HD Fp<C> sqr(const Fp<C>& a) {
+  return a * a;
+}
+template <class C>
+NMSM_HD Fp<C> dbl(const Fp<C>& a) {
+  return a + a;
+}
+
+// a^(p-2): modular.ts:980 `inv` (the reference uses extended Euclid, modular.ts:159-182; the value
+// is the same).  Single-thread latency path (final to-affine only); 0 maps to 0.
+template <class C>
+NMSM_HD Fp<C> inv(const Fp<C>& a) {
+  constexpr int N = C::N;
+  Fp<C> r = Fp<C>::one();
+  bool started = false;
+  for (int i = N - 1; i >= 0; i--) {
+    uint32_t e = C::P(i) - (i == 0 ? 2u : 0u);  // p is odd and p[0] >= 3 for every supported prime
+    for (int bit = 31; bit >= 0; bit--) {
+      if (started) r = sqr(r);
+      if ((e >> bit) & 1) {
+        r = r * a;
+        started = true;
+      }
+    }
+  }
+  return r;
+}
+
+}  // namespace nmsm

@@ -1,0 +1,418 @@
+// Per-thread bodies of the MSM / scalar-multiplication kernels.
+//
+// Each function is what ONE CUDA thread of the corresponding kernel in msm.cuh executes.  They are
+// written against plain pointers and a thread index so that tests/hostemu can drive exactly the same
+// code on the CPU (loops over the thread index, emulated PTX carry flag) — test infrastructure that
+// lets the limb arithmetic and the bucket bookkeeping be verified without a GPU.  The product
+// library only ever runs them inside the CUDA kernels.
+//
+// Pipeline (replaces /root/reference/src/abstract/curve.ts:863-905 `pippenger`):
+//   prepare -> count digits -> scan -> scatter -> accumulate -> fixup -> reduce -> window sum -> final
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "ec.cuh"
+
+#if defined(__CUDACC__)
+#define NMSM_NL __host__ __device__ __noinline__
+#else
+#define NMSM_NL inline
+#endif
+
+namespace nmsm {
+
+static constexpr int MAX_WINDOW_BITS = 16;
+static constexpr int SCALAR_WORDS = 8;
+
+struct MsmPlan {
+  int c;       // window bits
+  int W;       // windows
+  int B;       // buckets per window = 2^(c-1)
+  int G;       // W*B
+  int L;       // sorted entries per accumulate thread
+  int K;       // buckets per reduce chunk
+  int chunks;  // B / K
+};
+
+// ---------------------------------------------------------------------------------------------
+// plan selection: minimise  W * (n * MADD + 2 * B * ADD * overhead)  over the window size c
+// ---------------------------------------------------------------------------------------------
+template <class Cv>
+inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
+  using G = typename Cv::G;
+  const int bits = Cv::Fn::BITS;
+  int best_c = 2;
+  double best = 1e300;
+  for (int c = 2; c <= MAX_WINDOW_BITS; c++) {
+    int W = (bits + 1 + c - 1) / c;
+    double B = (double)(1u << (c - 1));
+    // reduce runs at lower occupancy and pays the chunk-offset multiplications: weight it 1.6x
+    double cost = (double)W * ((double)n * G::COST_MADD + 2.0 * B * G::COST_ADD * 1.6) + 9.0 * bits;
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  int c = (forced_c >= 1 && forced_c <= MAX_WINDOW_BITS) ? forced_c : best_c;
+  MsmPlan p;
+  p.c = c;
+  p.W = (bits + 1 + c - 1) / c;
+  p.B = 1 << (c - 1);
+  p.G = p.W * p.B;
+  double entries = (double)n * p.W;
+  double target_threads = (double)sm_count * 1024.0;
+  int L = (int)ceil(entries / target_threads);
+  if (L < 4) L = 4;
+  if (L > 32) L = 32;
+  p.L = L;
+  p.K = p.B < 16 ? p.B : 16;
+  p.chunks = p.B / p.K;
+  return p;
+}
+
+template <class Cv>
+inline uint64_t plan_modmuls(const MsmPlan& p, uint64_t entries) {
+  using G = typename Cv::G;
+  using F = typename G::Field;
+  // field-mul equivalents in the base field (Fp2 mul = 3)
+  uint64_t per = F::BASE_MULS;
+  uint64_t m = entries * G::COST_MADD + (uint64_t)p.W * 2ull * p.B * G::COST_ADD +
+               (uint64_t)p.W * p.c * G::COST_DBL;
+  return m * per;
+}
+
+// ---------------------------------------------------------------------------------------------
+// memory helpers: rows are multiples of 16 bytes -> 128-bit vector loads/stores on the device
+// ---------------------------------------------------------------------------------------------
+template <int WORDS>
+NMSM_HD void load_words(uint32_t* dst, const uint32_t* src) {
+  static_assert(WORDS % 4 == 0, "rows are 16-byte multiples");
+#if defined(__CUDA_ARCH__)
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int k = 0; k < WORDS / 4; k++) {
+    uint4 v = __ldg(s4 + k);
+    dst[4 * k + 0] = v.x;
+    dst[4 * k + 1] = v.y;
+    dst[4 * k + 2] = v.z;
+    dst[4 * k + 3] = v.w;
+  }
+#else
+  for (int k = 0; k < WORDS; k++) dst[k] = src[k];
+#endif
+}
+// same, for buffers written earlier by the same grid sequence (no read-only cache path)
+template <int WORDS>
+NMSM_HD void load_words_rw(uint32_t* dst, const uint32_t* src) {
+#if defined(__CUDA_ARCH__)
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int k = 0; k < WORDS / 4; k++) {
+    uint4 v = s4[k];
+    dst[4 * k + 0] = v.x;
+    dst[4 * k + 1] = v.y;
+    dst[4 * k + 2] = v.z;
+    dst[4 * k + 3] = v.w;
+  }
+#else
+  for (int k = 0; k < WORDS; k++) dst[k] = src[k];
+#endif
+}
+template <int WORDS>
+NMSM_HD void store_words(uint32_t* dst, const uint32_t* src) {
+#if defined(__CUDA_ARCH__)
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int k = 0; k < WORDS / 4; k++) d4[k] = make_uint4(src[4 * k], src[4 * k + 1], src[4 * k + 2], src[4 * k + 3]);
+#else
+  for (int k = 0; k < WORDS; k++) dst[k] = src[k];
+#endif
+}
+NMSM_HD uint32_t atomic_add_u32(unsigned int* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  uint32_t o = *p;
+  *p += v;
+  return o;
+#endif
+}
+NMSM_HD void atomic_min_u32(unsigned int* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  atomicMin(p, v);
+#else
+  if (v < *p) *p = v;
+#endif
+}
+
+template <class G>
+NMSM_HD typename G::Acc load_acc(const uint32_t* src) {
+  typename G::Acc a;
+  load_words_rw<G::ACC_WORDS>(reinterpret_cast<uint32_t*>(&a), src);
+  return a;
+}
+template <class G>
+NMSM_HD void save_acc(uint32_t* dst, const typename G::Acc& a) {
+  store_words<G::ACC_WORDS>(dst, reinterpret_cast<const uint32_t*>(&a));
+}
+template <class G>
+NMSM_HD typename G::Affine load_aff(const uint32_t* src) {
+  typename G::Affine a;
+  load_words<G::AFF_WORDS>(reinterpret_cast<uint32_t*>(&a), src);
+  return a;
+}
+
+// Out-of-line group operations for the cold kernels (everything except accumulate): one copy of
+// each formula per curve keeps code size and ptxas time bounded; the call overhead (accumulators
+// passed through local memory) is ~2% of a 14-multiplication addition.
+template <class G>
+NMSM_NL void nl_add(typename G::Acc& p, const typename G::Acc& q) { G::add(p, q); }
+template <class G>
+NMSM_NL void nl_dbl(typename G::Acc& p) { G::dbl(p); }
+template <class G>
+NMSM_NL void nl_madd(typename G::Acc& p, const typename G::Affine& a) { G::madd(p, a); }
+template <class G>
+NMSM_NL void nl_to_affine(const typename G::Acc& p, uint32_t* xy, uint32_t* inf) {
+  G::to_affine_canonical(p, xy, inf);
+}
+
+// c bits of a 256-bit little-endian scalar starting at bit `off`
+NMSM_HD uint32_t scalar_bits(const uint32_t* s, int off, int c) {
+  int w = off >> 5, sh = off & 31;
+  if (w >= SCALAR_WORDS) return 0;
+  uint64_t lo = s[w];
+  uint64_t hi = (w + 1 < SCALAR_WORDS) ? s[w + 1] : 0;
+  uint64_t v = (lo | (hi << 32)) >> sh;
+  return (uint32_t)v & ((1u << c) - 1u);
+}
+
+template <class Fn>
+NMSM_HD bool scalar_in_range(const uint32_t* s) {
+  uint32_t t = sub_cc(s[0], Fn::ORDER(0));
+#pragma unroll
+  for (int k = 1; k < SCALAR_WORDS; k++) t = subc_cc(s[k], Fn::ORDER(k));
+  (void)t;
+  return subc(0, 0) != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bodies
+// ---------------------------------------------------------------------------------------------
+// err[0] = min index of an out-of-range point coordinate, err[1] = min index of an invalid scalar
+template <class Cv>
+NMSM_HD void prepare_body(uint32_t i, const uint32_t* pts, uint32_t* aff, unsigned int* err) {
+  using G = typename Cv::G;
+  uint32_t in[G::IN_WORDS];
+  load_words<G::IN_WORDS>(in, pts + (size_t)i * G::IN_WORDS);
+  if (!G::input_in_range(in)) {
+    atomic_min_u32(&err[0], i);
+    return;
+  }
+  typename G::Affine a = G::prepare(in);
+  store_words<G::AFF_WORDS>(aff + (size_t)i * G::AFF_WORDS, reinterpret_cast<const uint32_t*>(&a));
+}
+
+// Signed-digit recoding shared by the count and scatter passes: digit d_w in [-(2^(c-1)-1), 2^(c-1)],
+// sum d_w 2^(cw) = s (the fixed-window analogue of curve.ts:454-472 signedWindowDigits).
+// Bucket id g = w*B + |d| - 1, weight |d|; the sign rides in bit 31 of the sorted entry.
+template <class Cv, bool SCATTER>
+NMSM_HD void digits_body(uint32_t i, const uint32_t* scalars, const MsmPlan& plan, unsigned int* counts_or_cursor,
+                         uint32_t* sorted, unsigned int* err) {
+  uint32_t s[SCALAR_WORDS];
+  load_words<SCALAR_WORDS>(s, scalars + (size_t)i * SCALAR_WORDS);
+  if (!scalar_in_range<typename Cv::Fn>(s)) {  // same decision in both passes keeps count == scatter
+    if (!SCATTER) atomic_min_u32(&err[1], i);
+    return;
+  }
+  const uint32_t half = 1u << (plan.c - 1);
+  uint32_t carry = 0;
+  for (int w = 0; w < plan.W; w++) {
+    uint32_t v = scalar_bits(s, w * plan.c, plan.c) + carry;
+    carry = 0;
+    uint32_t neg = 0;
+    if (v > half) {
+      v = (1u << plan.c) - v;
+      neg = 1;
+      carry = 1;
+    }
+    if (v != 0) {
+      uint32_t g = (uint32_t)w * (uint32_t)plan.B + (v - 1);
+      if (SCATTER) {
+        uint32_t pos = atomic_add_u32(&counts_or_cursor[g], 1u);
+        sorted[pos] = i | (neg << 31);
+      } else {
+        atomic_add_u32(&counts_or_cursor[g], 1u);
+      }
+    }
+  }
+}
+
+// Balanced bucket accumulation: thread t owns sorted[t*L, (t+1)*L).  Constant work per thread
+// whatever the bucket sizes; a bucket that is wholly inside the segment is written straight to
+// `buckets`, a bucket cut by the segment start goes to heads[t], one cut by the end to tails[t].
+template <class Cv>
+NMSM_HD void accumulate_body(uint32_t t, const uint32_t* aff, const uint32_t* sorted, const uint32_t* offsets,
+                             const MsmPlan& plan, uint32_t* buckets, uint32_t* heads, uint32_t* tails) {
+  using G = typename Cv::G;
+  const uint32_t T = offsets[plan.G];
+  const uint64_t seg64 = (uint64_t)t * (uint32_t)plan.L;
+  if (seg64 >= T) return;
+  const uint32_t seg = (uint32_t)seg64;
+  const uint32_t end = (T - seg > (uint32_t)plan.L) ? seg + plan.L : T;
+  // bucket containing `seg`: the last g with offsets[g] <= seg
+  uint32_t lo = 0, hi = plan.G;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= seg) lo = mid; else hi = mid;
+  }
+  uint32_t g = lo;
+  uint32_t bstart = offsets[g], bend = offsets[g + 1];
+  typename G::Acc acc = G::identity();
+  for (uint32_t pos = seg; pos < end; pos++) {
+    if (pos == bend) {
+      // bucket g is finished inside this segment
+      if (bstart >= seg) save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, acc);
+      else save_acc<G>(heads + (size_t)t * G::ACC_WORDS, acc);
+      acc = G::identity();
+      do { g++; } while (offsets[g + 1] <= pos);
+      bstart = offsets[g];
+      bend = offsets[g + 1];
+    }
+    uint32_t e = sorted[pos];
+    typename G::Affine a = load_aff<G>(aff + (size_t)(e & 0x7fffffffu) * G::AFF_WORDS);
+    a = G::cneg(a, (e >> 31) != 0);
+    G::madd(acc, a);
+  }
+  const bool head_open = bstart < seg;
+  const bool tail_open = bend > end;
+  if (!head_open && !tail_open) save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, acc);
+  else if (head_open) save_acc<G>(heads + (size_t)t * G::ACC_WORDS, acc);
+  else save_acc<G>(tails + (size_t)t * G::ACC_WORDS, acc);
+}
+
+// One thread per bucket: empty -> identity; straddling -> tails[ts] + heads[ts+1..te].
+template <class Cv>
+NMSM_HD void fixup_body(uint32_t g, const uint32_t* offsets, const MsmPlan& plan, uint32_t* buckets,
+                        const uint32_t* heads, const uint32_t* tails) {
+  using G = typename Cv::G;
+  uint32_t b0 = offsets[g], b1 = offsets[g + 1];
+  if (b0 == b1) {
+    save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, G::identity());
+    return;
+  }
+  uint32_t ts = b0 / plan.L, te = (b1 - 1) / plan.L;
+  if (ts == te) return;
+  typename G::Acc acc = load_acc<G>(tails + (size_t)ts * G::ACC_WORDS);
+  for (uint32_t t = ts + 1; t <= te; t++) nl_add<G>(acc, load_acc<G>(heads + (size_t)t * G::ACC_WORDS));
+  save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, acc);
+}
+
+// k * p for a small non-negative k (< 2^16): double-and-add, MSB first
+template <class G>
+NMSM_HD typename G::Acc small_mul(const typename G::Acc& p, uint32_t k) {
+  typename G::Acc r = G::identity();
+  for (int bit = 15; bit >= 0; bit--) {
+    nl_dbl<G>(r);
+    if ((k >> bit) & 1) nl_add<G>(r, p);
+  }
+  return r;
+}
+
+// Thread (w, k): chunk of K buckets -> sum_{b in chunk} (b+1) * bucket[w][b]
+// (the running-sum trick of curve.ts:897-900, 2 additions per bucket, plus lo * sum for the offset)
+template <class Cv>
+NMSM_HD void reduce_body(uint32_t id, const uint32_t* buckets, const MsmPlan& plan, uint32_t* chunk_out) {
+  using G = typename Cv::G;
+  uint32_t w = id / plan.chunks, k = id % plan.chunks;
+  uint32_t lo = k * plan.K;
+  const uint32_t* base = buckets + ((size_t)w * plan.B + lo) * G::ACC_WORDS;
+  typename G::Acc sum = G::identity(), wsum = G::identity();
+  for (int b = plan.K - 1; b >= 0; b--) {
+    nl_add<G>(sum, load_acc<G>(base + (size_t)b * G::ACC_WORDS));
+    nl_add<G>(wsum, sum);
+  }
+  if (lo != 0) nl_add<G>(wsum, small_mul<G>(sum, lo));
+  save_acc<G>(chunk_out + (size_t)id * G::ACC_WORDS, wsum);
+}
+
+// Horner over the window sums (curve.ts:901-902).  AFFINE_OUT: canonical affine + infinity flag,
+// else the raw accumulator (multi-GPU partial, folded later by fold_body).
+template <class Cv, bool AFFINE_OUT>
+NMSM_HD void final_body(const uint32_t* window_out, const MsmPlan& plan, uint32_t* out, uint32_t* out_inf) {
+  using G = typename Cv::G;
+  typename G::Acc acc = G::identity();
+  for (int w = plan.W - 1; w >= 0; w--) {
+    if (w != plan.W - 1)
+      for (int j = 0; j < plan.c; j++) nl_dbl<G>(acc);
+    nl_add<G>(acc, load_acc<G>(window_out + (size_t)w * G::ACC_WORDS));
+  }
+  if (AFFINE_OUT) {
+    uint32_t xy[G::IN_WORDS];
+    uint32_t inf;
+    nl_to_affine<G>(acc, xy, &inf);
+    for (int k = 0; k < G::IN_WORDS; k++) out[k] = xy[k];
+    *out_inf = inf;
+  } else {
+    save_acc<G>(out, acc);
+  }
+}
+
+// Fold `count` raw accumulators (e.g. one per GPU) and emit canonical affine.
+template <class Cv>
+NMSM_HD void fold_body(const uint32_t* accs, int count, uint32_t* out, uint32_t* out_inf) {
+  using G = typename Cv::G;
+  typename G::Acc acc = G::identity();
+  for (int i = 0; i < count; i++) nl_add<G>(acc, load_acc<G>(accs + (size_t)i * G::ACC_WORDS));
+  uint32_t xy[G::IN_WORDS];
+  uint32_t inf;
+  nl_to_affine<G>(acc, xy, &inf);
+  for (int k = 0; k < G::IN_WORDS; k++) out[k] = xy[k];
+  *out_inf = inf;
+}
+
+// k_i * P_i (Point.multiply / multiplyUnsafe, weierstrass.ts:900-928, edwards.ts:555-577): left-to-right
+// signed-binary (NAF) double-and-add with mixed additions, canonical affine out.  Public-input /
+// variable-time, like the reference's multiplyUnsafe; the value equals multiply()'s.
+template <class Cv>
+NMSM_HD void mul_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, int allow_zero, uint32_t* out_xy,
+                      uint32_t* out_inf, unsigned int* err) {
+  using G = typename Cv::G;
+  uint32_t in[G::IN_WORDS];
+  load_words<G::IN_WORDS>(in, pts + (size_t)i * G::IN_WORDS);
+  uint32_t s[SCALAR_WORDS + 1];
+  load_words<SCALAR_WORDS>(s, scalars + (size_t)i * SCALAR_WORDS);
+  s[SCALAR_WORDS] = 0;
+  bool bad_pt = !G::input_in_range(in);
+  bool bad_sc = !scalar_in_range<typename Cv::Fn>(s);
+  uint32_t nz = 0;
+  for (int k = 0; k < SCALAR_WORDS; k++) nz |= s[k];
+  if (!allow_zero && nz == 0) bad_sc = true;
+  if (bad_pt) atomic_min_u32(&err[0], i);
+  if (bad_sc) atomic_min_u32(&err[1], i);
+  if (bad_pt || bad_sc) return;
+  typename G::Affine P = G::prepare(in);
+  typename G::Affine Pn = G::neg(P);
+  // NAF digit at position j-1 is h_j - k_j with h = 3k
+  uint32_t h[SCALAR_WORDS + 1];
+  {
+    uint32_t d[SCALAR_WORDS + 1];
+    for (int k = 0; k < SCALAR_WORDS + 1; k++) d[k] = (s[k] << 1) | (k ? (s[k - 1] >> 31) : 0);
+    h[0] = add_cc(s[0], d[0]);
+    for (int k = 1; k < SCALAR_WORDS; k++) h[k] = addc_cc(s[k], d[k]);
+    h[SCALAR_WORDS] = addc(s[SCALAR_WORDS], d[SCALAR_WORDS]);
+  }
+  typename G::Acc acc = G::identity();
+  for (int j = 32 * SCALAR_WORDS + 1; j >= 1; j--) {
+    uint32_t hb = (h[j >> 5] >> (j & 31)) & 1, kb = (s[j >> 5] >> (j & 31)) & 1;
+    nl_dbl<G>(acc);
+    if (hb != kb) nl_madd<G>(acc, hb ? P : Pn);
+  }
+  uint32_t xy[G::IN_WORDS];
+  uint32_t inf;
+  nl_to_affine<G>(acc, xy, &inf);
+  store_words<G::IN_WORDS>(out_xy + (size_t)i * G::IN_WORDS, xy);
+  out_inf[i] = inf;
+}
+
+}  // namespace nmsm

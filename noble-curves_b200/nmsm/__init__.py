@@ -1,0 +1,431 @@
+"""nmsm — host-side mirror of noble-curves' scalar-multiplication / MSM surface over libnmsm.so.
+
+The reference's host language is TypeScript (no Node / N-API headers exist in this image, see
+INTEGRATION.md for the addon a maintainer would add); this Python layer mirrors the same names,
+argument meaning and error behaviour so the parity tests read like the reference's own tests:
+
+    pippenger(c, points, scalars)          /root/reference/src/abstract/curve.ts:863-905
+    mulAddUnsafe(c, points, scalars)       src/abstract/curve.ts:820-836 (same value, computed as an MSM)
+    Point.multiply / Point.multiplyUnsafe  src/abstract/weierstrass.ts:900-928, src/abstract/edwards.ts:555-577
+    Point.BASE / ZERO / fromAffine / toAffine / add / double / negate / equals / is0
+    secp256k1.Point, ed25519.Point, bn254.G1/G2.Point, bls12_381.G1/G2.Point
+
+plus the packed fast paths the reference lacks: msm_packed, msm_device, multiply_many.
+Every curve operation runs on the GPU through the C ABI; the host only marshals bytes and validates
+argument shapes.  Nothing here imports `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence
+
+from . import _lib
+from ._lib import NmsmError, PlanInfo, TIMING_NAMES, init  # noqa: F401
+
+SECP256K1, ED25519, BN254_G1, BN254_G2, BLS12_381_G1, BLS12_381_G2 = range(6)
+
+
+class _Field:
+    """Shape-compatible stand-in for the IField members the MSM surface reads (modular.ts:429-607)."""
+
+    def __init__(self, order: int, is_le: bool = False):
+        self.ORDER = order
+        self.BITS = order.bit_length()
+        self.BYTES = (self.BITS + 7) // 8
+        self.isLE = is_le
+
+    def isValid(self, num) -> bool:
+        return isinstance(num, int) and not isinstance(num, bool) and 0 <= num < self.ORDER
+
+    def isValidNot0(self, num) -> bool:
+        return self.isValid(num) and num != 0
+
+
+class _Field2:
+    def __init__(self, fp: _Field):
+        self.Fp = fp
+        self.ORDER = fp.ORDER * fp.ORDER
+        self.BITS = self.ORDER.bit_length()
+        self.BYTES = 2 * fp.BYTES
+
+    def isValid(self, num) -> bool:
+        return isinstance(num, tuple) and len(num) == 2 and self.Fp.isValid(num[0]) and self.Fp.isValid(num[1])
+
+
+def _coord_to_bytes(v, nbytes: int, parts: int) -> bytes:
+    if parts == 1:
+        return v.to_bytes(nbytes, "little")
+    return v[0].to_bytes(nbytes, "little") + v[1].to_bytes(nbytes, "little")
+
+
+def _coord_from_bytes(b: bytes, nbytes: int, parts: int):
+    if parts == 1:
+        return int.from_bytes(b[:nbytes], "little")
+    return (int.from_bytes(b[:nbytes], "little"), int.from_bytes(b[nbytes:2 * nbytes], "little"))
+
+
+def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, parts: int, edwards: bool):
+    base_fp = _Field(p, is_le=edwards)
+    Fp = base_fp if parts == 1 else _Field2(base_fp)
+    Fn = _Field(n, is_le=edwards)
+    fp_bytes = 48 if p.bit_length() > 256 else 32
+    zero_coord = 0 if parts == 1 else (0, 0)
+    one_coord = 1 if parts == 1 else (1, 0)
+
+    class Point:
+        """Affine host handle of a curve point; every group operation runs on the GPU."""
+
+        __slots__ = ("x", "y", "_inf")
+        CURVE_ID = curve_id
+        NAME = name
+
+        def __init__(self, x, y, _inf: bool = False):
+            if not Fp.isValid(x):
+                raise ValueError("bad point coordinate x")
+            if not Fp.isValid(y):
+                raise ValueError("bad point coordinate y")
+            self.x, self.y, self._inf = x, y, bool(_inf)
+
+        # -- noble's projective accessors (weierstrass.ts:687-704 / edwards.ts:370-385), Z = 1 ----
+        @property
+        def X(self):
+            return self.x
+
+        @property
+        def Y(self):
+            return one_coord if (self._inf and not edwards) else self.y
+
+        @property
+        def Z(self):
+            return zero_coord if (self._inf and not edwards) else one_coord
+
+        @staticmethod
+        def fromAffine(p):
+            """weierstrass.ts:711-718 / edwards.ts:396-402."""
+            if not isinstance(p, dict) or not Fp.isValid(p.get("x")) or not Fp.isValid(p.get("y")):
+                raise ValueError("invalid affine point")
+            x, y = p["x"], p["y"]
+            if not edwards and x == zero_coord and y == zero_coord:
+                return Point.ZERO
+            if edwards and x == 0 and y == 1:
+                return Point.ZERO
+            return Point(x, y)
+
+        def toAffine(self):
+            """weierstrass.ts:951-969 (ZERO -> (0,0)) / edwards.ts:595-609 (ZERO -> (0,1))."""
+            return {"x": self.x, "y": self.y}
+
+        def is0(self) -> bool:
+            return self._inf
+
+        def equals(self, other) -> bool:
+            if not isinstance(other, Point):
+                raise TypeError("Weierstrass Point expected" if not edwards else "EdwardsPoint expected")
+            return self._inf == other._inf and self.x == other.x and self.y == other.y
+
+        def negate(self):
+            if self._inf:
+                return self
+            if edwards:  # -(x, y) = (-x, y)   edwards.ts:497-500
+                return Point((-self.x) % p, self.y)
+            if parts == 1:  # weierstrass.ts:785-787
+                return Point(self.x, (-self.y) % p)
+            return Point(self.x, ((-self.y[0]) % p, (-self.y[1]) % p))
+
+        def add(self, other):
+            if not isinstance(other, Point):
+                raise TypeError("Weierstrass Point expected" if not edwards else "EdwardsPoint expected")
+            return _msm_points(Point, [self, other], [1, 1])
+
+        def subtract(self, other):
+            return self.add(other.negate())
+
+        def double(self):
+            return _msm_points(Point, [self], [2])
+
+        def multiply(self, scalar):
+            """weierstrass.ts:900-907 / edwards.ts:555-564: 1 <= scalar < n."""
+            if not Fn.isValidNot0(scalar):
+                raise ValueError(
+                    "invalid scalar: expected 1 <= sc < curve.n" if edwards else "invalid scalar: out of range"
+                )
+            return multiply_many(Point, [self], [scalar], unsafe=False)[0]
+
+        def multiplyUnsafe(self, scalar):
+            """weierstrass.ts:915-928 / edwards.ts:571-577: 0 <= scalar < n."""
+            if not Fn.isValid(scalar):
+                raise ValueError(
+                    "invalid scalar: expected 0 <= sc < curve.n" if edwards else "invalid scalar: out of range"
+                )
+            return multiply_many(Point, [self], [scalar], unsafe=True)[0]
+
+        def to_packed(self) -> bytes:
+            return _coord_to_bytes(self.x, fp_bytes, parts) + _coord_to_bytes(self.y, fp_bytes, parts)
+
+        @staticmethod
+        def from_packed(b: bytes, is_inf: int):
+            cb = fp_bytes * parts
+            if is_inf:
+                return Point.ZERO
+            return Point(_coord_from_bytes(b[:cb], fp_bytes, parts), _coord_from_bytes(b[cb:2 * cb], fp_bytes, parts))
+
+        def __repr__(self):
+            return f"<{name}.Point {'ZERO' if self._inf else self.toAffine()}>"
+
+    Point.__name__ = Point.__qualname__ = f"{name}_Point"
+    Point.Fp = Fp
+    Point.Fn = Fn
+    Point.FP_BYTES = fp_bytes
+    Point.PARTS = parts
+    Point.POINT_BYTES = 2 * fp_bytes * parts
+    Point.IS_EDWARDS = edwards
+    Point.cofactor = h
+    Point.BASE = Point(Gx, Gy)
+    Point.ZERO = Point(0, 1, True) if edwards else Point(zero_coord, zero_coord, True)
+    return Point
+
+
+# Parameter blocks: SURVEY §8 a17 (src/secp256k1.ts:48-56, src/ed25519.ts:49-63, src/bn254.ts:80-90,207-223,
+# src/bls12-381.ts:134-148,321-345).  tests/test_consts.py cross-checks them against the oracle's copies.
+_BLS_P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+_BLS_N = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+_BN_P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+_BN_N = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
+
+class _NS:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+secp256k1 = _NS(
+    Point=_make_point_class(
+        "secp256k1", SECP256K1,
+        2**256 - 2**32 - 977,
+        0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141, 1,
+        0x79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798,
+        0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8, 1, False,
+    )
+)
+ed25519 = _NS(
+    Point=_make_point_class(
+        "ed25519", ED25519,
+        2**255 - 19,
+        2**252 + 27742317777372353535851937790883648493, 8,
+        0x216936D3CD6E53FEC0A4E231FDD6DC5C692CC7609525A7B2C9562D608F25D51A,
+        0x6666666666666666666666666666666666666666666666666666666666666658, 1, True,
+    )
+)
+bn254 = _NS(
+    G1=_NS(Point=_make_point_class("bn254_G1", BN254_G1, _BN_P, _BN_N, 1, 1, 2, 1, False)),
+    G2=_NS(
+        Point=_make_point_class(
+            "bn254_G2", BN254_G2, _BN_P, _BN_N,
+            0x30644E72E131A029B85045B68181585E06CEECDA572A2489345F2299C0F9FA8D,
+            (10857046999023057135944570762232829481370756359578518086990519993285655852781,
+             11559732032986387107991004021392285783925812861821192530917403151452391805634),
+            (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+             4082367875863433681332203403145435568316851327593401208105741076214120093531),
+            2, False,
+        )
+    ),
+)
+bls12_381 = _NS(
+    G1=_NS(
+        Point=_make_point_class(
+            "bls12_381_G1", BLS12_381_G1, _BLS_P, _BLS_N, 0x396C8C005555E1568C00AAAB0000AAAB,
+            0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB,
+            0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1,
+            1, False,
+        )
+    ),
+    G2=_NS(
+        Point=_make_point_class(
+            "bls12_381_G2", BLS12_381_G2, _BLS_P, _BLS_N,
+            0x5D543A95414E7F1091D50792876A202CD91DE4547085ABAA68A205B2E5A7DDFA628F1CB4D9E82EF21537E293A6691AE1616EC6E786F0C70CF1C38E31C7238E5,
+            (0x024AA2B2F08F0A91260805272DC51051C6E47AD4FA403B02B4510B647AE3D1770BAC0326A805BBEFD48056C8C121BDB8,
+             0x13E02B6052719F607DACD3A088274F65596BD0D09920B61AB5DA61BBDC7F5049334CF11213945D57E5AC7D055D042B7E),
+            (0x0CE5D527727D6E118CC9CDC6DA2E351AADFD9BAA8CBDD3A76D429A695160D12C923AC9CC3BACA289E193548608B82801,
+             0x0606C4A02EA734CC32ACD2B02BC28B99CB3E287E85A763AF267492AB572E99AB3F370D275CEC1DA1AAA9075FF05F79BE),
+            2, False,
+        )
+    ),
+)
+
+CURVES = {
+    "secp256k1": secp256k1.Point,
+    "ed25519": ed25519.Point,
+    "bn254_G1": bn254.G1.Point,
+    "bn254_G2": bn254.G2.Point,
+    "bls12_381_G1": bls12_381.G1.Point,
+    "bls12_381_G2": bls12_381.G2.Point,
+}
+
+
+# ----------------------------------------------------------------------------------------------
+# validation (exact messages of curve.ts:390-404, :875)
+# ----------------------------------------------------------------------------------------------
+def _validate_msm_points(points, c) -> None:
+    if not isinstance(points, (list, tuple)):
+        raise TypeError('"points" expected Array, got type=' + type(points).__name__)
+    for i, p in enumerate(points):
+        if not isinstance(p, c):
+            raise ValueError("invalid point at index " + str(i))
+
+
+def _validate_msm_scalars(scalars, fn) -> None:
+    if not isinstance(scalars, (list, tuple)):
+        raise ValueError("array of scalars expected")
+    for i, s in enumerate(scalars):
+        if not fn.isValid(s):
+            raise ValueError("invalid scalar at index " + str(i))
+
+
+def _pack_points(points: Sequence) -> bytes:
+    return b"".join(p.to_packed() for p in points)
+
+
+def _pack_scalars(scalars: Sequence[int]) -> bytes:
+    return b"".join(s.to_bytes(32, "little") for s in scalars)
+
+
+def _raise_mapped(e: NmsmError):
+    # the C ABI already carries the reference's message text for point/scalar errors
+    raise ValueError(str(e)) from e
+
+
+def _msm_points(c, points, scalars):
+    out_xy, inf = msm_packed(c.CURVE_ID, _pack_points(points), _pack_scalars(scalars), len(points))
+    return c.from_packed(out_xy, inf)
+
+
+# ----------------------------------------------------------------------------------------------
+# public surface
+# ----------------------------------------------------------------------------------------------
+def msm_packed(curve_id: int, pts: bytes, scalars: bytes, n: int):
+    """Packed fast path: canonical little-endian affine points + 32-byte LE scalars -> (xy bytes, is_inf)."""
+    _lib.ensure_init()
+    lib = _lib.load()
+    pb = lib.nmsm_point_bytes(curve_id)
+    if pb <= 0:
+        raise ValueError("unknown curve id")
+    if len(pts) != n * pb or len(scalars) != n * 32:
+        raise ValueError("arrays of points and scalars must have equal length")
+    out = ctypes.create_string_buffer(pb)
+    inf = ctypes.c_int(0)
+    pbuf = ctypes.c_char_p(bytes(pts)) if n else None
+    sbuf = ctypes.c_char_p(bytes(scalars)) if n else None
+    rc = lib.nmsm_msm(curve_id, ctypes.cast(pbuf, ctypes.c_void_p), ctypes.cast(sbuf, ctypes.c_void_p), n,
+                      ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf))
+    try:
+        _lib.check(rc)
+    except NmsmError as e:
+        _raise_mapped(e)
+    return out.raw, inf.value
+
+
+def msm_device(curve_id: int, d_pts: int, d_scalars: int, n: int):
+    """Inputs already resident in device memory (raw device pointers, e.g. torch `tensor.data_ptr()`)."""
+    _lib.ensure_init()
+    lib = _lib.load()
+    pb = lib.nmsm_point_bytes(curve_id)
+    out = ctypes.create_string_buffer(pb)
+    inf = ctypes.c_int(0)
+    rc = lib.nmsm_msm_device(curve_id, ctypes.c_void_p(d_pts), ctypes.c_void_p(d_scalars), n,
+                             ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf))
+    try:
+        _lib.check(rc)
+    except NmsmError as e:
+        _raise_mapped(e)
+    return out.raw, inf.value
+
+
+def msm_host_ptr(curve_id: int, h_pts: int, h_scalars: int, n: int):
+    """End-to-end path on raw HOST pointers (e.g. pinned buffers): H2D + MSM + D2H inside the call."""
+    _lib.ensure_init()
+    lib = _lib.load()
+    pb = lib.nmsm_point_bytes(curve_id)
+    out = ctypes.create_string_buffer(pb)
+    inf = ctypes.c_int(0)
+    rc = lib.nmsm_msm(curve_id, ctypes.c_void_p(h_pts), ctypes.c_void_p(h_scalars), n,
+                      ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf))
+    try:
+        _lib.check(rc)
+    except NmsmError as e:
+        _raise_mapped(e)
+    return out.raw, inf.value
+
+
+def pippenger(c, points, scalars):
+    """Drop-in for noble's pippenger (curve.ts:863-905): validates like the reference, runs on the GPU."""
+    _validate_msm_points(points, c)
+    _validate_msm_scalars(scalars, c.Fn)
+    if len(points) != len(scalars):
+        raise ValueError("arrays of points and scalars must have equal length")
+    if len(points) == 0:
+        return c.ZERO
+    return _msm_points(c, points, scalars)
+
+
+def mulAddUnsafe(c, points, scalars):
+    """curve.ts:820-836 — same value as the Strauss–Shamir walk, evaluated as a (small) MSM."""
+    return pippenger(c, points, scalars)
+
+
+def multiply_many(c, points, scalars, unsafe: bool = False) -> List:
+    """Batch form of Point.multiply (unsafe=False: 1 <= k < n) / multiplyUnsafe (unsafe=True: 0 <= k < n)."""
+    _validate_msm_points(points, c)
+    if len(points) != len(scalars):
+        raise ValueError("arrays of points and scalars must have equal length")
+    for s in scalars:
+        ok = c.Fn.isValid(s) if unsafe else c.Fn.isValidNot0(s)
+        if not ok:
+            if c.IS_EDWARDS:
+                raise ValueError("invalid scalar: expected %d <= sc < curve.n" % (0 if unsafe else 1))
+            raise ValueError("invalid scalar: out of range")
+    n = len(points)
+    if n == 0:
+        return []
+    out_xy, infs = mul_batch_packed(c.CURVE_ID, _pack_points(points), _pack_scalars(scalars), n, unsafe)
+    pb = c.POINT_BYTES
+    return [c.from_packed(out_xy[i * pb:(i + 1) * pb], infs[i]) for i in range(n)]
+
+
+def mul_batch_packed(curve_id: int, pts: bytes, scalars: bytes, n: int, allow_zero: bool):
+    _lib.ensure_init()
+    lib = _lib.load()
+    pb = lib.nmsm_point_bytes(curve_id)
+    if len(pts) != n * pb or len(scalars) != n * 32:
+        raise ValueError("arrays of points and scalars must have equal length")
+    out = ctypes.create_string_buffer(max(1, n * pb))
+    infs = ctypes.create_string_buffer(max(1, n))
+    rc = lib.nmsm_mul_batch(curve_id, ctypes.cast(ctypes.c_char_p(bytes(pts)), ctypes.c_void_p),
+                            ctypes.cast(ctypes.c_char_p(bytes(scalars)), ctypes.c_void_p), n, 1 if allow_zero else 0,
+                            ctypes.cast(out, ctypes.c_void_p), ctypes.cast(infs, ctypes.c_void_p))
+    try:
+        _lib.check(rc)
+    except NmsmError as e:
+        _raise_mapped(e)
+    return out.raw[: n * pb], infs.raw[:n]
+
+
+def last_timing():
+    """(dict of per-kernel ms, PlanInfo) of the last MSM call when profiling is enabled."""
+    lib = _lib.load()
+    ms = (ctypes.c_float * _lib.TIMING_SLOTS)()
+    info = PlanInfo()
+    lib.nmsm_last_timing(ms, ctypes.byref(info))
+    return {k: float(ms[i]) for i, k in enumerate(TIMING_NAMES)}, info
+
+
+def set_profiling(enabled: bool) -> None:
+    _lib.load().nmsm_set_profiling(1 if enabled else 0)
+
+
+def set_window_bits(c: int) -> int:
+    return _lib.load().nmsm_set_window_bits(c)
+
+
+def bench_modmul(field: int, blocks_per_sm: int = 8, threads: int = 128, iters: int = 2000, ilp: int = 1) -> float:
+    _lib.ensure_init()
+    return float(_lib.load().nmsm_bench_modmul(field, blocks_per_sm, threads, iters, ilp))

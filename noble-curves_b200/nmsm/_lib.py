@@ -1,0 +1,132 @@
+"""ctypes binding of libnmsm.so (C ABI: include/nmsm.h).
+
+The library is built in-tree by `make -C noble-curves_b200` (see __graft_entry__.build()).  There is
+no CPU fallback: if the shared object is missing, or no CUDA device can be initialised, every
+operation raises — loudly — instead of computing anything on the host.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnmsm.so")
+
+NMSM_OK = 0
+ERR_ARG, ERR_SCALAR, ERR_POINT, ERR_LENGTH, ERR_CUDA = -1, -2, -3, -4, -5
+
+TIMING_SLOTS = 10
+TIMING_NAMES = ["prepare", "count", "scan", "scatter", "accumulate", "fixup", "reduce", "window_sum", "final", "total"]
+
+# every symbol include/nmsm.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "nmsm_init", "nmsm_shutdown", "nmsm_last_error", "nmsm_last_error_index", "nmsm_point_bytes",
+    "nmsm_acc_bytes", "nmsm_msm", "nmsm_msm_device", "nmsm_msm_partial_device", "nmsm_fold_partials_device",
+    "nmsm_mul_batch", "nmsm_set_window_bits", "nmsm_set_profiling", "nmsm_last_timing", "nmsm_bench_modmul",
+    "nmsm_host_alloc", "nmsm_host_free",
+]
+
+
+class PlanInfo(ctypes.Structure):
+    _fields_ = [
+        ("c", ctypes.c_int),
+        ("windows", ctypes.c_int),
+        ("buckets_per_window", ctypes.c_int),
+        ("entries_per_thread", ctypes.c_int),
+        ("reduce_chunk", ctypes.c_int),
+        ("sorted_entries", ctypes.c_uint64),
+        ("modmul_equiv", ctypes.c_uint64),
+        ("launches", ctypes.c_int),
+    ]
+
+
+class NmsmError(RuntimeError):
+    def __init__(self, code: int, message: str, index: int = -1):
+        super().__init__(message)
+        self.code = code
+        self.index = index
+
+
+_lib = None
+_lock = threading.Lock()
+_initialised_device = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libnmsm.so and declare prototypes.  Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make -C noble-curves_b200 -j8` "
+                "(there is no CPU fallback for the MSM / scalar-mult path)"
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        u8p = ctypes.c_void_p
+        lib.nmsm_init.argtypes = [ctypes.c_int]
+        lib.nmsm_init.restype = ctypes.c_int
+        lib.nmsm_shutdown.argtypes = []
+        lib.nmsm_shutdown.restype = None
+        lib.nmsm_last_error.argtypes = []
+        lib.nmsm_last_error.restype = ctypes.c_char_p
+        lib.nmsm_last_error_index.argtypes = []
+        lib.nmsm_last_error_index.restype = ctypes.c_longlong
+        lib.nmsm_point_bytes.argtypes = [ctypes.c_int]
+        lib.nmsm_point_bytes.restype = ctypes.c_int
+        lib.nmsm_acc_bytes.argtypes = [ctypes.c_int]
+        lib.nmsm_acc_bytes.restype = ctypes.c_int
+        lib.nmsm_msm.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_uint64, u8p, ctypes.POINTER(ctypes.c_int)]
+        lib.nmsm_msm.restype = ctypes.c_int
+        lib.nmsm_msm_device.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_uint64, u8p, ctypes.POINTER(ctypes.c_int)]
+        lib.nmsm_msm_device.restype = ctypes.c_int
+        lib.nmsm_msm_partial_device.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_uint64, u8p]
+        lib.nmsm_msm_partial_device.restype = ctypes.c_int
+        lib.nmsm_fold_partials_device.argtypes = [ctypes.c_int, u8p, ctypes.c_int, u8p, ctypes.POINTER(ctypes.c_int)]
+        lib.nmsm_fold_partials_device.restype = ctypes.c_int
+        lib.nmsm_mul_batch.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_uint64, ctypes.c_int, u8p, u8p]
+        lib.nmsm_mul_batch.restype = ctypes.c_int
+        lib.nmsm_set_window_bits.argtypes = [ctypes.c_int]
+        lib.nmsm_set_window_bits.restype = ctypes.c_int
+        lib.nmsm_set_profiling.argtypes = [ctypes.c_int]
+        lib.nmsm_set_profiling.restype = ctypes.c_int
+        lib.nmsm_last_timing.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(PlanInfo)]
+        lib.nmsm_last_timing.restype = ctypes.c_int
+        lib.nmsm_bench_modmul.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        lib.nmsm_bench_modmul.restype = ctypes.c_double
+        lib.nmsm_host_alloc.argtypes = [ctypes.c_size_t]
+        lib.nmsm_host_alloc.restype = ctypes.c_void_p
+        lib.nmsm_host_free.argtypes = [ctypes.c_void_p]
+        lib.nmsm_host_free.restype = None
+        _lib = lib
+        return lib
+
+
+def check(code: int) -> None:
+    if code == NMSM_OK:
+        return
+    lib = load()
+    msg = (lib.nmsm_last_error() or b"").decode()
+    raise NmsmError(code, msg, int(lib.nmsm_last_error_index()))
+
+
+def init(device: int | None = None) -> int:
+    """Bind the process to one GPU (default: LOCAL_RANK or 0).  Raises NmsmError without a device."""
+    global _initialised_device
+    lib = load()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _initialised_device == device:
+        return device
+    check(lib.nmsm_init(device))
+    _initialised_device = device
+    return device
+
+
+def ensure_init() -> None:
+    if _initialised_device is None:
+        init()

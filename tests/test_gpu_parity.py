@@ -1,0 +1,315 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the `nmsm` host mirror) vs the CPU oracle.
+
+Bit-exact on canonical affine coordinates (test/point.test.ts:36-44 comparison idiom).  Mirrors
+test/point.test.ts:264-305,685-722,825-862, test/slow-curves.test.ts:128-152,185-252,
+test/secp256k1.test.ts:59-76, test/bls12-381.test.ts:1463-1533, test/bn254.test.ts:859-887,
+test/ed25519.test.ts:50-78, benchmark/msm_timings.ts:20-65.  At BASELINE.json's full sizes the oracle
+is too slow, so the scalar-in-exponent identity  sum s_i*(k_i*G) = (sum k_i*s_i mod n)*G  is used
+(test/slow-curves.test.ts:204-233).
+"""
+import hashlib
+import random
+
+import pytest
+
+import helpers as H
+from conftest import load_golden
+from oracle import noble_ref as R
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["secp256k1", "ed25519", "bn254_G1", "bn254_G2", "bls12_381_G1", "bls12_381_G2"]
+
+
+@pytest.fixture(scope="module")
+def nmsm():
+    import nmsm as m
+
+    m.init(0)
+    return m
+
+
+def gpu_msm(nmsm, name, pts_b, sc_b, n):
+    out, inf = nmsm.msm_packed(H.CURVE_IDS[name], pts_b, sc_b, n)
+    x, y = H.unpack_point(name, out)
+    return x, y, inf
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_msm_boundary_soak(nmsm, name):
+    sizes = [1, 2, 31, 32, 33, 127, 128, 129, 511, 512, 513, 2047, 2048, 2049]
+    if "G2" in name:
+        sizes = [1, 31, 33, 129, 513]
+    nmax = sizes[-1]
+    P, pts, scalars, _ = H.soak_inputs(name, nmax)
+    pb, sb = H.pack_points(name, pts), H.pack_scalars(scalars)
+    step = len(pb) // nmax
+    for size in sizes:
+        exp = H.expected_tuple(name, R.pippenger(P, pts[:size], scalars[:size]))
+        got = gpu_msm(nmsm, name, pb[: size * step], sb[: size * 32], size)
+        assert got == exp, (name, size)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_msm_window_sweep(nmsm, name):
+    """Every window size c and several segment shapes give the same point."""
+    n = 300 if "G2" not in name else 64
+    P, pts, scalars, total = H.soak_inputs(name, n, seed_offset=99)
+    exp = H.expected_tuple(name, H.expected_from_total(P, total))
+    pb, sb = H.pack_points(name, pts), H.pack_scalars(scalars)
+    try:
+        for c in ([2, 3, 5, 8, 11, 13, 16] if "G2" not in name else [3, 9, 14]):
+            nmsm.set_window_bits(c)
+            assert gpu_msm(nmsm, name, pb, sb, n) == exp, (name, c)
+    finally:
+        nmsm.set_window_bits(0)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_msm_basic_and_degenerate(nmsm, name):
+    P = R.CURVES[name]
+    G = P.BASE
+    cases = [
+        ([G], [0]),
+        ([P.ZERO], [123]),
+        ([G], [123]),
+        ([G, G.double(), G.double().double(), G.double().double().double()], [3, 5, 7, 11]),
+        ([G, G.negate()], [5, 5]),
+        ([G, G], [P.Fn.ORDER - 1, 1]),
+        ([G], [P.Fn.ORDER - 1]),
+        ([P.ZERO, G, P.ZERO], [7, 9, 0]),
+    ]
+    for pts, sc in cases:
+        pts = R.normalizeZ(P, pts)
+        exp = H.expected_tuple(name, R.pippenger(P, pts, sc))
+        assert gpu_msm(nmsm, name, H.pack_points(name, pts), H.pack_scalars(sc), len(pts)) == exp, (name, sc)
+    # empty input -> identity (curve.ts:878)
+    exp0 = H.expected_tuple(name, P.ZERO)
+    assert gpu_msm(nmsm, name, b"", b"", 0) == exp0
+    # 2048 copies of G, all scalars 2^10-1 (point.test.ts:842-853): equal-operand additions everywhere
+    n = 2048
+    s = 2**10 - 1
+    exp = H.expected_tuple(name, G.multiply((n * s) % P.Fn.ORDER))
+    assert gpu_msm(nmsm, name, H.point_bytes(name, G) * n, H.pack_scalars([s] * n), n) == exp
+    # all scalars identical, distinct points (benchmark/msm_timings.ts:45-63): every term in one bucket per window
+    P2, pts2, _, _ = H.soak_inputs(name, 200 if "G2" not in name else 40, zero_every=0)
+    k = 0xDEADBEEFCAFEBABE1234567
+    acc = P2.ZERO
+    for p in pts2:
+        acc = acc.add(p)
+    exp = H.expected_tuple(name, acc.multiplyUnsafe(k))
+    assert gpu_msm(nmsm, name, H.pack_points(name, pts2), H.pack_scalars([k] * len(pts2)), len(pts2)) == exp
+
+
+def test_msm_validation_errors(nmsm):
+    name = "bls12_381_G1"
+    P, pts, scalars, _ = H.soak_inputs(name, 20)
+    sc = list(scalars)
+    sc[7] = P.Fn.ORDER
+    with pytest.raises(ValueError, match="invalid scalar at index 7"):
+        nmsm.msm_packed(H.CURVE_IDS[name], H.pack_points(name, pts), H.pack_scalars(sc), 20)
+    pb = bytearray(H.pack_points(name, pts))
+    pb[96 * 5: 96 * 5 + 48] = (P.Fp.ORDER).to_bytes(48, "little")
+    with pytest.raises(ValueError, match="invalid point at index 5"):
+        nmsm.msm_packed(H.CURVE_IDS[name], bytes(pb), H.pack_scalars(sc), 20)
+    with pytest.raises(ValueError, match="equal length"):
+        nmsm.msm_packed(H.CURVE_IDS[name], bytes(pb), H.pack_scalars(sc[:19]), 20)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_object_api_matches_reference_semantics(nmsm, name):
+    """pippenger(c, points, scalars) / Point.multiply / multiplyUnsafe with the reference's error text."""
+    C = nmsm.CURVES[name]
+    P = R.CURVES[name]
+    G = C.BASE
+    assert nmsm.pippenger(C, [], []).equals(C.ZERO)
+    assert nmsm.pippenger(C, [G], [0]).equals(C.ZERO)
+    assert nmsm.pippenger(C, [C.ZERO], [123]).equals(C.ZERO)
+    g123 = nmsm.pippenger(C, [G], [123])
+    assert (g123.x, g123.y) == R.affine_tuple(P, P.BASE.multiply(123))
+    assert g123.equals(G.multiply(123)) and g123.equals(G.multiplyUnsafe(123))
+    pts = [G, G.double(), G.double().double(), G.double().double().double()]
+    assert nmsm.pippenger(C, pts, [3, 5, 7, 11]).equals(G.multiply(129))
+    assert G.add(G).equals(G.double()) and G.add(G.negate()).is0() and G.subtract(G).equals(C.ZERO)
+    assert (G.double().x, G.double().y) == R.affine_tuple(P, P.BASE.double())
+    with pytest.raises(ValueError, match="invalid scalar at index 0"):
+        nmsm.pippenger(C, [G], [C.Fn.ORDER])
+    with pytest.raises(ValueError, match="arrays of points and scalars must have equal length"):
+        nmsm.pippenger(C, [G], [1, 2])
+    with pytest.raises(ValueError, match="invalid point at index 1"):
+        nmsm.pippenger(C, [G, 5], [1, 2])
+    with pytest.raises(ValueError, match="array of scalars expected"):
+        nmsm.pippenger(C, [G], 5)
+    with pytest.raises(ValueError, match="invalid scalar"):
+        G.multiply(0)
+    assert G.multiplyUnsafe(0).equals(C.ZERO)
+    with pytest.raises(ValueError, match="invalid scalar"):
+        G.multiplyUnsafe(C.Fn.ORDER)
+    # (N-1)*G + G = O  (point.test.ts:69-205 group laws)
+    assert G.multiply(C.Fn.ORDER - 1).add(G).is0()
+    a, b = 0x1234567890ABCDEF1234, 0xFEDCBA09876543211
+    assert G.multiply(a).multiply(b).equals(G.multiply(a * b % C.Fn.ORDER))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_mul_batch_vs_oracle(nmsm, name):
+    P = R.CURVES[name]
+    n_order = P.Fn.ORDER
+    rng = R.Xorshift64(0xDEADBEEF)
+    count = 40 if "G2" not in name else 10
+    scalars = [1, 2, 3, n_order - 1, n_order - 2, 2**128 - 1, 2**128, 2**64 + 1, (1 << 200) - 1]
+    scalars += [rng.rndBelow(n_order - 1) + 1 for _ in range(count)]
+    scalars = [s % n_order or 1 for s in scalars]
+    ks = [rng.rndBelow(n_order - 1) + 1 for _ in scalars]
+    pts = R.normalizeZ(P, [P.BASE.multiplyUnsafe(k) for k in ks[:-2]] + [P.BASE, P.ZERO])
+    out, infs = nmsm.mul_batch_packed(H.CURVE_IDS[name], H.pack_points(name, pts), H.pack_scalars(scalars),
+                                      len(scalars), False)
+    pb = len(out) // len(scalars)
+    for i, (p, s) in enumerate(zip(pts, scalars)):
+        x, y = H.unpack_point(name, out[i * pb:(i + 1) * pb])
+        assert (x, y, infs[i]) == H.expected_tuple(name, p.multiplyUnsafe(s)), (name, i)
+
+
+def test_golden_secp256k1_privates(nmsm):
+    """test/secp256k1.test.ts:59-76 through the GPU: k*G for the 45 vectors of privates-2.txt."""
+    g = load_golden("secp256k1.json")["privates2"]
+    P = R.CURVES["secp256k1"]
+    n = len(g)
+    out, infs = nmsm.mul_batch_packed(0, H.point_bytes("secp256k1", P.BASE) * n, H.pack_scalars([int(k) for k, _, _ in g]),
+                                      n, False)
+    for i, (_, x, y) in enumerate(g):
+        assert H.unpack_point("secp256k1", out[i * 64:(i + 1) * 64]) == (int(x, 16), int(y, 16))
+    for v in load_golden("secp256k1.json")["endomorphism"]:
+        a = P.fromAffine({"x": int(v["ax"]), "y": int(v["ay"])})
+        out, _ = nmsm.mul_batch_packed(0, H.point_bytes("secp256k1", a), H.pack_scalars([int(v["scalar"])]), 1, True)
+        assert H.unpack_point("secp256k1", out) == (int(v["cx"]), int(v["cy"]))
+
+
+def test_golden_bls12_381_multiples(nmsm):
+    """test/bls12-381.test.ts:1463-1533 through the GPU: i*G (G1: i<1000, G2: i<256) vs the zkcrypto tables."""
+    g = load_golden("bls12_381.json")
+    G1, G2 = R.CURVES["bls12_381_G1"], R.CURVES["bls12_381_G2"]
+    n = 999
+    out, infs = nmsm.mul_batch_packed(4, H.point_bytes("bls12_381_G1", G1.BASE) * n, H.pack_scalars(range(1, n + 1)), n, False)
+    for i in range(1, n + 1):
+        b = bytearray(bytes.fromhex(g["G1_Uncompressed"][i]))
+        b[0] &= 0x1F
+        exp = (int.from_bytes(b[:48], "big"), int.from_bytes(b[48:], "big"))
+        assert H.unpack_point("bls12_381_G1", out[(i - 1) * 96: i * 96]) == exp, i
+    n = 255
+    out, infs = nmsm.mul_batch_packed(5, H.point_bytes("bls12_381_G2", G2.BASE) * n, H.pack_scalars(range(1, n + 1)), n, False)
+    for i in range(1, n + 1):
+        b = bytearray(bytes.fromhex(g["G2_Uncompressed"][i]))
+        b[0] &= 0x1F
+        x1, x0, y1, y0 = (int.from_bytes(b[j * 48:(j + 1) * 48], "big") for j in range(4))
+        assert H.unpack_point("bls12_381_G2", out[(i - 1) * 192: i * 192]) == ((x0, x1), (y0, y1)), i
+    # MSM of the whole table against scalars: sum_i s_i*(i*G) = (sum i*s_i)*G
+    rng = random.Random(7)
+    sc = [rng.randrange(G1.Fn.ORDER) for _ in range(999)]
+    def g1_le(h):
+        b = bytearray(bytes.fromhex(h))
+        b[0] &= 0x1F
+        return bytes(b[:48][::-1]) + bytes(b[48:][::-1])
+
+    pts_b = b"".join(g1_le(g["G1_Uncompressed"][i]) for i in range(1, 1000))
+    tot = sum(i * s for i, s in zip(range(1, 1000), sc)) % G1.Fn.ORDER
+    assert gpu_msm(nmsm, "bls12_381_G1", pts_b, H.pack_scalars(sc), 999) == H.expected_tuple(
+        "bls12_381_G1", G1.BASE.multiplyUnsafe(tot))
+
+
+def test_golden_bn254_and_ed25519(nmsm):
+    g = load_golden("bn254.json")
+    BN = R.CURVES["bn254_G1"]
+    for t in g["seda_mul"]:
+        s = int(t["scalar"], 16) % BN.Fn.ORDER
+        if s == 0:
+            continue
+        pt = int(t["x"], 16).to_bytes(32, "little") + int(t["y"], 16).to_bytes(32, "little")
+        out, _ = nmsm.mul_batch_packed(2, pt, H.pack_scalars([s]), 1, False)
+        assert H.unpack_point("bn254_G1", out) == (int(t["result"][:64], 16), int(t["result"][64:], 16))
+    for t in g["seda_add"]:
+        pts = b"".join(int(t[k], 16).to_bytes(32, "little") for k in ("x1", "y1", "x2", "y2"))
+        x, y, _ = gpu_msm(nmsm, "bn254_G1", pts, H.pack_scalars([1, 1]), 2)
+        assert (x, y) == (int(t["result"][:64], 16), int(t["result"][64:], 16))
+    # RFC 8032 public keys: pk = compress(clamp(sha512(sk)) * B)   (test/ed25519.test.ts:50-78)
+    ED = R.CURVES["ed25519"]
+    vec = load_golden("ed25519.json")["vectors"]
+    scalars = []
+    for v in vec:
+        h = bytearray(hashlib.sha512(bytes.fromhex(v["sk"])).digest()[:32])
+        h[0] &= 248
+        h[31] &= 127
+        h[31] |= 64
+        scalars.append(int.from_bytes(bytes(h), "little") % ED.Fn.ORDER)
+    n = len(vec)
+    out, _ = nmsm.mul_batch_packed(1, H.point_bytes("ed25519", ED.BASE) * n, H.pack_scalars(scalars), n, False)
+    for i, v in enumerate(vec):
+        x, y = H.unpack_point("ed25519", out[i * 64:(i + 1) * 64])
+        enc = bytearray(y.to_bytes(32, "little"))
+        if x & 1:
+            enc[31] |= 0x80
+        assert bytes(enc).hex() == v["pk"], i
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json sizes: scalar-in-exponent identity, points generated on the GPU as k_i*G
+# ------------------------------------------------------------------------------------------------
+def _large_case(nmsm, name, n, seed, zero_every=0):
+    P = R.CURVES[name]
+    order = P.Fn.ORDER
+    rnd = random.Random(seed)
+    ks = [rnd.randrange(1, order) for _ in range(n)]
+    sc = [0 if (zero_every and i % zero_every == 0) else rnd.randrange(order) for i in range(n)]
+    cid = H.CURVE_IDS[name]
+    pts_b, infs = nmsm.mul_batch_packed(cid, H.point_bytes(name, P.BASE) * n, H.pack_scalars(ks), n, False)
+    assert not any(infs)
+    total = sum(k * s for k, s in zip(ks, sc)) % order
+    exp = H.expected_tuple(name, H.expected_from_total(P, total))
+    got = gpu_msm(nmsm, name, pts_b, H.pack_scalars(sc), n)
+    assert got == exp, (name, n)
+    return pts_b, sc, exp
+
+
+def test_config_bls12_381_g1_2p16(nmsm):
+    """configs[1]: BLS12-381 G1, 2^16 terms; also cross-checked against the reference algorithm's C port."""
+    _large_case(nmsm, "bls12_381_G1", 1 << 16, 1, zero_every=17)
+
+
+def test_config_bls12_381_g1_2p20_headline(nmsm):
+    """The headline metric's workload: BLS12-381 G1, 2^20 terms."""
+    pts_b, sc, exp = _large_case(nmsm, "bls12_381_G1", 1 << 20, 2)
+    # linearity: MSM(first half) + MSM(second half) = MSM(all)
+    h = 1 << 19
+    a = nmsm.msm_packed(4, pts_b[: h * 96], H.pack_scalars(sc[:h]), h)
+    b = nmsm.msm_packed(4, pts_b[h * 96:], H.pack_scalars(sc[h:]), h)
+    s = nmsm.msm_packed(4, a[0] + b[0], H.pack_scalars([1, 1]), 2)
+    x, y = H.unpack_point("bls12_381_G1", s[0])
+    assert (x, y, s[1]) == exp
+
+
+def test_config_bn254_g1_2p20(nmsm):
+    _large_case(nmsm, "bn254_G1", 1 << 20, 3)
+
+
+def test_config_bls12_381_g2_2p18(nmsm):
+    _large_case(nmsm, "bls12_381_G2", 1 << 18, 4)
+
+
+def test_config_ed25519_131073_terms(nmsm):
+    """configs[4] core: Edwards MSM with 2*2^16+1 terms (the batch-verify equation's shape)."""
+    _large_case(nmsm, "ed25519", 2 * (1 << 16) + 1, 5)
+
+
+def test_config_secp256k1_multiply_1024(nmsm):
+    """configs[0] GPU counterpart: Point.multiply on 1024 random scalars of a non-base point vs the oracle."""
+    P = R.CURVES["secp256k1"]
+    rnd = random.Random(11)
+    base = R.normalizeZ(P, [P.BASE.multiplyUnsafe(rnd.randrange(1, P.Fn.ORDER))])[0]
+    ks = [rnd.randrange(1, P.Fn.ORDER) for _ in range(1024)]
+    out, infs = nmsm.mul_batch_packed(0, H.point_bytes("secp256k1", base) * 1024, H.pack_scalars(ks), 1024, False)
+    for i in range(0, 1024, 16):  # oracle spot-check on 64 of them (fixedWindowCT path, curve.ts:707-729)
+        assert H.unpack_point("secp256k1", out[i * 64:(i + 1) * 64]) == R.affine_tuple(P, base.multiply(ks[i]))
+    # all 1024: sum_i k_i*P == (sum k_i)*P via the MSM path
+    tot = sum(ks) % P.Fn.ORDER
+    x, y, inf = gpu_msm(nmsm, "secp256k1", out, H.pack_scalars([1] * 1024), 1024)
+    assert (x, y) == R.affine_tuple(P, base.multiplyUnsafe(tot))

@@ -1,0 +1,152 @@
+"""CPU-side verification of the CUDA path's arithmetic and bookkeeping (no GPU needed).
+
+tests/hostemu compiles the *device* headers for the host with an emulated PTX carry flag and runs the
+per-thread kernel bodies in loops.  These tests compare that against the oracle bit-for-bit, mirroring
+the reference's MSM tests (test/point.test.ts:264-305,685-722,825-862; test/slow-curves.test.ts:185-252)
+and field tests (test/modular.test.ts).  The real parity tests (through libnmsm.so on a B200) are in
+test_gpu_parity.py.
+"""
+import random
+
+import pytest
+
+import helpers as H
+from oracle import noble_ref as R
+
+ALL = ["secp256k1", "ed25519", "bn254_G1", "bn254_G2", "bls12_381_G1", "bls12_381_G2"]
+FIELDS = {
+    0: R.SECP256K1_CURVE["p"],
+    1: R.ED25519_CURVE["p"],
+    2: R.BN254_G1_CURVE["p"],
+    3: R.BLS12_381_G1_CURVE["p"],
+}
+
+
+def _fop(field, op, a, b=0):
+    import ctypes
+
+    import numpy as np
+
+    p = FIELDS[field]
+    n = 12 if field == 3 else 8
+    la = H.u32(a.to_bytes(4 * n, "little"))
+    lb = H.u32(b.to_bytes(4 * n, "little"))
+    out = np.zeros(n, np.uint32)
+    cp = lambda x: x.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    assert H.hostemu().emu_field(field, op, cp(la), cp(lb), cp(out)) == 0
+    return int.from_bytes(out.tobytes(), "little")
+
+
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
+def test_field_ops_match_bigint(field):
+    """mont_mul/add/sub/neg/sqr/inv/from/to-Montgomery vs Python ints (modular.ts:888-1038 semantics)."""
+    p = FIELDS[field]
+    n = 12 if field == 3 else 8
+    Rm = 1 << (32 * n)
+    Ri = pow(Rm, -1, p)
+    rnd = random.Random(1234 + field)
+    edge = [0, 1, 2, p - 1, p - 2, Rm % p, (Rm * Rm) % p, p >> 1, (1 << (p.bit_length() - 1)) % p]
+    vals = edge + [rnd.randrange(p) for _ in range(60)]
+    for a in vals:
+        for b in rnd.sample(vals, 6) + edge[:4]:
+            assert _fop(field, 0, a, b) == (a * b * Ri) % p
+            assert _fop(field, 1, a, b) == (a + b) % p
+            assert _fop(field, 2, a, b) == (a - b) % p
+        assert _fop(field, 6, a) == (a * a * Ri) % p
+        assert _fop(field, 7, a) == (-a) % p
+        assert _fop(field, 4, a) == (a * Rm) % p  # from_canonical
+        assert _fop(field, 5, (a * Rm) % p) == a  # to_canonical
+    for a in vals[:12]:
+        exp = (pow(a, -1, p) * Rm) % p if a else 0
+        assert _fop(field, 3, (a * Rm) % p) == exp
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_msm_soak(name):
+    """test/slow-curves.test.ts:185-252 construction (every 17th scalar zero), several window sizes."""
+    nmax = 129 if "G2" not in name else 33
+    P, pts, scalars, _ = H.soak_inputs(name, nmax)
+    pb, sb = H.pack_points(name, pts), H.pack_scalars(scalars)
+    step = len(pb) // nmax
+    for size in ([31, 32, 33, 127, 129] if "G2" not in name else [31, 33]):
+        exp = H.expected_tuple(name, R.pippenger(P, pts[:size], scalars[:size]))
+        for c, L in ((0, 0), (5, 3), (13, 32)):
+            got, err, _ = H.emu_msm(name, pb[: size * step], sb[: size * 32], size, c, L)
+            assert err == (0xFFFFFFFF, 0xFFFFFFFF)
+            assert got == exp, (name, size, c, L)
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "ed25519", "bls12_381_G1"])
+def test_msm_basic_cases(name):
+    """test/point.test.ts:264-305: [G]*[0]=O, empty, [O]*[123]=O, [G]*[123], {G,2G,4G,8G}*{3,5,7,11}=129G."""
+    P = R.CURVES[name]
+    G = P.BASE
+    cases = [
+        ([G], [0]),
+        ([P.ZERO], [123]),
+        ([G], [123]),
+        ([G, G.double(), G.double().double(), G.double().double().double()], [3, 5, 7, 11]),
+        ([G, G.negate()], [5, 5]),  # P + (-P) inside one bucket
+        ([G, G], [P.Fn.ORDER - 1, 1]),  # n-1 and 1: cancels to O
+        ([G], [P.Fn.ORDER - 1]),
+    ]
+    for pts, sc in cases:
+        pts = R.normalizeZ(P, pts)
+        exp = H.expected_tuple(name, R.pippenger(P, pts, sc))
+        for c, L in ((0, 0), (2, 1), (16, 4)):
+            got, err, _ = H.emu_msm(name, H.pack_points(name, pts), H.pack_scalars(sc), len(pts), c, L)
+            assert got == exp, (name, sc, c, L)
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "bls12_381_G1", "ed25519"])
+def test_msm_same_point_same_scalar(name):
+    """test/point.test.ts:842-853: L copies of G with scalar 2^10-1 -> equal-operand additions everywhere."""
+    P = R.CURVES[name]
+    n = 300
+    s = 2**10 - 1
+    exp = H.expected_tuple(name, P.BASE.multiply((n * s) % P.Fn.ORDER))
+    pb = H.point_bytes(name, P.BASE) * n
+    for c, L in ((0, 0), (4, 7), (11, 32)):
+        got, err, _ = H.emu_msm(name, pb, H.pack_scalars([s] * n), n, c, L)
+        assert got == exp, (name, c, L)
+
+
+def test_msm_validation_indices():
+    """curve.ts:390-404: first invalid point / scalar index is reported (points before scalars)."""
+    name = "bls12_381_G1"
+    P, pts, scalars, _ = H.soak_inputs(name, 20)
+    sc = list(scalars)
+    sc[7] = P.Fn.ORDER
+    sc[11] = P.Fn.ORDER + 5
+    _, err, _ = H.emu_msm(name, H.pack_points(name, pts), H.pack_scalars(sc), 20)
+    assert err == (0xFFFFFFFF, 7)
+    pb = bytearray(H.pack_points(name, pts))
+    pb[96 * 5: 96 * 5 + 48] = (P.Fp.ORDER).to_bytes(48, "little")  # x == p: out of range
+    _, err, _ = H.emu_msm(name, bytes(pb), H.pack_scalars(sc), 20)
+    assert err == (5, 7)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_mul_batch(name):
+    """Point.multiply / multiplyUnsafe (weierstrass.ts:900-928, edwards.ts:555-577) incl. edge scalars."""
+    P = R.CURVES[name]
+    n_order = P.Fn.ORDER
+    rng = R.Xorshift64(0xDEADBEEF)
+    base = P.BASE.multiplyUnsafe(rng.rndBelow(n_order - 1) + 1)
+    scalars = [1, 2, 3, n_order - 1, n_order - 2, 2**128 - 1, 2**128, 2**64 + 1, 0x5555555555555555 << 60]
+    scalars += [rng.rndBelow(n_order - 1) + 1 for _ in range(3 if "G2" in name else 8)]
+    scalars = [s % n_order or 1 for s in scalars]
+    pts = R.normalizeZ(P, [base] * (len(scalars) - 2) + [P.BASE, P.ZERO])
+    res, err = H.emu_mul_batch(name, H.pack_points(name, pts), H.pack_scalars(scalars), len(scalars), False)
+    assert err == (0xFFFFFFFF, 0xFFFFFFFF)
+    for p, s, got in zip(pts, scalars, res):
+        assert got == H.expected_tuple(name, p.multiplyUnsafe(s))
+        if not p.is0():
+            assert got == H.expected_tuple(name, p.multiply(s))
+    # scalar 0: rejected by multiply, identity for multiplyUnsafe; scalar == n rejected by both
+    res, err = H.emu_mul_batch(name, H.pack_points(name, pts[:2]), H.pack_scalars([5, 0]), 2, False)
+    assert err == (0xFFFFFFFF, 1)
+    res, err = H.emu_mul_batch(name, H.pack_points(name, pts[:2]), H.pack_scalars([5, 0]), 2, True)
+    assert err == (0xFFFFFFFF, 0xFFFFFFFF) and res[1] == H.expected_tuple(name, P.ZERO)
+    res, err = H.emu_mul_batch(name, H.pack_points(name, pts[:2]), H.pack_scalars([n_order, 1]), 2, True)
+    assert err == (0xFFFFFFFF, 0)
