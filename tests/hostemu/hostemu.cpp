@@ -63,6 +63,34 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
   return 0;
 }
 
+// multi-GPU building blocks: raw accumulator of a shard, and the fold of several accumulators
+template <class Cv>
+static int emu_partial_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, uint32_t* out_acc) {
+  using G = typename Cv::G;
+  if (n == 0) {
+    typename G::Acc id = G::identity();
+    save_acc<G>(out_acc, id);
+    return 0;
+  }
+  std::vector<uint32_t> xy(G::IN_WORDS);
+  uint32_t inf, err[2], plan[4];
+  // run the full pipeline and lift its affine result back to a raw accumulator
+  int rc = emu_msm_t<Cv>(pts, scalars, n, 0, 0, xy.data(), &inf, err, plan);
+  if (rc) return rc;
+  typename G::Acc acc = G::identity();
+  if (!inf) {
+    typename G::Affine a = G::prepare(xy.data());
+    acc = G::from_affine(a);
+  }
+  save_acc<G>(out_acc, acc);
+  return 0;
+}
+template <class Cv>
+static int emu_fold_t(const uint32_t* accs, int count, uint32_t* out_xy, uint32_t* out_inf) {
+  fold_body<Cv>(accs, count, out_xy, out_inf);
+  return 0;
+}
+
 template <class Cv>
 static int emu_mul_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, int allow_zero, uint32_t* out_xy,
                      uint32_t* out_inf, uint32_t* err_out) {
@@ -109,6 +137,12 @@ int emu_msm(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n,
 int emu_mul_batch(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, int allow_zero,
                   uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out) {
   DISPATCH(curve, emu_mul_t<Cv>(pts, scalars, n, allow_zero, out_xy, out_inf, err_out));
+}
+int emu_msm_partial(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, uint32_t* out_acc) {
+  DISPATCH(curve, emu_partial_t<Cv>(pts, scalars, n, out_acc));
+}
+int emu_fold(int curve, const uint32_t* accs, int count, uint32_t* out_xy, uint32_t* out_inf) {
+  DISPATCH(curve, emu_fold_t<Cv>(accs, count, out_xy, out_inf));
 }
 // field: 0 secp256k1, 1 ed25519, 2 bn254, 3 bls12-381
 int emu_field(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
