@@ -57,7 +57,8 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   CK(C.buckets.ensure((size_t)plan.G * G::ACC_WORDS * 4));
   CK(C.heads.ensure(max_threads * G::ACC_WORDS * 4));
   CK(C.tails.ensure(max_threads * G::ACC_WORDS * 4));
-  CK(C.chunk_out.ensure((size_t)plan.W * plan.chunks * G::ACC_WORDS * 4));
+  CK(C.chunk_out.ensure((size_t)plan.W * plan.chunks * G::ACC_WORDS * 4 * 2));
+  CK(C.tile_sums.ensure((size_t)(plan.G / SCAN_TILE + 2) * 4));
   CK(C.window_out.ensure((size_t)plan.W * G::ACC_WORDS * 4));
 
   uint32_t* aff = (uint32_t*)C.aff.p;
@@ -68,7 +69,9 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   uint32_t* buckets = (uint32_t*)C.buckets.p;
   uint32_t* heads = (uint32_t*)C.heads.p;
   uint32_t* tails = (uint32_t*)C.tails.p;
-  uint32_t* chunk_out = (uint32_t*)C.chunk_out.p;
+  uint32_t* sums = (uint32_t*)C.chunk_out.p;
+  uint32_t* wsums = sums + (size_t)plan.W * plan.chunks * G::ACC_WORDS;
+  uint32_t* tile_sums = (uint32_t*)C.tile_sums.p;
   uint32_t* window_out = (uint32_t*)C.window_out.p;
   cudaStream_t st = C.stream;
   const uint32_t n32 = (uint32_t)n;
@@ -80,17 +83,22 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   EV(1);
   k_digits<Cv, false><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, counts, nullptr, d_err);
   EV(2);
-  k_scan<<<1, 1024, 0, st>>>(counts, (uint32_t)plan.G, offsets, cursor);
+  {
+    const unsigned int tiles = cdiv(plan.G, SCAN_TILE);
+    k_scan_tiles<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)plan.G, tile_sums);
+    k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)plan.G, tile_sums, offsets, cursor);
+  }
   EV(3);
   k_digits<Cv, true><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, cursor, sorted, d_err);
   EV(4);
   k_accumulate<Cv><<<cdiv(max_threads, 128), 128, 0, st>>>(aff, sorted, offsets, plan, buckets, heads, tails);
   EV(5);
-  k_fixup<Cv><<<cdiv(plan.G, 128), 128, 0, st>>>(offsets, plan, buckets, heads, tails);
-  EV(6);
-  k_reduce<Cv><<<cdiv((uint64_t)plan.W * plan.chunks, 128), 128, 0, st>>>(buckets, plan, chunk_out);
+  EV(6);  // (fixup is fused into k_reduce1; slot kept for the timing layout)
+  k_reduce1<Cv><<<cdiv((uint64_t)plan.W * plan.chunks, 128), 128, 0, st>>>(offsets, buckets, heads, tails, plan, sums,
+                                                                           wsums);
   EV(7);
-  k_window_sum<Cv><<<plan.W, 128, 4 * G::ACC_WORDS * 4, st>>>(chunk_out, plan, window_out);
+  k_reduce2<Cv><<<plan.W, REDUCE2_THREADS, (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4, st>>>(sums, wsums, plan,
+                                                                                          window_out);
   EV(8);
   if (d_out_acc)
     k_final<Cv, false><<<1, 32, 0, st>>>(window_out, plan, d_out_acc, nullptr);
@@ -116,7 +124,7 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   C.last_info.reduce_chunk = plan.K;
   C.last_info.sorted_entries = entries;
   C.last_info.modmul_equiv = plan_modmuls<Cv>(plan, entries);
-  C.last_info.launches = 9;
+  C.last_info.launches = 9;  // prepare, count, scan x2, scatter, accumulate, reduce1, reduce2, final
   if (C.profiling) {
     for (int k = 0; k < 9; k++) cudaEventElapsedTime(&C.last_ms[k], C.ev[k], C.ev[k + 1]);
     cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev[0], C.ev[9]);

@@ -86,6 +86,13 @@ NMSM_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 }
 
 template <class C>
+struct Fp;
+#if defined(__CUDACC__)
+template <class C>
+__device__ __noinline__ Fp<C> mul_call(Fp<C> a, Fp<C> b);
+#endif
+
+template <class C>
 struct Fp {
   static constexpr int N = C::N;
   static constexpr int LIMBS = C::N;    // 32-bit words per element
@@ -121,9 +128,13 @@ struct Fp {
   NMSM_HD bool operator!=(const Fp& o) const { return !(*this == o); }
 
   NMSM_HD friend Fp operator*(const Fp& a, const Fp& b) {
+#if defined(__CUDA_ARCH__) && defined(NMSM_MUL_NOINLINE)
+    return mul_call<C>(a, b);  // one shared copy of the 2N^2+N IMAD body: instruction-cache friendly
+#else
     Fp r;
     mont_mul<C>(r.v, a.v, b.v);
     return r;
+#endif
   }
   NMSM_HD friend Fp operator+(const Fp& a, const Fp& b) {
     Fp r;
@@ -175,6 +186,15 @@ struct Fp {
   }
 };
 
+#if defined(__CUDACC__)
+template <class C>
+__device__ __noinline__ Fp<C> mul_call(Fp<C> a, Fp<C> b) {
+  Fp<C> r;
+  mont_mul<C>(r.v, a.v, b.v);
+  return r;
+}
+#endif
+
 template <class C>
 NMSM_HD Fp<C> sqr(const Fp<C>& a) {
   return a * a;
@@ -184,24 +204,91 @@ NMSM_HD Fp<C> dbl(const Fp<C>& a) {
   return a + a;
 }
 
-// a^(p-2): modular.ts:980 `inv` (the reference uses extended Euclid, modular.ts:159-182; the value
-// is the same).  Single-thread latency path (final to-affine only); 0 maps to 0.
+// Modular inverse (modular.ts:980 `inv` -> :159-182; the reference runs extended Euclid on BigInt,
+// here a binary extended GCD on the limbs: ~2*BITS shift/subtract steps instead of a BITS-long
+// square-and-multiply chain, which matters because the final to-affine step is single-threaded).
+// Input and output in Montgomery form; 0 maps to 0.
 template <class C>
 NMSM_HD Fp<C> inv(const Fp<C>& a) {
   constexpr int N = C::N;
-  Fp<C> r = Fp<C>::one();
-  bool started = false;
-  for (int i = N - 1; i >= 0; i--) {
-    uint32_t e = C::P(i) - (i == 0 ? 2u : 0u);  // p is odd and p[0] >= 3 for every supported prime
-    for (int bit = 31; bit >= 0; bit--) {
-      if (started) r = sqr(r);
-      if ((e >> bit) & 1) {
-        r = r * a;
-        started = true;
-      }
+  if (a.is_zero()) return a;
+  // invariants: a * x1 == u (mod p), a * x2 == v (mod p), with a taken as the raw limbs
+  uint32_t u[N], v[N], x1[N], x2[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    u[k] = a.v[k];
+    v[k] = C::P(k);
+    x1[k] = (k == 0) ? 1u : 0u;
+    x2[k] = 0u;
+  }
+  auto is_one = [](const uint32_t* x) {
+    uint32_t t = x[0] ^ 1u;
+#pragma unroll
+    for (int k = 1; k < N; k++) t |= x[k];
+    return t == 0;
+  };
+  auto halve = [](uint32_t* x, uint32_t top) {  // (top:x) >> 1
+#pragma unroll
+    for (int k = 0; k < N - 1; k++) x[k] = (x[k] >> 1) | (x[k + 1] << 31);
+    x[N - 1] = (x[N - 1] >> 1) | (top << 31);
+  };
+  auto halve_mod = [&](uint32_t* x) {  // x/2 mod p
+    uint32_t top = 0;
+    if (x[0] & 1u) {
+      x[0] = add_cc(x[0], C::P(0));
+#pragma unroll
+      for (int k = 1; k < N; k++) x[k] = addc_cc(x[k], C::P(k));
+      top = addc(0, 0);
+    }
+    halve(x, top);
+  };
+  auto geq = [](const uint32_t* x, const uint32_t* y) {  // x >= y
+    uint32_t t = sub_cc(x[0], y[0]);
+#pragma unroll
+    for (int k = 1; k < N; k++) t = subc_cc(x[k], y[k]);
+    (void)t;
+    return subc(0, 0) == 0;
+  };
+  auto sub_plain = [](uint32_t* x, const uint32_t* y) {  // x -= y (x >= y)
+    x[0] = sub_cc(x[0], y[0]);
+#pragma unroll
+    for (int k = 1; k < N; k++) x[k] = subc_cc(x[k], y[k]);
+  };
+  auto sub_mod = [](uint32_t* x, const uint32_t* y) {  // x = x - y mod p
+    x[0] = sub_cc(x[0], y[0]);
+#pragma unroll
+    for (int k = 1; k < N; k++) x[k] = subc_cc(x[k], y[k]);
+    uint32_t mask = subc(0, 0);
+    x[0] = add_cc(x[0], C::P(0) & mask);
+#pragma unroll
+    for (int k = 1; k < N; k++) x[k] = addc_cc(x[k], C::P(k) & mask);
+  };
+  while (!is_one(u) && !is_one(v)) {
+    while (!(u[0] & 1u)) {
+      halve(u, 0);
+      halve_mod(x1);
+    }
+    while (!(v[0] & 1u)) {
+      halve(v, 0);
+      halve_mod(x2);
+    }
+    if (geq(u, v)) {
+      sub_plain(u, v);
+      sub_mod(x1, x2);
+    } else {
+      sub_plain(v, u);
+      sub_mod(x2, x1);
     }
   }
-  return r;
+  Fp<C> r, r2;
+  const bool pick_u = is_one(u);
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    r.v[k] = pick_u ? x1[k] : x2[k];
+    r2.v[k] = C::R2(k);
+  }
+  // raw inverse of aR is a^-1 R^-1; two Montgomery multiplications by R^2 lift it to a^-1 R
+  return (r * r2) * r2;
 }
 
 }  // namespace nmsm

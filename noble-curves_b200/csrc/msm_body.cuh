@@ -291,49 +291,62 @@ NMSM_HD void accumulate_body(uint32_t t, const uint32_t* aff, const uint32_t* so
   else save_acc<G>(tails + (size_t)t * G::ACC_WORDS, acc);
 }
 
-// One thread per bucket: empty -> identity; straddling -> tails[ts] + heads[ts+1..te].
+// Adds the value of bucket g into `sum`.  A bucket wholly inside one accumulate segment was written
+// to `buckets`; one that straddles segments is the sum of tails[ts] and heads[ts+1..te]; an empty
+// bucket contributes nothing.  (This stitching used to be a separate pass; fusing it here costs no
+// extra additions and removes a launch plus one write+read of every bucket.)
 template <class Cv>
-NMSM_HD void fixup_body(uint32_t g, const uint32_t* offsets, const MsmPlan& plan, uint32_t* buckets,
-                        const uint32_t* heads, const uint32_t* tails) {
+NMSM_HD void add_bucket(typename Cv::G::Acc& sum, uint32_t g, const uint32_t* offsets, const MsmPlan& plan,
+                        const uint32_t* buckets, const uint32_t* heads, const uint32_t* tails) {
   using G = typename Cv::G;
-  uint32_t b0 = offsets[g], b1 = offsets[g + 1];
-  if (b0 == b1) {
-    save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, G::identity());
+  const uint32_t b0 = offsets[g], b1 = offsets[g + 1];
+  if (b0 == b1) return;
+  const uint32_t ts = b0 / plan.L, te = (b1 - 1) / plan.L;
+  if (ts == te) {
+    nl_add<G>(sum, load_acc<G>(buckets + (size_t)g * G::ACC_WORDS));
     return;
   }
-  uint32_t ts = b0 / plan.L, te = (b1 - 1) / plan.L;
-  if (ts == te) return;
-  typename G::Acc acc = load_acc<G>(tails + (size_t)ts * G::ACC_WORDS);
-  for (uint32_t t = ts + 1; t <= te; t++) nl_add<G>(acc, load_acc<G>(heads + (size_t)t * G::ACC_WORDS));
-  save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, acc);
+  nl_add<G>(sum, load_acc<G>(tails + (size_t)ts * G::ACC_WORDS));
+  for (uint32_t t = ts + 1; t <= te; t++) nl_add<G>(sum, load_acc<G>(heads + (size_t)t * G::ACC_WORDS));
 }
 
-// k * p for a small non-negative k (< 2^16): double-and-add, MSB first
-template <class G>
-NMSM_HD typename G::Acc small_mul(const typename G::Acc& p, uint32_t k) {
-  typename G::Acc r = G::identity();
-  for (int bit = 15; bit >= 0; bit--) {
-    nl_dbl<G>(r);
-    if ((k >> bit) & 1) nl_add<G>(r, p);
-  }
-  return r;
-}
-
-// Thread (w, k): chunk of K buckets -> sum_{b in chunk} (b+1) * bucket[w][b]
-// (the running-sum trick of curve.ts:897-900, 2 additions per bucket, plus lo * sum for the offset)
+// Thread (w, k): chunk of K buckets of window w ->
+//   sums[id]  = sum_{b in chunk} B_b
+//   wsums[id] = sum_{b in chunk} (b - kK + 1) * B_b          (running-sum trick, curve.ts:897-900)
+// so that  sum_b (b+1) B_b = sum_k wsums_k + K * sum_k k * sums_k  (second level: reduce2).
 template <class Cv>
-NMSM_HD void reduce_body(uint32_t id, const uint32_t* buckets, const MsmPlan& plan, uint32_t* chunk_out) {
+NMSM_HD void reduce1_body(uint32_t id, const uint32_t* offsets, const uint32_t* buckets, const uint32_t* heads,
+                          const uint32_t* tails, const MsmPlan& plan, uint32_t* sums, uint32_t* wsums) {
   using G = typename Cv::G;
-  uint32_t w = id / plan.chunks, k = id % plan.chunks;
-  uint32_t lo = k * plan.K;
-  const uint32_t* base = buckets + ((size_t)w * plan.B + lo) * G::ACC_WORDS;
+  const uint32_t w = id / plan.chunks, k = id % plan.chunks;
+  const uint32_t g0 = w * plan.B + k * plan.K;
   typename G::Acc sum = G::identity(), wsum = G::identity();
   for (int b = plan.K - 1; b >= 0; b--) {
-    nl_add<G>(sum, load_acc<G>(base + (size_t)b * G::ACC_WORDS));
+    add_bucket<Cv>(sum, g0 + b, offsets, plan, buckets, heads, tails);
     nl_add<G>(wsum, sum);
   }
-  if (lo != 0) nl_add<G>(wsum, small_mul<G>(sum, lo));
-  save_acc<G>(chunk_out + (size_t)id * G::ACC_WORDS, wsum);
+  save_acc<G>(sums + (size_t)id * G::ACC_WORDS, sum);
+  save_acc<G>(wsums + (size_t)id * G::ACC_WORDS, wsum);
+}
+
+// Serial statement of the second level for one window (what k_reduce2 computes cooperatively):
+//   window_out[w] = sum_k wsums_k + K * sum_k k * sums_k
+template <class Cv>
+NMSM_HD void reduce2_serial(uint32_t w, const uint32_t* sums, const uint32_t* wsums, const MsmPlan& plan,
+                            uint32_t* window_out) {
+  using G = typename Cv::G;
+  typename G::Acc run = G::identity(), ksum = G::identity(), wtot = G::identity();
+  for (int k = plan.chunks - 1; k >= 0; k--) {
+    const size_t id = (size_t)w * plan.chunks + k;
+    nl_add<G>(wtot, load_acc<G>(wsums + id * G::ACC_WORDS));
+    if (k >= 1) {
+      nl_add<G>(run, load_acc<G>(sums + id * G::ACC_WORDS));
+      nl_add<G>(ksum, run);  // after the loop: sum_k k * sums_k
+    }
+  }
+  for (int j = 1; j < plan.K; j <<= 1) nl_dbl<G>(ksum);  // * K (power of two)
+  nl_add<G>(wtot, ksum);
+  save_acc<G>(window_out + (size_t)w * G::ACC_WORDS, wtot);
 }
 
 // Horner over the window sums (curve.ts:901-902).  AFFINE_OUT: canonical affine + infinity flag,

@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnmsm.so")
+LIB_PATH = os.environ.get("NMSM_LIB") or os.path.join(_HERE, "libnmsm.so")  # NMSM_LIB: build-variant experiments
 
 NMSM_OK = 0
 ERR_ARG, ERR_SCALAR, ERR_POINT, ERR_LENGTH, ERR_CUDA = -1, -2, -3, -4, -5

@@ -39,15 +39,13 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
   // launch geometry rounds the thread count up to whole blocks, so run a few idle threads too
   for (uint32_t t = 0; t < nthreads + 3; t++)
     accumulate_body<Cv>(t, aff.data(), sorted.data(), offsets.data(), plan, buckets.data(), heads.data(), tails.data());
-  for (uint32_t g = 0; g < (uint32_t)plan.G; g++) fixup_body<Cv>(g, offsets.data(), plan, buckets.data(), heads.data(), tails.data());
-  std::vector<uint32_t> chunk_out((size_t)plan.W * plan.chunks * G::ACC_WORDS);
-  for (uint32_t id = 0; id < (uint32_t)plan.W * plan.chunks; id++) reduce_body<Cv>(id, buckets.data(), plan, chunk_out.data());
+  const size_t nchunks = (size_t)plan.W * plan.chunks;
+  std::vector<uint32_t> sums(nchunks * G::ACC_WORDS), wsums(nchunks * G::ACC_WORDS);
+  for (uint32_t id = 0; id < nchunks; id++)
+    reduce1_body<Cv>(id, offsets.data(), buckets.data(), heads.data(), tails.data(), plan, sums.data(), wsums.data());
   std::vector<uint32_t> window_out((size_t)plan.W * G::ACC_WORDS);
-  for (int w = 0; w < plan.W; w++) {  // stands in for k_window_sum's shuffle tree
-    typename G::Acc acc = G::identity();
-    for (int k = 0; k < plan.chunks; k++) G::add(acc, load_acc<G>(chunk_out.data() + ((size_t)w * plan.chunks + k) * G::ACC_WORDS));
-    save_acc<G>(window_out.data() + (size_t)w * G::ACC_WORDS, acc);
-  }
+  for (int w = 0; w < plan.W; w++)  // serial statement of what k_reduce2 computes cooperatively
+    reduce2_serial<Cv>(w, sums.data(), wsums.data(), plan, window_out.data());
   final_body<Cv, true>(window_out.data(), plan, out_xy, out_inf);
   err_out[0] = err[0];
   err_out[1] = err[1];
