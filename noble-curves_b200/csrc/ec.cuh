@@ -19,6 +19,50 @@
 namespace nmsm {
 
 // ------------------------------------------------------------------------------------------
+// Lane-parallel field multiplications for the single-warp latency tails (k_final / k_fold).
+// The multiply pipe is occupied per WARP instruction (a lone thread pays ~0.95 us per 381-bit
+// mont_mul, measured), so the serial Horner / fold runs with every lane of one warp holding the
+// same replicated state; at each level of a point formula lane (l & 3) computes one of up to four
+// independent products and the results are broadcast back with warp shuffles.
+// ------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+template <class F>
+struct Par4 {
+  static constexpr int WORDS = sizeof(F) / 4;
+  __device__ static __forceinline__ F bcast(const F& z, int src) {
+    F r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&z);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < WORDS; k++) d[k] = __shfl_sync(0xffffffffu, s[k], src);
+    return r;
+  }
+  __device__ static __forceinline__ F pick(int l, const F& a0, const F& a1, const F& a2, const F& a3) {
+    F r;
+    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(&a0);
+    const uint32_t* p1 = reinterpret_cast<const uint32_t*>(&a1);
+    const uint32_t* p2 = reinterpret_cast<const uint32_t*>(&a2);
+    const uint32_t* p3 = reinterpret_cast<const uint32_t*>(&a3);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < WORDS; k++) d[k] = l == 0 ? p0[k] : (l == 1 ? p1[k] : (l == 2 ? p2[k] : p3[k]));
+    return r;
+  }
+  // r_k = a_k * b_k for k < 4, one product per lane, every lane receives all four
+  __device__ static __forceinline__ void mul4(F& r0, F& r1, F& r2, F& r3, const F& a0, const F& b0, const F& a1,
+                                              const F& b1, const F& a2, const F& b2, const F& a3, const F& b3) {
+    const int l = threadIdx.x & 3;
+    F x = pick(l, a0, a1, a2, a3), y = pick(l, b0, b1, b2, b3);
+    F z = x * y;
+    r0 = bcast(z, 0);
+    r1 = bcast(z, 1);
+    r2 = bcast(z, 2);
+    r3 = bcast(z, 3);
+  }
+};
+#endif
+
+// ------------------------------------------------------------------------------------------
 // Short Weierstrass, a = 0
 // ------------------------------------------------------------------------------------------
 template <class F>
@@ -146,6 +190,56 @@ struct SwXyzz {
     p.X = X3;
     p.Y = Y3;
   }
+#if defined(__CUDACC__)
+  // Warp-replicated versions of dbl / add (see Par4): 3 and 4 multiplication levels instead of 9 / 14.
+  __device__ static void par_dbl(Acc& p) {
+    if (is_identity(p)) return;
+    using P4 = Par4<F>;
+    F U = nmsm::dbl(p.Y);
+    F V, A, t2, t3;
+    P4::mul4(V, A, t2, t3, U, U, p.X, p.X, U, U, U, U);
+    F M = nmsm::dbl(A) + A;
+    F W, S, MM;
+    P4::mul4(W, S, MM, t3, U, V, p.X, V, M, M, M, M);
+    F X3 = MM - nmsm::dbl(S);
+    F y0, y1, zz, zzz;
+    P4::mul4(y0, y1, zz, zzz, M, S - X3, W, p.Y, V, p.ZZ, W, p.ZZZ);
+    p.X = X3;
+    p.Y = y0 - y1;
+    p.ZZ = zz;
+    p.ZZZ = zzz;
+  }
+  __device__ static void par_add(Acc& p, const Acc& q) {
+    if (is_identity(q)) return;
+    if (is_identity(p)) {
+      p = q;
+      return;
+    }
+    using P4 = Par4<F>;
+    F U1, U2, S1, S2;
+    P4::mul4(U1, U2, S1, S2, p.X, q.ZZ, q.X, p.ZZ, p.Y, q.ZZZ, q.Y, p.ZZZ);
+    F P = U2 - U1;
+    F R = S2 - S1;
+    if (P.is_zero()) {
+      if (R.is_zero())
+        par_dbl(p);
+      else
+        p = identity();
+      return;
+    }
+    F PP, RR, ZZ12, ZZZ12;
+    P4::mul4(PP, RR, ZZ12, ZZZ12, P, P, R, R, p.ZZ, q.ZZ, p.ZZZ, q.ZZZ);
+    F PPP, Q, ZZ3, t3;
+    P4::mul4(PPP, Q, ZZ3, t3, P, PP, U1, PP, ZZ12, PP, P, PP);
+    F X3 = RR - PPP - nmsm::dbl(Q);
+    F y0, y1, ZZZ3;
+    P4::mul4(y0, y1, ZZZ3, t3, R, Q - X3, S1, PPP, ZZZ12, PPP, R, R);
+    p.X = X3;
+    p.Y = y0 - y1;
+    p.ZZ = ZZ3;
+    p.ZZZ = ZZZ3;
+  }
+#endif
   // canonical affine output; identity -> (0, 0), flag 1 (weierstrass.ts:966)
   NMSM_HD static void to_affine_canonical(const Acc& p, uint32_t* xy, uint32_t* is_inf) {
     if (is_identity(p)) {
@@ -258,6 +352,34 @@ struct EdExt {
     p.T = E * H;
     p.Z = Fv * G;
   }
+#if defined(__CUDACC__)
+  // Warp-replicated versions (see Par4): 2 levels for doubling, 3 for addition.
+  __device__ static void par_dbl(Acc& p) {
+    using P4 = Par4<F>;
+    F A, B, Zs, XY;
+    F xy = p.X + p.Y;
+    P4::mul4(A, B, Zs, XY, p.X, p.X, p.Y, p.Y, p.Z, p.Z, xy, xy);
+    F C = nmsm::dbl(Zs);
+    F D = -A;
+    F E = XY - A - B;
+    F G = D + B;
+    F Fv = G - C;
+    F H = D - B;
+    P4::mul4(p.X, p.Y, p.T, p.Z, E, Fv, G, H, E, H, Fv, G);
+  }
+  __device__ static void par_add(Acc& p, const Acc& q) {
+    using P4 = Par4<F>;
+    F A, B, TT, ZZ;
+    P4::mul4(A, B, TT, ZZ, p.Y - p.X, q.Y - q.X, p.Y + p.X, q.Y + q.X, p.T, q.T, p.Z, q.Z);
+    F C = TT * d2();
+    F D = nmsm::dbl(ZZ);
+    F E = B - A;
+    F Fv = D - C;
+    F G = D + C;
+    F H = B + A;
+    P4::mul4(p.X, p.Y, p.T, p.Z, E, Fv, G, H, E, H, Fv, G);
+  }
+#endif
   // canonical affine output; identity -> (0, 1), flag 1 (edwards.ts:606)
   NMSM_HD static void to_affine_canonical(const Acc& p, uint32_t* xy, uint32_t* is_inf) {
     F iz = inv(p.Z);
@@ -274,31 +396,40 @@ struct EdExt {
 
 // Curve policies; ID values are the curve ids of the C ABI (include/nmsm.h)
 struct CurveSecp256k1 {
+  static constexpr bool GLV = false;
   using G = SwXyzz<Fp<FpSecp256k1>>;
   using Fn = Fn_secp256k1;
   static constexpr int ID = 0;
 };
 struct CurveEd25519 {
+  static constexpr bool GLV = false;
   using G = EdExt<Fp<FpEd25519>, Ed25519Consts>;
   using Fn = Fn_ed25519;
   static constexpr int ID = 1;
 };
 struct CurveBn254G1 {
+  static constexpr bool GLV = false;
   using G = SwXyzz<Fp<FpBn254>>;
   using Fn = Fn_bn254;
   static constexpr int ID = 2;
 };
 struct CurveBn254G2 {
+  static constexpr bool GLV = false;
   using G = SwXyzz<Fp2<FpBn254>>;
   using Fn = Fn_bn254;
   static constexpr int ID = 3;
 };
 struct CurveBls381G1 {
+  // terms are split as k = v1 + v2*lambda and accumulated against P and phi(P) = (beta*x, y): half as many
+  // windows, buckets and Horner doublings for the same number of mixed additions (msm_body.cuh glv_split)
+  static constexpr bool GLV = true;
+  using Glv = Bls381G1Glv;
   using G = SwXyzz<Fp<FpBls381>>;
   using Fn = Fn_bls12_381;
   static constexpr int ID = 4;
 };
 struct CurveBls381G2 {
+  static constexpr bool GLV = false;
   using G = SwXyzz<Fp2<FpBls381>>;
   using Fn = Fn_bls12_381;
   static constexpr int ID = 5;

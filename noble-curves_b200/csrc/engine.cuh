@@ -45,11 +45,11 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   }
 
   MsmPlan plan = make_plan<Cv>(n, C.forced_c, C.sm_count);
-  const uint64_t max_entries = n * (uint64_t)plan.W;
+  const uint64_t max_entries = n * (uint64_t)plan.W * (Cv::GLV ? 2 : 1);
   if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
   const uint64_t max_threads = (max_entries + plan.L - 1) / plan.L;
 
-  CK(C.aff.ensure(n * G::AFF_WORDS * 4));
+  CK(C.aff.ensure(n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
   CK(C.counts.ensure((size_t)(plan.G + 1) * 4));
   CK(C.offsets.ensure((size_t)(plan.G + 1) * 4));
   CK(C.cursor.ensure((size_t)(plan.G + 1) * 4));

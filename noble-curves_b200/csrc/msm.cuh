@@ -16,7 +16,8 @@
 //                  of buckets that straddle accumulate segments on the fly                 (W*B/K threads)
 //   k_reduce2      per-window second level: suffix scan + reduction of the chunk sums
 //                  (registers -> warp shuffles -> shared memory)                           (W blocks)
-//   k_final        Horner over windows (c doublings each) + one inversion to affine       (1 thread)
+//   k_final        Horner over windows (c doublings each) + one inversion to affine;
+//                  one warp, lanes share each formula's independent multiplications      (1 warp)
 //
 // No atomics touch curve points, so degenerate inputs (all scalars equal, all points equal —
 // test/point.test.ts:842-853, benchmark/msm_timings.ts:45-63) stay correct; they only lengthen the
@@ -33,7 +34,7 @@ template <class Cv>
 __global__ void k_prepare(const uint32_t* __restrict__ pts, uint32_t n, uint32_t* __restrict__ aff,
                           unsigned int* err) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) prepare_body<Cv>(i, pts, aff, err);
+  if (i < n) prepare_body<Cv>(i, n, pts, aff, err);
 }
 
 template <class Cv, bool SCATTER>
@@ -41,7 +42,7 @@ __global__ void k_digits(const uint32_t* __restrict__ scalars, uint32_t n, MsmPl
                          unsigned int* __restrict__ counts_or_cursor, uint32_t* __restrict__ sorted,
                          unsigned int* err) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) digits_body<Cv, SCATTER>(i, scalars, plan, counts_or_cursor, sorted, err);
+  if (i < n) digits_body<Cv, SCATTER>(i, n, scalars, plan, counts_or_cursor, sorted, err);
 }
 
 // Exclusive scan of the G bucket counters in two coalesced passes over SCAN_TILE-element tiles:
@@ -211,16 +212,45 @@ k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums,
   }
 }
 
+// Horner over the window sums (curve.ts:901-902) by ONE warp whose lanes hold replicated state and
+// split the independent multiplications of every point formula between them (ec.cuh Par4).
 template <class Cv, bool AFFINE_OUT>
-__global__ void k_final(const uint32_t* __restrict__ window_out, MsmPlan plan, uint32_t* __restrict__ out,
-                        uint32_t* __restrict__ out_inf) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) final_body<Cv, AFFINE_OUT>(window_out, plan, out, out_inf);
+__global__ void __launch_bounds__(32)
+k_final(const uint32_t* __restrict__ window_out, MsmPlan plan, uint32_t* __restrict__ out,
+        uint32_t* __restrict__ out_inf) {
+  using G = typename Cv::G;
+  typename G::Acc acc = G::identity();
+  for (int w = plan.W - 1; w >= 0; w--) {
+    if (w != plan.W - 1)
+      for (int j = 0; j < plan.c; j++) G::par_dbl(acc);
+    G::par_add(acc, load_acc<G>(window_out + (size_t)w * G::ACC_WORDS));
+  }
+  if (AFFINE_OUT) {
+    uint32_t xy[G::IN_WORDS];
+    uint32_t inf;
+    nl_to_affine<G>(acc, xy, &inf);
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < G::IN_WORDS; k++) out[k] = xy[k];
+      *out_inf = inf;
+    }
+  } else if (threadIdx.x == 0) {
+    save_acc<G>(out, acc);
+  }
 }
 
 template <class Cv>
-__global__ void k_fold(const uint32_t* __restrict__ accs, int count, uint32_t* __restrict__ out,
-                       uint32_t* __restrict__ out_inf) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) fold_body<Cv>(accs, count, out, out_inf);
+__global__ void __launch_bounds__(32)
+k_fold(const uint32_t* __restrict__ accs, int count, uint32_t* __restrict__ out, uint32_t* __restrict__ out_inf) {
+  using G = typename Cv::G;
+  typename G::Acc acc = G::identity();
+  for (int i = 0; i < count; i++) G::par_add(acc, load_acc<G>(accs + (size_t)i * G::ACC_WORDS));
+  uint32_t xy[G::IN_WORDS];
+  uint32_t inf;
+  nl_to_affine<G>(acc, xy, &inf);
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < G::IN_WORDS; k++) out[k] = xy[k];
+    *out_inf = inf;
+  }
 }
 
 template <class Cv>

@@ -41,14 +41,22 @@ struct MsmPlan {
 template <class Cv>
 inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
   using G = typename Cv::G;
-  const int bits = Cv::Fn::BITS;
+  // with GLV every scalar becomes two signed halves of at most 127 bits, each attached to its own point
+  const int bits = Cv::GLV ? 127 : Cv::Fn::BITS;
+  const double terms = (double)n * (Cv::GLV ? 2 : 1);
   int best_c = 2;
   double best = 1e300;
   for (int c = 2; c <= MAX_WINDOW_BITS; c++) {
     int W = (bits + 1 + c - 1) / c;
     double B = (double)(1u << (c - 1));
     // reduce runs at lower occupancy and pays the chunk-offset multiplications: weight it 1.6x
-    double cost = (double)W * ((double)n * G::COST_MADD + 2.0 * B * G::COST_ADD * 1.6) + 9.0 * bits;
+    double cost = (double)W * (terms * G::COST_MADD + 2.0 * B * G::COST_ADD * 1.6) + 9.0 * bits;
+    // A top window that holds only a few scalar bits funnels ~terms/2^top_bits entries into each of its
+    // buckets; buckets far larger than an accumulate segment are stitched serially in k_reduce1, so
+    // such plans are penalised by the length of that serial chain (one complete addition per segment).
+    int top_bits = bits + 1 - (W - 1) * c;
+    double per_bucket = terms / (double)(1u << (top_bits > 1 ? top_bits - 1 : 0));
+    if (top_bits < c && per_bucket > 64.0 * 32.0) cost += (per_bucket / 32.0) * G::COST_ADD * 2000.0;
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -60,7 +68,7 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
   p.W = (bits + 1 + c - 1) / c;
   p.B = 1 << (c - 1);
   p.G = p.W * p.B;
-  double entries = (double)n * p.W;
+  double entries = terms * p.W;
   double target_threads = (double)sm_count * 1024.0;
   int L = (int)ceil(entries / target_threads);
   if (L < 4) L = 4;
@@ -178,11 +186,11 @@ NMSM_NL void nl_to_affine(const typename G::Acc& p, uint32_t* xy, uint32_t* inf)
 }
 
 // c bits of a 256-bit little-endian scalar starting at bit `off`
-NMSM_HD uint32_t scalar_bits(const uint32_t* s, int off, int c) {
+NMSM_HD uint32_t scalar_bits(const uint32_t* s, int off, int c, int nwords = SCALAR_WORDS) {
   int w = off >> 5, sh = off & 31;
-  if (w >= SCALAR_WORDS) return 0;
+  if (w >= nwords) return 0;
   uint64_t lo = s[w];
-  uint64_t hi = (w + 1 < SCALAR_WORDS) ? s[w + 1] : 0;
+  uint64_t hi = (w + 1 < nwords) ? s[w + 1] : 0;
   uint64_t v = (lo | (hi << 32)) >> sh;
   return (uint32_t)v & ((1u << c) - 1u);
 }
@@ -197,11 +205,118 @@ NMSM_HD bool scalar_in_range(const uint32_t* s) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// GLV split for curves with r = lambda^2 + lambda + 1 (BLS12-381 G1):
+//   k = v1 + v2*lambda (mod r),  |v1|, |v2| <= lambda/2 + 1 < 2^127
+// q = floor(k / lambda) by a Barrett step with MU = floor(2^256 / lambda) (at most one correction),
+// then both halves are centred using lambda^2 + lambda = -1 (mod r).
+// ---------------------------------------------------------------------------------------------
+NMSM_HD bool gt4(const uint32_t* a, const uint32_t* b) {  // a > b, 4 limbs
+  for (int k = 3; k >= 0; k--) {
+    if (a[k] != b[k]) return a[k] > b[k];
+  }
+  return false;
+}
+NMSM_HD void sub4(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // r = a - b (a >= b)
+  uint64_t br = 0;
+  for (int k = 0; k < 4; k++) {
+    uint64_t t = (uint64_t)a[k] - b[k] - br;
+    r[k] = (uint32_t)t;
+    br = (t >> 63) & 1;
+  }
+}
+NMSM_HD void inc4(uint32_t* a) {
+  for (int k = 0; k < 4; k++)
+    if (++a[k] != 0) break;
+}
+NMSM_HD void dec4(uint32_t* a) {
+  for (int k = 0; k < 4; k++)
+    if (a[k]-- != 0) break;
+}
+template <class GC>
+NMSM_HD void glv_split(const uint32_t* k, uint32_t* m1, bool& neg1, uint32_t* m2, bool& neg2) {
+  uint32_t lam[4], half[4], lp1[4];
+  for (int i = 0; i < 4; i++) lam[i] = GC::LAMBDA(i);
+  for (int i = 0; i < 4; i++) half[i] = (lam[i] >> 1) | (i < 3 ? lam[i + 1] << 31 : 0);
+  for (int i = 0; i < 4; i++) lp1[i] = lam[i];
+  inc4(lp1);
+  // q = (k * MU) >> 256
+  uint32_t prod[13];
+  for (int i = 0; i < 13; i++) prod[i] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t carry = 0;
+    for (int j = 0; j < 5; j++) {
+      uint64_t t = (uint64_t)k[i] * GC::MU(j) + prod[i + j] + carry;
+      prod[i + j] = (uint32_t)t;
+      carry = t >> 32;
+    }
+    prod[i + 5] = (uint32_t)carry;
+  }
+  uint32_t q[5];
+  for (int i = 0; i < 5; i++) q[i] = prod[8 + i];
+  // r = k - q*lambda, low 5 limbs (0 <= r < 2*lambda)
+  uint32_t t[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < 5; i++) {
+    uint64_t carry = 0;
+    for (int j = 0; j < 4 && i + j < 5; j++) {
+      uint64_t x = (uint64_t)q[i] * lam[j] + t[i + j] + carry;
+      t[i + j] = (uint32_t)x;
+      carry = x >> 32;
+    }
+    if (i == 0) t[4] += (uint32_t)carry;  // only row 0 ends below limb 5; t[4] is still zero here
+  }
+  uint32_t r[5];
+  {
+    uint64_t br = 0;
+    for (int i = 0; i < 5; i++) {
+      uint64_t x = (uint64_t)k[i] - t[i] - br;
+      r[i] = (uint32_t)x;
+      br = (x >> 63) & 1;
+    }
+  }
+  if (r[4] != 0 || !gt4(lam, r)) {  // r >= lambda
+    uint64_t br = 0;
+    for (int i = 0; i < 4; i++) {
+      uint64_t x = (uint64_t)r[i] - lam[i] - br;
+      r[i] = (uint32_t)x;
+      br = (x >> 63) & 1;
+    }
+    inc4(q);
+  }
+  for (int i = 0; i < 4; i++) {
+    m1[i] = r[i];
+    m2[i] = q[i];
+  }
+  neg1 = false;
+  neg2 = false;
+  if (gt4(m1, half)) {  // v1 = k1 - lambda, borrow one lambda from v2
+    sub4(m1, lam, m1);
+    neg1 = true;
+    inc4(m2);
+  }
+  if (gt4(m2, half)) {  // v2 = k2 - (lambda + 1); (lambda + 1)*lambda = -1  =>  v1 -= 1
+    if (gt4(lp1, m2)) {
+      sub4(m2, lp1, m2);
+      neg2 = true;
+    } else {
+      sub4(m2, m2, lp1);
+    }
+    if (neg1) {
+      inc4(m1);
+    } else if ((m1[0] | m1[1] | m1[2] | m1[3]) == 0) {
+      m1[0] = 1;
+      neg1 = true;
+    } else {
+      dec4(m1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // bodies
 // ---------------------------------------------------------------------------------------------
 // err[0] = min index of an out-of-range point coordinate, err[1] = min index of an invalid scalar
 template <class Cv>
-NMSM_HD void prepare_body(uint32_t i, const uint32_t* pts, uint32_t* aff, unsigned int* err) {
+NMSM_HD void prepare_body(uint32_t i, uint32_t n, const uint32_t* pts, uint32_t* aff, unsigned int* err) {
   using G = typename Cv::G;
   uint32_t in[G::IN_WORDS];
   load_words<G::IN_WORDS>(in, pts + (size_t)i * G::IN_WORDS);
@@ -211,40 +326,60 @@ NMSM_HD void prepare_body(uint32_t i, const uint32_t* pts, uint32_t* aff, unsign
   }
   typename G::Affine a = G::prepare(in);
   store_words<G::AFF_WORDS>(aff + (size_t)i * G::AFF_WORDS, reinterpret_cast<const uint32_t*>(&a));
+  if constexpr (Cv::GLV) {  // phi(P) = (beta * x, y) at index n + i; (0,0) stays the identity
+    typename G::Field beta;
+    for (int k = 0; k < G::Field::LIMBS; k++) beta.v[k] = Cv::Glv::BETA_MONT(k);
+    a.x = a.x * beta;
+    store_words<G::AFF_WORDS>(aff + (size_t)(n + i) * G::AFF_WORDS, reinterpret_cast<const uint32_t*>(&a));
+  }
 }
 
-// Signed-digit recoding shared by the count and scatter passes: digit d_w in [-(2^(c-1)-1), 2^(c-1)],
-// sum d_w 2^(cw) = s (the fixed-window analogue of curve.ts:454-472 signedWindowDigits).
-// Bucket id g = w*B + |d| - 1, weight |d|; the sign rides in bit 31 of the sorted entry.
-template <class Cv, bool SCATTER>
-NMSM_HD void digits_body(uint32_t i, const uint32_t* scalars, const MsmPlan& plan, unsigned int* counts_or_cursor,
-                         uint32_t* sorted, unsigned int* err) {
-  uint32_t s[SCALAR_WORDS];
-  load_words<SCALAR_WORDS>(s, scalars + (size_t)i * SCALAR_WORDS);
-  if (!scalar_in_range<typename Cv::Fn>(s)) {  // same decision in both passes keeps count == scatter
-    if (!SCATTER) atomic_min_u32(&err[1], i);
-    return;
-  }
+// Signed-digit recoding of one magnitude shared by the count and scatter passes: digit d_w in
+// [-(2^(c-1)-1), 2^(c-1)], sum d_w 2^(cw) = m (the fixed-window analogue of curve.ts:454-472
+// signedWindowDigits).  Bucket id g = w*B + |d| - 1, weight |d|; the sign rides in bit 31 of the entry.
+template <bool SCATTER>
+NMSM_HD void emit_digits(const uint32_t* m, int nwords, uint32_t index, uint32_t flip, const MsmPlan& plan,
+                         unsigned int* counts_or_cursor, uint32_t* sorted) {
   const uint32_t half = 1u << (plan.c - 1);
   uint32_t carry = 0;
   for (int w = 0; w < plan.W; w++) {
-    uint32_t v = scalar_bits(s, w * plan.c, plan.c) + carry;
+    uint32_t v = scalar_bits(m, w * plan.c, plan.c, nwords) + carry;
     carry = 0;
-    uint32_t neg = 0;
+    uint32_t neg = flip;
     if (v > half) {
       v = (1u << plan.c) - v;
-      neg = 1;
+      neg ^= 1u;
       carry = 1;
     }
     if (v != 0) {
       uint32_t g = (uint32_t)w * (uint32_t)plan.B + (v - 1);
       if (SCATTER) {
         uint32_t pos = atomic_add_u32(&counts_or_cursor[g], 1u);
-        sorted[pos] = i | (neg << 31);
+        sorted[pos] = index | (neg << 31);
       } else {
         atomic_add_u32(&counts_or_cursor[g], 1u);
       }
     }
+  }
+}
+
+template <class Cv, bool SCATTER>
+NMSM_HD void digits_body(uint32_t i, uint32_t n, const uint32_t* scalars, const MsmPlan& plan,
+                         unsigned int* counts_or_cursor, uint32_t* sorted, unsigned int* err) {
+  uint32_t s[SCALAR_WORDS];
+  load_words<SCALAR_WORDS>(s, scalars + (size_t)i * SCALAR_WORDS);
+  if (!scalar_in_range<typename Cv::Fn>(s)) {  // same decision in both passes keeps count == scatter
+    if (!SCATTER) atomic_min_u32(&err[1], i);
+    return;
+  }
+  if constexpr (Cv::GLV) {
+    uint32_t m1[4], m2[4];
+    bool neg1, neg2;
+    glv_split<typename Cv::Glv>(s, m1, neg1, m2, neg2);
+    emit_digits<SCATTER>(m1, 4, i, neg1 ? 1u : 0u, plan, counts_or_cursor, sorted);
+    emit_digits<SCATTER>(m2, 4, n + i, neg2 ? 1u : 0u, plan, counts_or_cursor, sorted);
+  } else {
+    emit_digits<SCATTER>(s, SCALAR_WORDS, i, 0u, plan, counts_or_cursor, sorted);
   }
 }
 

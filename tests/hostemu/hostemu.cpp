@@ -21,18 +21,18 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
   MsmPlan plan = make_plan<Cv>(n, forced_c, 148);
   if (forced_L > 0) plan.L = forced_L;
   plan_out[0] = plan.c; plan_out[1] = plan.W; plan_out[2] = plan.B; plan_out[3] = plan.L;
-  std::vector<uint32_t> aff((size_t)n * G::AFF_WORDS);
+  std::vector<uint32_t> aff((size_t)n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS);
   std::vector<unsigned int> counts(plan.G + 1, 0), cursor(plan.G + 1, 0);
   std::vector<uint32_t> offsets(plan.G + 1, 0);
   unsigned int err[2] = {0xffffffffu, 0xffffffffu};
-  for (uint32_t i = 0; i < n; i++) prepare_body<Cv>(i, pts, aff.data(), err);
-  for (uint32_t i = 0; i < n; i++) digits_body<Cv, false>(i, scalars, plan, counts.data(), nullptr, err);
+  for (uint32_t i = 0; i < n; i++) prepare_body<Cv>(i, n, pts, aff.data(), err);
+  for (uint32_t i = 0; i < n; i++) digits_body<Cv, false>(i, n, scalars, plan, counts.data(), nullptr, err);
   uint32_t run = 0;
   for (int g = 0; g < plan.G; g++) { offsets[g] = run; cursor[g] = run; run += counts[g]; }
   offsets[plan.G] = run;
   const uint32_t T = run;
   std::vector<uint32_t> sorted(T ? T : 1);
-  for (uint32_t i = 0; i < n; i++) digits_body<Cv, true>(i, scalars, plan, cursor.data(), sorted.data(), err);
+  for (uint32_t i = 0; i < n; i++) digits_body<Cv, true>(i, n, scalars, plan, cursor.data(), sorted.data(), err);
   const uint32_t nthreads = (T + plan.L - 1) / plan.L;
   std::vector<uint32_t> buckets((size_t)plan.G * G::ACC_WORDS, 0xdeadbeefu);
   std::vector<uint32_t> heads((size_t)(nthreads + 1) * G::ACC_WORDS, 0xdeadbeefu), tails((size_t)(nthreads + 1) * G::ACC_WORDS, 0xdeadbeefu);
@@ -128,6 +128,14 @@ static void field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) 
 }
 
 extern "C" {
+// GLV split of one scalar (BLS12-381 G1): out = m1[4], m2[4], neg1, neg2
+int emu_glv_split(const uint32_t* k, uint32_t* out) {
+  bool n1, n2;
+  glv_split<Bls381G1Glv>(k, out, n1, out + 4, n2);
+  out[8] = n1;
+  out[9] = n2;
+  return 0;
+}
 int emu_msm(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, int forced_c, int forced_L,
             uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out) {
   DISPATCH(curve, emu_msm_t<Cv>(pts, scalars, n, forced_c, forced_L, out_xy, out_inf, err_out, plan_out));

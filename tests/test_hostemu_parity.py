@@ -150,3 +150,33 @@ def test_mul_batch(name):
     assert err == (0xFFFFFFFF, 0xFFFFFFFF) and res[1] == H.expected_tuple(name, P.ZERO)
     res, err = H.emu_mul_batch(name, H.pack_points(name, pts[:2]), H.pack_scalars([n_order, 1]), 2, True)
     assert err == (0xFFFFFFFF, 0)
+
+
+def test_glv_split_and_constants():
+    """BLS12-381 G1 GLV: k = v1 + v2*lambda (mod r), |v| < 2^127, and phi(P) = (beta*x, y) = lambda*P."""
+    import ctypes
+    import random as _r
+
+    import numpy as np
+
+    P = R.CURVES["bls12_381_G1"]
+    r, p = P.Fn.ORDER, P.Fp.ORDER
+    lam = 0xD201000000010000**2 - 1
+    beta = 0x1A0111EA397FE699EC02408663D4DE85AA0D857D89759AD4897D29650FB85F9B409427EB4F49FFFD8BFD00000000AAAC
+    assert lam * lam + lam + 1 == r and pow(beta, 3, p) == 1
+    g = P.BASE.toAffine()
+    assert R.affine_tuple(P, P.BASE.multiplyUnsafe(lam)) == (beta * g["x"] % p, g["y"])
+    rnd = _r.Random(5)
+    ks = [0, 1, 2, lam - 1, lam, lam + 1, lam // 2, lam // 2 + 1, lam // 2 + 2, r - 1, r - 2, r - lam, r - lam - 1,
+          lam * (lam // 2), lam * (lam // 2 + 1), lam * (lam // 2 + 1) + lam // 2 + 1]
+    ks += [rnd.randrange(r) for _ in range(3000)]
+    lib = H.hostemu()
+    for k in ks:
+        a = H.u32(k.to_bytes(32, "little"))
+        out = np.zeros(10, np.uint32)
+        lib.emu_glv_split(a.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+        m1 = int.from_bytes(out[:4].tobytes(), "little")
+        m2 = int.from_bytes(out[4:8].tobytes(), "little")
+        v1 = -m1 if out[8] else m1
+        v2 = -m2 if out[9] else m2
+        assert (v1 + v2 * lam - k) % r == 0 and m1 < 2**127 and m2 < 2**127, hex(k)
