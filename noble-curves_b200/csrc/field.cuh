@@ -85,11 +85,99 @@ NMSM_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   reduce_once<C>(r, top);
 }
 
+// Montgomery squaring, SOS order: the n(n-1)/2 off-diagonal products are formed once and doubled
+// (a one-bit shift of both column arrays), the n diagonal squares are added, then the n reduction rows
+// run as in mont_mul.  IMAD.WIDE-equivalents: n(n-1)/2 + n + n^2 + n  (n = 12: 234 vs 300; n = 8: 108 vs 136).
+// The reduction rows now add into limbs that already hold product bits, so their chain-end carries are
+// collected in a separate small-count array (Cw) and merged at the end.
+template <class C>
+NMSM_HD void mont_sqr(uint32_t* r, const uint32_t* a) {
+  constexpr int N = C::N;
+  uint32_t E[2 * N + 2], O[2 * N + 2], Cw[2 * N + 2];
+#pragma unroll
+  for (int k = 0; k < 2 * N + 2; k++) {
+    E[k] = 0;
+    O[k] = 0;
+    Cw[k] = 0;
+  }
+  // A1: off-diagonal products a_i * a_j (i < j) at absolute position i + j
+#pragma unroll
+  for (int i = 0; i < N - 1; i++) {
+    // (i + j) even -> E
+    if (i + 2 < N) {
+#pragma unroll
+      for (int j = i + 2; j < N; j += 2) {
+        E[i + j] = (j == i + 2) ? mad_lo_cc(a[i], a[j], E[i + j]) : madc_lo_cc(a[i], a[j], E[i + j]);
+        E[i + j + 1] = madc_hi_cc(a[i], a[j], E[i + j + 1]);
+      }
+      const int last = i + 2 + 2 * ((N - 1 - (i + 2)) / 2);  // largest j used
+      E[i + last + 2] = addc(E[i + last + 2], 0);
+    }
+    // (i + j) odd -> O
+#pragma unroll
+    for (int j = i + 1; j < N; j += 2) {
+      O[i + j] = (j == i + 1) ? mad_lo_cc(a[i], a[j], O[i + j]) : madc_lo_cc(a[i], a[j], O[i + j]);
+      O[i + j + 1] = madc_hi_cc(a[i], a[j], O[i + j + 1]);
+    }
+    {
+      const int last = i + 1 + 2 * ((N - 1 - (i + 1)) / 2);
+      O[i + last + 2] = addc(O[i + last + 2], 0);
+    }
+  }
+  // A2: double both column arrays (value(E) + value(O) is the off-diagonal sum)
+#pragma unroll
+  for (int k = 2 * N + 1; k >= 1; k--) {
+    E[k] = (E[k] << 1) | (E[k - 1] >> 31);
+    O[k] = (O[k] << 1) | (O[k - 1] >> 31);
+  }
+  E[0] <<= 1;
+  O[0] <<= 1;
+  // A3: diagonal squares a_i^2 at position 2i: one chain along E
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    E[2 * i] = (i == 0) ? mad_lo_cc(a[i], a[i], E[2 * i]) : madc_lo_cc(a[i], a[i], E[2 * i]);
+    E[2 * i + 1] = madc_hi_cc(a[i], a[i], E[2 * i + 1]);
+  }
+  E[2 * N] = addc(E[2 * N], 0);
+  // B: Montgomery reduction rows
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t* P1 = (i & 1) ? O : E;
+    uint32_t* P2 = (i & 1) ? E : O;
+    if (i > 0) P1[i] = add_cc(P1[i], P2[i]);  // carry continues into P2's chain at position i+1
+    const uint32_t m = P1[i] * C::INV;
+#pragma unroll
+    for (int j = 1; j < N; j += 2) {
+      P2[i + j] = (i == 0 && j == 1) ? mad_lo_cc(m, C::P(j), P2[i + j]) : madc_lo_cc(m, C::P(j), P2[i + j]);
+      P2[i + j + 1] = madc_hi_cc(m, C::P(j), P2[i + j + 1]);
+    }
+    Cw[i + N + 1] = addc(Cw[i + N + 1], 0);
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      P1[i + j] = (j == 0) ? mad_lo_cc(m, C::P(j), P1[i + j]) : madc_lo_cc(m, C::P(j), P1[i + j]);
+      P1[i + j + 1] = madc_hi_cc(m, C::P(j), P1[i + j + 1]);
+    }
+    Cw[i + N] = addc(Cw[i + N], 0);
+  }
+  // merge limbs N..2N of E + O + Cw
+  r[0] = add_cc(E[N], O[N]);
+#pragma unroll
+  for (int k = 1; k < N; k++) r[k] = addc_cc(E[N + k], O[N + k]);
+  uint32_t top = addc(E[2 * N], O[2 * N]);
+  r[0] = add_cc(r[0], Cw[N]);
+#pragma unroll
+  for (int k = 1; k < N; k++) r[k] = addc_cc(r[k], Cw[N + k]);
+  top = addc(top, Cw[2 * N]);
+  reduce_once<C>(r, top);
+}
+
 template <class C>
 struct Fp;
 #if defined(__CUDACC__)
 template <class C>
 __device__ __noinline__ Fp<C> mul_call(Fp<C> a, Fp<C> b);
+template <class C>
+__device__ __noinline__ Fp<C> sqr_call(Fp<C> a);
 #endif
 
 template <class C>
@@ -193,11 +281,23 @@ __device__ __noinline__ Fp<C> mul_call(Fp<C> a, Fp<C> b) {
   mont_mul<C>(r.v, a.v, b.v);
   return r;
 }
+template <class C>
+__device__ __noinline__ Fp<C> sqr_call(Fp<C> a) {
+  Fp<C> r;
+  mont_sqr<C>(r.v, a.v);
+  return r;
+}
 #endif
 
 template <class C>
 NMSM_HD Fp<C> sqr(const Fp<C>& a) {
-  return a * a;
+#if defined(__CUDA_ARCH__) && defined(NMSM_MUL_NOINLINE)
+  return sqr_call<C>(a);
+#else
+  Fp<C> r;
+  mont_sqr<C>(r.v, a.v);
+  return r;
+#endif
 }
 template <class C>
 NMSM_HD Fp<C> dbl(const Fp<C>& a) {

@@ -115,8 +115,11 @@ k_scan_apply(const unsigned int* __restrict__ counts, uint32_t G, const uint32_t
   if (base < G && base + SCAN_PER_THREAD >= G) offsets[G] = run;
 }
 
+#ifndef NMSM_ACC_MINBLOCKS
+#define NMSM_ACC_MINBLOCKS 1
+#endif
 template <class Cv>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, NMSM_ACC_MINBLOCKS)
 k_accumulate(const uint32_t* __restrict__ aff, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ offsets, MsmPlan plan, uint32_t* __restrict__ buckets,
              uint32_t* __restrict__ heads, uint32_t* __restrict__ tails) {
