@@ -6,9 +6,9 @@
 
 One "step" = one complete MSM (curve.ts:863-905 `pippenger` semantics) over one batch of synthetic
 (point, scalar) terms:  points P_i = k_i*G, scalars uniform in [0, n).  At N GPUs the term array is
-split contiguously across ranks, each rank reduces its shard to one raw accumulator, the accumulators
-are exchanged with one NCCL all-gather and folded (MSM is linear in its term set), so total work is
-fixed -> "scaling": "strong".
+sharded across ranks, each rank reduces its shard to one raw accumulator, the accumulators are
+exchanged with one NCCL all-gather and folded (MSM is linear in its term set).  Default "scaling": "weak":
+every GPU holds 2^20 terms of ONE MSM with N*2^20 terms; `--scaling strong` splits 2^20 terms over the GPUs.
 
 Timed numbers:
   value  — whole-job points/s with inputs already resident in HBM (CUDA path via nmsm_msm_device)
@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--logn", type=int, default=20, help="log2 of the MSM size (headline: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window", type=int, default=0, help="force window bits c (0 = cost model)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = 2^logn terms PER GPU (one MSM of N*2^logn terms); strong = 2^logn terms in total")
     return ap.parse_args()
 
 
@@ -142,24 +144,27 @@ def cpu_reference(n_sample, seed, max_seconds=30.0):
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's algorithm on this box's host cores (rank 0 only under torchrun).
+    Inputs are generated once; each step is one timed run of the C port on the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 1 << args.logn
-    res = None
-    vals = []
-    for _ in range(args.warmup + args.steps):
-        res = cpu_reference(None, 1)
-        vals.append(res)
-    vals = vals[args.warmup:]
-    pts_per_s = sum(v["points_per_s_at_full_size"] for v in vals) / len(vals)
+    from oracle import cpu_baseline as CB
+
+    n_full = 1 << args.logn
+    n_sample = CB.choose_sample(30.0, args.logn)
+    w = CB.Workload(n_sample, 1)
+    times = [w.run() for _ in range(args.warmup + args.steps)][args.warmup:]
+    res = CB.describe(n_sample, sum(times) / len(times), args.logn)
+    pts_per_s = res["points_per_s_at_full_size"]
     line = {
         "impl": "reference",
         "metric": "BLS12-381 G1 MSM points/sec at 2^%d scalars" % args.logn,
         "value": pts_per_s, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * n / pts_per_s, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u32-limb integer (381-bit Fp)", "data": "synthetic",
-        "config": {"workload": "BLS12-381 G1 MSM, N=2^%d, reference algorithm (curve.ts:863-905) on host cores" % args.logn},
+        "ms_per_step": 1e3 * n_full / pts_per_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64-limb integer (381-bit Fp, Montgomery)", "data": "synthetic",
+        "config": {"workload": "BLS12-381 G1 MSM, 2^%d terms, reference algorithm (curve.ts:863-905) on host cores; "
+                               "host-only: the same single-box workload at every --gpus" % args.logn},
         "cpu_baseline": {"value": pts_per_s, "unit": "points/s", "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": pts_per_s, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -194,9 +199,11 @@ def main():
     if args.window:
         nmsm.set_window_bits(args.window)
 
-    n_total = 1 << args.logn
-    n_local = n_total // world
-    lo = rank * n_local
+    # weak scaling (default): every GPU holds a 2^logn-term shard of ONE MSM with world*2^logn terms, so per-GPU
+    # work is fixed; strong: the 2^logn terms are split across the GPUs.  Either way: one all-gather + fold.
+    scaling = args.scaling if world > 1 else "weak"
+    n_local = (1 << args.logn) if scaling == "weak" else (1 << args.logn) // world
+    n_total = n_local * world
     # every rank generates only its own shard; seeds make shards disjoint and reproducible
     pts_b, sc_b, total_local = make_terms(nmsm, n_local, 1000 + rank)
     dev = torch.device("cuda", local_rank)
@@ -350,9 +357,11 @@ def main():
     line = {
         "metric": "BLS12-381 G1 MSM points/sec at 2^%d scalars" % args.logn,
         "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "u32-limb integer (381-bit Fp, Montgomery)", "data": "synthetic",
-        "config": {"workload": "BLS12-381 G1 Pippenger MSM, N=2^%d random points (k_i*G) x uniform scalars" % args.logn,
+        "config": {"workload": ("BLS12-381 G1 Pippenger MSM, 2^%d random terms (points k_i*G, uniform scalars) per GPU; "
+                                "at N GPUs one MSM of N*2^%d terms" % (args.logn, args.logn)) if scaling == "weak" else
+                               "BLS12-381 G1 Pippenger MSM, 2^%d terms in total split over the GPUs" % args.logn,
                    "terms": n_total, "terms_per_gpu": n_local, "parallelism": "term-sharded x%d, 1 all-gather of raw accumulators" % world,
                    "l2": "inputs+workspace (>=450 MB/GPU at N=2^20) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": len(pts_b) + len(sc_b),

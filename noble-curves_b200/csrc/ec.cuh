@@ -21,20 +21,24 @@ namespace nmsm {
 // ------------------------------------------------------------------------------------------
 // Lane-parallel field multiplications for the single-warp latency tails (k_final / k_fold).
 // The multiply pipe is occupied per WARP instruction (a lone thread pays ~0.95 us per 381-bit
-// mont_mul, measured), so the serial Horner / fold runs with every lane of one warp holding the
-// same replicated state; at each level of a point formula lane (l & 3) computes one of up to four
-// independent products and the results are broadcast back with warp shuffles.
+// mont_mul, measured), so latency-bound phases run each logical thread on a QUAD of 4 adjacent lanes
+// holding the same replicated state; at each level of a point formula lane (l & 3) computes one of up
+// to four independent products and the results are broadcast back inside the quad with warp shuffles
+// (quad-scoped masks, so different quads of a warp may diverge).
 // ------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
 template <class F>
 struct Par4 {
   static constexpr int WORDS = sizeof(F) / 4;
+  // broadcast from lane `src` (0..3) of the caller's quad (4 adjacent lanes); quads may be divergent
   __device__ static __forceinline__ F bcast(const F& z, int src) {
     F r;
     const uint32_t* s = reinterpret_cast<const uint32_t*>(&z);
     uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+    const unsigned qbase = threadIdx.x & 28u;  // blocks are multiples of 32 threads
+    const unsigned qmask = 0xFu << qbase;
 #pragma unroll
-    for (int k = 0; k < WORDS; k++) d[k] = __shfl_sync(0xffffffffu, s[k], src);
+    for (int k = 0; k < WORDS; k++) d[k] = __shfl_sync(qmask, s[k], qbase + src);
     return r;
   }
   __device__ static __forceinline__ F pick(int l, const F& a0, const F& a1, const F& a2, const F& a3) {

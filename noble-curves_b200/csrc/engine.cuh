@@ -59,6 +59,7 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   CK(C.tails.ensure(max_threads * G::ACC_WORDS * 4));
   CK(C.chunk_out.ensure((size_t)plan.W * plan.chunks * G::ACC_WORDS * 4 * 2));
   CK(C.tile_sums.ensure((size_t)(plan.G / SCAN_TILE + 2) * 4));
+  CK(C.blk.ensure((size_t)plan.W * REDUCE2_MAX_SPLITS * G::ACC_WORDS * 4 * 2));
   CK(C.window_out.ensure((size_t)plan.W * G::ACC_WORDS * 4));
 
   uint32_t* aff = (uint32_t*)C.aff.p;
@@ -72,6 +73,8 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   uint32_t* sums = (uint32_t*)C.chunk_out.p;
   uint32_t* wsums = sums + (size_t)plan.W * plan.chunks * G::ACC_WORDS;
   uint32_t* tile_sums = (uint32_t*)C.tile_sums.p;
+  uint32_t* blkP = (uint32_t*)C.blk.p;
+  uint32_t* blkQ = blkP + (size_t)plan.W * REDUCE2_MAX_SPLITS * G::ACC_WORDS;
   uint32_t* window_out = (uint32_t*)C.window_out.p;
   cudaStream_t st = C.stream;
   const uint32_t n32 = (uint32_t)n;
@@ -93,12 +96,23 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   EV(4);
   k_accumulate<Cv><<<cdiv(max_threads, 128), 128, 0, st>>>(aff, sorted, offsets, plan, buckets, heads, tails);
   EV(5);
-  EV(6);  // (fixup is fused into k_reduce1; slot kept for the timing layout)
-  k_reduce1<Cv><<<cdiv((uint64_t)plan.W * plan.chunks, 128), 128, 0, st>>>(offsets, buckets, heads, tails, plan, sums,
-                                                                           wsums);
+  EV(6);
+  {
+    // k_reduce1: one quad per chunk
+    const uint64_t quads = (uint64_t)plan.W * plan.chunks;
+    k_reduce1<Cv><<<cdiv(quads * 4, 128), 128, 0, st>>>(offsets, buckets, heads, tails, plan, sums, wsums);
+  }
   EV(7);
-  k_reduce2<Cv><<<plan.W, REDUCE2_THREADS, (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4, st>>>(sums, wsums, plan,
-                                                                                          window_out);
+  {
+    // k_reduce2 / k_reduce3: each window is split over <= 8 blocks of 64 quads x R chunks
+    int R = 4;
+    while ((plan.chunks + REDUCE2_LOGICAL * R - 1) / (REDUCE2_LOGICAL * R) > REDUCE2_MAX_SPLITS) R <<= 1;
+    const int splits = (plan.chunks + REDUCE2_LOGICAL * R - 1) / (REDUCE2_LOGICAL * R);
+    dim3 grid2(splits, plan.W);
+    k_reduce2<Cv><<<grid2, REDUCE2_THREADS, (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4, st>>>(sums, wsums, plan, R,
+                                                                                            blkP, blkQ);
+    k_reduce3<Cv><<<plan.W, 32, 0, st>>>(blkP, blkQ, plan, splits, R, window_out);
+  }
   EV(8);
   if (d_out_acc)
     k_final<Cv, false><<<1, 32, 0, st>>>(window_out, plan, d_out_acc, nullptr);
@@ -124,7 +138,7 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   C.last_info.reduce_chunk = plan.K;
   C.last_info.sorted_entries = entries;
   C.last_info.modmul_equiv = plan_modmuls<Cv>(plan, entries);
-  C.last_info.launches = 9;  // prepare, count, scan x2, scatter, accumulate, reduce1, reduce2, final
+  C.last_info.launches = 10;  // prepare, count, scan x2, scatter, accumulate, reduce1, reduce2, reduce3, final
   if (C.profiling) {
     for (int k = 0; k < 9; k++) cudaEventElapsedTime(&C.last_ms[k], C.ev[k], C.ev[k + 1]);
     cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev[0], C.ev[9]);

@@ -13,9 +13,10 @@
 //                  additions, emitting complete buckets or head/tail partials at bucket
 //                  boundaries — constant work per thread whatever the bucket sizes are     (T/L threads)
 //   k_reduce1      per-chunk running sums (2 additions per bucket), stitching the partials
-//                  of buckets that straddle accumulate segments on the fly                 (W*B/K threads)
-//   k_reduce2      per-window second level: suffix scan + reduction of the chunk sums
-//                  (registers -> warp shuffles -> shared memory)                           (W blocks)
+//                  of buckets that straddle accumulate segments on the fly                 (W*B/K quads)
+//   k_reduce2      second level: suffix scan + reduction of chunk sums inside blocks of
+//                  64 quads (registers -> quad/warp shuffles -> shared memory)             (W x splits blocks)
+//   k_reduce3      folds the <= 8 block results of every window                            (W warps)
 //   k_final        Horner over windows (c doublings each) + one inversion to affine;
 //                  one warp, lanes share each formula's independent multiplications      (1 warp)
 //
@@ -116,7 +117,7 @@ k_scan_apply(const unsigned int* __restrict__ counts, uint32_t G, const uint32_t
 }
 
 #ifndef NMSM_ACC_MINBLOCKS
-#define NMSM_ACC_MINBLOCKS 1
+#define NMSM_ACC_MINBLOCKS 4  // measured on B200 (BLS12-381 G1): 1 -> 6.41 ms, 3 -> 6.02 ms, 4 -> 5.91 ms per 2^20-term MSM
 #endif
 template <class Cv>
 __global__ void __launch_bounds__(128, NMSM_ACC_MINBLOCKS)
@@ -126,92 +127,158 @@ k_accumulate(const uint32_t* __restrict__ aff, const uint32_t* __restrict__ sort
   accumulate_body<Cv>(blockIdx.x * blockDim.x + threadIdx.x, aff, sorted, offsets, plan, buckets, heads, tails);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bucket reduction.  These phases have little parallel work, and a field multiplication occupies
+// the multiply pipe per WARP instruction, so every logical thread runs on a quad of 4 lanes
+// (ec.cuh Par4: 4 multiplication levels per addition instead of 14 dependent multiplications).
+//   sum_b (b+1) B_b  =  sum_k T_k + K * sum_k k * S_k        k over the M = B/K chunks   (k_reduce1)
+//   per block of Mb chunks:  P_s = sum T_k + K * sum (k - s*Mb) S_k ,  Q_s = sum S_k        (k_reduce2)
+//   window sum = sum_s P_s + K * Mb * sum_s s * Q_s                                          (k_reduce3)
+// ------------------------------------------------------------------------------------------------
 template <class Cv>
 __global__ void __launch_bounds__(128)
 k_reduce1(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ buckets,
           const uint32_t* __restrict__ heads, const uint32_t* __restrict__ tails, MsmPlan plan,
           uint32_t* __restrict__ sums, uint32_t* __restrict__ wsums) {
-  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id < (uint32_t)plan.W * plan.chunks) reduce1_body<Cv>(id, offsets, buckets, heads, tails, plan, sums, wsums);
+  using G = typename Cv::G;
+  const uint32_t id = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;  // logical thread = quad
+  if (id >= (uint32_t)plan.W * plan.chunks) return;                    // whole quads leave together
+  const uint32_t w = id / plan.chunks, k = id % plan.chunks;
+  const uint32_t g0 = w * plan.B + k * plan.K;
+  typename G::Acc sum = G::identity(), wsum = G::identity();
+  for (int b = plan.K - 1; b >= 0; b--) {
+    add_bucket<Cv, QuadOps<G>>(sum, g0 + b, offsets, plan, buckets, heads, tails);
+    G::par_add(wsum, sum);
+  }
+  if ((threadIdx.x & 3) == 0) {
+    save_acc<G>(sums + (size_t)id * G::ACC_WORDS, sum);
+    save_acc<G>(wsums + (size_t)id * G::ACC_WORDS, wsum);
+  }
 }
 
+// shuffle by `dq` logical lanes (quads); every lane of the warp must be converged here
 template <class G>
-__device__ __forceinline__ typename G::Acc shfl_down_acc(const typename G::Acc& a, int delta) {
+__device__ __forceinline__ typename G::Acc shfl_down_quads(const typename G::Acc& a, int dq) {
   typename G::Acc r;
   const uint32_t* s = reinterpret_cast<const uint32_t*>(&a);
   uint32_t* d = reinterpret_cast<uint32_t*>(&r);
 #pragma unroll
-  for (int k = 0; k < G::ACC_WORDS; k++) d[k] = __shfl_down_sync(0xffffffffu, s[k], delta);
+  for (int k = 0; k < G::ACC_WORDS; k++) d[k] = __shfl_down_sync(0xffffffffu, s[k], 4 * dq);
   return r;
 }
+template <class G>
+__device__ __forceinline__ void smem_put(uint32_t* smem, uint32_t slot, const typename G::Acc& a) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&a);
+  for (int k = 0; k < G::ACC_WORDS; k++) smem[slot * G::ACC_WORDS + k] = src[k];
+}
+template <class G>
+__device__ __forceinline__ typename G::Acc smem_get(const uint32_t* smem, uint32_t slot) {
+  typename G::Acc a;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&a);
+  for (int k = 0; k < G::ACC_WORDS; k++) dst[k] = smem[slot * G::ACC_WORDS + k];
+  return a;
+}
 
-// Second level of the bucket reduction, one block per window (see reduce2_serial for the maths):
-//   window_out[w] = sum_k wsums_k + K * sum_k k * sums_k ,  k over the M = B/K chunks of the window.
-// Thread j owns R consecutive chunks [jR, (j+1)R): serial running sums give its total s_j, its local
-// weighted sum w_j = sum (k - jR) sums_k and its wsums total; the cross-thread term R * sum_j j * s_j is
-// a suffix scan of s_j (warp shuffles + one shared-memory hop) followed by a block reduction.
-static constexpr int REDUCE2_THREADS = 256;
+static constexpr int REDUCE2_THREADS = 256;                   // 64 logical threads (quads), 8 warps
+static constexpr int REDUCE2_LOGICAL = REDUCE2_THREADS / 4;
+static constexpr int REDUCE2_MAX_SPLITS = 8;                  // k_reduce3 folds the splits of a window in one warp
+
+// grid (splits, W).  Logical thread lt owns R consecutive chunks; see the formulas above.
 template <class Cv>
 __global__ void __launch_bounds__(REDUCE2_THREADS)
-k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums, MsmPlan plan,
+k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums, MsmPlan plan, int R,
+          uint32_t* __restrict__ blkP, uint32_t* __restrict__ blkQ) {
+  using G = typename Cv::G;
+  using Acc = typename G::Acc;
+  extern __shared__ uint32_t smem[];  // 8 accumulators
+  const uint32_t s = blockIdx.x, w = blockIdx.y, splits = gridDim.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ql = lane >> 2;
+  const uint32_t lt = threadIdx.x >> 2;
+  constexpr uint32_t NW = REDUCE2_THREADS / 32;
+  const uint32_t M = plan.chunks;
+  const uint32_t Mb = REDUCE2_LOGICAL * R;
+  const uint32_t base = s * Mb + lt * R;
+  Acc S = G::identity(), WL = G::identity(), WT = G::identity();
+  for (uint32_t k = base + R; k-- > base;) {
+    if (k < M) {
+      const size_t id = (size_t)w * M + k;
+      G::par_add(WT, load_acc<G>(wsums + id * G::ACC_WORDS));
+      G::par_add(S, load_acc<G>(sums + id * G::ACC_WORDS));
+    }
+    if (k > base) G::par_add(WL, S);  // after the loop: sum (k - base) * S_k
+  }
+  // inclusive suffix scan of S over the 64 logical threads of the block
+  Acc SS = S;
+  for (int d = 1; d < 8; d <<= 1) {
+    __syncwarp();
+    Acc o = shfl_down_quads<G>(SS, d);
+    if (ql + d < 8) G::par_add(SS, o);
+  }
+  __syncwarp();
+  if (lane == 0) smem_put<G>(smem, warp, SS);  // warp totals
+  __syncthreads();
+  for (uint32_t q = warp + 1; q < NW; q++) G::par_add(SS, smem_get<G>(smem, q));
+  __syncthreads();
+  // per-thread contribution  WT + K * (WL + R * [lt >= 1] SS)
+  Acc V = G::identity();
+  if (lt >= 1) {
+    V = SS;
+    for (int r = 1; r < R; r <<= 1) G::par_dbl(V);
+  }
+  G::par_add(V, WL);
+  for (int j = 1; j < plan.K; j <<= 1) G::par_dbl(V);
+  G::par_add(V, WT);
+  // block reduction of V
+  for (int d = 4; d >= 1; d >>= 1) {
+    __syncwarp();
+    Acc o = shfl_down_quads<G>(V, d);
+    G::par_add(V, o);
+  }
+  if (lane == 0) smem_put<G>(smem, warp, V);
+  __syncthreads();
+  if (warp == 0 && ql == 0) {
+    for (uint32_t q = 1; q < NW; q++) G::par_add(V, smem_get<G>(smem, q));
+    if (lane == 0) {
+      save_acc<G>(blkP + ((size_t)w * splits + s) * G::ACC_WORDS, V);
+      save_acc<G>(blkQ + ((size_t)w * splits + s) * G::ACC_WORDS, SS);  // SS of logical thread 0 = block total
+    }
+  }
+}
+
+// grid W, one warp: quad s holds split s of the window.
+template <class Cv>
+__global__ void __launch_bounds__(32)
+k_reduce3(const uint32_t* __restrict__ blkP, const uint32_t* __restrict__ blkQ, MsmPlan plan, int splits, int R,
           uint32_t* __restrict__ window_out) {
   using G = typename Cv::G;
   using Acc = typename G::Acc;
-  extern __shared__ uint32_t smem[];  // (REDUCE2_THREADS/32) accumulators
-  const uint32_t w = blockIdx.x, tid = threadIdx.x;
-  const uint32_t lane = tid & 31, warp = tid >> 5;
-  constexpr uint32_t NW = REDUCE2_THREADS / 32;
-  const uint32_t M = plan.chunks;
-  const uint32_t R = M >= REDUCE2_THREADS ? M / REDUCE2_THREADS : 1;  // power of two
-  const uint32_t lo = tid * R;
-  Acc s = G::identity(), wl = G::identity(), wt = G::identity();
-  if (lo < M) {
-    for (uint32_t k = lo + R; k-- > lo;) {
-      const size_t id = (size_t)w * M + k;
-      nl_add<G>(wt, load_acc<G>(wsums + id * G::ACC_WORDS));
-      nl_add<G>(s, load_acc<G>(sums + id * G::ACC_WORDS));
-      if (k > lo) nl_add<G>(wl, s);  // after the loop: sum (k - lo) * sums_k
-    }
+  const uint32_t w = blockIdx.x, lane = threadIdx.x, ql = lane >> 2;
+  Acc P = G::identity(), Q = G::identity();
+  if (ql < (uint32_t)splits) {
+    P = load_acc<G>(blkP + ((size_t)w * splits + ql) * G::ACC_WORDS);
+    Q = load_acc<G>(blkQ + ((size_t)w * splits + ql) * G::ACC_WORDS);
   }
-  // inclusive suffix scan of s over the block: ss_j = sum_{i >= j} s_i
-  Acc ss = s;
-  for (int d = 1; d < 32; d <<= 1) {
-    Acc o = shfl_down_acc<G>(ss, d);
-    if (lane + d < 32) nl_add<G>(ss, o);
+  // sum_s s * Q_s = sum_{s >= 1} (suffix sum of Q at s)
+  for (int d = 1; d < 8; d <<= 1) {
+    __syncwarp();
+    Acc o = shfl_down_quads<G>(Q, d);
+    if (ql + d < 8) G::par_add(Q, o);
   }
-  auto put = [&](uint32_t slot, const Acc& a) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&a);
-    for (int k = 0; k < G::ACC_WORDS; k++) smem[slot * G::ACC_WORDS + k] = src[k];
-  };
-  auto get = [&](uint32_t slot) {
-    Acc a;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&a);
-    for (int k = 0; k < G::ACC_WORDS; k++) dst[k] = smem[slot * G::ACC_WORDS + k];
-    return a;
-  };
-  if (lane == 0) put(warp, ss);  // warp totals
-  __syncthreads();
-  for (uint32_t q = warp + 1; q < NW; q++) nl_add<G>(ss, get(q));
-  __syncthreads();
-  // per-thread contribution: wt + K * (wl + R * [j >= 1] ss_j)
-  Acc v = G::identity();
-  if (tid >= 1) {
-    v = ss;
-    for (uint32_t r = 1; r < R; r <<= 1) nl_dbl<G>(v);
+  Acc X = (ql >= 1) ? Q : G::identity();
+  for (int d = 4; d >= 1; d >>= 1) {
+    __syncwarp();
+    Acc o = shfl_down_quads<G>(X, d);
+    G::par_add(X, o);
+    __syncwarp();
+    Acc o2 = shfl_down_quads<G>(P, d);
+    G::par_add(P, o2);
   }
-  nl_add<G>(v, wl);
-  for (int j = 1; j < plan.K; j <<= 1) nl_dbl<G>(v);
-  nl_add<G>(v, wt);
-  // block reduction
-  for (int d = 16; d >= 1; d >>= 1) {
-    Acc o = shfl_down_acc<G>(v, d);
-    nl_add<G>(v, o);
-  }
-  if (lane == 0) put(warp, v);
-  __syncthreads();
-  if (tid == 0) {
-    for (uint32_t q = 1; q < NW; q++) nl_add<G>(v, get(q));
-    save_acc<G>(window_out + (size_t)w * G::ACC_WORDS, v);
+  // quad 0: window = P + K * Mb * X
+  if (ql == 0) {
+    const uint32_t scale = (uint32_t)plan.K * REDUCE2_LOGICAL * (uint32_t)R;  // power of two
+    for (uint32_t j = 1; j < scale; j <<= 1) G::par_dbl(X);
+    G::par_add(P, X);
+    if (lane == 0) save_acc<G>(window_out + (size_t)w * G::ACC_WORDS, P);
   }
 }
 

@@ -185,6 +185,33 @@ NMSM_NL void nl_to_affine(const typename G::Acc& p, uint32_t* xy, uint32_t* inf)
   G::to_affine_canonical(p, xy, inf);
 }
 
+// Group-operation policies for the reduction bodies: one logical thread per lane (out-of-line serial
+// formulas) or one logical thread per quad of lanes (ec.cuh Par4; device only).
+template <class G>
+struct SerialOps {
+  NMSM_HD static void add(typename G::Acc& p, const typename G::Acc& q) { nl_add<G>(p, q); }
+  NMSM_HD static void dbl(typename G::Acc& p) { nl_dbl<G>(p); }
+};
+#if defined(__CUDACC__)
+template <class G>
+struct QuadOps {
+  NMSM_HD static void add(typename G::Acc& p, const typename G::Acc& q) {
+#if defined(__CUDA_ARCH__)
+    G::par_add(p, q);
+#else
+    (void)p; (void)q;
+#endif
+  }
+  NMSM_HD static void dbl(typename G::Acc& p) {
+#if defined(__CUDA_ARCH__)
+    G::par_dbl(p);
+#else
+    (void)p;
+#endif
+  }
+};
+#endif
+
 // c bits of a 256-bit little-endian scalar starting at bit `off`
 NMSM_HD uint32_t scalar_bits(const uint32_t* s, int off, int c, int nwords = SCALAR_WORDS) {
   int w = off >> 5, sh = off & 31;
@@ -430,7 +457,7 @@ NMSM_HD void accumulate_body(uint32_t t, const uint32_t* aff, const uint32_t* so
 // to `buckets`; one that straddles segments is the sum of tails[ts] and heads[ts+1..te]; an empty
 // bucket contributes nothing.  (This stitching used to be a separate pass; fusing it here costs no
 // extra additions and removes a launch plus one write+read of every bucket.)
-template <class Cv>
+template <class Cv, class Ops>
 NMSM_HD void add_bucket(typename Cv::G::Acc& sum, uint32_t g, const uint32_t* offsets, const MsmPlan& plan,
                         const uint32_t* buckets, const uint32_t* heads, const uint32_t* tails) {
   using G = typename Cv::G;
@@ -438,18 +465,18 @@ NMSM_HD void add_bucket(typename Cv::G::Acc& sum, uint32_t g, const uint32_t* of
   if (b0 == b1) return;
   const uint32_t ts = b0 / plan.L, te = (b1 - 1) / plan.L;
   if (ts == te) {
-    nl_add<G>(sum, load_acc<G>(buckets + (size_t)g * G::ACC_WORDS));
+    Ops::add(sum, load_acc<G>(buckets + (size_t)g * G::ACC_WORDS));
     return;
   }
-  nl_add<G>(sum, load_acc<G>(tails + (size_t)ts * G::ACC_WORDS));
-  for (uint32_t t = ts + 1; t <= te; t++) nl_add<G>(sum, load_acc<G>(heads + (size_t)t * G::ACC_WORDS));
+  Ops::add(sum, load_acc<G>(tails + (size_t)ts * G::ACC_WORDS));
+  for (uint32_t t = ts + 1; t <= te; t++) Ops::add(sum, load_acc<G>(heads + (size_t)t * G::ACC_WORDS));
 }
 
 // Thread (w, k): chunk of K buckets of window w ->
 //   sums[id]  = sum_{b in chunk} B_b
 //   wsums[id] = sum_{b in chunk} (b - kK + 1) * B_b          (running-sum trick, curve.ts:897-900)
 // so that  sum_b (b+1) B_b = sum_k wsums_k + K * sum_k k * sums_k  (second level: reduce2).
-template <class Cv>
+template <class Cv, class Ops>
 NMSM_HD void reduce1_body(uint32_t id, const uint32_t* offsets, const uint32_t* buckets, const uint32_t* heads,
                           const uint32_t* tails, const MsmPlan& plan, uint32_t* sums, uint32_t* wsums) {
   using G = typename Cv::G;
@@ -457,8 +484,8 @@ NMSM_HD void reduce1_body(uint32_t id, const uint32_t* offsets, const uint32_t* 
   const uint32_t g0 = w * plan.B + k * plan.K;
   typename G::Acc sum = G::identity(), wsum = G::identity();
   for (int b = plan.K - 1; b >= 0; b--) {
-    add_bucket<Cv>(sum, g0 + b, offsets, plan, buckets, heads, tails);
-    nl_add<G>(wsum, sum);
+    add_bucket<Cv, Ops>(sum, g0 + b, offsets, plan, buckets, heads, tails);
+    Ops::add(wsum, sum);
   }
   save_acc<G>(sums + (size_t)id * G::ACC_WORDS, sum);
   save_acc<G>(wsums + (size_t)id * G::ACC_WORDS, wsum);

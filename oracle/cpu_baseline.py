@@ -83,41 +83,49 @@ def random_scalars(n: int, seed: int):
     return [rnd.randrange(order) for _ in range(n)]
 
 
-def time_bls_g1_msm(n_sample, seed: int = 1, max_seconds: float = 30.0, full_log2: int = 20):
-    """Time the C port on host cores.  Runs the full 2^full_log2 workload when a calibration run predicts
-    it fits in `max_seconds`, else a 2^16 sample extrapolated by the exact add-count ratio (labelled)."""
+class Workload:
+    """Inputs of one timed CPU run: generated once, then `run()` is the timed region."""
+
+    def __init__(self, n: int, seed: int = 1):
+        self.n = n
+        self.threads = host_threads()
+        self.pts, k0, ks = make_points_bls_g1(n, seed)
+        sc = random_scalars(n, seed)
+        self.sb = b"".join(s.to_bytes(32, "little") for s in sc)
+        order = R.CURVES["bls12_381_G1"].Fn.ORDER
+        tot, kk = 0, k0
+        for s in sc:
+            tot = (tot + kk * s) % order
+            kk = (kk + ks) % order
+        exp = R.CURVES["bls12_381_G1"].BASE.multiplyUnsafe(tot).toAffine() if tot else {"x": 0, "y": 0}
+        self.expected = (exp["x"], exp["y"])
+
+    def run(self) -> float:
+        t0 = time.perf_counter()
+        x, y, inf = c_pippenger_bls_g1(self.pts, self.sb, self.n, self.threads)
+        dt = time.perf_counter() - t0
+        assert (x, y) == self.expected, "C reference port produced a wrong MSM result"
+        return dt
+
+
+def choose_sample(max_seconds: float = 30.0, full_log2: int = 20) -> int:
+    """Full 2^full_log2 workload when a 2^13 calibration run predicts it fits the budget, else 2^16."""
     lib = load()
-    threads = host_threads()
+    w = Workload(1 << 13, 7)
+    tcal = w.run()
+    adds_cal = lib.ref_pippenger_add_count(1 << 13, 255)
+    adds_full = lib.ref_pippenger_add_count(1 << full_log2, 255)
+    return (1 << full_log2) if tcal * adds_full / adds_cal <= max_seconds / 3 else (1 << 16)
+
+
+def describe(n_sample: int, dt: float, full_log2: int = 20):
+    """points/s at the full size + the `cpu_baseline` fields for a run of `dt` seconds on n_sample terms."""
+    lib = load()
     full = 1 << full_log2
-    # calibration at 2^13
-    ncal = 1 << 13
-    pts, k0, ks = make_points_bls_g1(ncal, seed)
-    sc = random_scalars(ncal, seed)
-    sb = b"".join(s.to_bytes(32, "little") for s in sc)
-    t0 = time.perf_counter()
-    c_pippenger_bls_g1(pts, sb, ncal, threads)
-    tcal = time.perf_counter() - t0
-    adds_cal = lib.ref_pippenger_add_count(ncal, 255)
     adds_full = lib.ref_pippenger_add_count(full, 255)
-    predicted_full = tcal * adds_full / adds_cal
-    if n_sample is None:
-        n_sample = full if predicted_full <= max_seconds / 3 else (1 << 16)
-    pts, k0, ks = make_points_bls_g1(n_sample, seed)
-    sc = random_scalars(n_sample, seed)
-    sb = b"".join(s.to_bytes(32, "little") for s in sc)
-    t0 = time.perf_counter()
-    x, y, inf = c_pippenger_bls_g1(pts, sb, n_sample, threads)
-    dt = time.perf_counter() - t0
-    # self-check of the timed run: scalar-in-exponent identity
-    order = R.CURVES["bls12_381_G1"].Fn.ORDER
-    tot = 0
-    kk = k0
-    for s in sc:
-        tot = (tot + kk * s) % order
-        kk = (kk + ks) % order
-    exp = R.CURVES["bls12_381_G1"].BASE.multiplyUnsafe(tot).toAffine() if tot else {"x": 0, "y": 0}
-    assert (x, y) == (exp["x"], exp["y"]), "C reference port produced a wrong MSM result"
     adds_sample = lib.ref_pippenger_add_count(n_sample, 255)
+    threads = host_threads()
+    windows = 15 if n_sample == full else ((255 - 1) // max(1, (n_sample.bit_length() - 3))) + 1
     if n_sample == full:
         pps = full / dt
         sample = "full workload: one 2^%d-term MSM, %.2f s, %d point adds" % (full_log2, dt, adds_full)
@@ -125,6 +133,14 @@ def time_bls_g1_msm(n_sample, seed: int = 1, max_seconds: float = 30.0, full_log
         pps = full / (dt * adds_full / adds_sample)
         sample = ("2^%d-term MSM (%.2f s, %d adds), EXTRAPOLATED to 2^%d by the exact add-count ratio %d/%d"
                   % (n_sample.bit_length() - 1, dt, adds_sample, full_log2, adds_full, adds_sample))
-    return {"points_per_s_at_full_size": pps, "cores": min(threads, 15 if n_sample == full else 19),
-            "kind": "port", "sample": sample + "; C port of curve.ts:863-905 (oracle/ref_msm.c), windows spread over threads",
+    return {"points_per_s_at_full_size": pps, "cores": min(threads, windows), "kind": "port",
+            "sample": sample + "; C port of curve.ts:863-905 (oracle/ref_msm.c), windows spread over host threads",
             "seconds": dt, "n": n_sample}
+
+
+def time_bls_g1_msm(n_sample, seed: int = 1, max_seconds: float = 30.0, full_log2: int = 20):
+    """One-shot helper: pick the sample, build inputs, time one run."""
+    if n_sample is None:
+        n_sample = choose_sample(max_seconds, full_log2)
+    w = Workload(n_sample, seed)
+    return describe(n_sample, w.run(), full_log2)

@@ -42,7 +42,7 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
   const size_t nchunks = (size_t)plan.W * plan.chunks;
   std::vector<uint32_t> sums(nchunks * G::ACC_WORDS), wsums(nchunks * G::ACC_WORDS);
   for (uint32_t id = 0; id < nchunks; id++)
-    reduce1_body<Cv>(id, offsets.data(), buckets.data(), heads.data(), tails.data(), plan, sums.data(), wsums.data());
+    reduce1_body<Cv, SerialOps<G>>(id, offsets.data(), buckets.data(), heads.data(), tails.data(), plan, sums.data(), wsums.data());
   std::vector<uint32_t> window_out((size_t)plan.W * G::ACC_WORDS);
   for (int w = 0; w < plan.W; w++)  // serial statement of what k_reduce2 computes cooperatively
     reduce2_serial<Cv>(w, sums.data(), wsums.data(), plan, window_out.data());
