@@ -123,7 +123,7 @@ void nmsm_shutdown(void) {
   if (!C.ready) return;
   cudaStreamSynchronize(C.stream);
   for (Buf* b : {&C.in_pts, &C.in_scalars, &C.aff, &C.counts, &C.offsets, &C.cursor, &C.sorted, &C.buckets,
-                 &C.heads, &C.tails, &C.chunk_out, &C.window_out, &C.tile_sums, &C.blk, &C.result, &C.mul_out})
+                 &C.heads, &C.tails, &C.chunk_out, &C.window_out, &C.tile_sums, &C.blk, &C.tiles, &C.result, &C.mul_out})
     b->release();
   for (auto& ev : C.ev) cudaEventDestroy(ev);
   cudaFreeHost(C.h_result);

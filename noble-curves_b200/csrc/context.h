@@ -43,7 +43,7 @@ struct Context {
   int device = -1;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  Buf in_pts, in_scalars, aff, counts, offsets, cursor, sorted, buckets, heads, tails, chunk_out, window_out, tile_sums, blk,
+  Buf in_pts, in_scalars, aff, counts, offsets, cursor, sorted, buckets, heads, tails, chunk_out, window_out, tile_sums, blk, tiles,
       result, mul_out;
   uint32_t* h_result = nullptr;  // pinned staging for (xy | inf | err0 | err1)
   cudaEvent_t ev[NMSM_TIMING_SLOTS + 2] = {};

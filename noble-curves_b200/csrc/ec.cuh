@@ -27,7 +27,9 @@ namespace nmsm {
 // (quad-scoped masks, so different quads of a warp may diverge).
 // ------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
-template <class F>
+// FULLWARP = true: all 32 lanes hold the same state (k_final / k_fold) and shuffles use the full mask;
+// false: quads are independent logical threads (k_reduce2 / k_reduce3) and shuffles are quad-scoped.
+template <class F, bool FULLWARP>
 struct Par4 {
   static constexpr int WORDS = sizeof(F) / 4;
   // broadcast from lane `src` (0..3) of the caller's quad (4 adjacent lanes); quads may be divergent
@@ -35,8 +37,8 @@ struct Par4 {
     F r;
     const uint32_t* s = reinterpret_cast<const uint32_t*>(&z);
     uint32_t* d = reinterpret_cast<uint32_t*>(&r);
-    const unsigned qbase = threadIdx.x & 28u;  // blocks are multiples of 32 threads
-    const unsigned qmask = 0xFu << qbase;
+    const unsigned qbase = FULLWARP ? 0u : (threadIdx.x & 28u);  // blocks are multiples of 32 threads
+    const unsigned qmask = FULLWARP ? 0xffffffffu : (0xFu << qbase);
 #pragma unroll
     for (int k = 0; k < WORDS; k++) d[k] = __shfl_sync(qmask, s[k], qbase + src);
     return r;
@@ -196,9 +198,10 @@ struct SwXyzz {
   }
 #if defined(__CUDACC__)
   // Warp-replicated versions of dbl / add (see Par4): 3 and 4 multiplication levels instead of 9 / 14.
+  template <bool FW>
   __device__ static void par_dbl(Acc& p) {
     if (is_identity(p)) return;
-    using P4 = Par4<F>;
+    using P4 = Par4<F, FW>;
     F U = nmsm::dbl(p.Y);
     F V, A, t2, t3;
     P4::mul4(V, A, t2, t3, U, U, p.X, p.X, U, U, U, U);
@@ -213,20 +216,21 @@ struct SwXyzz {
     p.ZZ = zz;
     p.ZZZ = zzz;
   }
+  template <bool FW>
   __device__ static void par_add(Acc& p, const Acc& q) {
     if (is_identity(q)) return;
     if (is_identity(p)) {
       p = q;
       return;
     }
-    using P4 = Par4<F>;
+    using P4 = Par4<F, FW>;
     F U1, U2, S1, S2;
     P4::mul4(U1, U2, S1, S2, p.X, q.ZZ, q.X, p.ZZ, p.Y, q.ZZZ, q.Y, p.ZZZ);
     F P = U2 - U1;
     F R = S2 - S1;
     if (P.is_zero()) {
       if (R.is_zero())
-        par_dbl(p);
+        par_dbl<FW>(p);
       else
         p = identity();
       return;
@@ -358,8 +362,9 @@ struct EdExt {
   }
 #if defined(__CUDACC__)
   // Warp-replicated versions (see Par4): 2 levels for doubling, 3 for addition.
+  template <bool FW>
   __device__ static void par_dbl(Acc& p) {
-    using P4 = Par4<F>;
+    using P4 = Par4<F, FW>;
     F A, B, Zs, XY;
     F xy = p.X + p.Y;
     P4::mul4(A, B, Zs, XY, p.X, p.X, p.Y, p.Y, p.Z, p.Z, xy, xy);
@@ -371,8 +376,9 @@ struct EdExt {
     F H = D - B;
     P4::mul4(p.X, p.Y, p.T, p.Z, E, Fv, G, H, E, H, Fv, G);
   }
+  template <bool FW>
   __device__ static void par_add(Acc& p, const Acc& q) {
-    using P4 = Par4<F>;
+    using P4 = Par4<F, FW>;
     F A, B, TT, ZZ;
     P4::mul4(A, B, TT, ZZ, p.Y - p.X, q.Y - q.X, p.Y + p.X, q.Y + q.X, p.T, q.T, p.Z, q.Z);
     F C = TT * d2();

@@ -59,6 +59,8 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   CK(C.tails.ensure(max_threads * G::ACC_WORDS * 4));
   CK(C.chunk_out.ensure((size_t)plan.W * plan.chunks * G::ACC_WORDS * 4 * 2));
   CK(C.tile_sums.ensure((size_t)(plan.G / SCAN_TILE + 2) * 4));
+  const uint64_t ntile1 = max_threads / STITCH_FAN + 1, ntile2 = ntile1 / STITCH_FAN + 1;
+  CK(C.tiles.ensure((ntile1 + ntile2) * G::ACC_WORDS * 4));
   CK(C.blk.ensure((size_t)plan.W * REDUCE2_MAX_SPLITS * G::ACC_WORDS * 4 * 2));
   CK(C.window_out.ensure((size_t)plan.W * G::ACC_WORDS * 4));
 
@@ -73,6 +75,8 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   uint32_t* sums = (uint32_t*)C.chunk_out.p;
   uint32_t* wsums = sums + (size_t)plan.W * plan.chunks * G::ACC_WORDS;
   uint32_t* tile_sums = (uint32_t*)C.tile_sums.p;
+  uint32_t* tile1 = (uint32_t*)C.tiles.p;
+  uint32_t* tile2 = tile1 + ntile1 * G::ACC_WORDS;
   uint32_t* blkP = (uint32_t*)C.blk.p;
   uint32_t* blkQ = blkP + (size_t)plan.W * REDUCE2_MAX_SPLITS * G::ACC_WORDS;
   uint32_t* window_out = (uint32_t*)C.window_out.p;
@@ -98,9 +102,13 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   EV(5);
   EV(6);
   {
-    // k_reduce1: one quad per chunk
-    const uint64_t quads = (uint64_t)plan.W * plan.chunks;
-    k_reduce1<Cv><<<cdiv(quads * 4, 128), 128, 0, st>>>(offsets, buckets, heads, tails, plan, sums, wsums);
+    const uint64_t nchunks = (uint64_t)plan.W * plan.chunks;
+    // tile sums for buckets spanning many accumulate segments (no-ops for ordinary inputs)
+    k_stitch_tiles<Cv><<<cdiv(ntile1 * 32, 128), 128, 0, st>>>(offsets, plan, STITCH_FAN, (uint32_t)ntile1, heads, tile1);
+    k_stitch_tiles<Cv><<<cdiv(ntile2 * 32, 128), 128, 0, st>>>(offsets, plan, STITCH_FAN * STITCH_FAN, (uint32_t)ntile2,
+                                                                tile1, tile2);
+    k_reduce1<Cv><<<cdiv(nchunks, 128), 128, 0, st>>>(offsets, buckets, heads, tails, tile1, tile2, plan, sums,
+                                                         wsums);
   }
   EV(7);
   {
@@ -138,7 +146,7 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   C.last_info.reduce_chunk = plan.K;
   C.last_info.sorted_entries = entries;
   C.last_info.modmul_equiv = plan_modmuls<Cv>(plan, entries);
-  C.last_info.launches = 10;  // prepare, count, scan x2, scatter, accumulate, reduce1, reduce2, reduce3, final
+  C.last_info.launches = 12;  // prepare, count, scan x2, scatter, accumulate, stitch x2, reduce1, reduce2, reduce3, final
   if (C.profiling) {
     for (int k = 0; k < 9; k++) cudaEventElapsedTime(&C.last_ms[k], C.ev[k], C.ev[k + 1]);
     cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev[0], C.ev[9]);

@@ -12,8 +12,10 @@
 //   k_accumulate   every thread folds exactly L consecutive sorted entries with mixed
 //                  additions, emitting complete buckets or head/tail partials at bucket
 //                  boundaries — constant work per thread whatever the bucket sizes are     (T/L threads)
+//   k_stitch_tiles two levels of 32-way tile sums over the per-segment partials, only for buckets
+//                  that span > 32 / > 1024 segments (degenerate inputs)                    (T/L/32 warps)
 //   k_reduce1      per-chunk running sums (2 additions per bucket), stitching the partials
-//                  of buckets that straddle accumulate segments on the fly                 (W*B/K quads)
+//                  of buckets that straddle accumulate segments on the fly                 (W*B/K threads)
 //   k_reduce2      second level: suffix scan + reduction of chunk sums inside blocks of
 //                  64 quads (registers -> quad/warp shuffles -> shared memory)             (W x splits blocks)
 //   k_reduce3      folds the <= 8 block results of every window                            (W warps)
@@ -22,7 +24,7 @@
 //
 // No atomics touch curve points, so degenerate inputs (all scalars equal, all points equal —
 // test/point.test.ts:842-853, benchmark/msm_timings.ts:45-63) stay correct; they only lengthen the
-// serial stitch in k_reduce1.
+// stitch in k_reduce1 (bounded by the two tile levels).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -135,25 +137,47 @@ k_accumulate(const uint32_t* __restrict__ aff, const uint32_t* __restrict__ sort
 //   per block of Mb chunks:  P_s = sum T_k + K * sum (k - s*Mb) S_k ,  Q_s = sum S_k        (k_reduce2)
 //   window sum = sum_s P_s + K * Mb * sum_s s * Q_s                                          (k_reduce3)
 // ------------------------------------------------------------------------------------------------
+template <class G>
+__device__ __forceinline__ typename G::Acc shfl_down_acc(const typename G::Acc& a, int delta) {
+  typename G::Acc r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&a);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int k = 0; k < G::ACC_WORDS; k++) d[k] = __shfl_down_sync(0xffffffffu, s[k], delta);
+  return r;
+}
+
+// One warp per tile of 32 consecutive partials (level 1: heads, span 32 segments; level 2: tile1,
+// span 1024 segments).  Tiles that are not wholly inside one bucket exit after the bucket lookup,
+// which is every tile for ordinary inputs; see msm_body.cuh "stitching".
+template <class Cv>
+__global__ void __launch_bounds__(128)
+k_stitch_tiles(const uint32_t* __restrict__ offsets, MsmPlan plan, uint32_t span, uint32_t ntiles,
+               const uint32_t* __restrict__ in, uint32_t* __restrict__ out) {
+  using G = typename Cv::G;
+  const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (j >= ntiles) return;
+  if (!tile_is_uniform(offsets, plan, (uint64_t)j * span, span)) return;  // warp-uniform
+  typename G::Acc acc = load_acc<G>(in + ((size_t)j * STITCH_FAN + lane) * G::ACC_WORDS);
+  for (int d = 16; d >= 1; d >>= 1) {
+    typename G::Acc o = shfl_down_acc<G>(acc, d);
+    nl_add<G>(acc, o);
+  }
+  if (lane == 0) save_acc<G>(out + (size_t)j * G::ACC_WORDS, acc);
+}
+
+// One thread per chunk, out-of-line serial formulas: with >= 2 warps per SM sub-partition the multiply
+// pipe is shared anyway and the quad form only adds shuffle/select overhead (measured: 2.3 ms vs 1.5 ms).
 template <class Cv>
 __global__ void __launch_bounds__(128)
 k_reduce1(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ buckets,
-          const uint32_t* __restrict__ heads, const uint32_t* __restrict__ tails, MsmPlan plan,
+          const uint32_t* __restrict__ heads, const uint32_t* __restrict__ tails,
+          const uint32_t* __restrict__ tile1, const uint32_t* __restrict__ tile2, MsmPlan plan,
           uint32_t* __restrict__ sums, uint32_t* __restrict__ wsums) {
   using G = typename Cv::G;
-  const uint32_t id = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;  // logical thread = quad
-  if (id >= (uint32_t)plan.W * plan.chunks) return;                    // whole quads leave together
-  const uint32_t w = id / plan.chunks, k = id % plan.chunks;
-  const uint32_t g0 = w * plan.B + k * plan.K;
-  typename G::Acc sum = G::identity(), wsum = G::identity();
-  for (int b = plan.K - 1; b >= 0; b--) {
-    add_bucket<Cv, QuadOps<G>>(sum, g0 + b, offsets, plan, buckets, heads, tails);
-    G::par_add(wsum, sum);
-  }
-  if ((threadIdx.x & 3) == 0) {
-    save_acc<G>(sums + (size_t)id * G::ACC_WORDS, sum);
-    save_acc<G>(wsums + (size_t)id * G::ACC_WORDS, wsum);
-  }
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id < (uint32_t)plan.W * plan.chunks)
+    reduce1_body<Cv, SerialOps<G>>(id, offsets, buckets, heads, tails, tile1, tile2, plan, sums, wsums);
 }
 
 // shuffle by `dq` logical lanes (quads); every lane of the warp must be converged here
@@ -202,42 +226,42 @@ k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums,
   for (uint32_t k = base + R; k-- > base;) {
     if (k < M) {
       const size_t id = (size_t)w * M + k;
-      G::par_add(WT, load_acc<G>(wsums + id * G::ACC_WORDS));
-      G::par_add(S, load_acc<G>(sums + id * G::ACC_WORDS));
+      G::template par_add<false>(WT, load_acc<G>(wsums + id * G::ACC_WORDS));
+      G::template par_add<false>(S, load_acc<G>(sums + id * G::ACC_WORDS));
     }
-    if (k > base) G::par_add(WL, S);  // after the loop: sum (k - base) * S_k
+    if (k > base) G::template par_add<false>(WL, S);  // after the loop: sum (k - base) * S_k
   }
   // inclusive suffix scan of S over the 64 logical threads of the block
   Acc SS = S;
   for (int d = 1; d < 8; d <<= 1) {
     __syncwarp();
     Acc o = shfl_down_quads<G>(SS, d);
-    if (ql + d < 8) G::par_add(SS, o);
+    if (ql + d < 8) G::template par_add<false>(SS, o);
   }
   __syncwarp();
   if (lane == 0) smem_put<G>(smem, warp, SS);  // warp totals
   __syncthreads();
-  for (uint32_t q = warp + 1; q < NW; q++) G::par_add(SS, smem_get<G>(smem, q));
+  for (uint32_t q = warp + 1; q < NW; q++) G::template par_add<false>(SS, smem_get<G>(smem, q));
   __syncthreads();
   // per-thread contribution  WT + K * (WL + R * [lt >= 1] SS)
   Acc V = G::identity();
   if (lt >= 1) {
     V = SS;
-    for (int r = 1; r < R; r <<= 1) G::par_dbl(V);
+    for (int r = 1; r < R; r <<= 1) G::template par_dbl<false>(V);
   }
-  G::par_add(V, WL);
-  for (int j = 1; j < plan.K; j <<= 1) G::par_dbl(V);
-  G::par_add(V, WT);
+  G::template par_add<false>(V, WL);
+  for (int j = 1; j < plan.K; j <<= 1) G::template par_dbl<false>(V);
+  G::template par_add<false>(V, WT);
   // block reduction of V
   for (int d = 4; d >= 1; d >>= 1) {
     __syncwarp();
     Acc o = shfl_down_quads<G>(V, d);
-    G::par_add(V, o);
+    G::template par_add<false>(V, o);
   }
   if (lane == 0) smem_put<G>(smem, warp, V);
   __syncthreads();
   if (warp == 0 && ql == 0) {
-    for (uint32_t q = 1; q < NW; q++) G::par_add(V, smem_get<G>(smem, q));
+    for (uint32_t q = 1; q < NW; q++) G::template par_add<false>(V, smem_get<G>(smem, q));
     if (lane == 0) {
       save_acc<G>(blkP + ((size_t)w * splits + s) * G::ACC_WORDS, V);
       save_acc<G>(blkQ + ((size_t)w * splits + s) * G::ACC_WORDS, SS);  // SS of logical thread 0 = block total
@@ -262,22 +286,22 @@ k_reduce3(const uint32_t* __restrict__ blkP, const uint32_t* __restrict__ blkQ, 
   for (int d = 1; d < 8; d <<= 1) {
     __syncwarp();
     Acc o = shfl_down_quads<G>(Q, d);
-    if (ql + d < 8) G::par_add(Q, o);
+    if (ql + d < 8) G::template par_add<false>(Q, o);
   }
   Acc X = (ql >= 1) ? Q : G::identity();
   for (int d = 4; d >= 1; d >>= 1) {
     __syncwarp();
     Acc o = shfl_down_quads<G>(X, d);
-    G::par_add(X, o);
+    G::template par_add<false>(X, o);
     __syncwarp();
     Acc o2 = shfl_down_quads<G>(P, d);
-    G::par_add(P, o2);
+    G::template par_add<false>(P, o2);
   }
   // quad 0: window = P + K * Mb * X
   if (ql == 0) {
     const uint32_t scale = (uint32_t)plan.K * REDUCE2_LOGICAL * (uint32_t)R;  // power of two
-    for (uint32_t j = 1; j < scale; j <<= 1) G::par_dbl(X);
-    G::par_add(P, X);
+    for (uint32_t j = 1; j < scale; j <<= 1) G::template par_dbl<false>(X);
+    G::template par_add<false>(P, X);
     if (lane == 0) save_acc<G>(window_out + (size_t)w * G::ACC_WORDS, P);
   }
 }
@@ -292,8 +316,8 @@ k_final(const uint32_t* __restrict__ window_out, MsmPlan plan, uint32_t* __restr
   typename G::Acc acc = G::identity();
   for (int w = plan.W - 1; w >= 0; w--) {
     if (w != plan.W - 1)
-      for (int j = 0; j < plan.c; j++) G::par_dbl(acc);
-    G::par_add(acc, load_acc<G>(window_out + (size_t)w * G::ACC_WORDS));
+      for (int j = 0; j < plan.c; j++) G::template par_dbl<true>(acc);
+    G::template par_add<true>(acc, load_acc<G>(window_out + (size_t)w * G::ACC_WORDS));
   }
   if (AFFINE_OUT) {
     uint32_t xy[G::IN_WORDS];
@@ -313,7 +337,7 @@ __global__ void __launch_bounds__(32)
 k_fold(const uint32_t* __restrict__ accs, int count, uint32_t* __restrict__ out, uint32_t* __restrict__ out_inf) {
   using G = typename Cv::G;
   typename G::Acc acc = G::identity();
-  for (int i = 0; i < count; i++) G::par_add(acc, load_acc<G>(accs + (size_t)i * G::ACC_WORDS));
+  for (int i = 0; i < count; i++) G::template par_add<true>(acc, load_acc<G>(accs + (size_t)i * G::ACC_WORDS));
   uint32_t xy[G::IN_WORDS];
   uint32_t inf;
   nl_to_affine<G>(acc, xy, &inf);

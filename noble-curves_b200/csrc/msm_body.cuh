@@ -11,6 +11,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ec.cuh"
 
@@ -74,7 +75,13 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
   if (L < 4) L = 4;
   if (L > 32) L = 32;
   p.L = L;
-  p.K = p.B < 16 ? p.B : 16;
+  // reduce chunk: 8 buckets per thread keeps >= 1 warp per SM sub-partition busy down to ~150k buckets
+  int K = 8;
+#if !defined(__CUDA_ARCH__)
+  if (const char* e = getenv("NMSM_L")) { int v = atoi(e); if (v >= 1 && v <= 1024) p.L = v; }      // tuning experiments
+  if (const char* e = getenv("NMSM_K")) { int v = atoi(e); if (v >= 1 && (v & (v - 1)) == 0) K = v; }
+#endif
+  p.K = p.B < K ? p.B : K;
   p.chunks = p.B / p.K;
   return p;
 }
@@ -197,14 +204,14 @@ template <class G>
 struct QuadOps {
   NMSM_HD static void add(typename G::Acc& p, const typename G::Acc& q) {
 #if defined(__CUDA_ARCH__)
-    G::par_add(p, q);
+    G::template par_add<false>(p, q);
 #else
     (void)p; (void)q;
 #endif
   }
   NMSM_HD static void dbl(typename G::Acc& p) {
 #if defined(__CUDA_ARCH__)
-    G::par_dbl(p);
+    G::template par_dbl<false>(p);
 #else
     (void)p;
 #endif
@@ -457,9 +464,50 @@ NMSM_HD void accumulate_body(uint32_t t, const uint32_t* aff, const uint32_t* so
 // to `buckets`; one that straddles segments is the sum of tails[ts] and heads[ts+1..te]; an empty
 // bucket contributes nothing.  (This stitching used to be a separate pass; fusing it here costs no
 // extra additions and removes a launch plus one write+read of every bucket.)
+// ---- stitching of buckets that straddle accumulate segments -------------------------------------
+// Segment (= accumulate thread) t holds in heads[t] the partial of the bucket that was already open
+// when the segment started.  A bucket spanning segments ts..te is tails[ts] + heads[ts+1..te].  For
+// ordinary inputs that is 1-3 partials, but a bucket can span thousands of segments (all scalars
+// equal, benchmark/msm_timings.ts:45-63; a narrow top window).  Two levels of tile sums keep the
+// serial walk short: tile1[j] = sum heads[32j .. 32j+31], tile2[j] = sum heads[1024j .. 1024j+1023],
+// each defined only when all of its segments lie inside ONE bucket's (ts, te] range.
+static constexpr uint32_t STITCH_FAN = 32;
+
+// bucket containing sorted entry e: the last g with offsets[g] <= e
+NMSM_HD uint32_t bucket_of_entry(const uint32_t* offsets, uint32_t G, uint32_t e) {
+  uint32_t lo = 0, hi = G;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+// Do segments [t0, t0 + span) all hold a head partial of one and the same bucket?
+NMSM_HD bool tile_is_uniform(const uint32_t* offsets, const MsmPlan& plan, uint64_t t0, uint32_t span) {
+  const uint32_t T = offsets[plan.G];
+  const uint64_t e0 = t0 * (uint32_t)plan.L, e_last = (t0 + span - 1) * (uint32_t)plan.L;
+  if (e_last >= T) return false;
+  const uint32_t g = bucket_of_entry(offsets, plan.G, (uint32_t)e0);
+  return offsets[g] < e0 && offsets[g + 1] > e_last;
+}
+// serial statement of one tile sum (the kernel uses a warp-shuffle tree over the 32 inputs)
+template <class Cv>
+NMSM_HD void stitch_tile_serial(uint32_t j, uint32_t span, const uint32_t* offsets, const MsmPlan& plan,
+                                const uint32_t* in, uint32_t* out) {
+  using G = typename Cv::G;
+  if (!tile_is_uniform(offsets, plan, (uint64_t)j * span, span)) return;
+  typename G::Acc acc = G::identity();
+  for (uint32_t k = 0; k < STITCH_FAN; k++) nl_add<G>(acc, load_acc<G>(in + ((size_t)j * STITCH_FAN + k) * G::ACC_WORDS));
+  save_acc<G>(out + (size_t)j * G::ACC_WORDS, acc);
+}
+
+// Adds the value of bucket g into `sum`.  A bucket wholly inside one accumulate segment was written
+// to `buckets`; one that straddles segments is stitched from tails / heads / tile sums; an empty
+// bucket contributes nothing.
 template <class Cv, class Ops>
 NMSM_HD void add_bucket(typename Cv::G::Acc& sum, uint32_t g, const uint32_t* offsets, const MsmPlan& plan,
-                        const uint32_t* buckets, const uint32_t* heads, const uint32_t* tails) {
+                        const uint32_t* buckets, const uint32_t* heads, const uint32_t* tails,
+                        const uint32_t* tile1, const uint32_t* tile2) {
   using G = typename Cv::G;
   const uint32_t b0 = offsets[g], b1 = offsets[g + 1];
   if (b0 == b1) return;
@@ -469,7 +517,20 @@ NMSM_HD void add_bucket(typename Cv::G::Acc& sum, uint32_t g, const uint32_t* of
     return;
   }
   Ops::add(sum, load_acc<G>(tails + (size_t)ts * G::ACC_WORDS));
-  for (uint32_t t = ts + 1; t <= te; t++) Ops::add(sum, load_acc<G>(heads + (size_t)t * G::ACC_WORDS));
+  constexpr uint32_t F1 = STITCH_FAN, F2 = STITCH_FAN * STITCH_FAN;
+  uint32_t t = ts + 1;
+  while (t <= te) {
+    if ((t % F2) == 0 && te - t >= F2 - 1) {
+      Ops::add(sum, load_acc<G>(tile2 + (size_t)(t / F2) * G::ACC_WORDS));
+      t += F2;
+    } else if ((t % F1) == 0 && te - t >= F1 - 1) {
+      Ops::add(sum, load_acc<G>(tile1 + (size_t)(t / F1) * G::ACC_WORDS));
+      t += F1;
+    } else {
+      Ops::add(sum, load_acc<G>(heads + (size_t)t * G::ACC_WORDS));
+      t++;
+    }
+  }
 }
 
 // Thread (w, k): chunk of K buckets of window w ->
@@ -478,13 +539,14 @@ NMSM_HD void add_bucket(typename Cv::G::Acc& sum, uint32_t g, const uint32_t* of
 // so that  sum_b (b+1) B_b = sum_k wsums_k + K * sum_k k * sums_k  (second level: reduce2).
 template <class Cv, class Ops>
 NMSM_HD void reduce1_body(uint32_t id, const uint32_t* offsets, const uint32_t* buckets, const uint32_t* heads,
-                          const uint32_t* tails, const MsmPlan& plan, uint32_t* sums, uint32_t* wsums) {
+                          const uint32_t* tails, const uint32_t* tile1, const uint32_t* tile2, const MsmPlan& plan,
+                          uint32_t* sums, uint32_t* wsums) {
   using G = typename Cv::G;
   const uint32_t w = id / plan.chunks, k = id % plan.chunks;
   const uint32_t g0 = w * plan.B + k * plan.K;
   typename G::Acc sum = G::identity(), wsum = G::identity();
   for (int b = plan.K - 1; b >= 0; b--) {
-    add_bucket<Cv, Ops>(sum, g0 + b, offsets, plan, buckets, heads, tails);
+    add_bucket<Cv, Ops>(sum, g0 + b, offsets, plan, buckets, heads, tails, tile1, tile2);
     Ops::add(wsum, sum);
   }
   save_acc<G>(sums + (size_t)id * G::ACC_WORDS, sum);

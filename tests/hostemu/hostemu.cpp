@@ -35,14 +35,18 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
   for (uint32_t i = 0; i < n; i++) digits_body<Cv, true>(i, n, scalars, plan, cursor.data(), sorted.data(), err);
   const uint32_t nthreads = (T + plan.L - 1) / plan.L;
   std::vector<uint32_t> buckets((size_t)plan.G * G::ACC_WORDS, 0xdeadbeefu);
-  std::vector<uint32_t> heads((size_t)(nthreads + 1) * G::ACC_WORDS, 0xdeadbeefu), tails((size_t)(nthreads + 1) * G::ACC_WORDS, 0xdeadbeefu);
+  std::vector<uint32_t> heads((size_t)(nthreads + STITCH_FAN + 1) * G::ACC_WORDS, 0xdeadbeefu), tails((size_t)(nthreads + 1) * G::ACC_WORDS, 0xdeadbeefu);
   // launch geometry rounds the thread count up to whole blocks, so run a few idle threads too
   for (uint32_t t = 0; t < nthreads + 3; t++)
     accumulate_body<Cv>(t, aff.data(), sorted.data(), offsets.data(), plan, buckets.data(), heads.data(), tails.data());
   const size_t nchunks = (size_t)plan.W * plan.chunks;
   std::vector<uint32_t> sums(nchunks * G::ACC_WORDS), wsums(nchunks * G::ACC_WORDS);
+  const uint32_t ntile1 = nthreads / STITCH_FAN + 1, ntile2 = ntile1 / STITCH_FAN + 1;
+  std::vector<uint32_t> tile1((size_t)ntile1 * G::ACC_WORDS, 0xdeadbeefu), tile2((size_t)ntile2 * G::ACC_WORDS, 0xdeadbeefu);
+  for (uint32_t j = 0; j < ntile1; j++) stitch_tile_serial<Cv>(j, STITCH_FAN, offsets.data(), plan, heads.data(), tile1.data());
+  for (uint32_t j = 0; j < ntile2; j++) stitch_tile_serial<Cv>(j, STITCH_FAN * STITCH_FAN, offsets.data(), plan, tile1.data(), tile2.data());
   for (uint32_t id = 0; id < nchunks; id++)
-    reduce1_body<Cv, SerialOps<G>>(id, offsets.data(), buckets.data(), heads.data(), tails.data(), plan, sums.data(), wsums.data());
+    reduce1_body<Cv, SerialOps<G>>(id, offsets.data(), buckets.data(), heads.data(), tails.data(), tile1.data(), tile2.data(), plan, sums.data(), wsums.data());
   std::vector<uint32_t> window_out((size_t)plan.W * G::ACC_WORDS);
   for (int w = 0; w < plan.W; w++)  // serial statement of what k_reduce2 computes cooperatively
     reduce2_serial<Cv>(w, sums.data(), wsums.data(), plan, window_out.data());

@@ -180,3 +180,17 @@ def test_glv_split_and_constants():
         v1 = -m1 if out[8] else m1
         v2 = -m2 if out[9] else m2
         assert (v1 + v2 * lam - k) % r == 0 and m1 < 2**127 and m2 < 2**127, hex(k)
+
+
+@pytest.mark.parametrize("name", ["bls12_381_G1", "secp256k1"])
+def test_msm_giant_bucket_tile_stitching(name):
+    """One bucket spanning thousands of accumulate segments (all scalars equal) exercises both tile levels."""
+    P = R.CURVES[name]
+    n = 2600
+    s = 0x0F0F
+    exp = H.expected_tuple(name, P.BASE.multiply((n * s) % P.Fn.ORDER))
+    pb = H.point_bytes(name, P.BASE) * n
+    got, err, plan = H.emu_msm(name, pb, H.pack_scalars([s] * n), n, 4, 1)  # L = 1: 2600 segments per bucket
+    assert got == exp, plan
+    got, err, plan = H.emu_msm(name, pb, H.pack_scalars([s] * n), n, 4, 2)
+    assert got == exp, plan
