@@ -80,6 +80,14 @@ int nmsm_fold_partials_device(int curve, const void* d_accs, int count, uint8_t*
 int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero,
                    uint8_t* out_xy, uint8_t* out_is_inf);
 
+/* Device-resident point sets: validate + convert a point array once, then run many MSMs against it
+ * (fixed-base commitments).  The analogue of interleavedMSMUnsafe's captured tables
+ * (/root/reference/src/abstract/curve.ts:937-959): fewer scalars than points use the first n points
+ * (except on curves that run GLV internally — BLS12-381 G1 — where n must equal the set size). */
+int nmsm_points_upload(int curve, const uint8_t* pts, uint64_t n, uint64_t* out_handle);
+int nmsm_points_free(uint64_t handle);
+int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf);
+
 /* Tuning / introspection ------------------------------------------------------------------- */
 /* Force the window size c (0 = automatic cost model).  Returns the previous value. */
 int nmsm_set_window_bits(int c);

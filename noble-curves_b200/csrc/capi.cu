@@ -186,6 +186,43 @@ int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64
   return E->mul_batch(pts, scalars, n, allow_zero, out_xy, out_is_inf);
 }
 
+// ---- device-resident point sets (fixed-base reuse) ---------------------------------------------
+struct PointSet {
+  int curve;
+  uint64_t n;
+  uint32_t* d_prepared;
+};
+
+int nmsm_points_upload(int curve, const uint8_t* pts, uint64_t n, uint64_t* out_handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (!pts || !out_handle) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  uint32_t* d = nullptr;
+  if (int r = E->prepare_points(pts, n, &d)) return r;
+  PointSet* ps = new PointSet{curve, n, d};
+  *out_handle = (uint64_t)(uintptr_t)ps;
+  return NMSM_OK;
+}
+
+int nmsm_points_free(uint64_t handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PointSet* ps = (PointSet*)(uintptr_t)handle;
+  if (!ps) return fail(NMSM_ERR_ARG, "null handle");
+  cudaFree(ps->d_prepared);
+  delete ps;
+  return NMSM_OK;
+}
+
+int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  PointSet* ps = (PointSet*)(uintptr_t)handle;
+  if (!ps || !out_xy || !out_is_inf || (n && !scalars)) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(ps->curve);
+  return E->msm_prepared(ps->d_prepared, ps->n, scalars, n, out_xy, out_is_inf);
+}
+
 int nmsm_set_window_bits(int c) {
   int prev = g_ctx.forced_c;
   g_ctx.forced_c = (c >= 1 && c <= 16) ? c : 0;

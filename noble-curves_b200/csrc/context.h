@@ -88,6 +88,9 @@ struct EngineVTable {
   int (*fold)(const uint32_t* d_accs, int count, uint8_t* out_xy, int* out_is_inf);
   int (*mul_batch)(const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
                    uint8_t* out_is_inf);
+  int (*prepare_points)(const uint8_t* pts, uint64_t n, uint32_t** out_dev);
+  int (*msm_prepared)(const uint32_t* d_prepared, uint64_t n_points, const uint8_t* scalars, uint64_t n,
+                      uint8_t* out_xy, int* out_is_inf);
 };
 const EngineVTable* engine_secp256k1();
 const EngineVTable* engine_ed25519();

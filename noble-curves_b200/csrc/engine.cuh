@@ -22,8 +22,10 @@ struct Engine {
 
 // Runs the pipeline on device-resident canonical inputs.  If d_out_acc != nullptr the raw
 // accumulator is written there and no affine result is produced.
+// `d_prepared` != nullptr: points were validated and prepared once by prepare_points() (device-resident
+// handle, nmsm_points_upload); k_prepare is skipped.
 static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
-                   uint8_t* out_xy, int* out_is_inf) {
+                   uint8_t* out_xy, int* out_is_inf, const uint32_t* d_prepared = nullptr) {
   Context& C = g_ctx;
   if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
   const int RES_WORDS = G::IN_WORDS + 4;  // xy | inf | err_pt | err_sc | pad
@@ -49,7 +51,7 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
   const uint64_t max_threads = (max_entries + plan.L - 1) / plan.L;
 
-  CK(C.aff.ensure(n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
+  if (!d_prepared) CK(C.aff.ensure(n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
   CK(C.counts.ensure((size_t)(plan.G + 1) * 4));
   CK(C.offsets.ensure((size_t)(plan.G + 1) * 4));
   CK(C.cursor.ensure((size_t)(plan.G + 1) * 4));
@@ -64,7 +66,7 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   CK(C.blk.ensure((size_t)plan.W * REDUCE2_MAX_SPLITS * G::ACC_WORDS * 4 * 2));
   CK(C.window_out.ensure((size_t)plan.W * G::ACC_WORDS * 4));
 
-  uint32_t* aff = (uint32_t*)C.aff.p;
+  uint32_t* aff = d_prepared ? const_cast<uint32_t*>(d_prepared) : (uint32_t*)C.aff.p;
   unsigned int* counts = (unsigned int*)C.counts.p;
   uint32_t* offsets = (uint32_t*)C.offsets.p;
   unsigned int* cursor = (unsigned int*)C.cursor.p;
@@ -86,7 +88,7 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   EV(0);
   CK(cudaMemsetAsync(d_err, 0xff, 8, st));
   CK(cudaMemsetAsync(counts, 0, (size_t)(plan.G + 1) * 4, st));
-  k_prepare<Cv><<<cdiv(n, 128), 128, 0, st>>>(d_pts, n32, aff, d_err);
+  if (!d_prepared) k_prepare<Cv><<<cdiv(n, 128), 128, 0, st>>>(d_pts, n32, aff, d_err);
   EV(1);
   k_digits<Cv, false><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, counts, nullptr, d_err);
   EV(2);
@@ -158,6 +160,53 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   return NMSM_OK;
 }
 
+// Upload + validate + prepare a point set once (fixed-base reuse; the device-resident analogue of the
+// reference's captured tables in interleavedMSMUnsafe, curve.ts:937-959).  Returns a device buffer.
+static int prepare_points(const uint8_t* pts, uint64_t n, uint32_t** out_dev) {
+  Context& C = g_ctx;
+  if (n == 0 || n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be in [1, 2^31)");
+  uint32_t* d_aff = nullptr;
+  CK(cudaMalloc((void**)&d_aff, n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
+  cudaError_t e1 = C.in_pts.ensure(n * G::IN_WORDS * 4);
+  cudaError_t e2 = C.result.ensure((G::IN_WORDS + 4) * 4);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFree(d_aff); return cuda_fail(e1 != cudaSuccess ? e1 : e2, "workspace"); }
+  unsigned int* d_err = (unsigned int*)C.result.p;
+  cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, C.stream);
+  cudaMemsetAsync(d_err, 0xff, 8, C.stream);
+  k_prepare<Cv><<<cdiv(n, 128), 128, 0, C.stream>>>((const uint32_t*)C.in_pts.p, (uint32_t)n, d_aff, d_err);
+  unsigned int err[2] = {0, 0};
+  cudaMemcpyAsync(err, d_err, 8, cudaMemcpyDeviceToHost, C.stream);
+  cudaError_t e = cudaStreamSynchronize(C.stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { cudaFree(d_aff); return cuda_fail(e, "prepare_points"); }
+  if (err[0] != 0xffffffffu) {
+    cudaFree(d_aff);
+    return fail(NMSM_ERR_POINT, "invalid point at index " + std::to_string(err[0]), err[0]);
+  }
+  *out_dev = d_aff;
+  return NMSM_OK;
+}
+
+// MSM of host scalars against a prepared point set (scalars beyond the set are an error; fewer
+// scalars use the first n_scalars points, like interleavedMSMUnsafe's trailing zeros).
+static int run_msm_prepared(const uint32_t* d_prepared, uint64_t n_points, const uint8_t* scalars, uint64_t n,
+                            uint8_t* out_xy, int* out_is_inf) {
+  Context& C = g_ctx;
+  if (n > n_points) return fail(NMSM_ERR_LENGTH, "array of scalars must not be larger than array of points");
+  if (n) {
+    CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
+    CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
+  }
+  if (Cv::GLV && n != n_points)
+    return fail(NMSM_ERR_ARG, "this curve's prepared sets interleave P and phi(P): pass one scalar per point");
+  return run_msm(nullptr, (const uint32_t*)C.in_scalars.p, n, nullptr, out_xy, out_is_inf, d_prepared);
+}
+
+static int run_msm_dev(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
+                       uint8_t* out_xy, int* out_is_inf) {
+  return run_msm(d_pts, d_scalars, n, d_out_acc, out_xy, out_is_inf, nullptr);
+}
+
 static int run_msm_host(const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf) {
   Context& C = g_ctx;
   if (n) {
@@ -220,8 +269,9 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
 #define NMSM_DEFINE_ENGINE(FN, CURVE)                                                          \
   const EngineVTable* FN() {                                                                   \
     static const EngineVTable vt = {CURVE::G::IN_WORDS * 4,         CURVE::G::ACC_WORDS * 4,   \
-                                    &Engine<CURVE>::run_msm_host,   &Engine<CURVE>::run_msm,   \
-                                    &Engine<CURVE>::run_fold,       &Engine<CURVE>::run_mul_batch}; \
+                                    &Engine<CURVE>::run_msm_host,   &Engine<CURVE>::run_msm_dev,   \
+                                    &Engine<CURVE>::run_fold,       &Engine<CURVE>::run_mul_batch,  \
+                                    &Engine<CURVE>::prepare_points, &Engine<CURVE>::run_msm_prepared}; \
     return &vt;                                                                                \
   }
 

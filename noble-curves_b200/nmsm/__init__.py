@@ -409,6 +409,68 @@ def mul_batch_packed(curve_id: int, pts: bytes, scalars: bytes, n: int, allow_ze
     return out.raw[: n * pb], infs.raw[:n]
 
 
+class PointSet:
+    """Device-resident, validated and prepared point array (nmsm_points_upload): the fixed-base fast path."""
+
+    def __init__(self, curve_id: int, pts: bytes, n: int):
+        _lib.ensure_init()
+        self._lib = _lib.load()
+        self.curve_id, self.n = curve_id, n
+        h = ctypes.c_uint64(0)
+        try:
+            _lib.check(self._lib.nmsm_points_upload(curve_id, ctypes.cast(ctypes.c_char_p(bytes(pts)), ctypes.c_void_p),
+                                                    n, ctypes.byref(h)))
+        except NmsmError as e:
+            _raise_mapped(e)
+        self.handle = h.value
+
+    def msm(self, scalars: bytes, n: int):
+        pb = self._lib.nmsm_point_bytes(self.curve_id)
+        out = ctypes.create_string_buffer(pb)
+        inf = ctypes.c_int(0)
+        rc = self._lib.nmsm_msm_points(self.handle, ctypes.cast(ctypes.c_char_p(bytes(scalars)), ctypes.c_void_p), n,
+                                       ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf))
+        try:
+            _lib.check(rc)
+        except NmsmError as e:
+            _raise_mapped(e)
+        return out.raw, inf.value
+
+    def close(self):
+        if self.handle:
+            self._lib.nmsm_points_free(self.handle)
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def interleavedMSMUnsafe(c, points, windowSize: int = 4):
+    """curve.ts:937-959: captures a FIXED point set once and returns `scalars -> sum s_i*P_i`.  Here the
+    captured state is the device-resident prepared array; `windowSize` is accepted for signature
+    compatibility (the GPU schedule picks its own window).  Fewer scalars than points are zero-padded."""
+    if not (isinstance(windowSize, int) and 2 <= windowSize <= c.Fn.BITS):
+        raise ValueError("invalid window size, expected [2..%d], got W=%s" % (c.Fn.BITS, windowSize))
+    _validate_msm_points(points, c)
+    n = len(points)
+    ps = PointSet(c.CURVE_ID, _pack_points(points), n) if n else None
+
+    def run(scalars):
+        _validate_msm_scalars(scalars, c.Fn)
+        if len(scalars) > n:
+            raise ValueError("array of scalars must not be larger than array of points")
+        if n == 0:
+            return c.ZERO
+        padded = list(scalars) + [0] * (n - len(scalars))
+        out, inf = ps.msm(_pack_scalars(padded), n)
+        return c.from_packed(out, inf)
+
+    return run
+
+
 def last_timing():
     """(dict of per-kernel ms, PlanInfo) of the last MSM call when profiling is enabled."""
     lib = _lib.load()

@@ -24,7 +24,7 @@ EXPORTS = [
     "nmsm_init", "nmsm_shutdown", "nmsm_last_error", "nmsm_last_error_index", "nmsm_point_bytes",
     "nmsm_acc_bytes", "nmsm_msm", "nmsm_msm_device", "nmsm_msm_partial_device", "nmsm_fold_partials_device",
     "nmsm_mul_batch", "nmsm_set_window_bits", "nmsm_set_profiling", "nmsm_last_timing", "nmsm_bench_modmul",
-    "nmsm_host_alloc", "nmsm_host_free",
+    "nmsm_host_alloc", "nmsm_host_free", "nmsm_points_upload", "nmsm_points_free", "nmsm_msm_points",
 ]
 
 
@@ -102,6 +102,12 @@ def load() -> ctypes.CDLL:
         lib.nmsm_host_alloc.restype = ctypes.c_void_p
         lib.nmsm_host_free.argtypes = [ctypes.c_void_p]
         lib.nmsm_host_free.restype = None
+        lib.nmsm_points_upload.argtypes = [ctypes.c_int, u8p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+        lib.nmsm_points_upload.restype = ctypes.c_int
+        lib.nmsm_points_free.argtypes = [ctypes.c_uint64]
+        lib.nmsm_points_free.restype = ctypes.c_int
+        lib.nmsm_msm_points.argtypes = [ctypes.c_uint64, u8p, ctypes.c_uint64, u8p, ctypes.POINTER(ctypes.c_int)]
+        lib.nmsm_msm_points.restype = ctypes.c_int
         _lib = lib
         return lib
 

@@ -313,3 +313,29 @@ def test_config_secp256k1_multiply_1024(nmsm):
     tot = sum(ks) % P.Fn.ORDER
     x, y, inf = gpu_msm(nmsm, "secp256k1", out, H.pack_scalars([1] * 1024), 1024)
     assert (x, y) == R.affine_tuple(P, base.multiplyUnsafe(tot))
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "ed25519", "bls12_381_G1"])
+def test_fixed_point_set_handle(nmsm, name):
+    """interleavedMSMUnsafe (curve.ts:937-959) over a device-resident point set: several scalar vectors,
+    fewer scalars than points, too many scalars, invalid point at upload."""
+    C = nmsm.CURVES[name]
+    P, pts, scalars, _ = H.soak_inputs(name, 129)
+    cpts = [C.fromAffine(p.toAffine()) for p in pts]
+    msm = nmsm.interleavedMSMUnsafe(C, cpts, 5)
+    for size in (129, 33, 1):
+        exp = H.expected_tuple(name, R.pippenger(P, pts[:size], scalars[:size]))
+        got = msm(scalars[:size])
+        assert (got.x, got.y, 1 if got.is0() else 0) == exp, (name, size)
+    rnd = random.Random(3)
+    sc2 = [rnd.randrange(P.Fn.ORDER) for _ in range(129)]
+    exp = H.expected_tuple(name, R.pippenger(P, pts, sc2))
+    got = msm(sc2)
+    assert (got.x, got.y, 1 if got.is0() else 0) == exp
+    with pytest.raises(ValueError, match="must not be larger"):
+        msm(sc2 + [1])
+    pb = bytearray(H.pack_points(name, pts))
+    fb = H.FP_BYTES[name]
+    pb[3 * 2 * fb: 3 * 2 * fb + fb] = P.Fp.ORDER.to_bytes(fb, "little")
+    with pytest.raises(ValueError, match="invalid point at index 3"):
+        nmsm.PointSet(H.CURVE_IDS[name], bytes(pb), 129)
