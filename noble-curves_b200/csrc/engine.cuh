@@ -114,7 +114,7 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   }
   EV(7);
   {
-    // k_reduce2 / k_reduce3: each window is split over <= 8 blocks of 64 quads x R chunks
+    // k_reduce2 / k_reduce3: each window is split over <= 32 blocks of 32 quads x R chunks
     int R = 4;
     while ((plan.chunks + REDUCE2_LOGICAL * R - 1) / (REDUCE2_LOGICAL * R) > REDUCE2_MAX_SPLITS) R <<= 1;
     const int splits = (plan.chunks + REDUCE2_LOGICAL * R - 1) / (REDUCE2_LOGICAL * R);

@@ -17,8 +17,8 @@
 //   k_reduce1      per-chunk running sums (2 additions per bucket), stitching the partials
 //                  of buckets that straddle accumulate segments on the fly                 (W*B/K threads)
 //   k_reduce2      second level: suffix scan + reduction of chunk sums inside blocks of
-//                  64 quads (registers -> quad/warp shuffles -> shared memory)             (W x splits blocks)
-//   k_reduce3      folds the <= 8 block results of every window                            (W warps)
+//                  32 quads (registers -> quad/warp shuffles -> shared memory)             (W x splits blocks)
+//   k_reduce3      folds the <= 32 block results of every window                           (W warps)
 //   k_final        Horner over windows (c doublings each) + one inversion to affine;
 //                  one warp, lanes share each formula's independent multiplications      (1 warp)
 //
@@ -203,9 +203,9 @@ __device__ __forceinline__ typename G::Acc smem_get(const uint32_t* smem, uint32
   return a;
 }
 
-static constexpr int REDUCE2_THREADS = 256;                   // 64 logical threads (quads), 8 warps
+static constexpr int REDUCE2_THREADS = 128;                   // 32 logical threads (quads), 4 warps
 static constexpr int REDUCE2_LOGICAL = REDUCE2_THREADS / 4;
-static constexpr int REDUCE2_MAX_SPLITS = 8;                  // k_reduce3 folds the splits of a window in one warp
+static constexpr int REDUCE2_MAX_SPLITS = 32;                 // k_reduce3: 8 quads x up to 4 splits each
 
 // grid (splits, W).  Logical thread lt owns R consecutive chunks; see the formulas above.
 template <class Cv>
@@ -214,7 +214,7 @@ k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums,
           uint32_t* __restrict__ blkP, uint32_t* __restrict__ blkQ) {
   using G = typename Cv::G;
   using Acc = typename G::Acc;
-  extern __shared__ uint32_t smem[];  // 8 accumulators
+  extern __shared__ uint32_t smem[];  // one accumulator per warp
   const uint32_t s = blockIdx.x, w = blockIdx.y, splits = gridDim.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ql = lane >> 2;
   const uint32_t lt = threadIdx.x >> 2;
@@ -231,7 +231,7 @@ k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums,
     }
     if (k > base) G::template par_add<false>(WL, S);  // after the loop: sum (k - base) * S_k
   }
-  // inclusive suffix scan of S over the 64 logical threads of the block
+  // inclusive suffix scan of S over the logical threads of the block
   Acc SS = S;
   for (int d = 1; d < 8; d <<= 1) {
     __syncwarp();
@@ -269,7 +269,8 @@ k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums,
   }
 }
 
-// grid W, one warp: quad s holds split s of the window.
+// grid W, one warp: quad q folds splits [q*R3, (q+1)*R3) of the window, then the quads combine.
+//   window = sum_s P_s + K * Mb * sum_s s * Q_s
 template <class Cv>
 __global__ void __launch_bounds__(32)
 k_reduce3(const uint32_t* __restrict__ blkP, const uint32_t* __restrict__ blkQ, MsmPlan plan, int splits, int R,
@@ -277,32 +278,42 @@ k_reduce3(const uint32_t* __restrict__ blkP, const uint32_t* __restrict__ blkQ, 
   using G = typename Cv::G;
   using Acc = typename G::Acc;
   const uint32_t w = blockIdx.x, lane = threadIdx.x, ql = lane >> 2;
-  Acc P = G::identity(), Q = G::identity();
-  if (ql < (uint32_t)splits) {
-    P = load_acc<G>(blkP + ((size_t)w * splits + ql) * G::ACC_WORDS);
-    Q = load_acc<G>(blkQ + ((size_t)w * splits + ql) * G::ACC_WORDS);
+  const uint32_t R3 = (uint32_t)(splits + 7) / 8;  // splits is a power of two: R3 in {1, 2, 4}
+  const uint32_t lo = ql * R3;
+  Acc PT = G::identity(), QS = G::identity(), QL = G::identity();
+  for (uint32_t s = lo + R3; s-- > lo;) {
+    if (s < (uint32_t)splits) {
+      G::template par_add<false>(PT, load_acc<G>(blkP + ((size_t)w * splits + s) * G::ACC_WORDS));
+      G::template par_add<false>(QS, load_acc<G>(blkQ + ((size_t)w * splits + s) * G::ACC_WORDS));
+    }
+    if (s > lo) G::template par_add<false>(QL, QS);  // after the loop: sum (s - lo) * Q_s
   }
-  // sum_s s * Q_s = sum_{s >= 1} (suffix sum of Q at s)
+  // suffix scan of the quad totals: sum_s s*Q_s = sum_q [QL_q + R3 * q * QS_q] = sum QL + R3 * sum_{q>=1} SS_q
+  Acc SS = QS;
   for (int d = 1; d < 8; d <<= 1) {
     __syncwarp();
-    Acc o = shfl_down_quads<G>(Q, d);
-    if (ql + d < 8) G::template par_add<false>(Q, o);
+    Acc o = shfl_down_quads<G>(SS, d);
+    if (ql + d < 8) G::template par_add<false>(SS, o);
   }
-  Acc X = (ql >= 1) ? Q : G::identity();
+  Acc X = G::identity();
+  if (ql >= 1) {
+    X = SS;
+    for (uint32_t r = 1; r < R3; r <<= 1) G::template par_dbl<false>(X);
+  }
+  G::template par_add<false>(X, QL);
   for (int d = 4; d >= 1; d >>= 1) {
     __syncwarp();
     Acc o = shfl_down_quads<G>(X, d);
     G::template par_add<false>(X, o);
     __syncwarp();
-    Acc o2 = shfl_down_quads<G>(P, d);
-    G::template par_add<false>(P, o2);
+    Acc o2 = shfl_down_quads<G>(PT, d);
+    G::template par_add<false>(PT, o2);
   }
-  // quad 0: window = P + K * Mb * X
   if (ql == 0) {
-    const uint32_t scale = (uint32_t)plan.K * REDUCE2_LOGICAL * (uint32_t)R;  // power of two
+    const uint32_t scale = (uint32_t)plan.K * REDUCE2_LOGICAL * (uint32_t)R;  // K * Mb, a power of two
     for (uint32_t j = 1; j < scale; j <<= 1) G::template par_dbl<false>(X);
-    G::template par_add<false>(P, X);
-    if (lane == 0) save_acc<G>(window_out + (size_t)w * G::ACC_WORDS, P);
+    G::template par_add<false>(PT, X);
+    if (lane == 0) save_acc<G>(window_out + (size_t)w * G::ACC_WORDS, PT);
   }
 }
 
