@@ -88,6 +88,18 @@ int nmsm_points_upload(int curve, const uint8_t* pts, uint64_t n, uint64_t* out_
 int nmsm_points_free(uint64_t handle);
 int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf);
 
+/* Ed25519 batch verification (next-row f1).  The reference verifies one signature at a time
+ * (/root/reference/src/abstract/edwards.ts:942-989, ZIP-215 decoding by default, src/ed25519.ts:168); this checks
+ *   [8]( sum z_i*R_i + sum (z_i*k_i mod l)*A_i - (sum z_i*s_i mod l)*B ) == O ,  k_i = SHA-512(R_i||A_i||M_i) mod l
+ * on the GPU (decompression, SHA-512, scalar arithmetic mod l, Edwards MSM of 2n+1 terms).
+ * sigs: n x 64 B; pubkeys: n x 32 B; msgs: concatenated message bytes, message i = [msg_off[i], msg_off[i+1]);
+ * z16: n x 16 B caller-supplied random 128-bit coefficients (little-endian).
+ * out_ok = 1 iff every R_i/A_i decodes, every s_i < l and the batch equation holds.  out_bad_index = smallest
+ * index that can be rejected without the equation (undecodable point or s >= l), else -1. */
+int nmsm_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pubkeys, const uint8_t* msgs,
+                              const uint64_t* msg_off, uint64_t n, const uint8_t* z16, int* out_ok,
+                              long long* out_bad_index);
+
 /* Tuning / introspection ------------------------------------------------------------------- */
 /* Force the window size c (0 = automatic cost model).  Returns the previous value. */
 int nmsm_set_window_bits(int c);

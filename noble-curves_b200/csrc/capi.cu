@@ -123,7 +123,7 @@ void nmsm_shutdown(void) {
   if (!C.ready) return;
   cudaStreamSynchronize(C.stream);
   for (Buf* b : {&C.in_pts, &C.in_scalars, &C.aff, &C.counts, &C.offsets, &C.cursor, &C.sorted, &C.buckets,
-                 &C.heads, &C.tails, &C.chunk_out, &C.window_out, &C.tile_sums, &C.blk, &C.tiles, &C.result, &C.mul_out})
+                 &C.heads, &C.tails, &C.chunk_out, &C.window_out, &C.tile_sums, &C.blk, &C.tiles, &C.ed_scratch, &C.result, &C.mul_out})
     b->release();
   for (auto& ev : C.ev) cudaEventDestroy(ev);
   cudaFreeHost(C.h_result);
@@ -221,6 +221,17 @@ int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t
   if (!ps || !out_xy || !out_is_inf || (n && !scalars)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(ps->curve);
   return E->msm_prepared(ps->d_prepared, ps->n, scalars, n, out_xy, out_is_inf);
+}
+
+int nmsm_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pubkeys, const uint8_t* msgs,
+                              const uint64_t* msg_off, uint64_t n, const uint8_t* z16, int* out_ok,
+                              long long* out_bad_index) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (!out_ok || !out_bad_index || (n && (!sigs || !pubkeys || !msg_off || !z16)))
+    return fail(NMSM_ERR_ARG, "null pointer");
+  if (n && msg_off[n] && !msgs) return fail(NMSM_ERR_ARG, "null pointer");
+  return ed25519_verify_batch_impl(sigs, pubkeys, msgs, msg_off, n, z16, out_ok, out_bad_index);
 }
 
 int nmsm_set_window_bits(int c) {

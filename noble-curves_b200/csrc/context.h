@@ -43,7 +43,7 @@ struct Context {
   int device = -1;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  Buf in_pts, in_scalars, aff, counts, offsets, cursor, sorted, buckets, heads, tails, chunk_out, window_out, tile_sums, blk, tiles,
+  Buf in_pts, in_scalars, aff, counts, offsets, cursor, sorted, buckets, heads, tails, chunk_out, window_out, tile_sums, blk, tiles, ed_scratch,
       result, mul_out;
   uint32_t* h_result = nullptr;  // pinned staging for (xy | inf | err0 | err1)
   cudaEvent_t ev[NMSM_TIMING_SLOTS + 2] = {};
@@ -92,6 +92,8 @@ struct EngineVTable {
   int (*msm_prepared)(const uint32_t* d_prepared, uint64_t n_points, const uint8_t* scalars, uint64_t n,
                       uint8_t* out_xy, int* out_is_inf);
 };
+int ed25519_verify_batch_impl(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* msg_off,
+                              uint64_t n, const uint8_t* z16, int* out_ok, long long* out_bad_index);
 const EngineVTable* engine_secp256k1();
 const EngineVTable* engine_ed25519();
 const EngineVTable* engine_bn254g1();

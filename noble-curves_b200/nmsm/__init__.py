@@ -471,6 +471,43 @@ def interleavedMSMUnsafe(c, points, windowSize: int = 4):
     return run
 
 
+def ed25519_verify_batch(signatures, messages, public_keys, z: bytes | None = None):
+    """Batch form of ed25519.verify (edwards.ts:942-989, ZIP-215 decoding as ed25519's default): returns
+    (ok, bad_index).  ok is True iff every signature would be accepted individually (up to 2^-128);
+    bad_index is the first signature rejected without the group equation (undecodable point / s >= l), else -1.
+    `z`: optional n*16 bytes of caller randomness (default os.urandom)."""
+    import os
+    import struct
+
+    n = len(signatures)
+    if len(messages) != n or len(public_keys) != n:
+        raise ValueError("signatures, messages and public keys must have equal length")
+    for s, p in zip(signatures, public_keys):
+        if len(s) != 64 or len(p) != 32:
+            raise ValueError("signature expected 64 bytes, publicKey 32 bytes")
+    if z is None:
+        z = os.urandom(16 * n)
+    if len(z) != 16 * n:
+        raise ValueError("z must hold 16 bytes per signature")
+    _lib.ensure_init()
+    lib = _lib.load()
+    offs = [0]
+    for m in messages:
+        offs.append(offs[-1] + len(m))
+    blob = b"".join(bytes(m) for m in messages)
+    ok = ctypes.c_int(0)
+    bad = ctypes.c_longlong(-1)
+    cp = lambda b: ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p)  # noqa: E731
+    rc = lib.nmsm_ed25519_verify_batch(cp(b"".join(signatures)), cp(b"".join(public_keys)), cp(blob or b"\0"),
+                                       cp(struct.pack("<%dQ" % (n + 1), *offs)), n, cp(bytes(z)), ctypes.byref(ok),
+                                       ctypes.byref(bad))
+    try:
+        _lib.check(rc)
+    except NmsmError as e:
+        _raise_mapped(e)
+    return bool(ok.value), int(bad.value)
+
+
 def last_timing():
     """(dict of per-kernel ms, PlanInfo) of the last MSM call when profiling is enabled."""
     lib = _lib.load()

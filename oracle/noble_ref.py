@@ -1139,3 +1139,81 @@ def ed25519_public_key(sk: bytes) -> bytes:
     P = CURVES["ed25519"]
     scalar = int.from_bytes(bytes(head), "little") % P.Fn.ORDER
     return P.BASE.multiply(scalar).toBytes()
+
+
+# --------------------------------------------------------------------------------------
+# EdDSA verification for ed25519 (next-row f1: batch verification is checked against this)
+# --------------------------------------------------------------------------------------
+ED25519_SQRT_M1 = 19681161376707505956807079304988542015446066515923890162744021073123829784752  # src/ed25519.ts:100-102
+
+
+def ed25519_uv_ratio(u: int, v: int):
+    """src/ed25519.ts:104-121 `uvRatio`: sqrt(u/v) -> (isValid, value)."""
+    P = ED25519_CURVE["p"]
+    v3 = (v * v * v) % P
+    v7 = (v3 * v3 * v) % P
+    pw = pow((u * v7) % P, (P - 5) // 8, P)
+    x = (u * v3 * pw) % P
+    vx2 = (v * x * x) % P
+    root1 = x
+    root2 = (x * ED25519_SQRT_M1) % P
+    use1 = vx2 == u
+    use2 = vx2 == (-u) % P
+    no_root = vx2 == (-u * ED25519_SQRT_M1) % P
+    if use1:
+        x = root1
+    if use2 or no_root:
+        x = root2
+    if x & 1:  # isNegativeLE
+        x = (-x) % P
+    return (use1 or use2), x
+
+
+def ed25519_point_from_bytes(b: bytes, zip215: bool = False):
+    """src/abstract/edwards.ts:405-436 `Point.fromBytes` for ed25519."""
+    if len(b) != 32:
+        raise ValueError("point expected 32 bytes")
+    P = ED25519_CURVE["p"]
+    d = ED25519_CURVE["d"]
+    last = b[31]
+    normed = bytearray(b)
+    normed[31] = last & 0x7F
+    y = int.from_bytes(bytes(normed), "little")
+    mx = (1 << 256) if zip215 else P
+    if not (0 <= y < mx):
+        raise ValueError("point.y out of range")
+    y2 = (y * y) % P
+    u = (y2 - 1) % P
+    v = (d * y2 + 1) % P
+    ok, x = ed25519_uv_ratio(u, v)
+    if not ok:
+        raise ValueError("bad point: invalid y coordinate")
+    is_x_odd = (x & 1) == 1
+    is_last_odd = (last & 0x80) != 0
+    if not zip215 and x == 0 and is_last_odd:
+        raise ValueError("bad point: x=0 and x_0=1")
+    if is_last_odd != is_x_odd:
+        x = (-x) % P
+    Pt = CURVES["ed25519"]
+    return Pt(x, y % P, 1, (x * y) % P)
+
+
+def ed25519_verify(sig: bytes, msg: bytes, public_key: bytes, zip215: bool = True) -> bool:
+    """src/abstract/edwards.ts:942-989 `verify` (cofactored; ed25519's default is zip215=true, ed25519.ts:168)."""
+    Pt = CURVES["ed25519"]
+    L = Pt.Fn.ORDER
+    if len(sig) != 64 or len(public_key) != 32:
+        raise ValueError("bad lengths")
+    r = sig[:32]
+    s = int.from_bytes(sig[32:], "little")
+    try:
+        A = ed25519_point_from_bytes(public_key, zip215)
+        Rp = ed25519_point_from_bytes(r, zip215)
+        SB = Pt.BASE.multiplyUnsafe(s)  # raises when s >= l
+    except ValueError:
+        return False
+    if not zip215 and A.clearCofactor().is0():
+        return False
+    k = int.from_bytes(hashlib.sha512(r + public_key + msg).digest(), "little") % L
+    RkA = Rp.add(A.multiplyUnsafe(k))
+    return RkA.subtract(SB).clearCofactor().is0()

@@ -82,7 +82,9 @@ def ed25519():
         parts = line.strip().split(":")
         sk_pk, pk, msg, sig_msg = parts[0], parts[1], parts[2], parts[3]
         rows.append({"sk": sk_pk[:64], "pk": pk, "msg": msg, "sig": sig_msg[:128]})
-    dump("ed25519.json", {"vectors": rows})
+    zip215 = json.load(open(f"{REF}/ed25519/zip215.json"))  # test/ed25519.test.ts:392-405, message = "Zcash"
+    edge = json.load(open(f"{REF}/ed25519/edge-cases.json"))  # test/ed25519.test.ts:189-196
+    dump("ed25519.json", {"vectors": rows, "zip215": zip215, "edge_cases": edge})
 
 
 if __name__ == "__main__":

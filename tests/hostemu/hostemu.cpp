@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "msm_body.cuh"
+#include "ed25519_verify.cuh"
 
 using namespace nmsm;
 
@@ -131,7 +132,38 @@ static void field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) 
   for (int i = 0; i < P::N; i++) r[i] = z.v[i];
 }
 
+static int emu_ed_verify(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+                         const uint8_t* z16, int* out_ok, long long* out_bad) {
+  using Cv = CurveEd25519;
+  using G = Cv::G;
+  *out_ok = 0;
+  *out_bad = -1;
+  if (n == 0) { *out_ok = 1; return 0; }
+  const uint32_t terms = 2 * n + 1;
+  std::vector<uint32_t> pts((size_t)terms * 16), sc((size_t)terms * 8), zs((size_t)n * 8);
+  unsigned int bad = 0xffffffffu;
+  for (uint32_t i = 0; i < n; i++) ed_terms_body(i, n, sigs, pks, msgs, off, z16, pts.data(), sc.data(), zs.data(), &bad);
+  ed_finish_serial(n, zs.data(), pts.data(), sc.data());
+  std::vector<uint32_t> acc_words(G::ACC_WORDS);
+  int rc = emu_partial_t<Cv>(pts.data(), sc.data(), terms, acc_words.data());
+  if (rc) return rc;
+  G::Acc acc = load_acc<G>(acc_words.data());
+  for (int j = 0; j < 3; j++) G::dbl(acc);
+  if (bad != 0xffffffffu) { *out_bad = bad; return 0; }
+  *out_ok = G::is_identity(acc) ? 1 : 0;
+  return 0;
+}
+
 extern "C" {
+int emu_ed25519_decompress(const uint8_t* enc, uint32_t* out_xy) { return ed_decompress(enc, out_xy) ? 1 : 0; }
+int emu_sha512_rAM(const uint8_t* r, const uint8_t* a, const uint8_t* msg, uint64_t mlen, uint8_t* digest) {
+  sha512_rAM(r, a, msg, mlen, digest);
+  return 0;
+}
+int emu_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* off, uint32_t n,
+                             const uint8_t* z16, int* out_ok, long long* out_bad) {
+  return emu_ed_verify(sigs, pks, msgs, off, n, z16, out_ok, out_bad);
+}
 // GLV split of one scalar (BLS12-381 G1): out = m1[4], m2[4], neg1, neg2
 int emu_glv_split(const uint32_t* k, uint32_t* out) {
   bool n1, n2;

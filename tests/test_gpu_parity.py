@@ -339,3 +339,71 @@ def test_fixed_point_set_handle(nmsm, name):
     pb[3 * 2 * fb: 3 * 2 * fb + fb] = P.Fp.ORDER.to_bytes(fb, "little")
     with pytest.raises(ValueError, match="invalid point at index 3"):
         nmsm.PointSet(H.CURVE_IDS[name], bytes(pb), 129)
+
+
+# ------------------------------------------------------------------------------------------------
+# ed25519 batch verification: batch accepts <=> every individual reference verify accepts
+# ------------------------------------------------------------------------------------------------
+def test_ed25519_batch_verify_small(nmsm):
+    g = load_golden("ed25519.json")
+    vec = g["vectors"]
+    sigs = [bytes.fromhex(v["sig"]) for v in vec]
+    msgs = [bytes.fromhex(v["msg"]) for v in vec]
+    pks = [bytes.fromhex(v["pk"]) for v in vec]
+    assert all(R.ed25519_verify(s, m, p) for s, m, p in zip(sigs[:16], msgs[:16], pks[:16]))
+    assert nmsm.ed25519_verify_batch(sigs, msgs, pks) == (True, -1)
+    assert nmsm.ed25519_verify_batch([], [], []) == (True, -1)
+    assert nmsm.ed25519_verify_batch(sigs[:1], msgs[:1], pks[:1]) == (True, -1)
+    for idx, byte in ((5, 40), (77, 3), (127, 63)):
+        bad = list(sigs)
+        b = bytearray(bad[idx])
+        b[byte] ^= 1
+        bad[idx] = bytes(b)
+        indiv = R.ed25519_verify(bad[idx], msgs[idx], pks[idx])
+        ok, _ = nmsm.ed25519_verify_batch(bad, msgs, pks)
+        assert ok == indiv is False or ok == indiv
+    m2 = list(msgs)
+    m2[9] = m2[9] + b"\x00"
+    assert nmsm.ed25519_verify_batch(sigs, m2, pks)[0] is False
+    p2 = list(pks)
+    p2[3], p2[4] = p2[4], p2[3]
+    assert nmsm.ed25519_verify_batch(sigs, msgs, p2)[0] is False
+    b = bytearray(sigs[3])
+    b[63] |= 0xF0  # s >= l
+    bad = list(sigs)
+    bad[3] = bytes(b)
+    assert nmsm.ed25519_verify_batch(bad, msgs, pks) == (False, 3)
+
+
+def test_ed25519_batch_verify_zip215(nmsm):
+    """The 196 ZIP-215 vectors (test/ed25519.test.ts:392-405): each one alone must match the reference's verdict,
+    and all accepted ones together must pass as one batch (small-order and non-canonical encodings)."""
+    zs = load_golden("ed25519.json")["zip215"]
+    for v in zs:
+        sig, pk = bytes.fromhex(v["sig_bytes"]), bytes.fromhex(v["vk_bytes"])
+        assert R.ed25519_verify(sig, b"Zcash", pk) == v["valid_zip215"]
+        assert nmsm.ed25519_verify_batch([sig], [b"Zcash"], [pk])[0] == v["valid_zip215"], v
+    valid = [v for v in zs if v["valid_zip215"]]
+    assert nmsm.ed25519_verify_batch([bytes.fromhex(v["sig_bytes"]) for v in valid], [b"Zcash"] * len(valid),
+                                     [bytes.fromhex(v["vk_bytes"]) for v in valid])[0] is True
+
+
+def test_config_ed25519_batch_verify_2p16(nmsm):
+    """configs[4]: 2^16 signatures (the RFC 8032 vectors tiled), one Edwards MSM of 2*2^16+1 terms."""
+    import time
+
+    vec = load_golden("ed25519.json")["vectors"]
+    reps = (1 << 16) // len(vec)
+    sigs = [bytes.fromhex(v["sig"]) for v in vec] * reps
+    msgs = [bytes.fromhex(v["msg"]) for v in vec] * reps
+    pks = [bytes.fromhex(v["pk"]) for v in vec] * reps
+    assert len(sigs) == 1 << 16
+    t0 = time.perf_counter()
+    assert nmsm.ed25519_verify_batch(sigs, msgs, pks) == (True, -1)
+    dt = time.perf_counter() - t0
+    print("ed25519 batch verify 2^16 signatures: %.1f ms end-to-end through the Python binding" % (dt * 1e3))
+    bad = list(sigs)
+    b = bytearray(bad[40000])
+    b[33] ^= 0x10
+    bad[40000] = bytes(b)
+    assert nmsm.ed25519_verify_batch(bad, msgs, pks)[0] is False

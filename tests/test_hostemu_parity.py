@@ -194,3 +194,90 @@ def test_msm_giant_bucket_tile_stitching(name):
     assert got == exp, plan
     got, err, plan = H.emu_msm(name, pb, H.pack_scalars([s] * n), n, 4, 2)
     assert got == exp, plan
+
+
+# ---- ed25519 batch verification pieces (next-row f1) --------------------------------------------
+def _emu_ed_verify(sigs, msgs, pks, z):
+    import ctypes
+    import struct
+
+    lib = H.hostemu()
+    n = len(sigs)
+    offs = [0]
+    for m in msgs:
+        offs.append(offs[-1] + len(m))
+    ok, bad = ctypes.c_int(0), ctypes.c_longlong(-1)
+    rc = lib.emu_ed25519_verify_batch(b"".join(sigs), b"".join(pks), b"".join(msgs) or b"\0",
+                                      struct.pack("<%dQ" % (n + 1), *offs), n, z, ctypes.byref(ok), ctypes.byref(bad))
+    assert rc == 0
+    return bool(ok.value), int(bad.value)
+
+
+def test_ed25519_decompress_and_sha512_match_oracle():
+    import ctypes
+    import hashlib
+
+    import numpy as np
+
+    from conftest import load_golden
+
+    lib = H.hostemu()
+    g = load_golden("ed25519.json")
+    encs = [bytes.fromhex(v["pk"]) for v in g["vectors"][:24]] + [bytes.fromhex(v["vk_bytes"]) for v in g["zip215"][:40]]
+    encs += [bytes.fromhex(v["sig_bytes"])[:32] for v in g["zip215"][40:80]]
+    encs += [bytes([2] + [0] * 31), bytes([0xFF] * 32), bytes([0xEC] + [0xFF] * 30 + [0x7F])]
+    for e in encs:
+        out = np.zeros(16, np.uint32)
+        ok = lib.emu_ed25519_decompress(e, out.ctypes.data_as(ctypes.c_void_p))
+        try:
+            P = R.ed25519_point_from_bytes(e, True)
+            assert ok == 1
+            a = P.toAffine()
+            assert int.from_bytes(out[:8].tobytes(), "little") == a["x"] % R.ED25519_CURVE["p"]
+            assert int.from_bytes(out[8:].tobytes(), "little") == a["y"] % R.ED25519_CURVE["p"]
+        except ValueError:
+            assert ok == 0, e.hex()
+    for mlen in (0, 1, 47, 48, 63, 64, 111, 112, 127, 128, 200, 1000):
+        r, a, m = bytes(range(32)), bytes(range(32, 64)), bytes((7 * i) & 255 for i in range(mlen))
+        d = ctypes.create_string_buffer(64)
+        lib.emu_sha512_rAM(r, a, m or b"\0", ctypes.c_uint64(mlen), d)
+        assert d.raw == hashlib.sha512(r + a + m).digest(), mlen
+
+
+def test_ed25519_batch_verify_matches_individual_reference_verify():
+    """batch accepts <=> every individual verify (edwards.ts:942-989) accepts; incl. ZIP-215 cases."""
+    from conftest import load_golden
+
+    g = load_golden("ed25519.json")
+    vec = g["vectors"][:12]
+    sigs = [bytes.fromhex(v["sig"]) for v in vec]
+    msgs = [bytes.fromhex(v["msg"]) for v in vec]
+    pks = [bytes.fromhex(v["pk"]) for v in vec]
+    z = bytes((i * 37 + 11) & 255 for i in range(16 * len(vec)))
+    assert all(R.ed25519_verify(s, m, p) for s, m, p in zip(sigs, msgs, pks))
+    assert _emu_ed_verify(sigs, msgs, pks, z) == (True, -1)
+    bad = list(sigs)
+    b = bytearray(bad[5])
+    b[40] ^= 1  # corrupt s of one signature: individual verify fails, batch must fail
+    bad[5] = bytes(b)
+    assert R.ed25519_verify(bad[5], msgs[5], pks[5]) is False
+    assert _emu_ed_verify(bad, msgs, pks, z)[0] is False
+    m2 = list(msgs)
+    m2[0] = m2[0] + b"!"
+    assert _emu_ed_verify(sigs, m2, pks, z)[0] is False
+    # s >= l is rejected up front with its index
+    b = bytearray(sigs[3])
+    b[63] |= 0xF0
+    bad = list(sigs)
+    bad[3] = bytes(b)
+    assert _emu_ed_verify(bad, msgs, pks, z) == (False, 3)
+    # ZIP-215 vectors (message "Zcash"): each alone, and all valid ones in one batch
+    zs = g["zip215"]
+    valid = [v for v in zs if v["valid_zip215"]][:20]
+    invalid = [v for v in zs if not v["valid_zip215"]][:6]
+    for v in valid[:8] + invalid:
+        got = _emu_ed_verify([bytes.fromhex(v["sig_bytes"])], [b"Zcash"], [bytes.fromhex(v["vk_bytes"])], bytes(range(16)))
+        assert got[0] == v["valid_zip215"], v
+    allz = bytes((i * 5 + 3) & 255 for i in range(16 * len(valid)))
+    assert _emu_ed_verify([bytes.fromhex(v["sig_bytes"]) for v in valid], [b"Zcash"] * len(valid),
+                          [bytes.fromhex(v["vk_bytes"]) for v in valid], allz)[0] is True

@@ -188,3 +188,28 @@ def test_ed25519_rfc8032_public_keys():
     assert len(g) == 128
     for v in g[:64]:
         assert R.ed25519_public_key(bytes.fromhex(v["sk"])).hex() == v["pk"]
+
+
+def test_ed25519_verify_oracle_against_reference_vectors():
+    """EdDSA verify restatement (edwards.ts:942-989) vs test/vectors/ed25519: RFC 8032 signatures,
+    the 196 ZIP-215 cases (test/ed25519.test.ts:392-405) and the strict-mode edge cases (:189-196)."""
+    g = load_golden("ed25519.json")
+    for v in g["vectors"][:48]:
+        sig, msg, pk = bytes.fromhex(v["sig"]), bytes.fromhex(v["msg"]), bytes.fromhex(v["pk"])
+        assert R.ed25519_verify(sig, msg, pk) is True
+        bad = bytearray(sig)
+        bad[5] ^= 1
+        assert R.ed25519_verify(bytes(bad), msg, pk) is False
+        assert R.ed25519_verify(sig, msg + b"x", pk) is False
+    assert len(g["zip215"]) == 196
+    for v in g["zip215"]:
+        got = R.ed25519_verify(bytes.fromhex(v["sig_bytes"]), b"Zcash", bytes.fromhex(v["vk_bytes"]))
+        assert got == v["valid_zip215"], v
+    for i in (0, 1, 6, 7, 8, 9, 10, 11):
+        v = g["edge_cases"][i]
+        assert R.ed25519_verify(bytes.fromhex(v["signature"]), bytes.fromhex(v["message"]), bytes.fromhex(v["pub_key"]),
+                                zip215=False) is False
+    # s = l + 1 is rejected (test/ed25519.test.ts:406-414)
+    sig = bytes.fromhex("5866666666666666666666666666666666666666666666666666666666666666"
+                        "eed3f55c1a631258d69cf7a2def9de1400000000000000000000000000000010")
+    assert R.ed25519_verify(sig, b"Zcash", bytes.fromhex(g["zip215"][0]["vk_bytes"])) is False
