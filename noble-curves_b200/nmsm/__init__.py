@@ -159,6 +159,24 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
                 )
             return multiply_many(Point, [self], [scalar], unsafe=True)[0]
 
+        def precompute(self, windowSize: int = 8, isLazy: bool = True):
+            """weierstrass.ts:740-745 / edwards.ts:449-453: a cache hint in the reference; results never depend
+            on it, and the GPU schedule keeps no per-point tables, so this only validates and returns self."""
+            if not (isinstance(windowSize, int) and 1 <= windowSize <= Fn.BITS):
+                raise ValueError("invalid window size, expected [1..%d], got W=%s" % (Fn.BITS, windowSize))
+            return self
+
+        def clearCofactor(self):
+            """weierstrass.ts:977-982 / edwards.ts:611-618 ([h]P; identity map for cofactor-1 curves)."""
+            if h == 1:
+                return self
+            if h >= n:
+                raise NotImplementedError("cofactor >= group order: outside the accelerated scalar range")
+            return self.multiplyUnsafe(h)
+
+        def isSmallOrder(self) -> bool:
+            return self.is0() if h == 1 else self.clearCofactor().is0()
+
         def to_packed(self) -> bytes:
             return _coord_to_bytes(self.x, fp_bytes, parts) + _coord_to_bytes(self.y, fp_bytes, parts)
 
@@ -365,6 +383,23 @@ def pippenger(c, points, scalars):
     if len(points) == 0:
         return c.ZERO
     return _msm_points(c, points, scalars)
+
+
+def normalizeZ(c, points):
+    """curve.ts:311-326: batch projective -> affine.  Host handles are already canonical affine (every
+    GPU result is normalised on the device), so this validates and returns fresh equal points."""
+    _validate_msm_points(points, c)
+    return [c.from_packed(p.to_packed(), 1 if p.is0() else 0) for p in points]
+
+
+def aggregate_points(c, points):
+    """sum_i P_i (BLS aggregatePublicKeys / aggregateSignatures are exactly this, abstract/bls.ts:860,870):
+    an MSM with unit scalars; every term lands in one bucket, which the balanced-segment accumulate and the
+    tile stitching handle in parallel."""
+    _validate_msm_points(points, c)
+    if not points:
+        return c.ZERO
+    return _msm_points(c, points, [1] * len(points))
 
 
 def mulAddUnsafe(c, points, scalars):

@@ -407,3 +407,31 @@ def test_config_ed25519_batch_verify_2p16(nmsm):
     b[33] ^= 0x10
     bad[40000] = bytes(b)
     assert nmsm.ed25519_verify_batch(bad, msgs, pks)[0] is False
+
+
+@pytest.mark.parametrize("name", ["bls12_381_G1", "bls12_381_G2", "ed25519"])
+def test_aggregate_points_and_small_helpers(nmsm, name):
+    """f3: aggregation = sum of points (abstract/bls.ts:860,870), incl. 4096 terms in one bucket."""
+    C = nmsm.CURVES[name]
+    P = R.CURVES[name]
+    n = 4096 if name == "bls12_381_G1" else 300
+    _, pts, _, _ = H.soak_inputs(name, 40, zero_every=0)
+    reps = [pts[i % 40] for i in range(n)]
+    acc = P.ZERO
+    for p in pts:
+        acc = acc.add(p)
+    # sum of n points cycling through 40 distinct ones = (n // 40) * S + partial
+    exp = P.ZERO
+    full, rem = divmod(n, 40)
+    if full:
+        exp = acc.multiplyUnsafe(full) if full > 1 else acc
+    for p in pts[:rem]:
+        exp = exp.add(p)
+    cpts = [C.fromAffine(p.toAffine()) for p in pts]
+    got = nmsm.aggregate_points(C, [cpts[i % 40] for i in range(n)])
+    assert (got.x, got.y, 1 if got.is0() else 0) == H.expected_tuple(name, exp)
+    assert nmsm.aggregate_points(C, []).equals(C.ZERO)
+    assert nmsm.normalizeZ(C, cpts[:3])[2].equals(cpts[2])
+    assert cpts[0].precompute(6) is cpts[0]
+    if name == "ed25519":
+        assert cpts[0].clearCofactor().equals(cpts[0].multiplyUnsafe(8)) and not cpts[0].isSmallOrder()
