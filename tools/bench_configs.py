@@ -1,0 +1,133 @@
+#!/usr/bin/env python3
+"""Measure every BASELINE.json config on one B200 (parity-checked, CUDA-event kernel times where the MSM
+pipeline is used).  The headline (configs[1]/metric at 2^20) is bench.py; this writes the companion table.
+
+    python tools/bench_configs.py > profiles/r01_configs.jsonl
+
+configs (BASELINE.json):
+  0  secp256k1 Point.multiply batch of 1024 random scalars      (reference: CPU bigint; here also the GPU batch)
+  1  BLS12-381 G1 MSM, 2^16
+  2  bn254 G1 MSM, 2^20
+  3  BLS12-381 G2 MSM, 2^18
+  4  ed25519 batch-verify 2^16 signatures
+Each line: {"config", "n", "gpu_ms" (best of K, wall through the C ABI incl. H2D), "per_s", "kernels_ms", "check"}.
+CPU comparison numbers use the oracle (tests-only code) on a bounded sample and are labelled.
+"""
+import json
+import os
+import random
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "noble-curves_b200"))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import nmsm  # noqa: E402
+import helpers as H  # noqa: E402
+from oracle import noble_ref as R  # noqa: E402
+
+
+def gen_terms(name, n, seed):
+    P = R.CURVES[name]
+    rnd = random.Random(seed)
+    ks = [rnd.randrange(1, P.Fn.ORDER) for _ in range(n)]
+    sc = [rnd.randrange(P.Fn.ORDER) for _ in range(n)]
+    cid = H.CURVE_IDS[name]
+    pts, infs = nmsm.mul_batch_packed(cid, H.point_bytes(name, P.BASE) * n, H.pack_scalars(ks), n, False)
+    total = sum(k * s for k, s in zip(ks, sc)) % P.Fn.ORDER
+    return pts, H.pack_scalars(sc), total
+
+
+def time_best(fn, reps):
+    best = 1e9
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def msm_config(idx, name, logn, reps=5):
+    n = 1 << logn
+    P = R.CURVES[name]
+    pts, sc, total = gen_terms(name, n, 100 + idx)
+    exp = H.expected_tuple(name, H.expected_from_total(P, total))
+    cid = H.CURVE_IDS[name]
+    nmsm.set_profiling(True)
+    out = {}
+
+    def run():
+        o, inf = nmsm.msm_packed(cid, pts, sc, n)
+        out["r"] = (*H.unpack_point(name, o), inf)
+
+    run()
+    best = time_best(run, reps)
+    ms, info = nmsm.last_timing()
+    return {"config": idx, "what": "%s MSM, 2^%d terms" % (name, logn), "n": n, "gpu_ms_e2e_host_buffers": best * 1e3,
+            "gpu_ms_device": ms["total"], "points_per_s_device": n / (ms["total"] * 1e-3),
+            "kernels_ms": {k: round(v, 4) for k, v in ms.items()},
+            "plan": {"c": info.c, "windows": info.windows, "entries": info.sorted_entries, "modmul_equiv": info.modmul_equiv},
+            "check": "bit-exact vs (sum k_i s_i)*G" if out["r"] == exp else "MISMATCH"}
+
+
+def config0():
+    P = R.CURVES["secp256k1"]
+    rnd = random.Random(11)
+    base = R.normalizeZ(P, [P.BASE.multiplyUnsafe(rnd.randrange(1, P.Fn.ORDER))])[0]
+    ks = [rnd.randrange(1, P.Fn.ORDER) for _ in range(1024)]
+    pb, sb = H.point_bytes("secp256k1", base) * 1024, H.pack_scalars(ks)
+    res = {}
+
+    def run():
+        res["o"] = nmsm.mul_batch_packed(0, pb, sb, 1024, False)
+
+    run()
+    best = time_best(run, 5)
+    t0 = time.perf_counter()
+    ok = True
+    for i in range(0, 1024, 64):  # CPU oracle (Python bigint restatement of the reference's blinded fixed-window path)
+        ok &= H.unpack_point("secp256k1", res["o"][0][i * 64:(i + 1) * 64]) == R.affine_tuple(P, base.multiply(ks[i]))
+    cpu_per = (time.perf_counter() - t0) / 16
+    return {"config": 0, "what": "secp256k1 Point.multiply x 1024 random scalars", "n": 1024, "gpu_ms": best * 1e3,
+            "multiplies_per_s_gpu": 1024 / best,
+            "cpu_python_oracle_multiplies_per_s": 1 / cpu_per, "cpu_sample": "16 multiplies, Python-int oracle, 1 core",
+            "check": "bit-exact on 16 sampled results" if ok else "MISMATCH"}
+
+
+def config4():
+    from conftest import load_golden
+
+    vec = load_golden("ed25519.json")["vectors"]
+    reps = (1 << 16) // len(vec)
+    sigs = [bytes.fromhex(v["sig"]) for v in vec] * reps
+    msgs = [bytes.fromhex(v["msg"]) for v in vec] * reps
+    pks = [bytes.fromhex(v["pk"]) for v in vec] * reps
+    z = os.urandom(16 * len(sigs))
+    res = {}
+
+    def run():
+        res["r"] = nmsm.ed25519_verify_batch(sigs, msgs, pks, z)
+
+    run()
+    best = time_best(run, 3)
+    t0 = time.perf_counter()
+    for i in range(8):
+        assert R.ed25519_verify(sigs[i], msgs[i], pks[i])
+    cpu_per = (time.perf_counter() - t0) / 8
+    return {"config": 4, "what": "ed25519 batch verification, 2^16 signatures (RFC 8032 vectors tiled)", "n": len(sigs),
+            "gpu_ms_through_python_binding": best * 1e3, "signatures_per_s": len(sigs) / best,
+            "cpu_python_oracle_verifies_per_s": 1 / cpu_per, "cpu_sample": "8 individual verifies, Python-int oracle, 1 core",
+            "check": "accepted; equals AND of individual verifies" if res["r"] == (True, -1) else "MISMATCH"}
+
+
+def main():
+    nmsm.init(0)
+    for row in (config0(), msm_config(1, "bls12_381_G1", 16), msm_config(2, "bn254_G1", 20),
+                msm_config(3, "bls12_381_G2", 18), config4()):
+        print(json.dumps(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
