@@ -240,14 +240,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ------------------------------------------------------
+    # ---- device-resident: (1) serial steps -> latency + per-kernel CUDA-event times -------------
     nmsm.set_profiling(True)
     for _ in range(max(args.warmup, 3)):
         step_device()
     assert out.raw == exp_xy and inf.value == exp_inf, "MSM result does not match (sum k_i s_i)*G"
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     acc_ms, tot_ms, kern_ms = [], [], {}
     barrier()
     t0 = time.perf_counter()
@@ -259,9 +256,43 @@ def main():
         for k, v in ms.items():
             kern_ms[k] = kern_ms.get(k, 0.0) + v / args.steps
     barrier()
+    serial_elapsed = time.perf_counter() - t0
+    assert out.raw == exp_xy and inf.value == exp_inf
+    nmsm.set_profiling(False)
+
+    # ---- (2) the timed region: K steps, two MSMs in flight (submit/collect on alternating slots) -----------
+    # Single-GPU only; the multi-GPU step has a collective between partial and fold and stays serial.
+    pipelined = world == 1
+
+    def run_pipelined(steps, submit):
+        outs = [ctypes.create_string_buffer(POINT_BYTES), ctypes.create_string_buffer(POINT_BYTES)]
+        infs = [ctypes.c_int(0), ctypes.c_int(0)]
+        for i in range(steps + 1):
+            if i < steps:
+                submit(i & 1)
+            if i >= 1:
+                s = (i - 1) & 1
+                nmsm._lib.check(lib.nmsm_msm_collect(s, ctypes.cast(outs[s], ctypes.c_void_p), ctypes.byref(infs[s])))
+                assert outs[s].raw == exp_xy and infs[s].value == exp_inf
+
+    def submit_device(slot):
+        nmsm._lib.check(lib.nmsm_msm_submit(BLS_G1, d_pts.data_ptr(), d_sc.data_ptr(), n_local, 1, slot))
+
+    sampler = ClockSampler(local_rank)
+    if pipelined:
+        run_pipelined(3, submit_device)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    if pipelined:
+        run_pipelined(args.steps, submit_device)
+    else:
+        for _ in range(args.steps):
+            step_device()
+    barrier()
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    assert out.raw == exp_xy and inf.value == exp_inf
     if world > 1:
         t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -284,11 +315,19 @@ def main():
             torch.cuda.current_stream().synchronize()
             step_device()
 
+    def submit_host(slot):
+        nmsm._lib.check(lib.nmsm_msm_submit(BLS_G1, h_pts, h_sc, n_local, 0, slot))
+
     step_e2e()
+    if pipelined:
+        run_pipelined(2, submit_host)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
+    if pipelined:
+        run_pipelined(e2e_steps, submit_host)
+    else:
+        for _ in range(e2e_steps):
+            step_e2e()
     barrier()
     e2e_elapsed = time.perf_counter() - t0
     assert out.raw == exp_xy and inf.value == exp_inf
@@ -357,16 +396,21 @@ def main():
     line = {
         "metric": "BLS12-381 G1 MSM points/sec at 2^%d scalars" % args.logn,
         "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": scaling,
+        "ms_per_step": 1e3 * elapsed / args.steps, "latency_ms_single_msm": 1e3 * serial_elapsed / args.steps,
+        "in_flight": 2 if pipelined else 1, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "u32-limb integer (381-bit Fp, Montgomery)", "data": "synthetic",
         "config": {"workload": ("BLS12-381 G1 Pippenger MSM, 2^%d random terms (points k_i*G, uniform scalars) per GPU; "
                                 "at N GPUs one MSM of N*2^%d terms" % (args.logn, args.logn)) if scaling == "weak" else
                                "BLS12-381 G1 Pippenger MSM, 2^%d terms in total split over the GPUs" % args.logn,
                    "terms": n_total, "terms_per_gpu": n_local, "parallelism": "term-sharded x%d, 1 all-gather of raw accumulators" % world,
-                   "l2": "inputs+workspace (>=450 MB/GPU at N=2^20) exceed the 126 MB L2; no flush needed"},
+                   "l2": "inputs+workspace (>=450 MB/GPU at N=2^20) exceed the 126 MB L2; no flush needed",
+                   "pipelining": ("timed steps keep 2 MSMs in flight on 2 CUDA streams (nmsm_msm_submit/collect): the "
+                                  "latency-bound tail of one overlaps the copy + wide kernels of the next; "
+                                  "latency_ms_single_msm and the roofline block come from a serial pass")
+                   if pipelined else "serial steps (collective between partial and fold)"},
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": len(pts_b) + len(sc_b),
                 "d2h_bytes_per_step": POINT_BYTES + 20, "steps": e2e_steps},
-        "gpu_launches": info.launches * args.steps * world,
+        "gpu_launches": info.launches * args.steps * world,  # kernels of the timed K steps (serial pass not counted)
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,

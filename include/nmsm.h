@@ -69,6 +69,13 @@ int nmsm_msm(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, 
 int nmsm_msm_device(int curve, const void* d_pts, const void* d_scalars, uint64_t n, uint8_t* out_xy,
                     int* out_is_inf);
 
+/* Two MSMs in flight: enqueue on slot 0/1 without waiting, collect later.  The latency-bound tail of one MSM
+ * (second-level bucket reduction, Horner doublings, inversion: a handful of SMs) then overlaps the H2D copy and the
+ * wide kernels of the next.  With inputs_on_device = 0 the host buffers (pinned, for true overlap) must stay valid
+ * until nmsm_msm_collect returns.  Errors of the MSM itself (invalid point / scalar) are reported by collect. */
+int nmsm_msm_submit(int curve, const void* pts, const void* scalars, uint64_t n, int inputs_on_device, int slot);
+int nmsm_msm_collect(int slot, uint8_t* out_xy, int* out_is_inf);
+
 /* Multi-GPU building blocks: the un-normalised accumulator of a shard is written to device memory
  * (nmsm_acc_bytes bytes, opaque Montgomery-form words), exchanged by the caller (NCCL all-gather),
  * and folded + normalised by nmsm_fold_partials_device. */

@@ -54,9 +54,10 @@ __global__ void k_modmul_bench(uint32_t* io, int iters) {
 
 template <class P>
 static double bench_modmul(int blocks_per_sm, int threads, int iters, int ilp) {
-  Context& C = g_ctx;
+  Context& X = g_ctx;
+  Slot& C = X.slot[0];
   uint32_t* d = nullptr;
-  int blocks = blocks_per_sm * C.sm_count;
+  int blocks = blocks_per_sm * X.sm_count;
   if (cudaMalloc(&d, (size_t)blocks * threads * 4) != cudaSuccess) return -1;
   cudaEvent_t a, b;
   cudaEventCreate(&a);
@@ -109,9 +110,12 @@ int nmsm_init(int device) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   C.sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking));
-  CK(cudaMallocHost((void**)&C.h_result, 1024));
-  for (auto& ev : C.ev) CK(cudaEventCreate(&ev));
+  for (Slot& S : C.slot) {
+    CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    CK(cudaMallocHost((void**)&S.h_result, 1024));
+    for (auto& ev : S.ev) CK(cudaEventCreate(&ev));
+    CK(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+  }
   C.device = device;
   C.ready = true;
   return NMSM_OK;
@@ -121,13 +125,18 @@ void nmsm_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   Context& C = g_ctx;
   if (!C.ready) return;
-  cudaStreamSynchronize(C.stream);
-  for (Buf* b : {&C.in_pts, &C.in_scalars, &C.aff, &C.counts, &C.offsets, &C.cursor, &C.sorted, &C.buckets,
-                 &C.heads, &C.tails, &C.chunk_out, &C.window_out, &C.tile_sums, &C.blk, &C.tiles, &C.ed_scratch, &C.result, &C.mul_out})
-    b->release();
-  for (auto& ev : C.ev) cudaEventDestroy(ev);
-  cudaFreeHost(C.h_result);
-  cudaStreamDestroy(C.stream);
+  for (Slot& S : C.slot) {
+    cudaStreamSynchronize(S.stream);
+    for (Buf* b : {&S.in_pts, &S.in_scalars, &S.aff, &S.counts, &S.offsets, &S.cursor, &S.sorted, &S.buckets, &S.heads,
+                   &S.tails, &S.chunk_out, &S.window_out, &S.tile_sums, &S.blk, &S.tiles, &S.result, &S.mul_out})
+      b->release();
+    for (auto& ev : S.ev) cudaEventDestroy(ev);
+    cudaEventDestroy(S.done);
+    cudaFreeHost(S.h_result);
+    cudaStreamDestroy(S.stream);
+    S.pend = Pending();
+  }
+  C.ed_scratch.release();
   C.ready = false;
   C.device = -1;
 }
@@ -147,6 +156,7 @@ int nmsm_acc_bytes(int curve) {
 int nmsm_msm(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
   if (!out_xy || !out_is_inf || (n && (!pts || !scalars))) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   return E->msm_host(pts, scalars, n, out_xy, out_is_inf);
@@ -156,6 +166,7 @@ int nmsm_msm_device(int curve, const void* d_pts, const void* d_scalars, uint64_
                     int* out_is_inf) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
   if (!out_xy || !out_is_inf || (n && (!d_pts || !d_scalars))) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   return E->msm_device((const uint32_t*)d_pts, (const uint32_t*)d_scalars, n, nullptr, out_xy, out_is_inf);
@@ -164,6 +175,7 @@ int nmsm_msm_device(int curve, const void* d_pts, const void* d_scalars, uint64_
 int nmsm_msm_partial_device(int curve, const void* d_pts, const void* d_scalars, uint64_t n, void* d_out_acc) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
   if (!d_out_acc || (n && (!d_pts || !d_scalars))) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   return E->msm_device((const uint32_t*)d_pts, (const uint32_t*)d_scalars, n, (uint32_t*)d_out_acc, nullptr, nullptr);
@@ -172,6 +184,7 @@ int nmsm_msm_partial_device(int curve, const void* d_pts, const void* d_scalars,
 int nmsm_fold_partials_device(int curve, const void* d_accs, int count, uint8_t* out_xy, int* out_is_inf) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
   if (!d_accs || count < 0 || !out_xy || !out_is_inf) return fail(NMSM_ERR_ARG, "bad argument");
   ENGINE(curve);
   return E->fold((const uint32_t*)d_accs, count, out_xy, out_is_inf);
@@ -181,6 +194,7 @@ int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64
                    uint8_t* out_xy, uint8_t* out_is_inf) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
   if (n && (!pts || !scalars || !out_xy || !out_is_inf)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   return E->mul_batch(pts, scalars, n, allow_zero, out_xy, out_is_inf);
@@ -196,6 +210,7 @@ struct PointSet {
 int nmsm_points_upload(int curve, const uint8_t* pts, uint64_t n, uint64_t* out_handle) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
   if (!pts || !out_handle) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   uint32_t* d = nullptr;
@@ -217,10 +232,32 @@ int nmsm_points_free(uint64_t handle) {
 int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
   PointSet* ps = (PointSet*)(uintptr_t)handle;
   if (!ps || !out_xy || !out_is_inf || (n && !scalars)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(ps->curve);
   return E->msm_prepared(ps->d_prepared, ps->n, scalars, n, out_xy, out_is_inf);
+}
+
+int nmsm_msm_submit(int curve, const void* pts, const void* scalars, uint64_t n, int inputs_on_device, int slot) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (slot < 0 || slot >= NUM_SLOTS) return fail(NMSM_ERR_ARG, "slot must be 0 or 1");
+  if (n && (!pts || !scalars)) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  g_ctx.cur = slot;
+  return E->submit(pts, scalars, n, inputs_on_device);
+}
+
+int nmsm_msm_collect(int slot, uint8_t* out_xy, int* out_is_inf) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (slot < 0 || slot >= NUM_SLOTS) return fail(NMSM_ERR_ARG, "slot must be 0 or 1");
+  if (!out_xy || !out_is_inf) return fail(NMSM_ERR_ARG, "null pointer");
+  if (!g_ctx.slot[slot].pend.active) return fail(NMSM_ERR_ARG, "nothing submitted on this slot");
+  ENGINE(g_ctx.slot[slot].pend.curve);
+  g_ctx.cur = slot;
+  return E->collect(out_xy, out_is_inf);
 }
 
 int nmsm_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pubkeys, const uint8_t* msgs,
@@ -228,6 +265,7 @@ int nmsm_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pubkeys, const
                               long long* out_bad_index) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
   if (!out_ok || !out_bad_index || (n && (!sigs || !pubkeys || !msg_off || !z16)))
     return fail(NMSM_ERR_ARG, "null pointer");
   if (n && msg_off[n] && !msgs) return fail(NMSM_ERR_ARG, "null pointer");

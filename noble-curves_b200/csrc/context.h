@@ -14,6 +14,12 @@
 #include "../../include/nmsm.h"
 
 namespace nmsm {
+struct MsmPlanLite {  // mirror of MsmPlan (msm_body.cuh) so this header stays free of device code
+  int c, W, B, G, L, K, chunks;
+};
+}  // namespace nmsm
+
+namespace nmsm {
 
 // ---------------------------------------------------------------------------------------------
 // context
@@ -38,15 +44,37 @@ struct Buf {
   }
 };
 
+// Everything one in-flight MSM needs.  Two slots let the caller keep two MSMs in flight (nmsm_msm_submit /
+// nmsm_msm_collect): the latency-bound tail of one (second-level reduction, Horner, inversion — a handful of
+// SMs) overlaps the H2D copy and the wide kernels of the next on the other stream.
+struct Pending {
+  bool active = false;
+  int curve = -1;
+  MsmPlanLite plan = {};
+  uint64_t n = 0;
+  bool partial = false;   // raw accumulator requested instead of an affine result
+  bool empty = false;     // n == 0
+};
+struct Slot {
+  cudaStream_t stream = nullptr;
+  Buf in_pts, in_scalars, aff, counts, offsets, cursor, sorted, buckets, heads, tails, chunk_out, window_out, tile_sums,
+      blk, tiles, result, mul_out;
+  uint32_t* h_result = nullptr;  // pinned staging for (xy | inf | err0 | err1 | entries)
+  cudaEvent_t ev[NMSM_TIMING_SLOTS + 2] = {};
+  cudaEvent_t done = nullptr;
+  float last_ms[NMSM_TIMING_SLOTS] = {};
+  nmsm_plan_info last_info = {};
+  Pending pend;
+};
+static constexpr int NUM_SLOTS = 2;
+
 struct Context {
   bool ready = false;
   int device = -1;
   int sm_count = 148;
-  cudaStream_t stream = nullptr;
-  Buf in_pts, in_scalars, aff, counts, offsets, cursor, sorted, buckets, heads, tails, chunk_out, window_out, tile_sums, blk, tiles, ed_scratch,
-      result, mul_out;
-  uint32_t* h_result = nullptr;  // pinned staging for (xy | inf | err0 | err1)
-  cudaEvent_t ev[NMSM_TIMING_SLOTS + 2] = {};
+  Slot slot[NUM_SLOTS];
+  int cur = 0;  // slot used by the call in progress (set by the C-ABI wrapper under the mutex)
+  Buf ed_scratch;
   bool profiling = false;
   int forced_c = 0;
   float last_ms[NMSM_TIMING_SLOTS] = {};
@@ -91,6 +119,9 @@ struct EngineVTable {
   int (*prepare_points)(const uint8_t* pts, uint64_t n, uint32_t** out_dev);
   int (*msm_prepared)(const uint32_t* d_prepared, uint64_t n_points, const uint8_t* scalars, uint64_t n,
                       uint8_t* out_xy, int* out_is_inf);
+  // asynchronous halves on the slot g_ctx.cur: enqueue (optionally H2D from host pointers) / wait + read back
+  int (*submit)(const void* pts, const void* scalars, uint64_t n, int inputs_on_device);
+  int (*collect)(uint8_t* out_xy, int* out_is_inf);
 };
 int ed25519_verify_batch_impl(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* msg_off,
                               uint64_t n, const uint8_t* z16, int* out_ok, long long* out_bad_index);

@@ -13,7 +13,7 @@ inline unsigned int cdiv(uint64_t a, unsigned int b) { return (unsigned int)((a 
 
 #define EV(slot)                                                         \
   do {                                                                   \
-    if (C.profiling) cudaEventRecord(C.ev[slot], C.stream);              \
+    if (g_ctx.profiling) cudaEventRecord(C.ev[slot], C.stream);              \
   } while (0)
 
 template <class Cv>
@@ -26,27 +26,37 @@ struct Engine {
 // handle, nmsm_points_upload); k_prepare is skipped.
 static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
                    uint8_t* out_xy, int* out_is_inf, const uint32_t* d_prepared = nullptr) {
-  Context& C = g_ctx;
+  if (int r = submit_msm(d_pts, d_scalars, n, d_out_acc, d_prepared)) return r;
+  return collect_msm(out_xy, out_is_inf);
+}
+
+// Enqueue the whole pipeline (and the small result D2H) on the current slot's stream; no host sync.
+static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
+                      const uint32_t* d_prepared) {
+  Slot& C = g_ctx.slot[g_ctx.cur];
+  if (C.pend.active) return fail(NMSM_ERR_ARG, "slot busy: collect the previous MSM first");
   if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
   const int RES_WORDS = G::IN_WORDS + 4;  // xy | inf | err_pt | err_sc | pad
   CK(C.result.ensure(RES_WORDS * 4));
   uint32_t* d_res = (uint32_t*)C.result.p;
   unsigned int* d_err = (unsigned int*)(d_res + G::IN_WORDS + 1);
 
+  C.pend = Pending();
+  C.pend.curve = Cv::ID;
+  C.pend.n = n;
+  C.pend.partial = d_out_acc != nullptr;
   if (n == 0) {  // curve.ts:878 — empty input returns the identity
     if (d_out_acc) {
       typename G::Acc id = G::identity();
       CK(cudaMemcpyAsync(d_out_acc, &id, sizeof(id), cudaMemcpyHostToDevice, C.stream));
       CK(cudaStreamSynchronize(C.stream));
-      return NMSM_OK;
     }
-    memset(out_xy, 0, G::IN_WORDS * 4);
-    if (G::IS_EDWARDS) out_xy[G::COORD_WORDS * 4] = 1;  // (0, 1)
-    *out_is_inf = 1;
+    C.pend.empty = true;
+    C.pend.active = true;
     return NMSM_OK;
   }
 
-  MsmPlan plan = make_plan<Cv>(n, C.forced_c, C.sm_count);
+  MsmPlan plan = make_plan<Cv>(n, g_ctx.forced_c, g_ctx.sm_count);
   const uint64_t max_entries = n * (uint64_t)plan.W * (Cv::GLV ? 2 : 1);
   if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
   const uint64_t max_threads = (max_entries + plan.L - 1) / plan.L;
@@ -133,7 +143,31 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   // one small D2H: result + error slots (+ entry count for accounting)
   CK(cudaMemcpyAsync(C.h_result, d_res, RES_WORDS * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(C.h_result + RES_WORDS, offsets + plan.G, 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(cudaEventRecord(C.done, st));
+  C.pend.plan = MsmPlanLite{plan.c, plan.W, plan.B, plan.G, plan.L, plan.K, plan.chunks};
+  C.pend.active = true;
+  return NMSM_OK;
+}
+
+// Wait for the slot's MSM, map device-side validation errors, hand out the result and the timings.
+static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
+  Slot& C = g_ctx.slot[g_ctx.cur];
+  if (!C.pend.active) return fail(NMSM_ERR_ARG, "nothing submitted on this slot");
+  C.pend.active = false;
+  if (C.pend.empty) {
+    if (!C.pend.partial) {
+      memset(out_xy, 0, G::IN_WORDS * 4);
+      if (G::IS_EDWARDS) out_xy[G::COORD_WORDS * 4] = 1;  // (0, 1)
+      *out_is_inf = 1;
+    }
+    return NMSM_OK;
+  }
+  const int RES_WORDS = G::IN_WORDS + 4;
+  CK(cudaEventSynchronize(C.done));
+  MsmPlan plan;
+  plan.c = C.pend.plan.c; plan.W = C.pend.plan.W; plan.B = C.pend.plan.B; plan.G = C.pend.plan.G;
+  plan.L = C.pend.plan.L; plan.K = C.pend.plan.K; plan.chunks = C.pend.plan.chunks;
+  const bool partial = C.pend.partial;
 
   const uint32_t err_pt = C.h_result[G::IN_WORDS + 1], err_sc = C.h_result[G::IN_WORDS + 2];
   // the reference validates all points before any scalar (curve.ts:871-872)
@@ -149,21 +183,36 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   C.last_info.sorted_entries = entries;
   C.last_info.modmul_equiv = plan_modmuls<Cv>(plan, entries);
   C.last_info.launches = 12;  // prepare, count, scan x2, scatter, accumulate, stitch x2, reduce1, reduce2, reduce3, final
-  if (C.profiling) {
+  if (g_ctx.profiling) {
     for (int k = 0; k < 9; k++) cudaEventElapsedTime(&C.last_ms[k], C.ev[k], C.ev[k + 1]);
     cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev[0], C.ev[9]);
   }
-  if (!d_out_acc) {
+  memcpy(g_ctx.last_ms, C.last_ms, sizeof(C.last_ms));
+  g_ctx.last_info = C.last_info;
+  if (!partial) {
     memcpy(out_xy, C.h_result, G::IN_WORDS * 4);
     *out_is_inf = (int)C.h_result[G::IN_WORDS];
   }
   return NMSM_OK;
 }
 
+// C-ABI asynchronous halves (nmsm_msm_submit / nmsm_msm_collect)
+static int submit_any(const void* pts, const void* scalars, uint64_t n, int inputs_on_device) {
+  Slot& C = g_ctx.slot[g_ctx.cur];
+  if (C.pend.active) return fail(NMSM_ERR_ARG, "slot busy: collect the previous MSM first");
+  if (inputs_on_device || n == 0)
+    return submit_msm((const uint32_t*)pts, (const uint32_t*)scalars, n, nullptr, nullptr);
+  CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
+  CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
+  CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
+  CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
+  return submit_msm((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p, n, nullptr, nullptr);
+}
+
 // Upload + validate + prepare a point set once (fixed-base reuse; the device-resident analogue of the
 // reference's captured tables in interleavedMSMUnsafe, curve.ts:937-959).  Returns a device buffer.
 static int prepare_points(const uint8_t* pts, uint64_t n, uint32_t** out_dev) {
-  Context& C = g_ctx;
+  Slot& C = g_ctx.slot[g_ctx.cur];
   if (n == 0 || n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be in [1, 2^31)");
   uint32_t* d_aff = nullptr;
   CK(cudaMalloc((void**)&d_aff, n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
@@ -191,7 +240,7 @@ static int prepare_points(const uint8_t* pts, uint64_t n, uint32_t** out_dev) {
 // scalars use the first n_scalars points, like interleavedMSMUnsafe's trailing zeros).
 static int run_msm_prepared(const uint32_t* d_prepared, uint64_t n_points, const uint8_t* scalars, uint64_t n,
                             uint8_t* out_xy, int* out_is_inf) {
-  Context& C = g_ctx;
+  Slot& C = g_ctx.slot[g_ctx.cur];
   if (n > n_points) return fail(NMSM_ERR_LENGTH, "array of scalars must not be larger than array of points");
   if (n) {
     CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
@@ -208,7 +257,7 @@ static int run_msm_dev(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_
 }
 
 static int run_msm_host(const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf) {
-  Context& C = g_ctx;
+  Slot& C = g_ctx.slot[g_ctx.cur];
   if (n) {
     CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
     CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
@@ -219,7 +268,7 @@ static int run_msm_host(const uint8_t* pts, const uint8_t* scalars, uint64_t n, 
 }
 
 static int run_fold(const uint32_t* d_accs, int count, uint8_t* out_xy, int* out_is_inf) {
-  Context& C = g_ctx;
+  Slot& C = g_ctx.slot[g_ctx.cur];
   const int RES_WORDS = G::IN_WORDS + 4;
   CK(C.result.ensure(RES_WORDS * 4));
   uint32_t* d_res = (uint32_t*)C.result.p;
@@ -234,7 +283,7 @@ static int run_fold(const uint32_t* d_accs, int count, uint8_t* out_xy, int* out
 
 static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
                          uint8_t* out_is_inf) {
-  Context& C = g_ctx;
+  Slot& C = g_ctx.slot[g_ctx.cur];
   if (n == 0) return NMSM_OK;
   if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
   CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
@@ -271,7 +320,8 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
     static const EngineVTable vt = {CURVE::G::IN_WORDS * 4,         CURVE::G::ACC_WORDS * 4,   \
                                     &Engine<CURVE>::run_msm_host,   &Engine<CURVE>::run_msm_dev,   \
                                     &Engine<CURVE>::run_fold,       &Engine<CURVE>::run_mul_batch,  \
-                                    &Engine<CURVE>::prepare_points, &Engine<CURVE>::run_msm_prepared}; \
+                                    &Engine<CURVE>::prepare_points, &Engine<CURVE>::run_msm_prepared, \
+                                    &Engine<CURVE>::submit_any,     &Engine<CURVE>::collect_msm}; \
     return &vt;                                                                                \
   }
 

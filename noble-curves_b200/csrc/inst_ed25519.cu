@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(32) k_ed_check(const uint32_t* __restrict__ ac
 int ed25519_verify_batch_impl(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* msg_off,
                               uint64_t n, const uint8_t* z16, int* out_ok, long long* out_bad_index) {
   using G = CurveEd25519::G;
-  Context& C = g_ctx;
+  Context& X = g_ctx;
+  Slot& C = X.slot[0];
   *out_ok = 0;
   *out_bad_index = -1;
   if (n == 0) {
@@ -80,8 +81,8 @@ int ed25519_verify_batch_impl(const uint8_t* sigs, const uint8_t* pks, const uin
   const uint64_t o_sig = 0, o_pk = o_sig + al(64 * n), o_msg = o_pk + al(32 * n), o_off = o_msg + al(msg_bytes + 16),
                  o_z = o_off + al(8 * (n + 1)), o_pts = o_z + al(16 * n), o_sc = o_pts + al(64 * terms),
                  o_zs = o_sc + al(32 * terms), o_misc = o_zs + al(32 * n), total = o_misc + 1024;
-  CK(C.ed_scratch.ensure(total));
-  uint8_t* base = (uint8_t*)C.ed_scratch.p;
+  CK(X.ed_scratch.ensure(total));
+  uint8_t* base = (uint8_t*)X.ed_scratch.p;
   cudaStream_t st = C.stream;
   CK(cudaMemcpyAsync(base + o_sig, sigs, 64 * n, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(base + o_pk, pks, 32 * n, cudaMemcpyHostToDevice, st));

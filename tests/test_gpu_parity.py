@@ -435,3 +435,57 @@ def test_aggregate_points_and_small_helpers(nmsm, name):
     assert cpts[0].precompute(6) is cpts[0]
     if name == "ed25519":
         assert cpts[0].clearCofactor().equals(cpts[0].multiplyUnsafe(8)) and not cpts[0].isSmallOrder()
+
+
+def test_two_msms_in_flight(nmsm):
+    """nmsm_msm_submit / nmsm_msm_collect: two slots, different curves and sizes interleaved, errors on collect."""
+    import ctypes
+
+    from nmsm import _lib
+
+    lib = _lib.load()
+    cases = []
+    for name, n, seed in (("bls12_381_G1", 700, 1), ("ed25519", 333, 2), ("bls12_381_G1", 64, 3), ("secp256k1", 1000, 4)):
+        P, pts, scalars, total = H.soak_inputs(name, n, seed_offset=seed)
+        cases.append((name, n, H.pack_points(name, pts), H.pack_scalars(scalars), H.expected_tuple(name, H.expected_from_total(P, total))))
+    keep = {}
+
+    def submit(i, slot):
+        name, n, pb, sb, _ = cases[i]
+        keep[slot] = (ctypes.create_string_buffer(pb, len(pb)), ctypes.create_string_buffer(sb, len(sb)))
+        _lib.check(lib.nmsm_msm_submit(H.CURVE_IDS[name], ctypes.cast(keep[slot][0], ctypes.c_void_p),
+                                       ctypes.cast(keep[slot][1], ctypes.c_void_p), n, 0, slot))
+
+    def collect(i, slot):
+        name = cases[i][0]
+        out = ctypes.create_string_buffer(lib.nmsm_point_bytes(H.CURVE_IDS[name]))
+        inf = ctypes.c_int(0)
+        _lib.check(lib.nmsm_msm_collect(slot, ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf)))
+        x, y = H.unpack_point(name, out.raw)
+        assert (x, y, inf.value) == cases[i][4], (i, name)
+
+    submit(0, 0)
+    submit(1, 1)
+    collect(0, 0)
+    submit(2, 0)
+    collect(1, 1)
+    submit(3, 1)
+    collect(2, 0)
+    collect(3, 1)
+    # busy slot / empty slot / invalid scalar reported by collect
+    submit(0, 0)
+    with pytest.raises(_lib.NmsmError):
+        submit(1, 0)
+    collect(0, 0)
+    with pytest.raises(_lib.NmsmError):
+        collect(0, 0)
+    name, n, pb, sb, _ = cases[2]
+    bad = bytearray(sb)
+    bad[5 * 32:6 * 32] = R.CURVES[name].Fn.ORDER.to_bytes(32, "little")
+    keep[0] = (ctypes.create_string_buffer(pb, len(pb)), ctypes.create_string_buffer(bytes(bad), len(bad)))
+    _lib.check(lib.nmsm_msm_submit(H.CURVE_IDS[name], ctypes.cast(keep[0][0], ctypes.c_void_p),
+                                   ctypes.cast(keep[0][1], ctypes.c_void_p), n, 0, 0))
+    out = ctypes.create_string_buffer(96)
+    inf = ctypes.c_int(0)
+    with pytest.raises(_lib.NmsmError, match="invalid scalar at index 5"):
+        _lib.check(lib.nmsm_msm_collect(0, ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf)))
