@@ -37,27 +37,50 @@ struct MsmPlan {
 };
 
 // ---------------------------------------------------------------------------------------------
-// plan selection: minimise  W * (n * MADD + 2 * B * ADD * overhead)  over the window size c
+// plan selection: pick the window size c that minimises a TIME model of the pipeline, with constants
+// measured on B200 for BLS12-381 G1 (profiles/) and scaled by field size / formula cost for the others:
+//   accumulate   entries * 0.352 ns            (k_accumulate at ~88 % of the multiply-pipe bound)
+//   reduce1      max( buckets * (1 + parts) adds at 0.93 ns each  [throughput],
+//                     K * (1 + parts_top) dependent adds at ~30 us each  [one thread's chain] )
+//                where parts = accumulate segments a bucket straddles; the TOP window matters most: if it
+//                holds only a few scalar bits its buckets are huge and every reduce1 thread stitches
+//                parts_top partials per bucket
+//   reduce2/3    ~0.75 ms latency,  final  ~6.2 us per Horner doubling
 // ---------------------------------------------------------------------------------------------
 template <class Cv>
 inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
   using G = typename Cv::G;
+  using F = typename G::Field;
   // with GLV every scalar becomes two signed halves of at most 127 bits, each attached to its own point
   const int bits = Cv::GLV ? 127 : Cv::Fn::BITS;
   const double terms = (double)n * (Cv::GLV ? 2 : 1);
+  const double limb_ratio = (double)(F::LIMBS / F::BASE_MULS == 12 ? 1.0 : (8.0 * 8.0) / (12.0 * 12.0));
+  const double fscale = limb_ratio * F::BASE_MULS;                       // field multiplication cost vs 381-bit Fp
+  const double t_madd = 0.352e-6 * fscale * G::COST_MADD / 10.0;         // ms
+  const double t_add_tp = 0.93e-6 * fscale * G::COST_ADD / 14.0;         // ms, throughput
+  const double t_add_lat = 0.030 * fscale * G::COST_ADD / 14.0;          // ms, dependent chain (2 warps / sub-partition)
+  const double t_dbl_par = 0.0062 * fscale;                              // ms per Horner doubling (lane-parallel)
+  const int K = 8;
+  auto seg_len = [&](double entries) {
+    int L = (int)ceil(entries / ((double)sm_count * 1024.0));
+    return L < 4 ? 4 : (L > 32 ? 32 : L);
+  };
   int best_c = 2;
   double best = 1e300;
   for (int c = 2; c <= MAX_WINDOW_BITS; c++) {
-    int W = (bits + 1 + c - 1) / c;
-    double B = (double)(1u << (c - 1));
-    // reduce runs at lower occupancy and pays the chunk-offset multiplications: weight it 1.6x
-    double cost = (double)W * (terms * G::COST_MADD + 2.0 * B * G::COST_ADD * 1.6) + 9.0 * bits;
-    // A top window that holds only a few scalar bits funnels ~terms/2^top_bits entries into each of its
-    // buckets; buckets far larger than an accumulate segment are stitched serially in k_reduce1, so
-    // such plans are penalised by the length of that serial chain (one complete addition per segment).
-    int top_bits = bits + 1 - (W - 1) * c;
-    double per_bucket = terms / (double)(1u << (top_bits > 1 ? top_bits - 1 : 0));
-    if (top_bits < c && per_bucket > 64.0 * 32.0) cost += (per_bucket / 32.0) * G::COST_ADD * 2000.0;
+    const int W = (bits + 1 + c - 1) / c;
+    const double B = (double)(1u << (c - 1));
+    const double entries = terms * W;
+    const int L = seg_len(entries);
+    const double parts_avg = 1.0 + (terms / B) / L;
+    const int top_bits = bits + 1 - (W - 1) * c;                          // scalar bits left for the top window
+    const double per_bucket_top = terms / (double)(1u << (top_bits > 1 ? top_bits - 1 : 0));
+    double parts_top = 1.0 + per_bucket_top / L;
+    if (parts_top > 100.0) parts_top = 100.0 + per_bucket_top / L / 32.0;  // tile sums take over (k_stitch_tiles)
+    const double kk = B < K ? B : K;
+    const double t_acc = entries * t_madd;
+    const double t_r1a = W * B * (1.0 + parts_avg) * t_add_tp, t_r1b = kk * (1.0 + parts_top) * t_add_lat;
+    const double cost = t_acc + (t_r1a > t_r1b ? t_r1a : t_r1b) + 0.75 * fscale + (double)(W - 1) * c * t_dbl_par;
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -69,19 +92,14 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
   p.W = (bits + 1 + c - 1) / c;
   p.B = 1 << (c - 1);
   p.G = p.W * p.B;
-  double entries = terms * p.W;
-  double target_threads = (double)sm_count * 1024.0;
-  int L = (int)ceil(entries / target_threads);
-  if (L < 4) L = 4;
-  if (L > 32) L = 32;
-  p.L = L;
+  p.L = seg_len(terms * p.W);
   // reduce chunk: 8 buckets per thread keeps >= 1 warp per SM sub-partition busy down to ~150k buckets
-  int K = 8;
+  int Kc = K;
 #if !defined(__CUDA_ARCH__)
   if (const char* e = getenv("NMSM_L")) { int v = atoi(e); if (v >= 1 && v <= 1024) p.L = v; }      // tuning experiments
-  if (const char* e = getenv("NMSM_K")) { int v = atoi(e); if (v >= 1 && (v & (v - 1)) == 0) K = v; }
+  if (const char* e = getenv("NMSM_K")) { int v = atoi(e); if (v >= 1 && (v & (v - 1)) == 0) Kc = v; }
 #endif
-  p.K = p.B < K ? p.B : K;
+  p.K = p.B < Kc ? p.B : Kc;
   p.chunks = p.B / p.K;
   return p;
 }

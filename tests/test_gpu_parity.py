@@ -489,3 +489,24 @@ def test_two_msms_in_flight(nmsm):
     inf = ctypes.c_int(0)
     with pytest.raises(_lib.NmsmError, match="invalid scalar at index 5"):
         _lib.check(lib.nmsm_msm_collect(0, ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf)))
+
+
+@pytest.mark.parametrize("name", ["bls12_381_G1", "bn254_G1"])
+def test_msm_giant_buckets_large(nmsm, name):
+    """All scalars equal at N = 2^17 (benchmark/msm_timings.ts:45-63 shape): every window has ONE bucket holding
+    every term, i.e. thousands of accumulate segments per bucket -> both tile-sum levels of the stitching."""
+    n = 1 << 17
+    P = R.CURVES[name]
+    order = P.Fn.ORDER
+    rnd = random.Random(77)
+    ks = [rnd.randrange(1, order) for _ in range(n)]
+    cid = H.CURVE_IDS[name]
+    pts_b, infs = nmsm.mul_batch_packed(cid, H.point_bytes(name, P.BASE) * n, H.pack_scalars(ks), n, False)
+    for s in (0x1D3F5A7C9B2E4F60718293A4B5C6D7E8F9 % order, 1, order - 1):
+        total = (sum(ks) * s) % order
+        exp = H.expected_tuple(name, H.expected_from_total(P, total))
+        assert gpu_msm(nmsm, name, pts_b, H.pack_scalars([s] * n), n) == exp, (name, hex(s))
+    # half of the scalars equal, the rest random: a giant bucket next to ordinary ones
+    sc = [0xABCDEF0123456789 if i % 2 else rnd.randrange(order) for i in range(n)]
+    total = sum(k * s for k, s in zip(ks, sc)) % order
+    assert gpu_msm(nmsm, name, pts_b, H.pack_scalars(sc), n) == H.expected_tuple(name, H.expected_from_total(P, total))
