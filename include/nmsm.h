@@ -107,6 +107,13 @@ int nmsm_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pubkeys, const
                               const uint64_t* msg_off, uint64_t n, const uint8_t* z16, int* out_ok,
                               long long* out_bad_index);
 
+/* Batched wire-format decoding on the GPU (next-row f2): encodings -> canonical affine points in the packing
+ * above, ready for nmsm_msm.  secp256k1: 33-byte SEC1 compressed (weierstrass.ts:565-588); BLS12-381 G1: 48-byte
+ * Zcash-flag compressed (bls12-381.ts:377-468); ed25519: 32-byte RFC 8032 with ZIP-215 acceptance (edwards.ts:405-436).
+ * out_status[i]: 0 = invalid encoding, 1 = point, 2 = point at infinity.  Mirrors the reference's decode step only
+ * (no subgroup check).  Other curves: NMSM_ERR_ARG. */
+int nmsm_points_decode(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_xy, uint8_t* out_status);
+
 /* Tuning / introspection ------------------------------------------------------------------- */
 /* Force the window size c (0 = automatic cost model).  Returns the previous value. */
 int nmsm_set_window_bits(int c);

@@ -272,6 +272,14 @@ int nmsm_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pubkeys, const
   return ed25519_verify_batch_impl(sigs, pubkeys, msgs, msg_off, n, z16, out_ok, out_bad_index);
 }
 
+int nmsm_points_decode(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_xy, uint8_t* out_status) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
+  if (n && (!enc || !out_xy || !out_status)) return fail(NMSM_ERR_ARG, "null pointer");
+  return decode_points_impl(curve, enc, n, out_xy, out_status);
+}
+
 int nmsm_set_window_bits(int c) {
   int prev = g_ctx.forced_c;
   g_ctx.forced_c = (c >= 1 && c <= 16) ? c : 0;

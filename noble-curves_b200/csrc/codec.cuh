@@ -1,0 +1,118 @@
+// Wire-format decoding on the GPU: bytes -> canonical affine (x, y) in the C-ABI packing,
+// so callers can hand the encodings the reference's `fromBytes` consumes instead of bigints.
+//   secp256k1  SEC1 compressed, 33 B      /root/reference/src/abstract/weierstrass.ts:565-588 (pointFromBytes)
+//   BLS12-381 G1  Zcash-flag compressed, 48 B   src/bls12-381.ts:377-468 (coder.decode, parseMask/validateMask)
+//   ed25519    RFC 8032 / ZIP-215, 32 B   src/abstract/edwards.ts:405-436  (ed25519_verify.cuh ed_decompress)
+// Only the decode step is mirrored (coordinates from bytes); the reference's `Point.fromBytes` additionally runs
+// assertValidity (subgroup membership for cofactor > 1), which is a scalar multiplication of its own.
+#pragma once
+#include "ed25519_verify.cuh"
+
+namespace nmsm {
+
+// a^((p+1)/4) for p = 3 (mod 4); ok iff the result squares back to a  (weierstrass.ts:579 "y = y2 ^ (p+1)/4")
+template <class P>
+NMSM_HD Fp<P> fp_sqrt_3mod4(const Fp<P>& a, bool& ok) {
+  constexpr int N = P::N;
+  uint32_t e[N];  // (p + 1) >> 2
+  {
+    uint32_t t[N];
+    t[0] = add_cc(P::P(0), 1u);
+    for (int k = 1; k < N; k++) t[k] = addc_cc(P::P(k), 0u);
+    uint32_t top = addc(0, 0);  // only non-zero for p = 2^(32N) - 1, which no supported prime is
+    for (int k = 0; k < N - 1; k++) e[k] = (t[k] >> 2) | (t[k + 1] << 30);
+    e[N - 1] = (t[N - 1] >> 2) | (top << 30);
+  }
+  Fp<P> r = Fp<P>::one();
+  bool started = false;
+  for (int i = N - 1; i >= 0; i--)
+    for (int bit = 31; bit >= 0; bit--) {
+      if (started) r = sqr(r);
+      if ((e[i] >> bit) & 1) {
+        r = r * a;
+        started = true;
+      }
+    }
+  ok = sqr(r) == a;
+  return r;
+}
+
+template <int NBYTES>
+NMSM_HD void words_from_be_bytes(uint32_t* w, const uint8_t* b) {  // big-endian integer -> little-endian words
+  for (int k = 0; k < NBYTES / 4; k++) {
+    const uint8_t* q = b + NBYTES - 4 * (k + 1);
+    w[k] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+  }
+}
+
+// status: 0 = invalid encoding, 1 = affine point written, 2 = point at infinity ((0,0) written)
+NMSM_HD int sec1_decode_secp256k1(const uint8_t* enc, uint32_t* out_xy) {
+  using F = Fp<FpSecp256k1>;
+  const uint8_t head = enc[0];
+  if (head != 0x02 && head != 0x03) return 0;
+  uint32_t xw[8];
+  words_from_be_bytes<32>(xw, enc + 1);
+  if (!F::canonical_in_range(xw)) return 0;  // Fp.fromBytes rejects x >= p
+  const F x = F::from_canonical(xw);
+  F b;
+  for (int k = 0; k < 8; k++) b.v[k] = Secp256k1Consts::B_MONT(k);
+  bool ok;
+  F y = fp_sqrt_3mod4<FpSecp256k1>(sqr(x) * x + b, ok);
+  if (!ok) return 0;
+  uint32_t yw[8];
+  y.to_canonical(yw);
+  if (((yw[0] & 1u) != 0) != ((head & 1u) != 0)) {
+    y = -y;
+    y.to_canonical(yw);
+  }
+  for (int k = 0; k < 8; k++) {
+    out_xy[k] = xw[k];
+    out_xy[8 + k] = yw[k];
+  }
+  return 1;
+}
+
+NMSM_HD int zcash_decode_bls12_381_g1(const uint8_t* enc, uint32_t* out_xy) {
+  using F = Fp<FpBls381>;
+  const bool compressed = (enc[0] >> 7) & 1, infinity = (enc[0] >> 6) & 1, sort = (enc[0] >> 5) & 1;
+  if (!compressed) return 0;                    // this entry point takes the 48-byte compressed form only
+  if (compressed && infinity && sort) return 0;  // validateMask: 0xe0
+  uint8_t v[48];
+  for (int k = 0; k < 48; k++) v[k] = enc[k];
+  v[0] &= 0x1f;
+  if (infinity) {
+    for (int k = 0; k < 48; k++)
+      if (v[k]) return 0;  // non-canonical zero
+    for (int k = 0; k < 24; k++) out_xy[k] = 0;
+    return 2;
+  }
+  uint32_t xw[12];
+  words_from_be_bytes<48>(xw, v);
+  if (!F::canonical_in_range(xw)) return 0;
+  const F x = F::from_canonical(xw);
+  F b;
+  for (int k = 0; k < 12; k++) b.v[k] = Bls381G1Consts::B_MONT(k);
+  bool ok;
+  F y = fp_sqrt_3mod4<FpBls381>(sqr(x) * x + b, ok);
+  if (!ok) return 0;
+  // sortBit: y is the lexicographically larger root iff 2*y >= p  (bls12-381.ts:347-352)
+  uint32_t yw[12];
+  y.to_canonical(yw);
+  uint32_t d2[12];
+  for (int k = 11; k >= 1; k--) d2[k] = (yw[k] << 1) | (yw[k - 1] >> 31);
+  d2[0] = yw[0] << 1;  // 2y < 2^382: no overflow
+  const bool larger = !F::canonical_in_range(d2);
+  if (larger != sort) {
+    y = -y;
+    y.to_canonical(yw);
+  }
+  for (int k = 0; k < 12; k++) {
+    out_xy[k] = xw[k];
+    out_xy[12 + k] = yw[k];
+  }
+  return 1;
+}
+
+NMSM_HD int ed25519_decode(const uint8_t* enc, uint32_t* out_xy) { return ed_decompress(enc, out_xy) ? 1 : 0; }
+
+}  // namespace nmsm

@@ -125,6 +125,7 @@ struct EngineVTable {
 };
 int ed25519_verify_batch_impl(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* msg_off,
                               uint64_t n, const uint8_t* z16, int* out_ok, long long* out_bad_index);
+int decode_points_impl(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_xy, uint8_t* out_status);
 const EngineVTable* engine_secp256k1();
 const EngineVTable* engine_ed25519();
 const EngineVTable* engine_bn254g1();

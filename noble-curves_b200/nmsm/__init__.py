@@ -543,6 +543,23 @@ def ed25519_verify_batch(signatures, messages, public_keys, z: bytes | None = No
     return bool(ok.value), int(bad.value)
 
 
+def points_decode(curve_id: int, encodings: bytes, n: int):
+    """Batched `fromBytes` decode step on the GPU (secp256k1 SEC1-33, BLS12-381 G1 Zcash-48, ed25519-32):
+    returns (packed points, status bytes: 0 invalid / 1 point / 2 infinity)."""
+    _lib.ensure_init()
+    lib = _lib.load()
+    pb = lib.nmsm_point_bytes(curve_id)
+    out = ctypes.create_string_buffer(max(1, n * pb))
+    st = ctypes.create_string_buffer(max(1, n))
+    rc = lib.nmsm_points_decode(curve_id, ctypes.cast(ctypes.c_char_p(bytes(encodings)), ctypes.c_void_p), n,
+                                ctypes.cast(out, ctypes.c_void_p), ctypes.cast(st, ctypes.c_void_p))
+    try:
+        _lib.check(rc)
+    except NmsmError as e:
+        _raise_mapped(e)
+    return out.raw[: n * pb], st.raw[:n]
+
+
 def last_timing():
     """(dict of per-kernel ms, PlanInfo) of the last MSM call when profiling is enabled."""
     lib = _lib.load()

@@ -1217,3 +1217,63 @@ def ed25519_verify(sig: bytes, msg: bytes, public_key: bytes, zip215: bool = Tru
     k = int.from_bytes(hashlib.sha512(r + public_key + msg).digest(), "little") % L
     RkA = Rp.add(A.multiplyUnsafe(k))
     return RkA.subtract(SB).clearCofactor().is0()
+
+
+# --------------------------------------------------------------------------------------
+# Point codecs (next-row f2): the decode step of `fromBytes`
+# --------------------------------------------------------------------------------------
+def secp256k1_decode_sec1(b: bytes):
+    """src/abstract/weierstrass.ts:565-597 `pointFromBytes` for secp256k1 -> (x, y); raises ValueError."""
+    P = SECP256K1_CURVE["p"]
+    head, tail = b[0], b[1:]
+    if len(b) == 33 and head in (2, 3):
+        x = int.from_bytes(tail, "big")
+        if not (0 <= x < P):
+            raise ValueError("bad point: is not on curve, wrong x")
+        y2 = (x * x * x + 7) % P
+        y = pow(y2, (P + 1) // 4, P)
+        if (y * y) % P != y2:
+            raise ValueError("bad point: is not on curve, sqrt error")
+        if ((head & 1) == 1) != ((y & 1) == 1):
+            y = (-y) % P
+        return x, y
+    if len(b) == 65 and head == 4:
+        x, y = int.from_bytes(tail[:32], "big"), int.from_bytes(tail[32:], "big")
+        if not (0 <= x < P and 0 <= y < P) or (y * y - x * x * x - 7) % P:
+            raise ValueError("bad point: is not on curve")
+        return x, y
+    raise ValueError("bad point: got length %d" % len(b))
+
+
+def bls12_381_g1_decode(b: bytes):
+    """src/bls12-381.ts:377-468 `coder('G1').decode` (allowUncompressed) -> (x, y) with (0, 0) for infinity."""
+    P = BLS12_381_G1_CURVE["p"]
+    mask = b[0] & 0xE0
+    compressed, infinity, sort = bool(mask >> 7 & 1), bool(mask >> 6 & 1), bool(mask >> 5 & 1)
+    if (not compressed and not infinity and sort) or (not compressed and infinity and sort) or (compressed and infinity and sort):
+        raise ValueError("invalid encoding flag")
+    v = bytes([b[0] & 0x1F]) + b[1:]
+    ln = 48 if compressed else 96
+    if len(v) != ln:
+        raise ValueError("invalid G1 point: expected %d bytes" % ln)
+    if infinity:
+        if any(v):
+            raise ValueError("invalid G1 point: non-canonical zero")
+        return 0, 0
+    x = int.from_bytes(v[:48], "big")
+    if not (0 <= x < P):
+        raise ValueError("invalid field element")
+    if compressed:
+        y2 = (pow(x, 3, P) + 4) % P
+        y = pow(y2, (P + 1) // 4, P)
+        if (y * y) % P != y2:
+            raise ValueError("invalid G1 point: compressed")
+        if bool((y * 2) // P) != sort:
+            y = (-y) % P
+    else:
+        y = int.from_bytes(v[48:], "big")
+        if not (0 <= y < P):
+            raise ValueError("invalid field element")
+        if x == 0 and y == 0:
+            raise ValueError("invalid G1 point: uncompressed")
+    return x, y

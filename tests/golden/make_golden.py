@@ -44,6 +44,8 @@ def secp256k1():
         "pointFromScalar": [[v["d"], v["expected"]] for v in pts["pointFromScalar"]],
         "pointAdd": [[v["P"], v["Q"], v["expected"]] for v in pts["pointAdd"]],
         "endomorphism": json.load(open(f"{REF}/secp256k1/endomorphism.json")),
+        # test/secp256k1.test.ts:96-104 isPoint: 33-byte SEC1 encodings only (the decoder under test)
+        "isPoint33": [[v["P"], v["expected"]] for v in pts["isPoint"] if len(v["P"]) == 66],
     }
     dump("secp256k1.json", out)
 
@@ -54,6 +56,7 @@ def bls():
         # index i holds i*G (i = 0 is the point at infinity, Zcash flag encoding)
         "G1_Uncompressed": d["G1_Uncompressed"][:1000],
         "G2_Uncompressed": d["G2_Uncompressed"][:256],
+        "G1_Compressed": d["G1_Compressed"][:1000],  # test/bls12-381.test.ts:1463-1500 (Zcash-flag codec)
     }
     dump("bls12_381.json", out)
 

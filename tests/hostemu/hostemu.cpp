@@ -12,6 +12,7 @@
 
 #include "msm_body.cuh"
 #include "ed25519_verify.cuh"
+#include "codec.cuh"
 
 using namespace nmsm;
 
@@ -163,6 +164,12 @@ int emu_sha512_rAM(const uint8_t* r, const uint8_t* a, const uint8_t* msg, uint6
 int emu_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* off, uint32_t n,
                              const uint8_t* z16, int* out_ok, long long* out_bad) {
   return emu_ed_verify(sigs, pks, msgs, off, n, z16, out_ok, out_bad);
+}
+int emu_decode(int curve, const uint8_t* enc, uint32_t* out_xy) {
+  if (curve == 0) return sec1_decode_secp256k1(enc, out_xy);
+  if (curve == 4) return zcash_decode_bls12_381_g1(enc, out_xy);
+  if (curve == 1) return ed25519_decode(enc, out_xy);
+  return -1;
 }
 // GLV split of one scalar (BLS12-381 G1): out = m1[4], m2[4], neg1, neg2
 int emu_glv_split(const uint32_t* k, uint32_t* out) {

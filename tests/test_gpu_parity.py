@@ -510,3 +510,33 @@ def test_msm_giant_buckets_large(nmsm, name):
     sc = [0xABCDEF0123456789 if i % 2 else rnd.randrange(order) for i in range(n)]
     total = sum(k * s for k, s in zip(ks, sc)) % order
     assert gpu_msm(nmsm, name, pts_b, H.pack_scalars(sc), n) == H.expected_tuple(name, H.expected_from_total(P, total))
+
+
+def test_point_decoders_gpu(nmsm):
+    """nmsm_points_decode: 1000 compressed BLS12-381 G1 encodings and the secp256k1 isPoint list, then an MSM on the
+    decoded points (bytes in -> MSM out without host bigints)."""
+    gb = load_golden("bls12_381.json")
+    encs = [bytes.fromhex(c) for c in gb["G1_Compressed"]]
+    pts, st = nmsm.points_decode(4, b"".join(encs), len(encs))
+    assert st[0] == 2 and all(s == 1 for s in st[1:])
+    for i in (1, 2, 500, 999):
+        assert H.unpack_point("bls12_381_G1", pts[i * 96:(i + 1) * 96]) == R.bls12_381_g1_decode(encs[i])
+    rnd = random.Random(9)
+    G1 = R.CURVES["bls12_381_G1"]
+    sc = [rnd.randrange(G1.Fn.ORDER) for _ in encs]
+    tot = sum(i * s for i, s in enumerate(sc)) % G1.Fn.ORDER
+    assert gpu_msm(nmsm, "bls12_381_G1", pts, H.pack_scalars(sc), len(encs)) == H.expected_tuple(
+        "bls12_381_G1", G1.BASE.multiplyUnsafe(tot))
+    s = load_golden("secp256k1.json")["isPoint33"]
+    pts, st = nmsm.points_decode(0, b"".join(bytes.fromhex(e) for e, _ in s), len(s))
+    for i, (e, exp) in enumerate(s):
+        assert (st[i] == 1) == exp, e
+        if exp and i % 50 == 0:
+            assert H.unpack_point("secp256k1", pts[i * 64:(i + 1) * 64]) == R.secp256k1_decode_sec1(bytes.fromhex(e))
+    ed = load_golden("ed25519.json")["vectors"]
+    pts, st = nmsm.points_decode(1, b"".join(bytes.fromhex(v["pk"]) for v in ed), len(ed))
+    assert all(x == 1 for x in st)
+    a = R.ed25519_point_from_bytes(bytes.fromhex(ed[7]["pk"]), True).toAffine()
+    assert H.unpack_point("ed25519", pts[7 * 64:8 * 64]) == (a["x"], a["y"])
+    with pytest.raises(ValueError, match="no decoder"):
+        nmsm.points_decode(2, b"", 0) if False else nmsm.points_decode(2, bytes(64), 1)

@@ -281,3 +281,50 @@ def test_ed25519_batch_verify_matches_individual_reference_verify():
     allz = bytes((i * 5 + 3) & 255 for i in range(16 * len(valid)))
     assert _emu_ed_verify([bytes.fromhex(v["sig_bytes"]) for v in valid], [b"Zcash"] * len(valid),
                           [bytes.fromhex(v["vk_bytes"]) for v in valid], allz)[0] is True
+
+
+def test_point_decoders_match_oracle():
+    """codec.cuh (SEC1-33 secp256k1, Zcash-48 BLS12-381 G1) vs the oracle decode restatements on the reference's vectors
+    plus flag / range edge cases."""
+    import ctypes
+
+    import numpy as np
+
+    from conftest import load_golden
+
+    lib = H.hostemu()
+
+    def emu(curve, enc, words):
+        out = np.zeros(words, np.uint32)
+        st = lib.emu_decode(curve, enc, out.ctypes.data_as(ctypes.c_void_p))
+        half = words // 2
+        return st, int.from_bytes(out[:half].tobytes(), "little"), int.from_bytes(out[half:].tobytes(), "little")
+
+    g = load_golden("bls12_381.json")["G1_Compressed"]
+    cases = [bytes.fromhex(c) for c in g[:60]] + [bytes.fromhex(g[777])]
+    p = R.BLS12_381_G1_CURVE["p"]
+    cases += [bytes([0xC0] + [0] * 47), bytes([0xE0] + [0] * 47), bytes([0xC0] + [0] * 46 + [1]), bytes([0x40] + [0] * 47),
+              bytes([0x80]) + bytes(47), (p | (1 << 383)).to_bytes(48, "big"), bytes([0x9F] + [0xFF] * 47),
+              bytes([0x80]) + (5).to_bytes(47, "big"), bytes([0xA0]) + (5).to_bytes(47, "big")]
+    for enc in cases:
+        st, x, y = emu(4, enc, 24)
+        try:
+            ex, ey = R.bls12_381_g1_decode(enc)
+            if not (enc[0] & 0x80):
+                raise ValueError("uncompressed form not taken by this entry point")
+            assert (st, x, y) == ((2 if (ex, ey) == (0, 0) else 1), ex, ey), enc.hex()
+        except ValueError:
+            assert st == 0, enc.hex()
+    s = load_golden("secp256k1.json")["isPoint33"]
+    sample = s[:80] + [c for c in s if not c[1]]
+    pk = R.SECP256K1_CURVE["p"]
+    sample += [["02" + pk.to_bytes(32, "big").hex(), False], ["05" + "11" * 32, False], ["02" + "00" * 32, None]]
+    for enc_hex, exp in sample:
+        enc = bytes.fromhex(enc_hex)
+        st, x, y = emu(0, enc, 16)
+        try:
+            ex, ey = R.secp256k1_decode_sec1(enc)
+            assert (st, x, y) == (1, ex, ey), enc_hex
+            assert exp in (True, None)
+        except ValueError:
+            assert st == 0, enc_hex

@@ -213,3 +213,22 @@ def test_ed25519_verify_oracle_against_reference_vectors():
     sig = bytes.fromhex("5866666666666666666666666666666666666666666666666666666666666666"
                         "eed3f55c1a631258d69cf7a2def9de1400000000000000000000000000000010")
     assert R.ed25519_verify(sig, b"Zcash", bytes.fromhex(g["zip215"][0]["vk_bytes"])) is False
+
+
+def test_codec_oracle_against_reference_vectors():
+    """Decode restatements vs test/vectors: zkcrypto compressed G1 i*G (test/bls12-381.test.ts:1463-1500) and the
+    secp256k1 isPoint list (test/secp256k1.test.ts:96-104, 33-byte encodings)."""
+    g = load_golden("bls12_381.json")
+    for i, (c, u) in enumerate(zip(g["G1_Compressed"], g["G1_Uncompressed"])):
+        assert R.bls12_381_g1_decode(bytes.fromhex(c)) == R.bls12_381_g1_decode(bytes.fromhex(u)), i
+        if i:
+            assert R.bls12_381_g1_decode(bytes.fromhex(c)) == R.affine_tuple(G1, g1_decode_uncompressed(u))
+    s = load_golden("secp256k1.json")
+    assert len(s["isPoint33"]) > 1000
+    for enc, exp in s["isPoint33"]:
+        try:
+            x, y = R.secp256k1_decode_sec1(bytes.fromhex(enc))
+            ok = (y * y - x * x * x - 7) % SECP.Fp.ORDER == 0
+        except ValueError:
+            ok = False
+        assert ok == exp, enc
