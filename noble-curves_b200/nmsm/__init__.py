@@ -177,6 +177,54 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
         def isSmallOrder(self) -> bool:
             return self.is0() if h == 1 else self.clearCofactor().is0()
 
+        def isTorsionFree(self) -> bool:
+            """weierstrass.ts:971-975 / edwards.ts:584-586: n*P == O, evaluated as (n-1)*P + P on the GPU."""
+            if self._inf:
+                return True
+            return self.multiplyUnsafe(n - 1).add(self).is0()
+
+        def toBytes(self, isCompressed: bool = True) -> bytes:
+            """Wire encodings of the reference: SEC1 (weierstrass.ts:541-563), Zcash flags for BLS12-381
+            (bls12-381.ts:377-402), RFC 8032 for ed25519 (edwards.ts:620-628).  Pure byte packing on the host."""
+            if edwards:
+                b = bytearray(self.y.to_bytes(32, "little"))
+                if self.x & 1:
+                    b[31] |= 0x80
+                return bytes(b)
+            if name.startswith("bls12_381"):
+                if parts != 1:
+                    raise NotImplementedError("G2 wire format is not part of the accelerated path")
+                if self._inf:
+                    return bytes([0xC0 if isCompressed else 0x40]) + bytes(47 if isCompressed else 95)
+                xb = bytearray(self.x.to_bytes(48, "big"))
+                if isCompressed:
+                    xb[0] |= 0x80 | (0x20 if (self.y * 2) // p else 0)
+                    return bytes(xb)
+                return bytes(xb) + self.y.to_bytes(48, "big")
+            if parts != 1:
+                raise NotImplementedError("Fp2 curves: wire format is not part of the accelerated path")
+            if self._inf:
+                raise ValueError("bad point: ZERO")
+            xb = self.x.to_bytes(fp_bytes, "big")
+            if isCompressed:
+                return bytes([3 if self.y & 1 else 2]) + xb
+            return b"\x04" + xb + self.y.to_bytes(fp_bytes, "big")
+
+        @staticmethod
+        def fromBytes(b: bytes):
+            """Point.fromBytes (weierstrass.ts:720-724, edwards.ts:405-436): decode on the GPU (nmsm_points_decode),
+            then the reference's validity check (subgroup membership where the cofactor is not 1)."""
+            enc_len = {"secp256k1": 33, "bls12_381_G1": 48, "ed25519": 32}.get(name)
+            if enc_len is None or len(b) != enc_len:
+                raise ValueError("bad point: got length %d, expected compressed=%s" % (len(b), enc_len))
+            out, st = points_decode(curve_id, bytes(b), 1)
+            if st[0] == 0:
+                raise ValueError("bad point: is not on curve" if not edwards else "bad point: invalid y coordinate")
+            P_ = Point.from_packed(out, 1 if st[0] == 2 else 0)
+            if name == "bls12_381_G1" and not P_.isTorsionFree():
+                raise ValueError("bad point: not in prime-order subgroup")
+            return P_
+
         def to_packed(self) -> bytes:
             return _coord_to_bytes(self.x, fp_bytes, parts) + _coord_to_bytes(self.y, fp_bytes, parts)
 

@@ -540,3 +540,41 @@ def test_point_decoders_gpu(nmsm):
     assert H.unpack_point("ed25519", pts[7 * 64:8 * 64]) == (a["x"], a["y"])
     with pytest.raises(ValueError, match="no decoder"):
         nmsm.points_decode(2, b"", 0) if False else nmsm.points_decode(2, bytes(64), 1)
+
+
+def test_point_codec_roundtrip_object_api(nmsm):
+    """Point.toBytes / Point.fromBytes of the host mirror against the reference's encodings."""
+    gb = load_golden("bls12_381.json")
+    C = nmsm.CURVES["bls12_381_G1"]
+    for i in (0, 1, 2, 77, 999):
+        enc = bytes.fromhex(gb["G1_Compressed"][i])
+        Pt = C.fromBytes(enc)
+        assert Pt.toBytes(True) == enc and Pt.toBytes(False).hex() == gb["G1_Uncompressed"][i]
+        assert Pt.equals(C.BASE.multiply(i)) if i else Pt.is0()
+    S = nmsm.CURVES["secp256k1"]
+    for k, x, y in load_golden("secp256k1.json")["privates2"][:10]:
+        Pt = S.BASE.multiply(int(k))
+        enc = Pt.toBytes(True)
+        assert enc[1:].hex() == x and S.fromBytes(enc).equals(Pt)
+        assert Pt.toBytes(False).hex() == "04" + x + y
+    with pytest.raises(ValueError, match="bad point"):
+        S.fromBytes(bytes([2]) + S.Fp.ORDER.to_bytes(32, "big"))
+    E = nmsm.CURVES["ed25519"]
+    for v in load_golden("ed25519.json")["vectors"][:8]:
+        pk = bytes.fromhex(v["pk"])
+        assert E.fromBytes(pk).toBytes() == pk
+    # a point of the full curve group that is NOT in G1's prime-order subgroup must be rejected (assertValidity)
+    p = R.BLS12_381_G1_CURVE["p"]
+    x = 3
+    while True:
+        y2 = (x**3 + 4) % p
+        y = pow(y2, (p + 1) // 4, p)
+        if y * y % p == y2:
+            cand = R.CURVES["bls12_381_G1"].fromAffine({"x": x, "y": y})
+            if not cand.multiplyUnsafe(R.CURVES["bls12_381_G1"].Fn.ORDER - 1).add(cand).is0():
+                break
+        x += 1
+    xb = bytearray(x.to_bytes(48, "big"))
+    xb[0] |= 0x80 | (0x20 if (y * 2) // p else 0)
+    with pytest.raises(ValueError, match="subgroup"):
+        C.fromBytes(bytes(xb))
