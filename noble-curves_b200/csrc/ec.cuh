@@ -406,25 +406,32 @@ struct EdExt {
 
 // Curve policies; ID values are the curve ids of the C ABI (include/nmsm.h)
 struct CurveSecp256k1 {
-  static constexpr bool GLV = false;
+  // lattice GLV with the reference's own endomorphism data (secp256k1.ts:58-64)
+  static constexpr bool GLV = true;
+  static constexpr int GLV_KIND = 2;
+  using Glv = Secp256k1Glv;
   using G = SwXyzz<Fp<FpSecp256k1>>;
   using Fn = Fn_secp256k1;
   static constexpr int ID = 0;
 };
 struct CurveEd25519 {
   static constexpr bool GLV = false;
+  static constexpr int GLV_KIND = 0;
   using G = EdExt<Fp<FpEd25519>, Ed25519Consts>;
   using Fn = Fn_ed25519;
   static constexpr int ID = 1;
 };
 struct CurveBn254G1 {
-  static constexpr bool GLV = false;
+  static constexpr bool GLV = true;
+  static constexpr int GLV_KIND = 2;
+  using Glv = Bn254G1Glv;
   using G = SwXyzz<Fp<FpBn254>>;
   using Fn = Fn_bn254;
   static constexpr int ID = 2;
 };
 struct CurveBn254G2 {
   static constexpr bool GLV = false;
+  static constexpr int GLV_KIND = 0;
   using G = SwXyzz<Fp2<FpBn254>>;
   using Fn = Fn_bn254;
   static constexpr int ID = 3;
@@ -433,6 +440,7 @@ struct CurveBls381G1 {
   // terms are split as k = v1 + v2*lambda and accumulated against P and phi(P) = (beta*x, y): half as many
   // windows, buckets and Horner doublings for the same number of mixed additions (msm_body.cuh glv_split)
   static constexpr bool GLV = true;
+  static constexpr int GLV_KIND = 1;  // r = lambda^2 + lambda + 1: one Barrett division, msm_body.cuh glv_split
   using Glv = Bls381G1Glv;
   using G = SwXyzz<Fp<FpBls381>>;
   using Fn = Fn_bls12_381;
@@ -440,6 +448,7 @@ struct CurveBls381G1 {
 };
 struct CurveBls381G2 {
   static constexpr bool GLV = false;
+  static constexpr int GLV_KIND = 0;
   using G = SwXyzz<Fp2<FpBls381>>;
   using Fn = Fn_bls12_381;
   static constexpr int ID = 5;

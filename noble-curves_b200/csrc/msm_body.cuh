@@ -36,6 +36,12 @@ struct MsmPlan {
   int chunks;  // B / K
 };
 
+template <class Cv>
+constexpr int glv_bits() {
+  if constexpr (Cv::GLV) return Cv::Glv::BITS;
+  else return Cv::Fn::BITS;
+}
+
 // ---------------------------------------------------------------------------------------------
 // plan selection: pick the window size c that minimises a TIME model of the pipeline, with constants
 // measured on B200 for BLS12-381 G1 (profiles/) and scaled by field size / formula cost for the others:
@@ -52,7 +58,7 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
   using G = typename Cv::G;
   using F = typename G::Field;
   // with GLV every scalar becomes two signed halves of at most 127 bits, each attached to its own point
-  const int bits = Cv::GLV ? 127 : Cv::Fn::BITS;
+  const int bits = glv_bits<Cv>();
   const double terms = (double)n * (Cv::GLV ? 2 : 1);
   const double limb_ratio = (double)(F::LIMBS / F::BASE_MULS == 12 ? 1.0 : (8.0 * 8.0) / (12.0 * 12.0));
   const double fscale = limb_ratio * F::BASE_MULS;                       // field multiplication cost vs 381-bit Fp
@@ -363,6 +369,82 @@ NMSM_HD void glv_split(const uint32_t* k, uint32_t* m1, bool& neg1, uint32_t* m2
   }
 }
 
+// Lattice GLV split (secp256k1, bn254 G1), the device form of weierstrass.ts:121-148 `_splitEndoScalar`:
+//   c1 = round(b2*k/n) = (k*G1 + 2^383) >> 384,  c2 = round(-b1*k/n) = (k*G2 + 2^383) >> 384
+//   k1 = k - c1*a1 - c2*a2,   k2 = -c1*b1 - c2*b2 = c1*|b1| - c2*b2      (a1, a2, b2 > 0 > b1)
+// evaluated in 320-bit two's complement; outputs are 5-limb magnitudes (< 2^BITS) and signs.
+template <class GC>
+NMSM_HD void glv_split_lattice(const uint32_t* k, uint32_t* m1, bool& neg1, uint32_t* m2, bool& neg2) {
+  auto mul_shift = [&](auto g, uint32_t* c) {  // c[5] = (k * g + 2^383) >> 384
+    uint32_t prod[17];
+    for (int i = 0; i < 17; i++) prod[i] = 0;
+    for (int i = 0; i < 8; i++) {
+      uint64_t carry = 0;
+      for (int j = 0; j < 9; j++) {
+        uint64_t t = (uint64_t)k[i] * g(j) + prod[i + j] + carry;
+        prod[i + j] = (uint32_t)t;
+        carry = t >> 32;
+      }
+      prod[i + 9] = (uint32_t)carry;
+    }
+    uint64_t carry = 0x80000000ull;  // + 2^383: bit 31 of limb 11
+    for (int i = 11; i < 17; i++) {
+      uint64_t t = (uint64_t)prod[i] + carry;
+      prod[i] = (uint32_t)t;
+      carry = t >> 32;
+    }
+    for (int i = 0; i < 5; i++) c[i] = prod[12 + i];
+  };
+  auto mul5 = [](const uint32_t* a, auto b, uint32_t* r) {  // r[10] = a[5] * b[5]
+    for (int i = 0; i < 10; i++) r[i] = 0;
+    for (int i = 0; i < 5; i++) {
+      uint64_t carry = 0;
+      for (int j = 0; j < 5; j++) {
+        uint64_t t = (uint64_t)a[i] * b(j) + r[i + j] + carry;
+        r[i + j] = (uint32_t)t;
+        carry = t >> 32;
+      }
+      r[i + 5] = (uint32_t)carry;
+    }
+  };
+  auto sub10 = [](uint32_t* x, const uint32_t* y) {  // x -= y mod 2^320
+    uint64_t br = 0;
+    for (int i = 0; i < 10; i++) {
+      uint64_t t = (uint64_t)x[i] - y[i] - br;
+      x[i] = (uint32_t)t;
+      br = (t >> 63) & 1;
+    }
+  };
+  auto abs10 = [](uint32_t* x, bool& neg) {  // two's complement -> magnitude
+    neg = (x[9] >> 31) != 0;
+    if (neg) {
+      uint64_t carry = 1;
+      for (int i = 0; i < 10; i++) {
+        uint64_t t = (uint64_t)(~x[i]) + carry;
+        x[i] = (uint32_t)t;
+        carry = t >> 32;
+      }
+    }
+  };
+  uint32_t c1[5], c2[5], t[10], v1[10], v2[10];
+  mul_shift([](int j) { return GC::G1(j); }, c1);
+  mul_shift([](int j) { return GC::G2(j); }, c2);
+  for (int i = 0; i < 10; i++) v1[i] = i < 8 ? k[i] : 0;
+  mul5(c1, [](int j) { return GC::A1(j); }, t);
+  sub10(v1, t);
+  mul5(c2, [](int j) { return GC::A2(j); }, t);
+  sub10(v1, t);
+  mul5(c1, [](int j) { return GC::B1ABS(j); }, v2);
+  mul5(c2, [](int j) { return GC::B2(j); }, t);
+  sub10(v2, t);
+  abs10(v1, neg1);
+  abs10(v2, neg2);
+  for (int i = 0; i < 5; i++) {
+    m1[i] = v1[i];
+    m2[i] = v2[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // bodies
 // ---------------------------------------------------------------------------------------------
@@ -424,12 +506,18 @@ NMSM_HD void digits_body(uint32_t i, uint32_t n, const uint32_t* scalars, const 
     if (!SCATTER) atomic_min_u32(&err[1], i);
     return;
   }
-  if constexpr (Cv::GLV) {
+  if constexpr (Cv::GLV_KIND == 1) {
     uint32_t m1[4], m2[4];
     bool neg1, neg2;
     glv_split<typename Cv::Glv>(s, m1, neg1, m2, neg2);
     emit_digits<SCATTER>(m1, 4, i, neg1 ? 1u : 0u, plan, counts_or_cursor, sorted);
     emit_digits<SCATTER>(m2, 4, n + i, neg2 ? 1u : 0u, plan, counts_or_cursor, sorted);
+  } else if constexpr (Cv::GLV_KIND == 2) {
+    uint32_t m1[5], m2[5];
+    bool neg1, neg2;
+    glv_split_lattice<typename Cv::Glv>(s, m1, neg1, m2, neg2);
+    emit_digits<SCATTER>(m1, 5, i, neg1 ? 1u : 0u, plan, counts_or_cursor, sorted);
+    emit_digits<SCATTER>(m2, 5, n + i, neg2 ? 1u : 0u, plan, counts_or_cursor, sorted);
   } else {
     emit_digits<SCATTER>(s, SCALAR_WORDS, i, 0u, plan, counts_or_cursor, sorted);
   }

@@ -179,6 +179,15 @@ int emu_glv_split(const uint32_t* k, uint32_t* out) {
   out[9] = n2;
   return 0;
 }
+// lattice GLV split (curve 0 = secp256k1, 2 = bn254 G1): out = m1[5], m2[5], neg1, neg2
+int emu_glv_split_lattice(int curve, const uint32_t* k, uint32_t* out) {
+  bool n1, n2;
+  if (curve == 0) glv_split_lattice<Secp256k1Glv>(k, out, n1, out + 5, n2);
+  else glv_split_lattice<Bn254G1Glv>(k, out, n1, out + 5, n2);
+  out[10] = n1;
+  out[11] = n2;
+  return 0;
+}
 int emu_msm(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, int forced_c, int forced_L,
             uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out) {
   DISPATCH(curve, emu_msm_t<Cv>(pts, scalars, n, forced_c, forced_L, out_xy, out_inf, err_out, plan_out));

@@ -328,3 +328,40 @@ def test_point_decoders_match_oracle():
             assert exp in (True, None)
         except ValueError:
             assert st == 0, enc_hex
+
+
+@pytest.mark.parametrize("cid,name,lam,bits", [
+    (0, "secp256k1", 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72, 129),
+    (2, "bn254_G1", 0x30644E72E131A029048B6E193FD84104CC37A73FEC2BC5E9B8CA0B2D36636F23, 127),
+])
+def test_glv_lattice_split(cid, name, lam, bits):
+    """glv_split_lattice: k = v1 + v2*lambda (mod n) with short halves; phi(P) = (beta*x, y) = lambda*P; for secp256k1
+    the halves equal the reference's _splitEndoScalar (weierstrass.ts:121-148) via the oracle."""
+    import ctypes
+    import random as _r
+
+    import numpy as np
+
+    P = R.CURVES[name]
+    n, p = P.Fn.ORDER, P.Fp.ORDER
+    assert (lam * lam + lam + 1) % n == 0
+    lg = P.BASE.multiplyUnsafe(lam).toAffine()
+    g = P.BASE.toAffine()
+    assert lg["y"] == g["y"] and (lg["x"] * pow(g["x"], -1, p)) % p in (
+        0x7AE96A2B657C07106E64479EAC3434E99CF0497512F58995C1396C28719501EE,
+        0x30644E72E131A0295E6DD9E7E0ACCCB0C28F069FBB966E3DE4BD44E5607CFD48)
+    rnd = _r.Random(8)
+    ks = [0, 1, 2, n - 1, n - 2, lam, lam + 1, lam - 1, n >> 1, (n >> 1) + 1] + [rnd.randrange(n) for _ in range(3000)]
+    lib = H.hostemu()
+    for k in ks:
+        a = H.u32(k.to_bytes(32, "little"))
+        out = np.zeros(12, np.uint32)
+        lib.emu_glv_split_lattice(cid, a.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+        m1 = int.from_bytes(out[:5].tobytes(), "little")
+        m2 = int.from_bytes(out[5:10].tobytes(), "little")
+        v1 = -m1 if out[10] else m1
+        v2 = -m2 if out[11] else m2
+        assert (v1 + v2 * lam - k) % n == 0 and m1 >> bits == 0 and m2 >> bits == 0, hex(k)
+        if name == "secp256k1":
+            k1neg, k1, k2neg, k2 = R.split_endo_scalar(k, R.SECP256K1_ENDO["basises"], n)
+            assert (m1, m2) == (k1, k2) and (not m1 or bool(out[10]) == k1neg) and (not m2 or bool(out[11]) == k2neg)
