@@ -261,8 +261,9 @@ def main():
     nmsm.set_profiling(False)
 
     # ---- (2) the timed region: K steps, two MSMs in flight (submit/collect on alternating slots) -----------
-    # Single-GPU only; the multi-GPU step has a collective between partial and fold and stays serial.
-    pipelined = world == 1
+    # At N > 1 the shard reduction of step i overlaps the all-gather + fold of step i-1 the same way.
+    pipelined = True
+    d_accs = [torch.zeros(acc_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
 
     def run_pipelined(steps, submit):
         outs = [ctypes.create_string_buffer(POINT_BYTES), ctypes.create_string_buffer(POINT_BYTES)]
@@ -272,11 +273,27 @@ def main():
                 submit(i & 1)
             if i >= 1:
                 s = (i - 1) & 1
-                nmsm._lib.check(lib.nmsm_msm_collect(s, ctypes.cast(outs[s], ctypes.c_void_p), ctypes.byref(infs[s])))
+                collect(s, outs[s], infs[s])
                 assert outs[s].raw == exp_xy and infs[s].value == exp_inf
 
-    def submit_device(slot):
-        nmsm._lib.check(lib.nmsm_msm_submit(BLS_G1, d_pts.data_ptr(), d_sc.data_ptr(), n_local, 1, slot))
+    def submit_device(slot, pts_t=None, sc_t=None):
+        pts_t = d_pts if pts_t is None else pts_t
+        sc_t = d_sc if sc_t is None else sc_t
+        if world == 1:
+            nmsm._lib.check(lib.nmsm_msm_submit(BLS_G1, pts_t.data_ptr(), sc_t.data_ptr(), n_local, 1, slot))
+        else:
+            nmsm._lib.check(lib.nmsm_msm_submit_partial(BLS_G1, pts_t.data_ptr(), sc_t.data_ptr(), n_local,
+                                                        d_accs[slot].data_ptr(), slot))
+
+    def collect(slot, o, f):
+        if world == 1:
+            nmsm._lib.check(lib.nmsm_msm_collect(slot, ctypes.cast(o, ctypes.c_void_p), ctypes.byref(f)))
+        else:  # shard done -> one all-gather of the raw accumulators -> fold
+            nmsm._lib.check(lib.nmsm_msm_collect(slot, None, None))
+            dist.all_gather_into_tensor(d_all, d_accs[slot])
+            torch.cuda.current_stream().synchronize()
+            nmsm._lib.check(lib.nmsm_fold_partials_device(BLS_G1, d_all.data_ptr(), world, ctypes.cast(o, ctypes.c_void_p),
+                                                          ctypes.byref(f)))
 
     sampler = ClockSampler(local_rank)
     if pipelined:
@@ -305,6 +322,7 @@ def main():
     ctypes.memmove(h_pts, pts_b, len(pts_b))
     ctypes.memmove(h_sc, sc_b, len(sc_b))
     e2e_steps = max(3, min(args.steps, 10))
+    e2e_bufs = [(d_pts, d_sc), (torch.empty_like(d_pts), torch.empty_like(d_sc))] if world > 1 else None
 
     def step_e2e():
         if world == 1:
@@ -316,7 +334,14 @@ def main():
             step_device()
 
     def submit_host(slot):
-        nmsm._lib.check(lib.nmsm_msm_submit(BLS_G1, h_pts, h_sc, n_local, 0, slot))
+        if world == 1:
+            nmsm._lib.check(lib.nmsm_msm_submit(BLS_G1, h_pts, h_sc, n_local, 0, slot))
+        else:  # multi-GPU e2e: H2D on torch's stream into this slot's device buffers, then the sharded step
+            tp, ts = e2e_bufs[slot]
+            tp.copy_(torch.frombuffer((ctypes.c_uint8 * len(pts_b)).from_address(h_pts), dtype=torch.uint8), non_blocking=True)
+            ts.copy_(torch.frombuffer((ctypes.c_uint8 * len(sc_b)).from_address(h_sc), dtype=torch.uint8), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            submit_device(slot, tp, ts)
 
     step_e2e()
     if pipelined:
@@ -407,7 +432,7 @@ def main():
                    "pipelining": ("timed steps keep 2 MSMs in flight on 2 CUDA streams (nmsm_msm_submit/collect): the "
                                   "latency-bound tail of one overlaps the copy + wide kernels of the next; "
                                   "latency_ms_single_msm and the roofline block come from a serial pass")
-                   if pipelined else "serial steps (collective between partial and fold)"},
+                   + ("; at N>1 the all-gather + fold of step i-1 overlaps the shard reduction of step i" if world > 1 else "")},
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": len(pts_b) + len(sc_b),
                 "d2h_bytes_per_step": POINT_BYTES + 20, "steps": e2e_steps},
         "gpu_launches": info.launches * args.steps * world,  # kernels of the timed K steps (serial pass not counted)

@@ -75,6 +75,8 @@ int nmsm_msm_device(int curve, const void* d_pts, const void* d_scalars, uint64_
  * until nmsm_msm_collect returns.  Errors of the MSM itself (invalid point / scalar) are reported by collect. */
 int nmsm_msm_submit(int curve, const void* pts, const void* scalars, uint64_t n, int inputs_on_device, int slot);
 int nmsm_msm_collect(int slot, uint8_t* out_xy, int* out_is_inf);
+/* Same for a multi-GPU shard: the raw accumulator lands in d_out_acc (device); collect with NULL outputs. */
+int nmsm_msm_submit_partial(int curve, const void* d_pts, const void* d_scalars, uint64_t n, void* d_out_acc, int slot);
 
 /* Multi-GPU building blocks: the un-normalised accumulator of a shard is written to device memory
  * (nmsm_acc_bytes bytes, opaque Montgomery-form words), exchanged by the caller (NCCL all-gather),

@@ -197,11 +197,12 @@ static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
 }
 
 // C-ABI asynchronous halves (nmsm_msm_submit / nmsm_msm_collect)
-static int submit_any(const void* pts, const void* scalars, uint64_t n, int inputs_on_device) {
+static int submit_any(const void* pts, const void* scalars, uint64_t n, int inputs_on_device, void* d_out_acc) {
   Slot& C = g_ctx.slot[g_ctx.cur];
   if (C.pend.active) return fail(NMSM_ERR_ARG, "slot busy: collect the previous MSM first");
+  if (d_out_acc && !inputs_on_device) return fail(NMSM_ERR_ARG, "raw-accumulator output needs device-resident inputs");
   if (inputs_on_device || n == 0)
-    return submit_msm((const uint32_t*)pts, (const uint32_t*)scalars, n, nullptr, nullptr);
+    return submit_msm((const uint32_t*)pts, (const uint32_t*)scalars, n, (uint32_t*)d_out_acc, nullptr);
   CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
   CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
   CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, C.stream));

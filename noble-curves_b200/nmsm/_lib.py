@@ -25,7 +25,7 @@ EXPORTS = [
     "nmsm_acc_bytes", "nmsm_msm", "nmsm_msm_device", "nmsm_msm_partial_device", "nmsm_fold_partials_device",
     "nmsm_mul_batch", "nmsm_set_window_bits", "nmsm_set_profiling", "nmsm_last_timing", "nmsm_bench_modmul",
     "nmsm_host_alloc", "nmsm_host_free", "nmsm_points_upload", "nmsm_points_free", "nmsm_msm_points",
-    "nmsm_ed25519_verify_batch", "nmsm_msm_submit", "nmsm_msm_collect", "nmsm_points_decode",
+    "nmsm_ed25519_verify_batch", "nmsm_msm_submit", "nmsm_msm_collect", "nmsm_points_decode", "nmsm_msm_submit_partial",
 ]
 
 
@@ -118,6 +118,8 @@ def load() -> ctypes.CDLL:
         lib.nmsm_msm_collect.restype = ctypes.c_int
         lib.nmsm_points_decode.argtypes = [ctypes.c_int, u8p, ctypes.c_uint64, u8p, u8p]
         lib.nmsm_points_decode.restype = ctypes.c_int
+        lib.nmsm_msm_submit_partial.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_uint64, u8p, ctypes.c_int]
+        lib.nmsm_msm_submit_partial.restype = ctypes.c_int
         _lib = lib
         return lib
 
