@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--logn", type=int, default=20, help="log2 of the MSM size (headline: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window", type=int, default=0, help="force window bits c (0 = cost model)")
+    ap.add_argument("--in-flight", type=int, default=2, choices=[1, 2, 3, 4], help="MSMs kept in flight in the timed region")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = 2^logn terms PER GPU (one MSM of N*2^logn terms); strong = 2^logn terms in total")
     return ap.parse_args()
@@ -263,18 +264,23 @@ def main():
     # ---- (2) the timed region: K steps, two MSMs in flight (submit/collect on alternating slots) -----------
     # At N > 1 the shard reduction of step i overlaps the all-gather + fold of step i-1 the same way.
     pipelined = True
-    d_accs = [torch.zeros(acc_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    NF = args.in_flight
+    d_accs = [torch.zeros(acc_bytes, dtype=torch.uint8, device=dev) for _ in range(NF)]
 
     def run_pipelined(steps, submit):
-        outs = [ctypes.create_string_buffer(POINT_BYTES), ctypes.create_string_buffer(POINT_BYTES)]
-        infs = [ctypes.c_int(0), ctypes.c_int(0)]
-        for i in range(steps + 1):
-            if i < steps:
-                submit(i & 1)
-            if i >= 1:
-                s = (i - 1) & 1
-                collect(s, outs[s], infs[s])
-                assert outs[s].raw == exp_xy and infs[s].value == exp_inf
+        outs = [ctypes.create_string_buffer(POINT_BYTES) for _ in range(NF)]
+        infs = [ctypes.c_int(0) for _ in range(NF)]
+        def take(s):
+            collect(s, outs[s], infs[s])
+            assert outs[s].raw == exp_xy and infs[s].value == exp_inf
+
+        for i in range(steps):
+            s = i % NF
+            if i >= NF:  # the slot still holds step i - NF
+                take(s)
+            submit(s)
+        for j in range(max(0, steps - NF), steps):
+            take(j % NF)
 
     def submit_device(slot, pts_t=None, sc_t=None):
         pts_t = d_pts if pts_t is None else pts_t
@@ -322,7 +328,7 @@ def main():
     ctypes.memmove(h_pts, pts_b, len(pts_b))
     ctypes.memmove(h_sc, sc_b, len(sc_b))
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_bufs = [(d_pts, d_sc), (torch.empty_like(d_pts), torch.empty_like(d_sc))] if world > 1 else None
+    e2e_bufs = ([(d_pts, d_sc)] + [(torch.empty_like(d_pts), torch.empty_like(d_sc)) for _ in range(NF - 1)]) if world > 1 else None
 
     def step_e2e():
         if world == 1:
@@ -422,14 +428,14 @@ def main():
         "metric": "BLS12-381 G1 MSM points/sec at 2^%d scalars" % args.logn,
         "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": 1e3 * elapsed / args.steps, "latency_ms_single_msm": 1e3 * serial_elapsed / args.steps,
-        "in_flight": 2 if pipelined else 1, "higher_is_better": True, "scaling": scaling,
+        "in_flight": NF, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "u32-limb integer (381-bit Fp, Montgomery)", "data": "synthetic",
         "config": {"workload": ("BLS12-381 G1 Pippenger MSM, 2^%d random terms (points k_i*G, uniform scalars) per GPU; "
                                 "at N GPUs one MSM of N*2^%d terms" % (args.logn, args.logn)) if scaling == "weak" else
                                "BLS12-381 G1 Pippenger MSM, 2^%d terms in total split over the GPUs" % args.logn,
                    "terms": n_total, "terms_per_gpu": n_local, "parallelism": "term-sharded x%d, 1 all-gather of raw accumulators" % world,
                    "l2": "inputs+workspace (>=450 MB/GPU at N=2^20) exceed the 126 MB L2; no flush needed",
-                   "pipelining": ("timed steps keep 2 MSMs in flight on 2 CUDA streams (nmsm_msm_submit/collect): the "
+                   "pipelining": ("timed steps keep several MSMs in flight (see in_flight) on separate CUDA streams (nmsm_msm_submit/collect): the "
                                   "latency-bound tail of one overlaps the copy + wide kernels of the next; "
                                   "latency_ms_single_msm and the roofline block come from a serial pass")
                    + ("; at N>1 the all-gather + fold of step i-1 overlaps the shard reduction of step i" if world > 1 else "")},

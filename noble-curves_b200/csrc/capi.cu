@@ -242,7 +242,7 @@ int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t
 int nmsm_msm_submit(int curve, const void* pts, const void* scalars, uint64_t n, int inputs_on_device, int slot) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
-  if (slot < 0 || slot >= NUM_SLOTS) return fail(NMSM_ERR_ARG, "slot must be 0 or 1");
+  if (slot < 0 || slot >= NUM_SLOTS) return fail(NMSM_ERR_ARG, "slot out of range (0..3)");
   if (n && (!pts || !scalars)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   g_ctx.cur = slot;
@@ -252,7 +252,7 @@ int nmsm_msm_submit(int curve, const void* pts, const void* scalars, uint64_t n,
 int nmsm_msm_submit_partial(int curve, const void* d_pts, const void* d_scalars, uint64_t n, void* d_out_acc, int slot) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
-  if (slot < 0 || slot >= NUM_SLOTS) return fail(NMSM_ERR_ARG, "slot must be 0 or 1");
+  if (slot < 0 || slot >= NUM_SLOTS) return fail(NMSM_ERR_ARG, "slot out of range (0..3)");
   if (!d_out_acc || (n && (!d_pts || !d_scalars))) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   g_ctx.cur = slot;
@@ -262,7 +262,7 @@ int nmsm_msm_submit_partial(int curve, const void* d_pts, const void* d_scalars,
 int nmsm_msm_collect(int slot, uint8_t* out_xy, int* out_is_inf) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
-  if (slot < 0 || slot >= NUM_SLOTS) return fail(NMSM_ERR_ARG, "slot must be 0 or 1");
+  if (slot < 0 || slot >= NUM_SLOTS) return fail(NMSM_ERR_ARG, "slot out of range (0..3)");
   if (!g_ctx.slot[slot].pend.active) return fail(NMSM_ERR_ARG, "nothing submitted on this slot");
   if (!g_ctx.slot[slot].pend.partial && (!out_xy || !out_is_inf)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(g_ctx.slot[slot].pend.curve);

@@ -66,7 +66,7 @@ struct Slot {
   nmsm_plan_info last_info = {};
   Pending pend;
 };
-static constexpr int NUM_SLOTS = 2;
+static constexpr int NUM_SLOTS = 4;
 
 struct Context {
   bool ready = false;
