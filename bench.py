@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--logn", type=int, default=20, help="log2 of the MSM size (headline: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window", type=int, default=0, help="force window bits c (0 = cost model)")
-    ap.add_argument("--in-flight", type=int, default=2, choices=[1, 2, 3, 4], help="MSMs kept in flight in the timed region")
+    ap.add_argument("--in-flight", type=int, default=4, choices=[1, 2, 3, 4], help="MSMs kept in flight in the timed region")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = 2^logn terms PER GPU (one MSM of N*2^logn terms); strong = 2^logn terms in total")
     return ap.parse_args()
