@@ -69,10 +69,12 @@ int nmsm_msm(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, 
 int nmsm_msm_device(int curve, const void* d_pts, const void* d_scalars, uint64_t n, uint8_t* out_xy,
                     int* out_is_inf);
 
-/* Two MSMs in flight: enqueue on slot 0/1 without waiting, collect later.  The latency-bound tail of one MSM
+/* Several MSMs in flight: enqueue on slot 0..NMSM_SLOTS-1 without waiting, collect later (each slot has its own
+ * stream and workspace; one outstanding MSM per slot).  The latency-bound tail of one MSM
  * (second-level bucket reduction, Horner doublings, inversion: a handful of SMs) then overlaps the H2D copy and the
  * wide kernels of the next.  With inputs_on_device = 0 the host buffers (pinned, for true overlap) must stay valid
  * until nmsm_msm_collect returns.  Errors of the MSM itself (invalid point / scalar) are reported by collect. */
+#define NMSM_SLOTS 4
 int nmsm_msm_submit(int curve, const void* pts, const void* scalars, uint64_t n, int inputs_on_device, int slot);
 int nmsm_msm_collect(int slot, uint8_t* out_xy, int* out_is_inf);
 /* Same for a multi-GPU shard: the raw accumulator lands in d_out_acc (device); collect with NULL outputs. */
@@ -123,8 +125,8 @@ int nmsm_set_window_bits(int c);
 /* Plan + per-kernel device times (ms, CUDA events on the library stream) of the last MSM call.
  * `ms` receives NMSM_TIMING_SLOTS floats; see the NMSM_T_* indices. */
 enum {
-  NMSM_T_PREPARE = 0, NMSM_T_COUNT, NMSM_T_SCAN, NMSM_T_SCATTER, NMSM_T_ACCUMULATE, NMSM_T_FIXUP,
-  NMSM_T_REDUCE, NMSM_T_WINDOW_SUM, NMSM_T_FINAL, NMSM_T_TOTAL, NMSM_TIMING_SLOTS
+  NMSM_T_PREPARE = 0, NMSM_T_COUNT, NMSM_T_SCAN, NMSM_T_SCATTER, NMSM_T_ACCUMULATE, NMSM_T_STITCH,
+  NMSM_T_REDUCE1, NMSM_T_REDUCE23, NMSM_T_FINAL, NMSM_T_TOTAL, NMSM_TIMING_SLOTS
 };
 typedef struct {
   int c, windows, buckets_per_window, entries_per_thread, reduce_chunk;

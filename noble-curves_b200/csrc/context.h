@@ -44,7 +44,7 @@ struct Buf {
   }
 };
 
-// Everything one in-flight MSM needs.  Two slots let the caller keep two MSMs in flight (nmsm_msm_submit /
+// Everything one in-flight MSM needs.  NMSM_SLOTS slots let the caller keep several MSMs in flight (nmsm_msm_submit /
 // nmsm_msm_collect): the latency-bound tail of one (second-level reduction, Horner, inversion — a handful of
 // SMs) overlaps the H2D copy and the wide kernels of the next on the other stream.
 struct Pending {
@@ -66,7 +66,7 @@ struct Slot {
   nmsm_plan_info last_info = {};
   Pending pend;
 };
-static constexpr int NUM_SLOTS = 4;
+static constexpr int NUM_SLOTS = NMSM_SLOTS;  // include/nmsm.h
 
 struct Context {
   bool ready = false;

@@ -112,13 +112,13 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   EV(4);
   k_accumulate<Cv><<<cdiv(max_threads, 128), 128, 0, st>>>(aff, sorted, offsets, plan, buckets, heads, tails);
   EV(5);
+  // tile sums for buckets spanning many accumulate segments (no-ops for ordinary inputs)
+  k_stitch_tiles<Cv><<<cdiv(ntile1 * 32, 128), 128, 0, st>>>(offsets, plan, STITCH_FAN, (uint32_t)ntile1, heads, tile1);
+  k_stitch_tiles<Cv><<<cdiv(ntile2 * 32, 128), 128, 0, st>>>(offsets, plan, STITCH_FAN * STITCH_FAN, (uint32_t)ntile2,
+                                                              tile1, tile2);
   EV(6);
   {
     const uint64_t nchunks = (uint64_t)plan.W * plan.chunks;
-    // tile sums for buckets spanning many accumulate segments (no-ops for ordinary inputs)
-    k_stitch_tiles<Cv><<<cdiv(ntile1 * 32, 128), 128, 0, st>>>(offsets, plan, STITCH_FAN, (uint32_t)ntile1, heads, tile1);
-    k_stitch_tiles<Cv><<<cdiv(ntile2 * 32, 128), 128, 0, st>>>(offsets, plan, STITCH_FAN * STITCH_FAN, (uint32_t)ntile2,
-                                                                tile1, tile2);
     k_reduce1<Cv><<<cdiv(nchunks, 128), 128, 0, st>>>(offsets, buckets, heads, tails, tile1, tile2, plan, sums,
                                                          wsums);
   }

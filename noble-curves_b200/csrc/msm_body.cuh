@@ -7,7 +7,7 @@
 // library only ever runs them inside the CUDA kernels.
 //
 // Pipeline (replaces /root/reference/src/abstract/curve.ts:863-905 `pippenger`):
-//   prepare -> count digits -> scan -> scatter -> accumulate -> fixup -> reduce -> window sum -> final
+//   prepare -> count digits -> scan -> scatter -> accumulate -> stitch -> reduce1 -> reduce2/3 -> final
 #pragma once
 #include <math.h>
 #include <stdint.h>

@@ -17,7 +17,7 @@ NMSM_OK = 0
 ERR_ARG, ERR_SCALAR, ERR_POINT, ERR_LENGTH, ERR_CUDA = -1, -2, -3, -4, -5
 
 TIMING_SLOTS = 10
-TIMING_NAMES = ["prepare", "count", "scan", "scatter", "accumulate", "fixup", "reduce", "window_sum", "final", "total"]
+TIMING_NAMES = ["prepare", "count", "scan", "scatter", "accumulate", "stitch", "reduce1", "reduce23", "final", "total"]
 
 # every symbol include/nmsm.h declares (tests check that the library exports all of them)
 EXPORTS = [
