@@ -94,10 +94,18 @@ int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64
 /* Device-resident point sets: validate + convert a point array once, then run many MSMs against it
  * (fixed-base commitments).  The analogue of interleavedMSMUnsafe's captured tables
  * (/root/reference/src/abstract/curve.ts:937-959): fewer scalars than points use the first n points
- * (except on curves that run GLV internally — BLS12-381 G1 — where n must equal the set size). */
+ * (except on curves that run GLV internally — secp256k1, bn254 G1, BLS12-381 G1 — where n must equal the set
+ * size). */
 int nmsm_points_upload(int curve, const uint8_t* pts, uint64_t n, uint64_t* out_handle);
 int nmsm_points_free(uint64_t handle);
 int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf);
+/* Fixed-base table for the set (next-row f4): stores 2^(c*j) * P_i for j = 0..levels-1 on the device, the counterpart
+ * of Point.precompute / the per-point window tables interleavedMSMUnsafe builds once
+ * (/root/reference/src/abstract/curve.ts:532-577,937-951).  Later nmsm_msm_points calls then use ONE bucket window
+ * of 2^(c-1) buckets for all digits: no Horner doublings and 1/W of the bucket reduction.  window_bits = 0 lets the
+ * cost model choose (19 for 2^20 BLS12-381 G1 points: 7 levels, 1.4 GB); the choice is returned.  One-off cost:
+ * levels-1 kernels of c doublings + one inversion per point. */
+int nmsm_points_precompute(uint64_t handle, int window_bits, int* out_window_bits, int* out_levels);
 
 /* Ed25519 batch verification (next-row f1).  The reference verifies one signature at a time
  * (/root/reference/src/abstract/edwards.ts:942-989, ZIP-215 decoding by default, src/ed25519.ts:168); this checks

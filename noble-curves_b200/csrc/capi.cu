@@ -205,6 +205,8 @@ struct PointSet {
   int curve;
   uint64_t n;
   uint32_t* d_prepared;
+  int table_c;       // 0: level 0 only; else window bits of the fixed-base table in d_prepared
+  int table_levels;
 };
 
 int nmsm_points_upload(int curve, const uint8_t* pts, uint64_t n, uint64_t* out_handle) {
@@ -215,7 +217,7 @@ int nmsm_points_upload(int curve, const uint8_t* pts, uint64_t n, uint64_t* out_
   ENGINE(curve);
   uint32_t* d = nullptr;
   if (int r = E->prepare_points(pts, n, &d)) return r;
-  PointSet* ps = new PointSet{curve, n, d};
+  PointSet* ps = new PointSet{curve, n, d, 0, 1};
   *out_handle = (uint64_t)(uintptr_t)ps;
   return NMSM_OK;
 }
@@ -236,7 +238,24 @@ int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t
   PointSet* ps = (PointSet*)(uintptr_t)handle;
   if (!ps || !out_xy || !out_is_inf || (n && !scalars)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(ps->curve);
-  return E->msm_prepared(ps->d_prepared, ps->n, scalars, n, out_xy, out_is_inf);
+  return E->msm_prepared(ps->d_prepared, ps->n, ps->table_c, scalars, n, out_xy, out_is_inf);
+}
+
+int nmsm_points_precompute(uint64_t handle, int window_bits, int* out_window_bits, int* out_levels) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
+  PointSet* ps = (PointSet*)(uintptr_t)handle;
+  if (!ps) return fail(NMSM_ERR_ARG, "null handle");
+  if (ps->table_c) return fail(NMSM_ERR_ARG, "point set already carries a table");
+  ENGINE(ps->curve);
+  int c = 0, levels = 0;
+  if (int r = E->precompute_table(&ps->d_prepared, ps->n, window_bits, &c, &levels)) return r;
+  ps->table_c = c;
+  ps->table_levels = levels;
+  if (out_window_bits) *out_window_bits = c;
+  if (out_levels) *out_levels = levels;
+  return NMSM_OK;
 }
 
 int nmsm_msm_submit(int curve, const void* pts, const void* scalars, uint64_t n, int inputs_on_device, int slot) {

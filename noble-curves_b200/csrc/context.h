@@ -15,7 +15,7 @@
 
 namespace nmsm {
 struct MsmPlanLite {  // mirror of MsmPlan (msm_body.cuh) so this header stays free of device code
-  int c, W, B, G, L, K, chunks;
+  int c, W, B, G, L, K, chunks, D;
 };
 }  // namespace nmsm
 
@@ -117,8 +117,11 @@ struct EngineVTable {
   int (*mul_batch)(const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
                    uint8_t* out_is_inf);
   int (*prepare_points)(const uint8_t* pts, uint64_t n, uint32_t** out_dev);
-  int (*msm_prepared)(const uint32_t* d_prepared, uint64_t n_points, const uint8_t* scalars, uint64_t n,
+  // table_c != 0: d_prepared carries the fixed-base table built by precompute_table for that window size
+  int (*msm_prepared)(const uint32_t* d_prepared, uint64_t n_points, int table_c, const uint8_t* scalars, uint64_t n,
                       uint8_t* out_xy, int* out_is_inf);
+  // replaces *d_prepared (level 0) by a buffer holding all levels 2^(c*j) * P; c_req = 0 picks c by the cost model
+  int (*precompute_table)(uint32_t** d_prepared, uint64_t n_points, int c_req, int* out_c, int* out_levels);
   // asynchronous halves on the slot g_ctx.cur: enqueue (optionally H2D from host pointers) / wait + read back
   int (*submit)(const void* pts, const void* scalars, uint64_t n, int inputs_on_device, void* d_out_acc);
   int (*collect)(uint8_t* out_xy, int* out_is_inf);

@@ -263,6 +263,13 @@ struct SwXyzz {
     y.to_canonical(xy + F::LIMBS);
     *is_inf = 0;
   }
+  // Montgomery-form affine (the layout k_accumulate gathers); identity -> (0, 0)
+  NMSM_HD static Affine to_affine_prepared(const Acc& p) {
+    if (is_identity(p)) return Affine{F::zero(), F::zero()};
+    F i3 = inv(p.ZZZ);
+    F t = p.ZZ * i3;
+    return Affine{p.X * sqr(t), p.Y * i3};
+  }
   NMSM_HD static void store_acc(uint32_t* dst, const Acc& p) {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
     for (int k = 0; k < ACC_WORDS; k++) dst[k] = s[k];
@@ -397,6 +404,12 @@ struct EdExt {
     x.to_canonical(xy);
     y.to_canonical(xy + F::LIMBS);
     *is_inf = (x.is_zero() && y == F::one()) ? 1u : 0u;
+  }
+  // prepared form (y - x, y + x, 2d*x*y) of an accumulator
+  NMSM_HD static Affine to_affine_prepared(const Acc& p) {
+    F iz = inv(p.Z);
+    F x = p.X * iz, y = p.Y * iz;
+    return Affine{y - x, y + x, x * y * d2()};
   }
   NMSM_HD static void store_acc(uint32_t* dst, const Acc& p) {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);

@@ -24,15 +24,17 @@ struct Engine {
 // accumulator is written there and no affine result is produced.
 // `d_prepared` != nullptr: points were validated and prepared once by prepare_points() (device-resident
 // handle, nmsm_points_upload); k_prepare is skipped.
+// `table_c` != 0: d_prepared holds table_digits(table_c) levels of `table_points` points each (precompute_table).
 static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
-                   uint8_t* out_xy, int* out_is_inf, const uint32_t* d_prepared = nullptr) {
-  if (int r = submit_msm(d_pts, d_scalars, n, d_out_acc, d_prepared)) return r;
+                   uint8_t* out_xy, int* out_is_inf, const uint32_t* d_prepared = nullptr, int table_c = 0,
+                   uint64_t table_points = 0) {
+  if (int r = submit_msm(d_pts, d_scalars, n, d_out_acc, d_prepared, table_c, table_points)) return r;
   return collect_msm(out_xy, out_is_inf);
 }
 
 // Enqueue the whole pipeline (and the small result D2H) on the current slot's stream; no host sync.
 static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
-                      const uint32_t* d_prepared) {
+                      const uint32_t* d_prepared, int table_c = 0, uint64_t table_points = 0) {
   Slot& C = g_ctx.slot[g_ctx.cur];
   if (C.pend.active) return fail(NMSM_ERR_ARG, "slot busy: collect the previous MSM first");
   if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
@@ -56,9 +58,12 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
     return NMSM_OK;
   }
 
-  MsmPlan plan = make_plan<Cv>(n, g_ctx.forced_c, g_ctx.sm_count);
-  const uint64_t max_entries = n * (uint64_t)plan.W * (Cv::GLV ? 2 : 1);
+  MsmPlan plan = table_c ? make_table_plan<Cv>(table_points, table_c, g_ctx.sm_count)
+                         : make_plan<Cv>(n, g_ctx.forced_c, g_ctx.sm_count);
+  const uint64_t max_entries = n * (uint64_t)plan.D * (Cv::GLV ? 2 : 1);
   if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
+  // one window split over up to 256 blocks when there is only one (fixed-base tables), else <= 32 per window
+  const int max_splits = plan.W == 1 ? REDUCE2_MAX_SPLITS_1W : REDUCE2_MAX_SPLITS;
   const uint64_t max_threads = (max_entries + plan.L - 1) / plan.L;
 
   if (!d_prepared) CK(C.aff.ensure(n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
@@ -73,7 +78,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   CK(C.tile_sums.ensure((size_t)(plan.G / SCAN_TILE + 2) * 4));
   const uint64_t ntile1 = max_threads / STITCH_FAN + 1, ntile2 = ntile1 / STITCH_FAN + 1;
   CK(C.tiles.ensure((ntile1 + ntile2) * G::ACC_WORDS * 4));
-  CK(C.blk.ensure((size_t)plan.W * REDUCE2_MAX_SPLITS * G::ACC_WORDS * 4 * 2));
+  CK(C.blk.ensure(((size_t)plan.W * max_splits + 1) * G::ACC_WORDS * 4 * 2));
   CK(C.window_out.ensure((size_t)plan.W * G::ACC_WORDS * 4));
 
   uint32_t* aff = d_prepared ? const_cast<uint32_t*>(d_prepared) : (uint32_t*)C.aff.p;
@@ -90,7 +95,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   uint32_t* tile1 = (uint32_t*)C.tiles.p;
   uint32_t* tile2 = tile1 + ntile1 * G::ACC_WORDS;
   uint32_t* blkP = (uint32_t*)C.blk.p;
-  uint32_t* blkQ = blkP + (size_t)plan.W * REDUCE2_MAX_SPLITS * G::ACC_WORDS;
+  uint32_t* blkQ = blkP + ((size_t)plan.W * max_splits + 1) * G::ACC_WORDS;
   uint32_t* window_out = (uint32_t*)C.window_out.p;
   cudaStream_t st = C.stream;
   const uint32_t n32 = (uint32_t)n;
@@ -124,14 +129,24 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   }
   EV(7);
   {
-    // k_reduce2 / k_reduce3: each window is split over <= 32 blocks of 32 quads x R chunks
+    // k_reduce2 / k_reduce3: each window is split over <= max_splits blocks of 32 quads x R chunks
     int R = 4;
-    while ((plan.chunks + REDUCE2_LOGICAL * R - 1) / (REDUCE2_LOGICAL * R) > REDUCE2_MAX_SPLITS) R <<= 1;
+    while ((plan.chunks + REDUCE2_LOGICAL * R - 1) / (REDUCE2_LOGICAL * R) > max_splits) R <<= 1;
     const int splits = (plan.chunks + REDUCE2_LOGICAL * R - 1) / (REDUCE2_LOGICAL * R);
+    const size_t smem2 = (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4;
     dim3 grid2(splits, plan.W);
-    k_reduce2<Cv><<<grid2, REDUCE2_THREADS, (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4, st>>>(sums, wsums, plan, R,
-                                                                                            blkP, blkQ);
-    k_reduce3<Cv><<<plan.W, 32, 0, st>>>(blkP, blkQ, plan, splits, R, window_out);
+    k_reduce2<Cv><<<grid2, REDUCE2_THREADS, smem2, st>>>(sums, wsums, plan, R, blkP, blkQ);
+    if (splits <= REDUCE2_MAX_SPLITS) {
+      k_reduce3<Cv><<<plan.W, 32, 0, st>>>(blkP, blkQ, plan, splits, R, window_out);
+    } else {
+      // second application of k_reduce2 to its own outputs: chunks := splits, K := K * Mb (msm.cuh)
+      MsmPlan p3 = plan;
+      p3.chunks = splits;
+      p3.K = plan.K * REDUCE2_LOGICAL * R;
+      const int R3 = (splits + REDUCE2_LOGICAL - 1) / REDUCE2_LOGICAL;
+      uint32_t* scratchQ = blkQ + (size_t)plan.W * max_splits * G::ACC_WORDS;  // block total, unused
+      k_reduce2<Cv><<<dim3(1, plan.W), REDUCE2_THREADS, smem2, st>>>(blkQ, blkP, p3, R3, window_out, scratchQ);
+    }
   }
   EV(8);
   if (d_out_acc)
@@ -144,7 +159,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   CK(cudaMemcpyAsync(C.h_result, d_res, RES_WORDS * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(C.h_result + RES_WORDS, offsets + plan.G, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(C.done, st));
-  C.pend.plan = MsmPlanLite{plan.c, plan.W, plan.B, plan.G, plan.L, plan.K, plan.chunks};
+  C.pend.plan = MsmPlanLite{plan.c, plan.W, plan.B, plan.G, plan.L, plan.K, plan.chunks, plan.D};
   C.pend.active = true;
   return NMSM_OK;
 }
@@ -166,7 +181,7 @@ static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
   CK(cudaEventSynchronize(C.done));
   MsmPlan plan;
   plan.c = C.pend.plan.c; plan.W = C.pend.plan.W; plan.B = C.pend.plan.B; plan.G = C.pend.plan.G;
-  plan.L = C.pend.plan.L; plan.K = C.pend.plan.K; plan.chunks = C.pend.plan.chunks;
+  plan.L = C.pend.plan.L; plan.K = C.pend.plan.K; plan.chunks = C.pend.plan.chunks; plan.D = C.pend.plan.D;
   const bool partial = C.pend.partial;
 
   const uint32_t err_pt = C.h_result[G::IN_WORDS + 1], err_sc = C.h_result[G::IN_WORDS + 2];
@@ -239,8 +254,8 @@ static int prepare_points(const uint8_t* pts, uint64_t n, uint32_t** out_dev) {
 
 // MSM of host scalars against a prepared point set (scalars beyond the set are an error; fewer
 // scalars use the first n_scalars points, like interleavedMSMUnsafe's trailing zeros).
-static int run_msm_prepared(const uint32_t* d_prepared, uint64_t n_points, const uint8_t* scalars, uint64_t n,
-                            uint8_t* out_xy, int* out_is_inf) {
+static int run_msm_prepared(const uint32_t* d_prepared, uint64_t n_points, int table_c, const uint8_t* scalars,
+                            uint64_t n, uint8_t* out_xy, int* out_is_inf) {
   Slot& C = g_ctx.slot[g_ctx.cur];
   if (n > n_points) return fail(NMSM_ERR_LENGTH, "array of scalars must not be larger than array of points");
   if (n) {
@@ -249,7 +264,39 @@ static int run_msm_prepared(const uint32_t* d_prepared, uint64_t n_points, const
   }
   if (Cv::GLV && n != n_points)
     return fail(NMSM_ERR_ARG, "this curve's prepared sets interleave P and phi(P): pass one scalar per point");
-  return run_msm(nullptr, (const uint32_t*)C.in_scalars.p, n, nullptr, out_xy, out_is_inf, d_prepared);
+  return run_msm(nullptr, (const uint32_t*)C.in_scalars.p, n, nullptr, out_xy, out_is_inf, d_prepared, table_c,
+                 n_points);
+}
+
+// Fixed-base table for a prepared set: levels j = 0..D-1 hold 2^(c*j) * P_i (and 2^(c*j) * phi(P_i) for the GLV
+// curves), each level in the prepared affine layout.  The device-resident counterpart of the per-point wNAF
+// tables interleavedMSMUnsafe captures (curve.ts:937-959) and of Point.precompute (curve.ts:532-577): built once,
+// every later MSM over the set needs one bucket window instead of W and no Horner doublings.
+static int precompute_table(uint32_t** d_prepared, uint64_t n_points, int c_req, int* out_c, int* out_levels) {
+  Slot& C = g_ctx.slot[g_ctx.cur];
+  const uint64_t terms = n_points * (Cv::GLV ? 2 : 1);
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const int c = (c_req >= 4 && c_req <= MAX_TABLE_BITS) ? c_req
+                                                         : choose_table_bits<Cv>(n_points, g_ctx.sm_count, 0.5 * (double)free_b);
+  if (c_req != 0 && c != c_req) return fail(NMSM_ERR_ARG, "table window bits must be 0 (automatic) or in [4, 22]");
+  const int D = table_digits<Cv>(c);
+  if (terms * (uint64_t)D >= (1ull << 31)) return fail(NMSM_ERR_ARG, "points * levels must be < 2^31");
+  const size_t level_bytes = (size_t)terms * G::AFF_WORDS * 4;
+  uint32_t* tbl = nullptr;
+  CK(cudaMalloc((void**)&tbl, level_bytes * D));
+  cudaMemcpyAsync(tbl, *d_prepared, level_bytes, cudaMemcpyDeviceToDevice, C.stream);
+  for (int j = 1; j < D; j++)
+    k_table_level<Cv><<<cdiv(terms, 128), 128, 0, C.stream>>>(tbl + (size_t)(j - 1) * terms * G::AFF_WORDS,
+                                                               tbl + (size_t)j * terms * G::AFF_WORDS, (uint32_t)terms, c);
+  cudaError_t e = cudaStreamSynchronize(C.stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { cudaFree(tbl); return cuda_fail(e, "precompute_table"); }
+  cudaFree(*d_prepared);
+  *d_prepared = tbl;
+  *out_c = c;
+  *out_levels = D;
+  return NMSM_OK;
 }
 
 static int run_msm_dev(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
@@ -322,6 +369,7 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
                                     &Engine<CURVE>::run_msm_host,   &Engine<CURVE>::run_msm_dev,   \
                                     &Engine<CURVE>::run_fold,       &Engine<CURVE>::run_mul_batch,  \
                                     &Engine<CURVE>::prepare_points, &Engine<CURVE>::run_msm_prepared, \
+                                    &Engine<CURVE>::precompute_table,                              \
                                     &Engine<CURVE>::submit_any,     &Engine<CURVE>::collect_msm}; \
     return &vt;                                                                                \
   }

@@ -136,6 +136,9 @@ k_accumulate(const uint32_t* __restrict__ aff, const uint32_t* __restrict__ sort
 //   sum_b (b+1) B_b  =  sum_k T_k + K * sum_k k * S_k        k over the M = B/K chunks   (k_reduce1)
 //   per block of Mb chunks:  P_s = sum T_k + K * sum (k - s*Mb) S_k ,  Q_s = sum S_k        (k_reduce2)
 //   window sum = sum_s P_s + K * Mb * sum_s s * Q_s                                          (k_reduce3)
+// The last line has the shape of the first (T := P, S := Q, K := K * Mb): when one window is split over more
+// than 32 blocks (fixed-base tables: a single window of up to 2^21 buckets) k_reduce2 runs a second time on its
+// own outputs instead of k_reduce3.
 // ------------------------------------------------------------------------------------------------
 template <class G>
 __device__ __forceinline__ typename G::Acc shfl_down_acc(const typename G::Acc& a, int delta) {
@@ -206,6 +209,7 @@ __device__ __forceinline__ typename G::Acc smem_get(const uint32_t* smem, uint32
 static constexpr int REDUCE2_THREADS = 128;                   // 32 logical threads (quads), 4 warps
 static constexpr int REDUCE2_LOGICAL = REDUCE2_THREADS / 4;
 static constexpr int REDUCE2_MAX_SPLITS = 32;                 // k_reduce3: 8 quads x up to 4 splits each
+static constexpr int REDUCE2_MAX_SPLITS_1W = 256;             // single-window plans: folded by a second k_reduce2
 
 // grid (splits, W).  Logical thread lt owns R consecutive chunks; see the formulas above.
 template <class Cv>
@@ -356,6 +360,14 @@ k_fold(const uint32_t* __restrict__ accs, int count, uint32_t* __restrict__ out,
     for (int k = 0; k < G::IN_WORDS; k++) out[k] = xy[k];
     *out_inf = inf;
   }
+}
+
+// Fixed-base tables: level j+1 = 2^c * level j for every point of the set (nmsm_points_precompute).
+template <class Cv>
+__global__ void __launch_bounds__(128)
+k_table_level(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next, uint32_t count, int c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) table_level_body<Cv>(i, prev, next, c);
 }
 
 template <class Cv>

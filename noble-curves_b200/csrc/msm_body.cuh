@@ -24,16 +24,20 @@
 namespace nmsm {
 
 static constexpr int MAX_WINDOW_BITS = 16;
+static constexpr int MAX_TABLE_BITS = 22;  // fixed-base tables: one bucket set of 2^(c-1) buckets
 static constexpr int SCALAR_WORDS = 8;
 
 struct MsmPlan {
   int c;       // window bits
-  int W;       // windows
+  int W;       // bucket windows (1 when the point set carries precomputed 2^(c*j) multiples)
   int B;       // buckets per window = 2^(c-1)
   int G;       // W*B
   int L;       // sorted entries per accumulate thread
   int K;       // buckets per reduce chunk
   int chunks;  // B / K
+  int D;       // signed digits per (half-)scalar; == W unless stride != 0
+  uint32_t stride;  // 0: digit w goes to bucket window w.  != 0 (fixed-base tables): every digit goes to the
+                    // single bucket window and selects the point  index + w * stride  = 2^(c*w) * P_index
 };
 
 template <class Cv>
@@ -107,6 +111,62 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
 #endif
   p.K = p.B < Kc ? p.B : Kc;
   p.chunks = p.B / p.K;
+  p.D = p.W;
+  p.stride = 0;
+  return p;
+}
+
+// Fixed-base tables (nmsm_points_precompute): level j of the table holds 2^(c*j) * P_i for every point of the
+// set, so all D digits of a scalar land in ONE bucket window: 1/W of the bucket reduction, no Horner doublings,
+// and c can grow past 16 because the reduce cost no longer multiplies by W.  Same time model as make_plan.
+template <class Cv>
+inline int table_digits(int c) { return (glv_bits<Cv>() + 1 + c - 1) / c; }
+
+template <class Cv>
+inline int choose_table_bits(uint64_t n_points, int sm_count, double mem_budget_bytes) {
+  using G = typename Cv::G;
+  using F = typename G::Field;
+  const double terms = (double)n_points * (Cv::GLV ? 2 : 1);
+  const double limb_ratio = (double)(F::LIMBS / F::BASE_MULS == 12 ? 1.0 : (8.0 * 8.0) / (12.0 * 12.0));
+  const double fscale = limb_ratio * F::BASE_MULS;
+  const double t_madd = 0.352e-6 * fscale * G::COST_MADD / 10.0;
+  const double t_add_tp = 0.93e-6 * fscale * G::COST_ADD / 14.0;
+  const double t_add_lat = 0.030 * fscale * G::COST_ADD / 14.0;
+  int best_c = 4;
+  double best = 1e300;
+  for (int c = 4; c <= MAX_TABLE_BITS; c++) {
+    const int D = table_digits<Cv>(c);
+    if ((double)D * terms * G::AFF_WORDS * 4.0 > mem_budget_bytes && c > 4) continue;
+    const double B = (double)(1u << (c - 1));
+    const double entries = terms * D;
+    int L = (int)ceil(entries / ((double)sm_count * 1024.0));
+    L = L < 4 ? 4 : (L > 32 ? 32 : L);
+    const double parts = 1.0 + (entries / B) / L;
+    const double kk = B < 8 ? B : 8;
+    const double t_r1a = B * (1.0 + parts) * t_add_tp, t_r1b = kk * (1.0 + parts) * t_add_lat;
+    const double cost = entries * t_madd + (t_r1a > t_r1b ? t_r1a : t_r1b);
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
+}
+
+template <class Cv>
+inline MsmPlan make_table_plan(uint64_t n_points, int c, int sm_count) {
+  MsmPlan p;
+  const double terms = (double)n_points * (Cv::GLV ? 2 : 1);
+  p.c = c;
+  p.W = 1;
+  p.B = 1 << (c - 1);
+  p.G = p.B;
+  p.D = table_digits<Cv>(c);
+  p.stride = (uint32_t)(n_points * (Cv::GLV ? 2 : 1));
+  int L = (int)ceil(terms * p.D / ((double)sm_count * 1024.0));
+  p.L = L < 4 ? 4 : (L > 32 ? 32 : L);
+  p.K = p.B < 8 ? p.B : 8;
+  p.chunks = p.B / p.K;
   return p;
 }
 
@@ -117,7 +177,7 @@ inline uint64_t plan_modmuls(const MsmPlan& p, uint64_t entries) {
   // field-mul equivalents in the base field (Fp2 mul = 3)
   uint64_t per = F::BASE_MULS;
   uint64_t m = entries * G::COST_MADD + (uint64_t)p.W * 2ull * p.B * G::COST_ADD +
-               (uint64_t)p.W * p.c * G::COST_DBL;
+               (uint64_t)(p.W - 1) * p.c * G::COST_DBL;
   return m * per;
 }
 
@@ -468,6 +528,18 @@ NMSM_HD void prepare_body(uint32_t i, uint32_t n, const uint32_t* pts, uint32_t*
   }
 }
 
+// One level of a fixed-base table: next[i] = 2^c * prev[i], back in the prepared affine layout (one xgcd
+// inversion per point; a one-off cost paid by nmsm_points_precompute).
+template <class Cv>
+NMSM_HD void table_level_body(uint32_t i, const uint32_t* prev, uint32_t* next, int c) {
+  using G = typename Cv::G;
+  typename G::Affine a = load_aff<G>(prev + (size_t)i * G::AFF_WORDS);
+  typename G::Acc acc = G::from_affine(a);
+  for (int j = 0; j < c; j++) nl_dbl<G>(acc);
+  a = G::to_affine_prepared(acc);
+  store_words<G::AFF_WORDS>(next + (size_t)i * G::AFF_WORDS, reinterpret_cast<const uint32_t*>(&a));
+}
+
 // Signed-digit recoding of one magnitude shared by the count and scatter passes: digit d_w in
 // [-(2^(c-1)-1), 2^(c-1)], sum d_w 2^(cw) = m (the fixed-window analogue of curve.ts:454-472
 // signedWindowDigits).  Bucket id g = w*B + |d| - 1, weight |d|; the sign rides in bit 31 of the entry.
@@ -476,7 +548,7 @@ NMSM_HD void emit_digits(const uint32_t* m, int nwords, uint32_t index, uint32_t
                          unsigned int* counts_or_cursor, uint32_t* sorted) {
   const uint32_t half = 1u << (plan.c - 1);
   uint32_t carry = 0;
-  for (int w = 0; w < plan.W; w++) {
+  for (int w = 0; w < plan.D; w++) {
     uint32_t v = scalar_bits(m, w * plan.c, plan.c, nwords) + carry;
     carry = 0;
     uint32_t neg = flip;
@@ -486,10 +558,10 @@ NMSM_HD void emit_digits(const uint32_t* m, int nwords, uint32_t index, uint32_t
       carry = 1;
     }
     if (v != 0) {
-      uint32_t g = (uint32_t)w * (uint32_t)plan.B + (v - 1);
+      const uint32_t g = (plan.stride ? 0u : (uint32_t)w * (uint32_t)plan.B) + (v - 1);
       if (SCATTER) {
         uint32_t pos = atomic_add_u32(&counts_or_cursor[g], 1u);
-        sorted[pos] = index | (neg << 31);
+        sorted[pos] = (index + (uint32_t)w * plan.stride) | (neg << 31);
       } else {
         atomic_add_u32(&counts_or_cursor[g], 1u);
       }

@@ -506,6 +506,15 @@ class PointSet:
         except NmsmError as e:
             _raise_mapped(e)
         self.handle = h.value
+        self.table_bits, self.table_levels = 0, 1
+
+    def precompute(self, window_bits: int = 0):
+        """Build the fixed-base table 2^(c*j) * P_i on the device (nmsm_points_precompute; the analogue of
+        Point.precompute, curve.ts:532-577, for a whole set).  Returns (window bits, levels)."""
+        c, lv = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(self._lib.nmsm_points_precompute(self.handle, int(window_bits), ctypes.byref(c), ctypes.byref(lv)))
+        self.table_bits, self.table_levels = c.value, lv.value
+        return c.value, lv.value
 
     def msm(self, scalars: bytes, n: int):
         pb = self._lib.nmsm_point_bytes(self.curve_id)
@@ -531,15 +540,18 @@ class PointSet:
             pass
 
 
-def interleavedMSMUnsafe(c, points, windowSize: int = 4):
+def interleavedMSMUnsafe(c, points, windowSize: int = 4, precompute: bool = True):
     """curve.ts:937-959: captures a FIXED point set once and returns `scalars -> sum s_i*P_i`.  Here the
-    captured state is the device-resident prepared array; `windowSize` is accepted for signature
-    compatibility (the GPU schedule picks its own window).  Fewer scalars than points are zero-padded."""
+    captured state is the device-resident prepared array plus (precompute=True, like the reference's per-point
+    tables built at capture time) the fixed-base table of nmsm_points_precompute; `windowSize` is accepted for
+    signature compatibility (the GPU schedule picks its own window).  Fewer scalars than points are zero-padded."""
     if not (isinstance(windowSize, int) and 2 <= windowSize <= c.Fn.BITS):
         raise ValueError("invalid window size, expected [2..%d], got W=%s" % (c.Fn.BITS, windowSize))
     _validate_msm_points(points, c)
     n = len(points)
     ps = PointSet(c.CURVE_ID, _pack_points(points), n) if n else None
+    if ps is not None and precompute:
+        ps.precompute(0)
 
     def run(scalars):
         _validate_msm_scalars(scalars, c.Fn)

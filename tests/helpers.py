@@ -110,7 +110,8 @@ def u32(b: bytes):
     return np.frombuffer(b, dtype=np.uint32).copy()
 
 
-def emu_msm(name, pts_b: bytes, scalars_b: bytes, n: int, forced_c=0, forced_L=0):
+def emu_msm(name, pts_b: bytes, scalars_b: bytes, n: int, forced_c=0, forced_L=0, table_c=0):
+    """table_c != 0: the fixed-base table route (levels 2^(c*j)*P, one bucket window)."""
     lib = hostemu()
     cb = FP_BYTES[name] * PARTS[name]
     pts = u32(pts_b) if n else np.zeros(4, np.uint32)
@@ -120,7 +121,10 @@ def emu_msm(name, pts_b: bytes, scalars_b: bytes, n: int, forced_c=0, forced_L=0
     err = np.zeros(2, np.uint32)
     plan = np.zeros(4, np.uint32)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
-    rc = lib.emu_msm(CURVE_IDS[name], p(pts), p(sc), n, forced_c, forced_L, p(out), p(inf), p(err), p(plan))
+    if table_c:
+        rc = lib.emu_msm_table(CURVE_IDS[name], p(pts), p(sc), n, table_c, forced_L, p(out), p(inf), p(err), p(plan))
+    else:
+        rc = lib.emu_msm(CURVE_IDS[name], p(pts), p(sc), n, forced_c, forced_L, p(out), p(inf), p(err), p(plan))
     assert rc == 0, rc
     x, y = unpack_point(name, out.tobytes())
     return (x, y, int(inf[0])), (int(err[0]), int(err[1])), tuple(int(v) for v in plan)

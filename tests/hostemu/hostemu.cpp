@@ -18,16 +18,23 @@ using namespace nmsm;
 
 template <class Cv>
 static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, int forced_c, int forced_L,
-                     uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out) {
+                     uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out, int table_c = 0) {
   using G = typename Cv::G;
-  MsmPlan plan = make_plan<Cv>(n, forced_c, 148);
+  // table_c != 0: fixed-base table route (nmsm_points_precompute + nmsm_msm_points)
+  MsmPlan plan = table_c ? make_table_plan<Cv>(n, table_c, 148) : make_plan<Cv>(n, forced_c, 148);
   if (forced_L > 0) plan.L = forced_L;
   plan_out[0] = plan.c; plan_out[1] = plan.W; plan_out[2] = plan.B; plan_out[3] = plan.L;
-  std::vector<uint32_t> aff((size_t)n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS);
+  const size_t terms = (size_t)n * (Cv::GLV ? 2 : 1);
+  std::vector<uint32_t> aff(terms * G::AFF_WORDS * (table_c ? plan.D : 1));
   std::vector<unsigned int> counts(plan.G + 1, 0), cursor(plan.G + 1, 0);
   std::vector<uint32_t> offsets(plan.G + 1, 0);
   unsigned int err[2] = {0xffffffffu, 0xffffffffu};
   for (uint32_t i = 0; i < n; i++) prepare_body<Cv>(i, n, pts, aff.data(), err);
+  if (table_c && err[0] == 0xffffffffu)
+    for (int j = 1; j < plan.D; j++)
+      for (uint32_t i = 0; i < terms; i++)
+        table_level_body<Cv>(i, aff.data() + (size_t)(j - 1) * terms * G::AFF_WORDS,
+                             aff.data() + (size_t)j * terms * G::AFF_WORDS, plan.c);
   for (uint32_t i = 0; i < n; i++) digits_body<Cv, false>(i, n, scalars, plan, counts.data(), nullptr, err);
   uint32_t run = 0;
   for (int g = 0; g < plan.G; g++) { offsets[g] = run; cursor[g] = run; run += counts[g]; }
@@ -187,6 +194,10 @@ int emu_glv_split_lattice(int curve, const uint32_t* k, uint32_t* out) {
   out[10] = n1;
   out[11] = n2;
   return 0;
+}
+int emu_msm_table(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, int table_c, int forced_L,
+                  uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out) {
+  DISPATCH(curve, emu_msm_t<Cv>(pts, scalars, n, 0, forced_L, out_xy, out_inf, err_out, plan_out, table_c));
 }
 int emu_msm(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, int forced_c, int forced_L,
             uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out) {

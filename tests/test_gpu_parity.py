@@ -341,6 +341,55 @@ def test_fixed_point_set_handle(nmsm, name):
         nmsm.PointSet(H.CURVE_IDS[name], bytes(pb), 129)
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_fixed_base_table_small(nmsm, name):
+    """nmsm_points_precompute: the table route must give the plain route's answer for every table
+    window size, including c > 16 (single window of up to 2^21 buckets, folded by k_reduce2 twice), with identity
+    points, cancelling pairs and n-1 scalars in the set."""
+    n = 200 if "G2" not in name else 60
+    P, pts, scalars, _ = H.soak_inputs(name, n, seed_offset=9)
+    pts[3] = P.ZERO
+    pts[8] = pts[7].negate()
+    scalars[8] = scalars[7]
+    scalars[9] = P.Fn.ORDER - 1
+    pts = R.normalizeZ(P, pts)
+    pb, sb = H.pack_points(name, pts), H.pack_scalars(scalars)
+    exp = H.expected_tuple(name, R.pippenger(P, pts, scalars))
+    cid = H.CURVE_IDS[name]
+    for c in (0, 4, 11, 16, 19, 22):
+        ps = nmsm.PointSet(cid, pb, n)
+        got_c, levels = ps.precompute(c)
+        assert (c == 0 or got_c == c) and levels >= 1
+        for _ in range(2):  # the table is reused
+            out, inf = ps.msm(sb, n)
+            assert (*H.unpack_point(name, out), inf) == exp, (name, c)
+        zero = ps.msm(H.pack_scalars([0] * n), n)
+        assert zero[1] == 1
+        with pytest.raises(Exception, match="already carries a table"):
+            ps.precompute(c)
+        ps.close()
+    ps = nmsm.PointSet(cid, pb, n)
+    with pytest.raises(Exception, match="table window bits"):
+        ps.precompute(3)
+    ps.close()
+
+
+@pytest.mark.parametrize("name,logn", [("bls12_381_G1", 20), ("bls12_381_G2", 16), ("ed25519", 17)])
+def test_fixed_base_table_large(nmsm, name, logn):
+    """Fixed-base table at BASELINE sizes: same result as (sum k_i s_i) * G and as the plain MSM."""
+    n = 1 << logn
+    pts_b, sc, exp = _large_case(nmsm, name, n, 40 + logn)
+    ps = nmsm.PointSet(H.CURVE_IDS[name], pts_b, n)
+    c, levels = ps.precompute(0)
+    assert 8 <= c <= 22
+    sb = H.pack_scalars(sc)
+    out, inf = ps.msm(sb, n)
+    assert (*H.unpack_point(name, out), inf) == exp
+    ms, info = nmsm.last_timing()
+    assert info.windows == 1 and info.c == c
+    ps.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # ed25519 batch verification (SURVEY §8 f1): batch accepts <=> every individual reference verify accepts
 # ------------------------------------------------------------------------------------------------

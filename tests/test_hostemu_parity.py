@@ -76,6 +76,28 @@ def test_msm_soak(name):
             assert got == exp, (name, size, c, L)
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_msm_fixed_base_table_route(name):
+    """nmsm_points_precompute route: levels 2^(c*j)*P_i, every digit into ONE bucket window (MsmPlan.stride).
+    Same soak construction; table window sizes below, at and above the 16-bit limit of the ordinary plan, and
+    identity points / cancelling pairs / n-1 scalars so that table levels of O and -P are exercised."""
+    nmax = 67 if "G2" not in name else 19
+    P, pts, scalars, _ = H.soak_inputs(name, nmax, seed_offset=5)
+    pts[3] = P.ZERO
+    pts[8] = pts[7].negate()
+    scalars[8] = scalars[7]
+    scalars[9] = P.Fn.ORDER - 1
+    pts = R.normalizeZ(P, pts)
+    pb, sb = H.pack_points(name, pts), H.pack_scalars(scalars)
+    step = len(pb) // nmax
+    for size, c, L in ((nmax, 7, 0), (nmax, 13, 5), (33 if "G2" not in name else 9, 17, 0), (5, 4, 1)):
+        exp = H.expected_tuple(name, R.pippenger(P, pts[:size], scalars[:size]))
+        got, err, plan = H.emu_msm(name, pb[: size * step], sb[: size * 32], size, 0, L, table_c=c)
+        assert err == (0xFFFFFFFF, 0xFFFFFFFF)
+        assert plan[0] == c and plan[1] == 1 and plan[2] == 1 << (c - 1)
+        assert got == exp, (name, size, c, L)
+
+
 @pytest.mark.parametrize("name", ["secp256k1", "ed25519", "bls12_381_G1"])
 def test_msm_basic_cases(name):
     """test/point.test.ts:264-305: [G]*[0]=O, empty, [O]*[123]=O, [G]*[123], {G,2G,4G,8G}*{3,5,7,11}=129G."""

@@ -72,6 +72,40 @@ def msm_config(idx, name, logn, reps=5):
             "check": "bit-exact vs (sum k_i s_i)*G" if out["r"] == exp else "MISMATCH"}
 
 
+def fixed_base_config(tag, name, logn, reps=5):
+    """Same workload through a device-resident point set with a fixed-base table (nmsm_points_precompute)."""
+    n = 1 << logn
+    P = R.CURVES[name]
+    pts, sc, total = gen_terms(name, n, 300 + logn)
+    exp = H.expected_tuple(name, H.expected_from_total(P, total))
+    cid = H.CURVE_IDS[name]
+    nmsm.set_profiling(True)
+    rows = {}
+    for label, pre in (("plain_set", False), ("table", True)):
+        ps = nmsm.PointSet(cid, pts, n)
+        t0 = time.perf_counter()
+        c, levels = ps.precompute(0) if pre else (0, 1)
+        t_pre = time.perf_counter() - t0
+        out = {}
+
+        def run():
+            o, inf = ps.msm(sc, n)
+            out["r"] = (*H.unpack_point(name, o), inf)
+
+        run()
+        best = time_best(run, reps)
+        ms, info = nmsm.last_timing()
+        rows[label] = {"gpu_ms_host_scalars": best * 1e3, "gpu_ms_device": ms["total"],
+                       "points_per_s_device": n / (ms["total"] * 1e-3),
+                       "kernels_ms": {k: round(v, 4) for k, v in ms.items()},
+                       "plan": {"c": info.c, "windows": info.windows, "entries": info.sorted_entries},
+                       "table": {"window_bits": c, "levels": levels, "precompute_ms": t_pre * 1e3} if pre else None,
+                       "check": "bit-exact vs (sum k_i s_i)*G" if out["r"] == exp else "MISMATCH"}
+        ps.close()
+    return {"config": tag, "what": "%s fixed-base MSM, 2^%d terms (point set resident on the device)" % (name, logn),
+            "n": n, **rows}
+
+
 def config0():
     P = R.CURVES["secp256k1"]
     rnd = random.Random(11)
@@ -124,9 +158,14 @@ def config4():
 
 def main():
     nmsm.init(0)
-    for row in (config0(), msm_config(1, "bls12_381_G1", 16), msm_config(2, "bn254_G1", 20),
-                msm_config(3, "bls12_381_G2", 18), config4()):
-        print(json.dumps(row), flush=True)
+    if "--fixed-base" in sys.argv:
+        rows = (lambda: fixed_base_config("f4-a", "bls12_381_G1", 20), lambda: fixed_base_config("f4-b", "bls12_381_G1", 16),
+                lambda: fixed_base_config("f4-c", "bls12_381_G2", 18), lambda: fixed_base_config("f4-d", "bn254_G1", 20))
+    else:
+        rows = (config0, lambda: msm_config(1, "bls12_381_G1", 16), lambda: msm_config(2, "bn254_G1", 20),
+                lambda: msm_config(3, "bls12_381_G2", 18), config4)
+    for row in rows:
+        print(json.dumps(row()), flush=True)
 
 
 if __name__ == "__main__":
