@@ -107,6 +107,16 @@ int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t
  * levels-1 kernels of c doublings + one inversion per point. */
 int nmsm_points_precompute(uint64_t handle, int window_bits, int* out_window_bits, int* out_levels);
 
+/* Fixed-point multiplication tables (next-row f4): the device-resident form of Point.precompute(W) and the cached
+ * signed-window multiply it enables (/root/reference/src/abstract/curve.ts:532-577 table, :588-606 walk; used by
+ * BASE.multiply in getPublicKey / sign, weierstrass.ts:1168,1519).  The table holds d * 2^(16 j) * P for
+ * d in [1, 2^15] and every 16-bit digit position j, so k * P is 16-17 gathered mixed additions and no doublings.
+ * nmsm_point_table_mul_batch: out[i] = scalars[i] * P, same ranges / outputs as nmsm_mul_batch. */
+int nmsm_point_table_create(int curve, const uint8_t* point_xy, uint64_t* out_handle);
+int nmsm_point_table_free(uint64_t handle);
+int nmsm_point_table_mul_batch(uint64_t handle, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
+                               uint8_t* out_is_inf);
+
 /* Ed25519 batch verification (next-row f1).  The reference verifies one signature at a time
  * (/root/reference/src/abstract/edwards.ts:942-989, ZIP-215 decoding by default, src/ed25519.ts:168); this checks
  *   [8]( sum z_i*R_i + sum (z_i*k_i mod l)*A_i - (sum z_i*s_i mod l)*B ) == O ,  k_i = SHA-512(R_i||A_i||M_i) mod l

@@ -258,6 +258,46 @@ int nmsm_points_precompute(uint64_t handle, int window_bits, int* out_window_bit
   return NMSM_OK;
 }
 
+// ---- fixed-point multiplication tables -----------------------------------------------------------
+struct PointTable {
+  int curve;
+  uint32_t* d_tbl;
+  int levels;
+};
+
+int nmsm_point_table_create(int curve, const uint8_t* point_xy, uint64_t* out_handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
+  if (!point_xy || !out_handle) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  uint32_t* d = nullptr;
+  int levels = 0;
+  if (int r = E->build_point_table(point_xy, &d, &levels)) return r;
+  *out_handle = (uint64_t)(uintptr_t) new PointTable{curve, d, levels};
+  return NMSM_OK;
+}
+
+int nmsm_point_table_free(uint64_t handle) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  PointTable* pt = (PointTable*)(uintptr_t)handle;
+  if (!pt) return fail(NMSM_ERR_ARG, "null handle");
+  cudaFree(pt->d_tbl);
+  delete pt;
+  return NMSM_OK;
+}
+
+int nmsm_point_table_mul_batch(uint64_t handle, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
+                               uint8_t* out_is_inf) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
+  PointTable* pt = (PointTable*)(uintptr_t)handle;
+  if (!pt || (n && (!scalars || !out_xy || !out_is_inf))) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(pt->curve);
+  return E->table_mul_batch(pt->d_tbl, scalars, n, allow_zero, out_xy, out_is_inf);
+}
+
 int nmsm_msm_submit(int curve, const void* pts, const void* scalars, uint64_t n, int inputs_on_device, int slot) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;

@@ -122,6 +122,10 @@ struct EngineVTable {
                       uint8_t* out_xy, int* out_is_inf);
   // replaces *d_prepared (level 0) by a buffer holding all levels 2^(c*j) * P; c_req = 0 picks c by the cost model
   int (*precompute_table)(uint32_t** d_prepared, uint64_t n_points, int c_req, int* out_c, int* out_levels);
+  // fixed-point multiplication table d * 2^(16 j) * P and the batch multiply through it
+  int (*build_point_table)(const uint8_t* point_xy, uint32_t** out_tbl, int* out_levels);
+  int (*table_mul_batch)(const uint32_t* tbl, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
+                         uint8_t* out_is_inf);
   // asynchronous halves on the slot g_ctx.cur: enqueue (optionally H2D from host pointers) / wait + read back
   int (*submit)(const void* pts, const void* scalars, uint64_t n, int inputs_on_device, void* d_out_acc);
   int (*collect)(uint8_t* out_xy, int* out_is_inf);

@@ -299,6 +299,66 @@ static int precompute_table(uint32_t** d_prepared, uint64_t n_points, int c_req,
   return NMSM_OK;
 }
 
+// Fixed-point table (nmsm_point_table_create): validate P, level 0 = d*P (d <= 2^15), then levels 2^(16 j).
+static int build_point_table(const uint8_t* point_xy, uint32_t** out_tbl, int* out_levels) {
+  Slot& C = g_ctx.slot[g_ctx.cur];
+  constexpr int LV = point_table_levels<Cv>();
+  uint32_t in[G::IN_WORDS];
+  memcpy(in, point_xy, sizeof(in));
+  if (!G::input_in_range(in)) return fail(NMSM_ERR_POINT, "invalid point at index 0", 0);
+  CK(C.in_pts.ensure(G::IN_WORDS * 4));
+  CK(C.aff.ensure(2 * G::AFF_WORDS * 4));
+  CK(C.result.ensure((G::IN_WORDS + 4) * 4));
+  unsigned int* d_err = (unsigned int*)C.result.p;
+  uint32_t* tbl = nullptr;
+  const size_t level_words = (size_t)PT_HALF * G::AFF_WORDS;
+  CK(cudaMalloc((void**)&tbl, level_words * 4 * LV));
+  cudaStream_t st = C.stream;
+  cudaMemcpyAsync(C.in_pts.p, point_xy, G::IN_WORDS * 4, cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(d_err, 0xff, 8, st);
+  k_prepare<Cv><<<1, 1, 0, st>>>((const uint32_t*)C.in_pts.p, 1u, (uint32_t*)C.aff.p, d_err);
+  k_table_base<Cv><<<cdiv(PT_HALF, 128), 128, 0, st>>>((const uint32_t*)C.aff.p, tbl);
+  for (int j = 1; j < LV; j++)
+    k_table_level<Cv><<<cdiv(PT_HALF, 128), 128, 0, st>>>(tbl + (size_t)(j - 1) * level_words, tbl + (size_t)j * level_words,
+                                                           PT_HALF, PT_BITS);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { cudaFree(tbl); return cuda_fail(e, "build_point_table"); }
+  *out_tbl = tbl;
+  *out_levels = LV;
+  return NMSM_OK;
+}
+
+// out[i] = scalars[i] * P through the table: the batch form of a precomputed point's multiply / multiplyUnsafe.
+static int table_mul_batch(const uint32_t* tbl, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
+                           uint8_t* out_is_inf) {
+  Slot& C = g_ctx.slot[g_ctx.cur];
+  if (n == 0) return NMSM_OK;
+  if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
+  CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
+  CK(C.mul_out.ensure(n * (G::IN_WORDS + 1) * 4 + 16));
+  CK(C.result.ensure(64));
+  unsigned int* d_err = (unsigned int*)C.result.p;
+  uint32_t* d_xy = (uint32_t*)C.mul_out.p;
+  uint32_t* d_inf = d_xy + n * G::IN_WORDS;
+  cudaStream_t st = C.stream;
+  CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(d_err, 0xff, 8, st));
+  k_table_mul<Cv><<<cdiv(n, 128), 128, 0, st>>>(tbl, (const uint32_t*)C.in_scalars.p, (uint32_t)n, allow_zero, d_xy,
+                                                   d_inf, d_err);
+  CK(cudaGetLastError());
+  std::vector<uint32_t> inf(n);
+  unsigned int err[2];
+  CK(cudaMemcpyAsync(err, d_err, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_xy, d_xy, n * G::IN_WORDS * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(inf.data(), d_inf, n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (err[1] != 0xffffffffu)
+    return fail(NMSM_ERR_SCALAR, "invalid scalar: out of range (index " + std::to_string(err[1]) + ")", err[1]);
+  for (uint64_t i = 0; i < n; i++) out_is_inf[i] = (uint8_t)inf[i];
+  return NMSM_OK;
+}
+
 static int run_msm_dev(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
                        uint8_t* out_xy, int* out_is_inf) {
   return run_msm(d_pts, d_scalars, n, d_out_acc, out_xy, out_is_inf, nullptr);
@@ -370,6 +430,7 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
                                     &Engine<CURVE>::run_fold,       &Engine<CURVE>::run_mul_batch,  \
                                     &Engine<CURVE>::prepare_points, &Engine<CURVE>::run_msm_prepared, \
                                     &Engine<CURVE>::precompute_table,                              \
+                                    &Engine<CURVE>::build_point_table, &Engine<CURVE>::table_mul_batch, \
                                     &Engine<CURVE>::submit_any,     &Engine<CURVE>::collect_msm}; \
     return &vt;                                                                                \
   }

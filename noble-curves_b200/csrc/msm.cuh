@@ -370,6 +370,31 @@ k_table_level(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next, ui
   if (i < count) table_level_body<Cv>(i, prev, next, c);
 }
 
+// Fixed-point multiplication tables (nmsm_point_table_*): level 0 = d * P, then k_table_level per level.
+template <class Cv>
+__global__ void __launch_bounds__(128)
+k_table_base(const uint32_t* __restrict__ p_aff, uint32_t* __restrict__ level0) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < PT_HALF) table_base_body<Cv>(i, p_aff, level0);
+}
+
+// out[i] = scalars[i] * P: `levels` gathered mixed additions per thread, then canonical affine.
+template <class Cv>
+__global__ void __launch_bounds__(128)
+k_table_mul(const uint32_t* __restrict__ tbl, const uint32_t* __restrict__ scalars, uint32_t n, int allow_zero,
+            uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_inf, unsigned int* err) {
+  using G = typename Cv::G;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename G::Acc acc;
+  if (!table_mul_body<Cv>(i, tbl, scalars, allow_zero, acc, err)) return;
+  uint32_t xy[G::IN_WORDS];
+  uint32_t inf;
+  nl_to_affine<G>(acc, xy, &inf);
+  store_words<G::IN_WORDS>(out_xy + (size_t)i * G::IN_WORDS, xy);
+  out_inf[i] = inf;
+}
+
 template <class Cv>
 __global__ void __launch_bounds__(128)
 k_mul_batch(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars, uint32_t n,

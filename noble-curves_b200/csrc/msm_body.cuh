@@ -165,7 +165,11 @@ inline MsmPlan make_table_plan(uint64_t n_points, int c, int sm_count) {
   p.stride = (uint32_t)(n_points * (Cv::GLV ? 2 : 1));
   int L = (int)ceil(terms * p.D / ((double)sm_count * 1024.0));
   p.L = L < 4 ? 4 : (L > 32 ? 32 : L);
-  p.K = p.B < 8 ? p.B : 8;
+  int Kc = 8;
+#if !defined(__CUDA_ARCH__)
+  if (const char* e = getenv("NMSM_TK")) { int v = atoi(e); if (v >= 1 && (v & (v - 1)) == 0) Kc = v; }  // tuning experiments
+#endif
+  p.K = p.B < Kc ? p.B : Kc;
   p.chunks = p.B / p.K;
   return p;
 }
@@ -538,6 +542,66 @@ NMSM_HD void table_level_body(uint32_t i, const uint32_t* prev, uint32_t* next, 
   for (int j = 0; j < c; j++) nl_dbl<G>(acc);
   a = G::to_affine_prepared(acc);
   store_words<G::AFF_WORDS>(next + (size_t)i * G::AFF_WORDS, reinterpret_cast<const uint32_t*>(&a));
+}
+
+// ---- fixed-point multiplication tables (nmsm_point_table_*) -------------------------------------------
+// The device-resident form of Point.precompute(W) + the cached signed-window walk (curve.ts:532-577 table,
+// :588-606 walk): tbl[j][d-1] = d * 2^(16 j) * P for d in [1, 2^15], j < levels, prepared affine layout.  One
+// multiplication is then `levels` mixed additions and NO doublings; the table (36-107 MB) lives in L2/HBM.
+static constexpr int PT_BITS = 16;
+static constexpr uint32_t PT_HALF = 1u << (PT_BITS - 1);
+// BITS is a template parameter only so that tests/hostemu can run the same bodies with small tables
+template <class Cv, int BITS = PT_BITS>
+constexpr int point_table_levels() { return (Cv::Fn::BITS + 1 + BITS - 1) / BITS; }
+
+// level 0 entry i: (i + 1) * P by BITS double-and-add steps
+template <class Cv, int BITS = PT_BITS>
+NMSM_HD void table_base_body(uint32_t i, const uint32_t* p_aff, uint32_t* level0) {
+  using G = typename Cv::G;
+  const typename G::Affine P = load_aff<G>(p_aff);
+  typename G::Acc acc = G::identity();
+  const uint32_t k = i + 1;
+  for (int b = BITS - 1; b >= 0; b--) {
+    nl_dbl<G>(acc);
+    if ((k >> b) & 1u) nl_madd<G>(acc, P);
+  }
+  typename G::Affine a = G::to_affine_prepared(acc);
+  store_words<G::AFF_WORDS>(level0 + (size_t)i * G::AFF_WORDS, reinterpret_cast<const uint32_t*>(&a));
+}
+
+// k * P from the table as an un-normalised accumulator.  Returns false (and records the index) for a scalar
+// outside Point.multiply's range 1 <= k < n (allow_zero: multiplyUnsafe's 0 <= k < n).
+template <class Cv, int BITS = PT_BITS>
+NMSM_HD bool table_mul_body(uint32_t i, const uint32_t* tbl, const uint32_t* scalars, int allow_zero,
+                            typename Cv::G::Acc& acc, unsigned int* err) {
+  using G = typename Cv::G;
+  constexpr uint32_t HALF = 1u << (BITS - 1);
+  uint32_t s[SCALAR_WORDS];
+  load_words<SCALAR_WORDS>(s, scalars + (size_t)i * SCALAR_WORDS);
+  uint32_t nz = 0;
+  for (int k = 0; k < SCALAR_WORDS; k++) nz |= s[k];
+  acc = G::identity();
+  if (!scalar_in_range<typename Cv::Fn>(s) || (!allow_zero && nz == 0)) {
+    atomic_min_u32(&err[1], i);
+    return false;
+  }
+  uint32_t carry = 0;
+  for (int w = 0; w < point_table_levels<Cv, BITS>(); w++) {
+    uint32_t v = scalar_bits(s, w * BITS, BITS) + carry;
+    carry = 0;
+    bool neg = false;
+    if (v > HALF) {
+      v = (1u << BITS) - v;
+      neg = true;
+      carry = 1;
+    }
+    if (v != 0) {
+      typename G::Affine a = load_aff<G>(tbl + ((size_t)w * HALF + (v - 1)) * G::AFF_WORDS);
+      a = G::cneg(a, neg);
+      nl_madd<G>(acc, a);
+    }
+  }
+  return true;
 }
 
 // Signed-digit recoding of one magnitude shared by the count and scatter passes: digit d_w in

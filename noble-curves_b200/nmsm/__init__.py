@@ -160,10 +160,16 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
             return multiply_many(Point, [self], [scalar], unsafe=True)[0]
 
         def precompute(self, windowSize: int = 8, isLazy: bool = True):
-            """weierstrass.ts:740-745 / edwards.ts:449-453: a cache hint in the reference; results never depend
-            on it, and the GPU schedule keeps no per-point tables, so this only validates and returns self."""
+            """weierstrass.ts:740-745 / edwards.ts:449-453: a cache hint in the reference; results never depend on
+            it.  Here it marks the point for a device-resident multiplication table (nmsm_point_table_create; the
+            GPU picks its own 16-bit windows, `windowSize` is only validated).  Like the reference's WeakMap cache
+            (curve.ts:412,532) the table is built at the first multiply (isLazy) or now, and multiply_many /
+            multiply / multiplyUnsafe of this point then take the table route."""
             if not (isinstance(windowSize, int) and 1 <= windowSize <= Fn.BITS):
                 raise ValueError("invalid window size, expected [1..%d], got W=%s" % (Fn.BITS, windowSize))
+            _TABLE_MARKS.add((Point.CURVE_ID, self.x, self.y))
+            if not isLazy:
+                _table_for(Point, self)
             return self
 
         def clearCofactor(self):
@@ -455,8 +461,68 @@ def mulAddUnsafe(c, points, scalars):
     return pippenger(c, points, scalars)
 
 
+class PointTable:
+    """Device-resident multiplication table of ONE point (nmsm_point_table_create): d * 2^(16 j) * P."""
+
+    def __init__(self, curve_id: int, point_xy: bytes):
+        _lib.ensure_init()
+        self._lib = _lib.load()
+        self.curve_id = curve_id
+        h = ctypes.c_uint64(0)
+        try:
+            _lib.check(self._lib.nmsm_point_table_create(curve_id, ctypes.cast(ctypes.c_char_p(bytes(point_xy)), ctypes.c_void_p),
+                                                         ctypes.byref(h)))
+        except NmsmError as e:
+            _raise_mapped(e)
+        self.handle = h.value
+
+    def mul_batch(self, scalars: bytes, n: int, allow_zero: bool):
+        pb = self._lib.nmsm_point_bytes(self.curve_id)
+        if len(scalars) != n * 32:
+            raise ValueError("expected 32 bytes per scalar")
+        out = ctypes.create_string_buffer(max(1, n * pb))
+        infs = ctypes.create_string_buffer(max(1, n))
+        rc = self._lib.nmsm_point_table_mul_batch(self.handle, ctypes.cast(ctypes.c_char_p(bytes(scalars)), ctypes.c_void_p), n,
+                                                  1 if allow_zero else 0, ctypes.cast(out, ctypes.c_void_p),
+                                                  ctypes.cast(infs, ctypes.c_void_p))
+        try:
+            _lib.check(rc)
+        except NmsmError as e:
+            _raise_mapped(e)
+        return out.raw[: n * pb], infs.raw[:n]
+
+    def close(self):
+        if self.handle:
+            self._lib.nmsm_point_table_free(self.handle)
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# points marked by Point.precompute(), and the few most recently used device tables (36-107 MB each)
+_TABLE_MARKS: set = set()
+_TABLES: dict = {}
+_TABLES_MAX = 4
+
+
+def _table_for(c, point) -> PointTable:
+    key = (c.CURVE_ID, point.x, point.y)
+    t = _TABLES.pop(key, None)
+    if t is None:
+        t = PointTable(c.CURVE_ID, _pack_points([point]))
+        while len(_TABLES) >= _TABLES_MAX:
+            _TABLES.pop(next(iter(_TABLES))).close()
+    _TABLES[key] = t  # most recently used last
+    return t
+
+
 def multiply_many(c, points, scalars, unsafe: bool = False) -> List:
-    """Batch form of Point.multiply (unsafe=False: 1 <= k < n) / multiplyUnsafe (unsafe=True: 0 <= k < n)."""
+    """Batch form of Point.multiply (unsafe=False: 1 <= k < n) / multiplyUnsafe (unsafe=True: 0 <= k < n).
+    When every entry of `points` is the same precomputed point (Point.precompute) the device table route is used."""
     _validate_msm_points(points, c)
     if len(points) != len(scalars):
         raise ValueError("arrays of points and scalars must have equal length")
@@ -469,7 +535,11 @@ def multiply_many(c, points, scalars, unsafe: bool = False) -> List:
     n = len(points)
     if n == 0:
         return []
-    out_xy, infs = mul_batch_packed(c.CURVE_ID, _pack_points(points), _pack_scalars(scalars), n, unsafe)
+    p0 = points[0]
+    if (c.CURVE_ID, p0.x, p0.y) in _TABLE_MARKS and not p0.is0() and all(q is p0 or q.equals(p0) for q in points):
+        out_xy, infs = _table_for(c, p0).mul_batch(_pack_scalars(scalars), n, unsafe)
+    else:
+        out_xy, infs = mul_batch_packed(c.CURVE_ID, _pack_points(points), _pack_scalars(scalars), n, unsafe)
     pb = c.POINT_BYTES
     return [c.from_packed(out_xy[i * pb:(i + 1) * pb], infs[i]) for i in range(n)]
 

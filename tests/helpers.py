@@ -130,6 +130,28 @@ def emu_msm(name, pts_b: bytes, scalars_b: bytes, n: int, forced_c=0, forced_L=0
     return (x, y, int(inf[0])), (int(err[0]), int(err[1])), tuple(int(v) for v in plan)
 
 
+def emu_point_table(name, point_b: bytes, scalars_b: bytes, n: int, allow_zero: bool, table_bits=8):
+    """nmsm_point_table_* bodies with a table_bits-wide table; returns ([(x, y, inf) or None if rejected], err)."""
+    lib = hostemu()
+    cb = FP_BYTES[name] * PARTS[name]
+    pt, sc = u32(point_b), u32(scalars_b)
+    out = np.zeros(n * 2 * cb // 4, np.uint32)
+    inf = np.zeros(n, np.uint32)
+    err = np.zeros(2, np.uint32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    rc = lib.emu_point_table(CURVE_IDS[name], table_bits, p(pt), p(sc), n, 1 if allow_zero else 0, p(out), p(inf), p(err))
+    assert rc == 0
+    ob = out.tobytes()
+    res = []
+    for i in range(n):
+        if inf[i] == 9:
+            res.append(None)
+        else:
+            x, y = unpack_point(name, ob[i * 2 * cb:(i + 1) * 2 * cb])
+            res.append((x, y, int(inf[i])))
+    return res, (int(err[0]), int(err[1]))
+
+
 def emu_mul_batch(name, pts_b: bytes, scalars_b: bytes, n: int, allow_zero: bool):
     lib = hostemu()
     cb = FP_BYTES[name] * PARTS[name]

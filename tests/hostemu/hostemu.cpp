@@ -112,6 +112,33 @@ static int emu_mul_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
   return 0;
 }
 
+// Fixed-point multiplication table (nmsm_point_table_*) with TB-bit digits: the production bodies, small table.
+template <class Cv, int TB>
+static int emu_point_table_t(const uint32_t* point_xy, const uint32_t* scalars, uint32_t n, int allow_zero,
+                             uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out) {
+  using G = typename Cv::G;
+  constexpr int LV = point_table_levels<Cv, TB>();
+  constexpr uint32_t HALF = 1u << (TB - 1);
+  unsigned int err[2] = {0xffffffffu, 0xffffffffu};
+  std::vector<uint32_t> aff(2 * G::AFF_WORDS);
+  prepare_body<Cv>(0, 1, point_xy, aff.data(), err);
+  const size_t level_words = (size_t)HALF * G::AFF_WORDS;
+  std::vector<uint32_t> tbl(level_words * LV);
+  for (uint32_t i = 0; i < HALF; i++) table_base_body<Cv, TB>(i, aff.data(), tbl.data());
+  for (int j = 1; j < LV; j++)
+    for (uint32_t i = 0; i < HALF; i++)
+      table_level_body<Cv>(i, tbl.data() + (size_t)(j - 1) * level_words, tbl.data() + (size_t)j * level_words, TB);
+  for (uint32_t i = 0; i < n; i++) {
+    typename G::Acc acc;
+    out_inf[i] = 9;
+    if (!table_mul_body<Cv, TB>(i, tbl.data(), scalars, allow_zero, acc, err)) continue;
+    nl_to_affine<G>(acc, out_xy + (size_t)i * G::IN_WORDS, out_inf + i);
+  }
+  err_out[0] = err[0];
+  err_out[1] = err[1];
+  return 0;
+}
+
 #define DISPATCH(curve, EXPR)                                        \
   switch (curve) {                                                   \
     case 0: { using Cv = CurveSecp256k1; return EXPR; }              \
@@ -194,6 +221,13 @@ int emu_glv_split_lattice(int curve, const uint32_t* k, uint32_t* out) {
   out[10] = n1;
   out[11] = n2;
   return 0;
+}
+int emu_point_table(int curve, int table_bits, const uint32_t* point_xy, const uint32_t* scalars, uint32_t n,
+                    int allow_zero, uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out) {
+  if (table_bits == 5) {
+    DISPATCH(curve, (emu_point_table_t<Cv, 5>(point_xy, scalars, n, allow_zero, out_xy, out_inf, err_out)));
+  }
+  DISPATCH(curve, (emu_point_table_t<Cv, 8>(point_xy, scalars, n, allow_zero, out_xy, out_inf, err_out)));
 }
 int emu_msm_table(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, int table_c, int forced_L,
                   uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out) {

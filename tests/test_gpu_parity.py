@@ -374,6 +374,83 @@ def test_fixed_base_table_small(nmsm, name):
     ps.close()
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_point_table_multiply(nmsm, name):
+    """nmsm_point_table_* (Point.precompute + cached multiply, curve.ts:532-606): table route equals
+    the oracle's multiply and the generic nmsm_mul_batch for edge and random scalars; range errors as multiply's."""
+    P = R.CURVES[name]
+    C = nmsm.CURVES[name]
+    order = P.Fn.ORDER
+    rnd = random.Random(77)
+    base_o = R.normalizeZ(P, [P.BASE.multiplyUnsafe(rnd.randrange(1, order))])[0]
+    n = 300
+    ks = [1, 2, 32767, 32768, 32769, 65535, 65536, order - 1, order - 2, 2**128 - 1, 2**128,
+          (1 << (order.bit_length() - 1)) - 1, 0x5555555555555555 << 60]
+    ks = [k % order or 1 for k in ks] + [rnd.randrange(1, order) for _ in range(n - len(ks))]
+    tbl = nmsm.PointTable(H.CURVE_IDS[name], H.point_bytes(name, base_o))
+    out, infs = tbl.mul_batch(H.pack_scalars(ks), n, False)
+    ref, rinfs = nmsm.mul_batch_packed(H.CURVE_IDS[name], H.point_bytes(name, base_o) * n, H.pack_scalars(ks), n, False)
+    assert out == ref and infs == rinfs
+    pb = len(out) // n
+    for i in list(range(13)) + [50, 299]:
+        assert (*H.unpack_point(name, out[i * pb:(i + 1) * pb]), infs[i]) == H.expected_tuple(name, base_o.multiply(ks[i]))
+    with pytest.raises(ValueError, match="invalid scalar"):
+        tbl.mul_batch(H.pack_scalars([5, 0]), 2, False)
+    out0, inf0 = tbl.mul_batch(H.pack_scalars([5, 0]), 2, True)
+    assert inf0[1] == 1
+    with pytest.raises(ValueError, match="invalid scalar"):
+        tbl.mul_batch(H.pack_scalars([order]), 1, True)
+    tbl.close()
+    # object API: precompute() marks the point, multiply_many / multiply then use the table
+    bp = C.fromAffine(base_o.toAffine()).precompute(8, False)
+    got = nmsm.multiply_many(C, [bp] * 5, ks[7:12])
+    for g, k in zip(got, ks[7:12]):
+        assert (g.x, g.y, 1 if g.is0() else 0) == H.expected_tuple(name, base_o.multiply(k))
+    one = bp.multiply(ks[20])
+    assert (one.x, one.y) == H.expected_tuple(name, base_o.multiply(ks[20]))[:2]
+    with pytest.raises(ValueError, match="invalid point"):
+        bad = bytearray(H.point_bytes(name, base_o))
+        fb = H.FP_BYTES[name]
+        bad[:fb] = P.Fp.ORDER.to_bytes(fb, "little")
+        nmsm.PointTable(H.CURVE_IDS[name], bytes(bad))
+
+
+def test_point_table_getpublickey_batch(nmsm):
+    """BASE.multiply at rate (getPublicKey, weierstrass.ts:1168 / ed25519 RFC 8032 vectors): 2^16 secp256k1 keys through
+    the table against the generic batch; the 128 RFC 8032 public keys from their clamped secret scalars."""
+    P = R.CURVES["secp256k1"]
+    n = 1 << 16
+    rnd = random.Random(5)
+    ks = [rnd.randrange(1, P.Fn.ORDER) for _ in range(n)]
+    sb = H.pack_scalars(ks)
+    gb = H.point_bytes("secp256k1", P.BASE)
+    tbl = nmsm.PointTable(0, gb)
+    out, infs = tbl.mul_batch(sb, n, False)
+    ref, _ = nmsm.mul_batch_packed(0, gb * n, sb, n, False)
+    assert out == ref and not any(infs)
+    for i in (0, 1, 777, n - 1):
+        assert H.unpack_point("secp256k1", out[i * 64:(i + 1) * 64]) == R.affine_tuple(P, P.BASE.multiply(ks[i]))
+    tbl.close()
+    ED = R.CURVES["ed25519"]
+    vec = load_golden("ed25519.json")["vectors"]
+    scalars = []
+    for v in vec:
+        h = bytearray(hashlib.sha512(bytes.fromhex(v["sk"])).digest()[:32])
+        h[0] &= 248
+        h[31] &= 127
+        h[31] |= 64
+        scalars.append(int.from_bytes(bytes(h), "little") % ED.Fn.ORDER)
+    tbl = nmsm.PointTable(1, H.point_bytes("ed25519", ED.BASE))
+    out, _ = tbl.mul_batch(H.pack_scalars(scalars), len(vec), False)
+    for i, v in enumerate(vec):
+        x, y = H.unpack_point("ed25519", out[i * 64:(i + 1) * 64])
+        enc = bytearray(y.to_bytes(32, "little"))
+        if x & 1:
+            enc[31] |= 0x80
+        assert bytes(enc).hex() == v["pk"], i
+    tbl.close()
+
+
 @pytest.mark.parametrize("name,logn", [("bls12_381_G1", 20), ("bls12_381_G2", 16), ("ed25519", 17)])
 def test_fixed_base_table_large(nmsm, name, logn):
     """Fixed-base table at BASELINE sizes: same result as (sum k_i s_i) * G and as the plain MSM."""

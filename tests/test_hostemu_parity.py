@@ -174,6 +174,36 @@ def test_mul_batch(name):
     assert err == (0xFFFFFFFF, 0)
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_point_table_multiply(name):
+    """nmsm_point_table_* bodies (Point.precompute + cached multiply, curve.ts:532-606) with small tables: signed
+    digits with carries through every level (n-1, 2^k-1, alternating bits), both scalar ranges."""
+    P = R.CURVES[name]
+    n_order = P.Fn.ORDER
+    rng = R.Xorshift64(0xFACADE)
+    base = R.normalizeZ(P, [P.BASE.multiplyUnsafe(rng.rndBelow(n_order - 1) + 1)])[0]
+    scalars = [1, 2, 15, 16, 17, 128, 129, 255, 256, n_order - 1, n_order - 2, 2**128 - 1, 2**128,
+               0x5555555555555555 << 60, (1 << (n_order.bit_length() - 1)) - 1]
+    scalars += [rng.rndBelow(n_order - 1) + 1 for _ in range(2 if "G2" in name else 6)]
+    scalars = [s % n_order or 1 for s in scalars]
+    pb = H.point_bytes(name, base)
+    for tb in ((5, 8) if "G2" not in name else (8,)):
+        res, err = H.emu_point_table(name, pb, H.pack_scalars(scalars), len(scalars), False, table_bits=tb)
+        assert err == (0xFFFFFFFF, 0xFFFFFFFF)
+        for s, got in zip(scalars, res):
+            assert got == H.expected_tuple(name, base.multiply(s)), (name, tb, s)
+    res, err = H.emu_point_table(name, pb, H.pack_scalars([5, 0, 7]), 3, False)
+    assert err == (0xFFFFFFFF, 1) and res[1] is None
+    res, err = H.emu_point_table(name, pb, H.pack_scalars([5, 0, 7]), 3, True)
+    assert err == (0xFFFFFFFF, 0xFFFFFFFF) and res[1] == H.expected_tuple(name, P.ZERO)
+    assert res[2] == H.expected_tuple(name, base.multiplyUnsafe(7))
+    res, err = H.emu_point_table(name, pb, H.pack_scalars([n_order, 1]), 2, True)
+    assert err == (0xFFFFFFFF, 0) and res[0] is None
+    # the identity as the table point: every multiple is the identity
+    res, err = H.emu_point_table(name, H.point_bytes(name, P.ZERO), H.pack_scalars([3, n_order - 1]), 2, True)
+    assert res == [H.expected_tuple(name, P.ZERO)] * 2
+
+
 def test_glv_split_and_constants():
     """BLS12-381 G1 GLV: k = v1 + v2*lambda (mod r), |v| < 2^127, and phi(P) = (beta*x, y) = lambda*P."""
     import ctypes

@@ -106,6 +106,42 @@ def fixed_base_config(tag, name, logn, reps=5):
             "n": n, **rows}
 
 
+def point_table_config(tag, name, logn, reps=3):
+    """k_i * G for 2^logn random scalars: generic nmsm_mul_batch vs the fixed-point table (nmsm_point_table_*)."""
+    n = 1 << logn
+    P = R.CURVES[name]
+    rnd = random.Random(500 + logn)
+    ks = [rnd.randrange(1, P.Fn.ORDER) for _ in range(n)]
+    sb = H.pack_scalars(ks)
+    gb = H.point_bytes(name, P.BASE)
+    cid = H.CURVE_IDS[name]
+    t0 = time.perf_counter()
+    tbl = nmsm.PointTable(cid, gb)
+    t_build = time.perf_counter() - t0
+    res = {}
+
+    def run_tbl():
+        res["t"] = tbl.mul_batch(sb, n, False)
+
+    run_tbl()
+    best_t = time_best(run_tbl, reps)
+    ng = min(n, 1 << 16)
+
+    def run_gen():
+        res["g"] = nmsm.mul_batch_packed(cid, gb * ng, sb[: ng * 32], ng, False)
+
+    run_gen()
+    best_g = time_best(run_gen, reps)
+    pb = len(gb)
+    ok = res["t"][0][: ng * pb] == res["g"][0]
+    ok &= H.unpack_point(name, res["t"][0][(n - 1) * pb:]) == R.affine_tuple(P, P.BASE.multiply(ks[-1]))
+    tbl.close()
+    return {"config": tag, "what": "%s BASE.multiply x 2^%d random scalars (getPublicKey shape), host buffers in and out" % (name, logn),
+            "n": n, "table_ms": best_t * 1e3, "table_multiplies_per_s": n / best_t, "table_build_ms": t_build * 1e3,
+            "generic_mul_batch_n": ng, "generic_ms": best_g * 1e3, "generic_multiplies_per_s": ng / best_g,
+            "check": "table == generic batch bit-exact; oracle spot check" if ok else "MISMATCH"}
+
+
 def config0():
     P = R.CURVES["secp256k1"]
     rnd = random.Random(11)
@@ -160,11 +196,16 @@ def main():
     nmsm.init(0)
     if "--fixed-base" in sys.argv:
         rows = (lambda: fixed_base_config("f4-a", "bls12_381_G1", 20), lambda: fixed_base_config("f4-b", "bls12_381_G1", 16),
-                lambda: fixed_base_config("f4-c", "bls12_381_G2", 18), lambda: fixed_base_config("f4-d", "bn254_G1", 20))
+                lambda: fixed_base_config("f4-c", "bls12_381_G2", 18), lambda: fixed_base_config("f4-d", "bn254_G1", 20),
+                lambda: point_table_config("f4-e", "secp256k1", 20), lambda: point_table_config("f4-f", "ed25519", 20),
+                lambda: point_table_config("f4-g", "bls12_381_G1", 18))
     else:
         rows = (config0, lambda: msm_config(1, "bls12_381_G1", 16), lambda: msm_config(2, "bn254_G1", 20),
                 lambda: msm_config(3, "bls12_381_G2", 18), config4)
-    for row in rows:
+    only = os.environ.get("NMSM_ROWS")  # e.g. NMSM_ROWS=0,2 : positions in the row list
+    for i, row in enumerate(rows):
+        if only and str(i) not in only.split(","):
+            continue
         print(json.dumps(row()), flush=True)
 
 
