@@ -248,6 +248,8 @@ struct SwXyzz {
     p.ZZZ = ZZZ3;
   }
 #endif
+  // the value whose inverse normalisation needs (batched across a warp by k_table_mul); never zero
+  NMSM_HD static F inv_target(const Acc& p) { return is_identity(p) ? F::one() : p.ZZZ; }
   // canonical affine output; identity -> (0, 0), flag 1 (weierstrass.ts:966)
   NMSM_HD static void to_affine_canonical(const Acc& p, uint32_t* xy, uint32_t* is_inf) {
     if (is_identity(p)) {
@@ -255,8 +257,15 @@ struct SwXyzz {
       *is_inf = 1;
       return;
     }
-    F i3 = inv(p.ZZZ);       // 1/Z^3
-    F t = p.ZZ * i3;         // 1/Z
+    to_affine_canonical_with_inv(p, inv(p.ZZZ), xy, is_inf);
+  }
+  NMSM_HD static void to_affine_canonical_with_inv(const Acc& p, const F& i3, uint32_t* xy, uint32_t* is_inf) {
+    if (is_identity(p)) {
+      for (int k = 0; k < 2 * F::LIMBS; k++) xy[k] = 0;
+      *is_inf = 1;
+      return;
+    }
+    F t = p.ZZ * i3;         // 1/Z  (i3 = 1/Z^3)
     F x = p.X * sqr(t);      // X / Z^2
     F y = p.Y * i3;          // Y / Z^3
     x.to_canonical(xy);
@@ -397,9 +406,12 @@ struct EdExt {
     P4::mul4(p.X, p.Y, p.T, p.Z, E, Fv, G, H, E, H, Fv, G);
   }
 #endif
+  NMSM_HD static F inv_target(const Acc& p) { return p.Z; }  // Z != 0 for every point of the complete formulas
   // canonical affine output; identity -> (0, 1), flag 1 (edwards.ts:606)
   NMSM_HD static void to_affine_canonical(const Acc& p, uint32_t* xy, uint32_t* is_inf) {
-    F iz = inv(p.Z);
+    to_affine_canonical_with_inv(p, inv(p.Z), xy, is_inf);
+  }
+  NMSM_HD static void to_affine_canonical_with_inv(const Acc& p, const F& iz, uint32_t* xy, uint32_t* is_inf) {
     F x = p.X * iz, y = p.Y * iz;
     x.to_canonical(xy);
     y.to_canonical(xy + F::LIMBS);

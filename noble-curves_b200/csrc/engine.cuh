@@ -62,8 +62,15 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
                          : make_plan<Cv>(n, g_ctx.forced_c, g_ctx.sm_count);
   const uint64_t max_entries = n * (uint64_t)plan.D * (Cv::GLV ? 2 : 1);
   if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
-  // one window split over up to 256 blocks when there is only one (fixed-base tables), else <= 32 per window
-  const int max_splits = plan.W == 1 ? REDUCE2_MAX_SPLITS_1W : REDUCE2_MAX_SPLITS;
+  // bucket reduction levels: every k_reduce2 pass shrinks the per-window chunk count by REDUCE2_CHUNKS_PER_BLOCK
+  // until <= REDUCE2_MAX_SPLITS block results per window remain for k_reduce3 (one pass for the ordinary plans)
+  size_t blk_entries = 0;
+  for (uint64_t m = plan.chunks;;) {
+    const uint64_t sp = (m + REDUCE2_CHUNKS_PER_BLOCK - 1) / REDUCE2_CHUNKS_PER_BLOCK;
+    blk_entries += sp;
+    if (sp <= REDUCE2_MAX_SPLITS) break;
+    m = sp;
+  }
   const uint64_t max_threads = (max_entries + plan.L - 1) / plan.L;
 
   if (!d_prepared) CK(C.aff.ensure(n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
@@ -78,7 +85,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   CK(C.tile_sums.ensure((size_t)(plan.G / SCAN_TILE + 2) * 4));
   const uint64_t ntile1 = max_threads / STITCH_FAN + 1, ntile2 = ntile1 / STITCH_FAN + 1;
   CK(C.tiles.ensure((ntile1 + ntile2) * G::ACC_WORDS * 4));
-  CK(C.blk.ensure(((size_t)plan.W * max_splits + 1) * G::ACC_WORDS * 4 * 2));
+  CK(C.blk.ensure((size_t)plan.W * blk_entries * G::ACC_WORDS * 4 * 2));
   CK(C.window_out.ensure((size_t)plan.W * G::ACC_WORDS * 4));
 
   uint32_t* aff = d_prepared ? const_cast<uint32_t*>(d_prepared) : (uint32_t*)C.aff.p;
@@ -94,8 +101,6 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   uint32_t* tile_sums = (uint32_t*)C.tile_sums.p;
   uint32_t* tile1 = (uint32_t*)C.tiles.p;
   uint32_t* tile2 = tile1 + ntile1 * G::ACC_WORDS;
-  uint32_t* blkP = (uint32_t*)C.blk.p;
-  uint32_t* blkQ = blkP + ((size_t)plan.W * max_splits + 1) * G::ACC_WORDS;
   uint32_t* window_out = (uint32_t*)C.window_out.p;
   cudaStream_t st = C.stream;
   const uint32_t n32 = (uint32_t)n;
@@ -129,23 +134,25 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   }
   EV(7);
   {
-    // k_reduce2 / k_reduce3: each window is split over <= max_splits blocks of 32 quads x R chunks
-    int R = 4;
-    while ((plan.chunks + REDUCE2_LOGICAL * R - 1) / (REDUCE2_LOGICAL * R) > max_splits) R <<= 1;
-    const int splits = (plan.chunks + REDUCE2_LOGICAL * R - 1) / (REDUCE2_LOGICAL * R);
+    // msm.cuh "Bucket reduction": P/Q of one level are the T/S of the next (chunks := splits, K := K * Mb)
     const size_t smem2 = (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4;
-    dim3 grid2(splits, plan.W);
-    k_reduce2<Cv><<<grid2, REDUCE2_THREADS, smem2, st>>>(sums, wsums, plan, R, blkP, blkQ);
-    if (splits <= REDUCE2_MAX_SPLITS) {
-      k_reduce3<Cv><<<plan.W, 32, 0, st>>>(blkP, blkQ, plan, splits, R, window_out);
-    } else {
-      // second application of k_reduce2 to its own outputs: chunks := splits, K := K * Mb (msm.cuh)
-      MsmPlan p3 = plan;
-      p3.chunks = splits;
-      p3.K = plan.K * REDUCE2_LOGICAL * R;
-      const int R3 = (splits + REDUCE2_LOGICAL - 1) / REDUCE2_LOGICAL;
-      uint32_t* scratchQ = blkQ + (size_t)plan.W * max_splits * G::ACC_WORDS;  // block total, unused
-      k_reduce2<Cv><<<dim3(1, plan.W), REDUCE2_THREADS, smem2, st>>>(blkQ, blkP, p3, R3, window_out, scratchQ);
+    MsmPlan pl = plan;
+    const uint32_t *S = sums, *T = wsums;
+    uint32_t* base = (uint32_t*)C.blk.p;
+    for (;;) {
+      const int splits = (pl.chunks + REDUCE2_CHUNKS_PER_BLOCK - 1) / REDUCE2_CHUNKS_PER_BLOCK;
+      uint32_t* blkP = base;
+      uint32_t* blkQ = base + (size_t)plan.W * splits * G::ACC_WORDS;
+      base = blkQ + (size_t)plan.W * splits * G::ACC_WORDS;
+      k_reduce2<Cv><<<dim3(splits, plan.W), REDUCE2_THREADS, smem2, st>>>(S, T, pl, REDUCE2_R, blkP, blkQ);
+      if (splits <= REDUCE2_MAX_SPLITS) {
+        k_reduce3<Cv><<<plan.W, 32, 0, st>>>(blkP, blkQ, pl, splits, REDUCE2_R, window_out);
+        break;
+      }
+      S = blkQ;
+      T = blkP;
+      pl.chunks = splits;
+      pl.K *= REDUCE2_CHUNKS_PER_BLOCK;
     }
   }
   EV(8);
@@ -209,6 +216,14 @@ static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
     *out_is_inf = (int)C.h_result[G::IN_WORDS];
   }
   return NMSM_OK;
+}
+
+// single-kernel calls (multiply batches): device time of the kernel between ev[0] and ev[1] -> NMSM_T_TOTAL
+static void note_kernel_time(Slot& C) {
+  if (!g_ctx.profiling) return;
+  memset(C.last_ms, 0, sizeof(C.last_ms));
+  cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev[0], C.ev[1]);
+  memcpy(g_ctx.last_ms, C.last_ms, sizeof(C.last_ms));
 }
 
 // C-ABI asynchronous halves (nmsm_msm_submit / nmsm_msm_collect)
@@ -344,8 +359,10 @@ static int table_mul_batch(const uint32_t* tbl, const uint8_t* scalars, uint64_t
   cudaStream_t st = C.stream;
   CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(d_err, 0xff, 8, st));
+  EV(0);
   k_table_mul<Cv><<<cdiv(n, 128), 128, 0, st>>>(tbl, (const uint32_t*)C.in_scalars.p, (uint32_t)n, allow_zero, d_xy,
                                                    d_inf, d_err);
+  EV(1);
   CK(cudaGetLastError());
   std::vector<uint32_t> inf(n);
   unsigned int err[2];
@@ -353,6 +370,7 @@ static int table_mul_batch(const uint32_t* tbl, const uint8_t* scalars, uint64_t
   CK(cudaMemcpyAsync(out_xy, d_xy, n * G::IN_WORDS * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(inf.data(), d_inf, n * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  note_kernel_time(C);
   if (err[1] != 0xffffffffu)
     return fail(NMSM_ERR_SCALAR, "invalid scalar: out of range (index " + std::to_string(err[1]) + ")", err[1]);
   for (uint64_t i = 0; i < n; i++) out_is_inf[i] = (uint8_t)inf[i];
@@ -405,8 +423,10 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
   CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(d_err, 0xff, 8, st));
+  EV(0);
   k_mul_batch<Cv><<<cdiv(n, 128), 128, 0, st>>>((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p,
                                                    (uint32_t)n, allow_zero, d_xy, d_inf, d_err);
+  EV(1);
   CK(cudaGetLastError());
   std::vector<uint32_t> inf(n);
   unsigned int err[2];
@@ -414,6 +434,7 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
   CK(cudaMemcpyAsync(out_xy, d_xy, n * G::IN_WORDS * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(inf.data(), d_inf, n * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  note_kernel_time(C);
   if (err[0] != 0xffffffffu) return fail(NMSM_ERR_POINT, "invalid point at index " + std::to_string(err[0]), err[0]);
   if (err[1] != 0xffffffffu)
     return fail(NMSM_ERR_SCALAR, "invalid scalar: out of range (index " + std::to_string(err[1]) + ")", err[1]);

@@ -136,9 +136,9 @@ k_accumulate(const uint32_t* __restrict__ aff, const uint32_t* __restrict__ sort
 //   sum_b (b+1) B_b  =  sum_k T_k + K * sum_k k * S_k        k over the M = B/K chunks   (k_reduce1)
 //   per block of Mb chunks:  P_s = sum T_k + K * sum (k - s*Mb) S_k ,  Q_s = sum S_k        (k_reduce2)
 //   window sum = sum_s P_s + K * Mb * sum_s s * Q_s                                          (k_reduce3)
-// The last line has the shape of the first (T := P, S := Q, K := K * Mb): when one window is split over more
-// than 32 blocks (fixed-base tables: a single window of up to 2^21 buckets) k_reduce2 runs a second time on its
-// own outputs instead of k_reduce3.
+// The last line has the shape of the first (T := P, S := Q, K := K * Mb): when a window has more than 32 * Mb
+// chunks (fixed-base tables: a single window of up to 2^21 buckets) k_reduce2 is applied again to its own
+// outputs until <= 32 block results per window are left for k_reduce3.
 // ------------------------------------------------------------------------------------------------
 template <class G>
 __device__ __forceinline__ typename G::Acc shfl_down_acc(const typename G::Acc& a, int delta) {
@@ -209,7 +209,8 @@ __device__ __forceinline__ typename G::Acc smem_get(const uint32_t* smem, uint32
 static constexpr int REDUCE2_THREADS = 128;                   // 32 logical threads (quads), 4 warps
 static constexpr int REDUCE2_LOGICAL = REDUCE2_THREADS / 4;
 static constexpr int REDUCE2_MAX_SPLITS = 32;                 // k_reduce3: 8 quads x up to 4 splits each
-static constexpr int REDUCE2_MAX_SPLITS_1W = 256;             // single-window plans: folded by a second k_reduce2
+static constexpr int REDUCE2_R = 4;                           // chunks per logical thread
+static constexpr int REDUCE2_CHUNKS_PER_BLOCK = REDUCE2_LOGICAL * REDUCE2_R;
 
 // grid (splits, W).  Logical thread lt owns R consecutive chunks; see the formulas above.
 template <class Cv>
@@ -370,6 +371,37 @@ k_table_level(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next, ui
   if (i < count) table_level_body<Cv>(i, prev, next, c);
 }
 
+// One field inversion per warp (Montgomery's trick across the lanes): every lane passes a non-zero z and gets
+// 1/z.  Inclusive prefix and suffix products by shuffles (5 + 5 multiplications per lane), one inversion of the
+// warp total computed redundantly in all lanes (same operand, no divergence), two more multiplications.
+// All 32 lanes must call it.
+template <class F>
+__device__ __forceinline__ F shfl_field(const F& a, int src_lane) {
+  F r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&a);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(F) / 4); k++) d[k] = __shfl_sync(0xffffffffu, s[k], src_lane);
+  return r;
+}
+template <class F>
+__device__ __noinline__ F warp_batch_inverse(const F& z) {
+  const int lane = threadIdx.x & 31;
+  F pre = z, suf = z;
+  for (int d = 1; d < 32; d <<= 1) {
+    F a = shfl_field(pre, lane >= d ? lane - d : lane);
+    F b = shfl_field(suf, lane + d < 32 ? lane + d : lane);
+    if (lane >= d) pre = pre * a;
+    if (lane + d < 32) suf = suf * b;
+  }
+  F r = inv(shfl_field(pre, 31));
+  F left = shfl_field(pre, lane > 0 ? lane - 1 : 0);
+  F right = shfl_field(suf, lane < 31 ? lane + 1 : 31);
+  if (lane > 0) r = r * left;
+  if (lane < 31) r = r * right;
+  return r;
+}
+
 // Fixed-point multiplication tables (nmsm_point_table_*): level 0 = d * P, then k_table_level per level.
 template <class Cv>
 __global__ void __launch_bounds__(128)
@@ -385,12 +417,13 @@ k_table_mul(const uint32_t* __restrict__ tbl, const uint32_t* __restrict__ scala
             uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_inf, unsigned int* err) {
   using G = typename Cv::G;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  typename G::Acc acc;
-  if (!table_mul_body<Cv>(i, tbl, scalars, allow_zero, acc, err)) return;
+  typename G::Acc acc = G::identity();
+  const bool ok = i < n && table_mul_body<Cv>(i, tbl, scalars, allow_zero, acc, err);
+  const typename G::Field iz = warp_batch_inverse(G::inv_target(acc));  // whole warp, also the idle lanes
+  if (!ok) return;
   uint32_t xy[G::IN_WORDS];
   uint32_t inf;
-  nl_to_affine<G>(acc, xy, &inf);
+  G::to_affine_canonical_with_inv(acc, iz, xy, &inf);
   store_words<G::IN_WORDS>(out_xy + (size_t)i * G::IN_WORDS, xy);
   out_inf[i] = inf;
 }

@@ -122,10 +122,13 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
 template <class Cv>
 inline int table_digits(int c) { return (glv_bits<Cv>() + 1 + c - 1) / c; }
 
+static constexpr int TABLE_REDUCE_CHUNK = 2;  // buckets per k_reduce1 thread in table mode (measured: 2 < 4 < 8)
+
 template <class Cv>
 inline int choose_table_bits(uint64_t n_points, int sm_count, double mem_budget_bytes) {
   using G = typename Cv::G;
   using F = typename G::Field;
+  const int bits = glv_bits<Cv>();
   const double terms = (double)n_points * (Cv::GLV ? 2 : 1);
   const double limb_ratio = (double)(F::LIMBS / F::BASE_MULS == 12 ? 1.0 : (8.0 * 8.0) / (12.0 * 12.0));
   const double fscale = limb_ratio * F::BASE_MULS;
@@ -141,9 +144,14 @@ inline int choose_table_bits(uint64_t n_points, int sm_count, double mem_budget_
     const double entries = terms * D;
     int L = (int)ceil(entries / ((double)sm_count * 1024.0));
     L = L < 4 ? 4 : (L > 32 ? 32 : L);
-    const double parts = 1.0 + (entries / B) / L;
-    const double kk = B < 8 ? B : 8;
-    const double t_r1a = B * (1.0 + parts) * t_add_tp, t_r1b = kk * (1.0 + parts) * t_add_lat;
+    // the top digit holds only top_bits scalar bits: its values pile onto the lowest 2^(top_bits-1) buckets,
+    // whose partials one k_reduce1 thread stitches serially (same effect as the narrow top window in make_plan)
+    const int top_bits = bits + 1 - (D - 1) * c;
+    const double heavy = terms / (double)(1u << (top_bits > 1 ? top_bits - 1 : 0));
+    double parts_top = 1.0 + (entries / B + heavy) / L;
+    if (parts_top > 100.0) parts_top = 100.0 + (entries / B + heavy) / L / 32.0;
+    const double kk = B < TABLE_REDUCE_CHUNK ? B : TABLE_REDUCE_CHUNK;
+    const double t_r1a = (entries / L + 2.0 * B) * t_add_tp, t_r1b = kk * (1.0 + parts_top) * t_add_lat;
     const double cost = entries * t_madd + (t_r1a > t_r1b ? t_r1a : t_r1b);
     if (cost < best) {
       best = cost;
@@ -165,7 +173,7 @@ inline MsmPlan make_table_plan(uint64_t n_points, int c, int sm_count) {
   p.stride = (uint32_t)(n_points * (Cv::GLV ? 2 : 1));
   int L = (int)ceil(terms * p.D / ((double)sm_count * 1024.0));
   p.L = L < 4 ? 4 : (L > 32 ? 32 : L);
-  int Kc = 8;
+  int Kc = TABLE_REDUCE_CHUNK;
 #if !defined(__CUDA_ARCH__)
   if (const char* e = getenv("NMSM_TK")) { int v = atoi(e); if (v >= 1 && (v & (v - 1)) == 0) Kc = v; }  // tuning experiments
 #endif
@@ -552,7 +560,7 @@ static constexpr int PT_BITS = 16;
 static constexpr uint32_t PT_HALF = 1u << (PT_BITS - 1);
 // BITS is a template parameter only so that tests/hostemu can run the same bodies with small tables
 template <class Cv, int BITS = PT_BITS>
-constexpr int point_table_levels() { return (Cv::Fn::BITS + 1 + BITS - 1) / BITS; }
+NMSM_HD constexpr int point_table_levels() { return (Cv::Fn::BITS + 1 + BITS - 1) / BITS; }
 
 // level 0 entry i: (i + 1) * P by BITS double-and-add steps
 template <class Cv, int BITS = PT_BITS>
@@ -586,7 +594,8 @@ NMSM_HD bool table_mul_body(uint32_t i, const uint32_t* tbl, const uint32_t* sca
     return false;
   }
   uint32_t carry = 0;
-  for (int w = 0; w < point_table_levels<Cv, BITS>(); w++) {
+  constexpr int LEVELS = point_table_levels<Cv, BITS>();
+  for (int w = 0; w < LEVELS; w++) {
     uint32_t v = scalar_bits(s, w * BITS, BITS) + carry;
     carry = 0;
     bool neg = false;
