@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--logn", type=int, default=20, help="log2 of the MSM size (headline: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fixed-base", action="store_true", help="skip the fixed-base table companion measurement")
     ap.add_argument("--window", type=int, default=0, help="force window bits c (0 = cost model)")
     ap.add_argument("--in-flight", type=int, default=4, choices=[1, 2, 3, 4], help="MSMs kept in flight in the timed region")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -369,6 +370,43 @@ def main():
     e2e_value = n_total * e2e_steps / e2e_elapsed
     lib.nmsm_host_free(h_pts)
     lib.nmsm_host_free(h_sc)
+    main_timing = nmsm.last_timing()  # plan + kernel times of the general MSM, before the fixed-base pass below
+
+    # ---- companion number (not the headline): the same MSM over a device-resident point set with a fixed-base
+    # table (nmsm_points_precompute): scalars resident on the device, same pipelined loop ----------
+    fixed = None
+    if world == 1 and not args.no_fixed_base:
+        h, tc, lv = ctypes.c_uint64(0), ctypes.c_int(0), ctypes.c_int(0)
+        nmsm._lib.check(lib.nmsm_points_upload(BLS_G1, ctypes.cast(ctypes.c_char_p(pts_b), ctypes.c_void_p), n_local, ctypes.byref(h)))
+        t0 = time.perf_counter()
+        nmsm._lib.check(lib.nmsm_points_precompute(h, 0, ctypes.byref(tc), ctypes.byref(lv)))
+        t_pre = time.perf_counter() - t0
+
+        def submit_fixed(slot):
+            nmsm._lib.check(lib.nmsm_msm_points_submit(h, d_sc.data_ptr(), n_local, 1, slot))
+
+        nmsm.set_profiling(True)
+        for _ in range(3):
+            submit_fixed(0)
+            collect(0, out, inf)
+            assert out.raw == exp_xy and inf.value == exp_inf
+        fms, finfo = nmsm.last_timing()
+        nmsm.set_profiling(False)
+        run_pipelined(2 * NF + 1, submit_fixed)
+        barrier()
+        t0 = time.perf_counter()
+        run_pipelined(args.steps, submit_fixed)
+        barrier()
+        f_el = time.perf_counter() - t0
+        fixed = {"value": n_local * args.steps / f_el, "unit": "points/s", "ms_per_step": 1e3 * f_el / args.steps,
+                 "latency_ms_single_msm": fms["total"], "in_flight": NF,
+                 "table": {"window_bits": tc.value, "levels": lv.value, "bytes": lv.value * 2 * n_local * 96,
+                           "precompute_ms": t_pre * 1e3},
+                 "plan": {"c": finfo.c, "windows": finfo.windows, "sorted_entries": finfo.sorted_entries},
+                 "kernel_ms_breakdown": {k: round(v, 4) for k, v in fms.items()},
+                 "note": "device-resident point set + table 2^(c*j)*P (nmsm_points_precompute); companion to `value`, "
+                         "which stays the general MSM with points passed per call"}
+        lib.nmsm_points_free(h)
 
     if rank != 0:
         if world > 1:
@@ -376,7 +414,7 @@ def main():
         return
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
-    ms, info = nmsm.last_timing()
+    ms, info = main_timing
     peak = 0.0
     for (bps, thr, ilp) in ((4, 128, 1), (8, 128, 1), (4, 256, 1), (4, 128, 2), (8, 128, 2), (2, 256, 2)):
         peak = max(peak, nmsm.bench_modmul(1, bps, thr, 3000, ilp))
@@ -447,6 +485,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "fixed_base": fixed,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

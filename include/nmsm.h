@@ -106,6 +106,10 @@ int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t
  * cost model choose (19 for 2^20 BLS12-381 G1 points: 7 levels, 1.4 GB); the choice is returned.  One-off cost:
  * levels-1 kernels of c doublings + one inversion per point. */
 int nmsm_points_precompute(uint64_t handle, int window_bits, int* out_window_bits, int* out_levels);
+/* Asynchronous nmsm_msm_points on a slot (collect with nmsm_msm_collect): the prover loop over a fixed SRS.  The
+ * scalars may already be on the device (scalars_on_device = 1, 16-byte aligned); host scalars must stay valid until
+ * the collect. */
+int nmsm_msm_points_submit(uint64_t handle, const void* scalars, uint64_t n, int scalars_on_device, int slot);
 
 /* Fixed-point multiplication tables (next-row f4): the device-resident form of Point.precompute(W) and the cached
  * signed-window multiply it enables (/root/reference/src/abstract/curve.ts:532-577 table, :588-606 walk; used by

@@ -241,6 +241,17 @@ int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t
   return E->msm_prepared(ps->d_prepared, ps->n, ps->table_c, scalars, n, out_xy, out_is_inf);
 }
 
+int nmsm_msm_points_submit(uint64_t handle, const void* scalars, uint64_t n, int scalars_on_device, int slot) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (slot < 0 || slot >= NUM_SLOTS) return fail(NMSM_ERR_ARG, "slot out of range (0..3)");
+  PointSet* ps = (PointSet*)(uintptr_t)handle;
+  if (!ps || (n && !scalars)) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(ps->curve);
+  g_ctx.cur = slot;
+  return E->submit_prepared(ps->d_prepared, ps->n, ps->table_c, scalars, n, scalars_on_device);
+}
+
 int nmsm_points_precompute(uint64_t handle, int window_bits, int* out_window_bits, int* out_levels) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;

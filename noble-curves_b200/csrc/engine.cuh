@@ -271,16 +271,25 @@ static int prepare_points(const uint8_t* pts, uint64_t n, uint32_t** out_dev) {
 // scalars use the first n_scalars points, like interleavedMSMUnsafe's trailing zeros).
 static int run_msm_prepared(const uint32_t* d_prepared, uint64_t n_points, int table_c, const uint8_t* scalars,
                             uint64_t n, uint8_t* out_xy, int* out_is_inf) {
+  if (int r = submit_prepared(d_prepared, n_points, table_c, scalars, n, 0)) return r;
+  return collect_msm(out_xy, out_is_inf);
+}
+
+// asynchronous half (nmsm_msm_points_submit): scalars from the host (copied on the slot's stream) or the device
+static int submit_prepared(const uint32_t* d_prepared, uint64_t n_points, int table_c, const void* scalars, uint64_t n,
+                           int scalars_on_device) {
   Slot& C = g_ctx.slot[g_ctx.cur];
+  if (C.pend.active) return fail(NMSM_ERR_ARG, "slot busy: collect the previous MSM first");
   if (n > n_points) return fail(NMSM_ERR_LENGTH, "array of scalars must not be larger than array of points");
-  if (n) {
-    CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
-    CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
-  }
   if (Cv::GLV && n != n_points)
     return fail(NMSM_ERR_ARG, "this curve's prepared sets interleave P and phi(P): pass one scalar per point");
-  return run_msm(nullptr, (const uint32_t*)C.in_scalars.p, n, nullptr, out_xy, out_is_inf, d_prepared, table_c,
-                 n_points);
+  const uint32_t* d_scalars = (const uint32_t*)scalars;
+  if (n && !scalars_on_device) {
+    CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
+    CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
+    d_scalars = (const uint32_t*)C.in_scalars.p;
+  }
+  return submit_msm(nullptr, d_scalars, n, nullptr, d_prepared, table_c, n_points);
 }
 
 // Fixed-base table for a prepared set: levels j = 0..D-1 hold 2^(c*j) * P_i (and 2^(c*j) * phi(P_i) for the GLV
@@ -452,7 +461,8 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
                                     &Engine<CURVE>::prepare_points, &Engine<CURVE>::run_msm_prepared, \
                                     &Engine<CURVE>::precompute_table,                              \
                                     &Engine<CURVE>::build_point_table, &Engine<CURVE>::table_mul_batch, \
-                                    &Engine<CURVE>::submit_any,     &Engine<CURVE>::collect_msm}; \
+                                    &Engine<CURVE>::submit_any,     &Engine<CURVE>::collect_msm,    \
+                                    &Engine<CURVE>::submit_prepared};                              \
     return &vt;                                                                                \
   }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "nmsm_init", "nmsm_shutdown", "nmsm_last_error", "nmsm_last_error_index", "nmsm_point_bytes",
     "nmsm_acc_bytes", "nmsm_msm", "nmsm_msm_device", "nmsm_msm_partial_device", "nmsm_fold_partials_device",
     "nmsm_mul_batch", "nmsm_set_window_bits", "nmsm_set_profiling", "nmsm_last_timing", "nmsm_bench_modmul",
-    "nmsm_host_alloc", "nmsm_host_free", "nmsm_points_upload", "nmsm_points_free", "nmsm_msm_points", "nmsm_points_precompute", "nmsm_point_table_create", "nmsm_point_table_free",
+    "nmsm_host_alloc", "nmsm_host_free", "nmsm_points_upload", "nmsm_points_free", "nmsm_msm_points", "nmsm_points_precompute", "nmsm_msm_points_submit", "nmsm_point_table_create", "nmsm_point_table_free",
     "nmsm_point_table_mul_batch",
     "nmsm_ed25519_verify_batch", "nmsm_msm_submit", "nmsm_msm_collect", "nmsm_points_decode", "nmsm_msm_submit_partial",
 ]
@@ -113,6 +113,8 @@ def load() -> ctypes.CDLL:
         lib.nmsm_points_precompute.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                                ctypes.POINTER(ctypes.c_int)]
         lib.nmsm_points_precompute.restype = ctypes.c_int
+        lib.nmsm_msm_points_submit.argtypes = [ctypes.c_uint64, u8p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
+        lib.nmsm_msm_points_submit.restype = ctypes.c_int
         lib.nmsm_point_table_create.argtypes = [ctypes.c_int, u8p, ctypes.POINTER(ctypes.c_uint64)]
         lib.nmsm_point_table_create.restype = ctypes.c_int
         lib.nmsm_point_table_free.argtypes = [ctypes.c_uint64]
