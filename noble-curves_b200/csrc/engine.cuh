@@ -301,10 +301,12 @@ static int precompute_table(uint32_t** d_prepared, uint64_t n_points, int c_req,
   const uint64_t terms = n_points * (Cv::GLV ? 2 : 1);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  const int c = (c_req >= 4 && c_req <= MAX_TABLE_BITS) ? c_req
-                                                         : choose_table_bits<Cv>(n_points, g_ctx.sm_count, 0.5 * (double)free_b);
-  if (c_req != 0 && c != c_req) return fail(NMSM_ERR_ARG, "table window bits must be 0 (automatic) or in [4, 22]");
-  const int D = table_digits<Cv>(c);
+  if (c_req != 0 && (c_req < 4 || c_req > MAX_TABLE_BITS))
+    return fail(NMSM_ERR_ARG, "table window bits must be 0 (automatic) or in [4, 22]");
+  // the request is an upper bound on the digit width; the scalar bits are then spread evenly over the digits
+  const int c = c_req ? canonical_table_bits<Cv>(c_req) : choose_table_bits<Cv>(n_points, g_ctx.sm_count, 0.5 * (double)free_b);
+  const MsmPlan tp = make_table_plan<Cv>(n_points, c, g_ctx.sm_count);
+  const int D = tp.D;
   if (terms * (uint64_t)D >= (1ull << 31)) return fail(NMSM_ERR_ARG, "points * levels must be < 2^31");
   const size_t level_bytes = (size_t)terms * G::AFF_WORDS * 4;
   uint32_t* tbl = nullptr;
@@ -312,7 +314,8 @@ static int precompute_table(uint32_t** d_prepared, uint64_t n_points, int c_req,
   cudaMemcpyAsync(tbl, *d_prepared, level_bytes, cudaMemcpyDeviceToDevice, C.stream);
   for (int j = 1; j < D; j++)
     k_table_level<Cv><<<cdiv(terms, 128), 128, 0, C.stream>>>(tbl + (size_t)(j - 1) * terms * G::AFF_WORDS,
-                                                               tbl + (size_t)j * terms * G::AFF_WORDS, (uint32_t)terms, c);
+                                                               tbl + (size_t)j * terms * G::AFF_WORDS, (uint32_t)terms,
+                                                               digit_width(tp, j - 1));
   cudaError_t e = cudaStreamSynchronize(C.stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { cudaFree(tbl); return cuda_fail(e, "precompute_table"); }

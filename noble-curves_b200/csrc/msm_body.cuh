@@ -37,8 +37,13 @@ struct MsmPlan {
   int chunks;  // B / K
   int D;       // signed digits per (half-)scalar; == W unless stride != 0
   uint32_t stride;  // 0: digit w goes to bucket window w.  != 0 (fixed-base tables): every digit goes to the
-                    // single bucket window and selects the point  index + w * stride  = 2^(c*w) * P_index
+                    // single bucket window and selects the point  index + w * stride  = 2^(offset_w) * P_index
+  int wb, r;        // digit w is  wb + (w < r)  bits wide and starts at bit  w * wb + min(w, r).  Ordinary plans:
+                    // wb = c, r = 0.  Table plans spread the bits+1 scalar bits evenly over the D digits so that no
+                    // digit is much narrower than the others (a narrow digit piles its terms onto few buckets)
 };
+NMSM_HD int digit_width(const MsmPlan& p, int w) { return p.wb + (w < p.r ? 1 : 0); }
+NMSM_HD int digit_offset(const MsmPlan& p, int w) { return w * p.wb + (w < p.r ? w : p.r); }
 
 template <class Cv>
 constexpr int glv_bits() {
@@ -113,22 +118,38 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
   p.chunks = p.B / p.K;
   p.D = p.W;
   p.stride = 0;
+  p.wb = p.c;
+  p.r = 0;
   return p;
 }
 
-// Fixed-base tables (nmsm_points_precompute): level j of the table holds 2^(c*j) * P_i for every point of the
+// Fixed-base tables (nmsm_points_precompute): level j of the table holds 2^(offset_j) * P_i for every point of the
 // set, so all D digits of a scalar land in ONE bucket window: 1/W of the bucket reduction, no Horner doublings,
 // and c can grow past 16 because the reduce cost no longer multiplies by W.  Same time model as make_plan.
+// A table is identified by its window bits c; D = ceil((bits+1)/c) digits of width floor/ceil((bits+1)/D).
 template <class Cv>
 inline int table_digits(int c) { return (glv_bits<Cv>() + 1 + c - 1) / c; }
+// the (c, D) pair with D = ceil(T/c) and c = ceil(T/D) reached from a requested upper bound on the digit width
+template <class Cv>
+inline int canonical_table_bits(int c_req) {
+  const int T = glv_bits<Cv>() + 1;
+  int c = c_req;
+  for (int it = 0; it < 8; it++) {
+    const int D = (T + c - 1) / c;
+    const int c2 = (T + D - 1) / D;
+    if (c2 == c) break;
+    c = c2;
+  }
+  return c;
+}
 
-static constexpr int TABLE_REDUCE_CHUNK = 2;  // buckets per k_reduce1 thread in table mode (measured: 2 < 4 < 8)
+static constexpr int TABLE_REDUCE_CHUNK = 8;  // buckets per k_reduce1 thread in table mode
 
 template <class Cv>
 inline int choose_table_bits(uint64_t n_points, int sm_count, double mem_budget_bytes) {
   using G = typename Cv::G;
   using F = typename G::Field;
-  const int bits = glv_bits<Cv>();
+  const int T = glv_bits<Cv>() + 1;
   const double terms = (double)n_points * (Cv::GLV ? 2 : 1);
   const double limb_ratio = (double)(F::LIMBS / F::BASE_MULS == 12 ? 1.0 : (8.0 * 8.0) / (12.0 * 12.0));
   const double fscale = limb_ratio * F::BASE_MULS;
@@ -137,19 +158,20 @@ inline int choose_table_bits(uint64_t n_points, int sm_count, double mem_budget_
   const double t_add_lat = 0.030 * fscale * G::COST_ADD / 14.0;
   int best_c = 4;
   double best = 1e300;
-  for (int c = 4; c <= MAX_TABLE_BITS; c++) {
+  for (int c0 = 4; c0 <= MAX_TABLE_BITS; c0++) {
+    const int c = canonical_table_bits<Cv>(c0);
+    if (c != c0) continue;
     const int D = table_digits<Cv>(c);
     if ((double)D * terms * G::AFF_WORDS * 4.0 > mem_budget_bytes && c > 4) continue;
+    const int wb = T / D, r = T % D;
     const double B = (double)(1u << (c - 1));
     const double entries = terms * D;
     int L = (int)ceil(entries / ((double)sm_count * 1024.0));
     L = L < 4 ? 4 : (L > 32 ? 32 : L);
-    // the top digit holds only top_bits scalar bits: its values pile onto the lowest 2^(top_bits-1) buckets,
-    // whose partials one k_reduce1 thread stitches serially (same effect as the narrow top window in make_plan)
-    const int top_bits = bits + 1 - (D - 1) * c;
-    const double heavy = terms / (double)(1u << (top_bits > 1 ? top_bits - 1 : 0));
-    double parts_top = 1.0 + (entries / B + heavy) / L;
-    if (parts_top > 100.0) parts_top = 100.0 + (entries / B + heavy) / L / 32.0;
+    // r digits are c bits wide, D - r only c - 1: the lower half of the buckets receives all D digits
+    const double load_low = r ? terms * ((double)(D - r) / (double)(1u << (wb - 1)) + (double)r / (double)(1u << wb))
+                              : entries / B;
+    const double parts_top = 1.0 + load_low / L;
     const double kk = B < TABLE_REDUCE_CHUNK ? B : TABLE_REDUCE_CHUNK;
     const double t_r1a = (entries / L + 2.0 * B) * t_add_tp, t_r1b = kk * (1.0 + parts_top) * t_add_lat;
     const double cost = entries * t_madd + (t_r1a > t_r1b ? t_r1a : t_r1b);
@@ -161,15 +183,19 @@ inline int choose_table_bits(uint64_t n_points, int sm_count, double mem_budget_
   return best_c;
 }
 
+// `c` must be canonical (canonical_table_bits)
 template <class Cv>
 inline MsmPlan make_table_plan(uint64_t n_points, int c, int sm_count) {
   MsmPlan p;
+  const int T = glv_bits<Cv>() + 1;
   const double terms = (double)n_points * (Cv::GLV ? 2 : 1);
-  p.c = c;
-  p.W = 1;
-  p.B = 1 << (c - 1);
-  p.G = p.B;
   p.D = table_digits<Cv>(c);
+  p.wb = T / p.D;
+  p.r = T % p.D;
+  p.c = p.wb + (p.r ? 1 : 0);
+  p.W = 1;
+  p.B = 1 << (p.c - 1);
+  p.G = p.B;
   p.stride = (uint32_t)(n_points * (Cv::GLV ? 2 : 1));
   int L = (int)ceil(terms * p.D / ((double)sm_count * 1024.0));
   p.L = L < 4 ? 4 : (L > 32 ? 32 : L);
@@ -619,14 +645,15 @@ NMSM_HD bool table_mul_body(uint32_t i, const uint32_t* tbl, const uint32_t* sca
 template <bool SCATTER>
 NMSM_HD void emit_digits(const uint32_t* m, int nwords, uint32_t index, uint32_t flip, const MsmPlan& plan,
                          unsigned int* counts_or_cursor, uint32_t* sorted) {
-  const uint32_t half = 1u << (plan.c - 1);
   uint32_t carry = 0;
   for (int w = 0; w < plan.D; w++) {
-    uint32_t v = scalar_bits(m, w * plan.c, plan.c, nwords) + carry;
+    const int width = digit_width(plan, w);
+    const uint32_t half = 1u << (width - 1);
+    uint32_t v = scalar_bits(m, digit_offset(plan, w), width, nwords) + carry;
     carry = 0;
     uint32_t neg = flip;
     if (v > half) {
-      v = (1u << plan.c) - v;
+      v = (1u << width) - v;
       neg ^= 1u;
       carry = 1;
     }
@@ -752,56 +779,74 @@ NMSM_HD void stitch_tile_serial(uint32_t j, uint32_t span, const uint32_t* offse
   save_acc<G>(out + (size_t)j * G::ACC_WORDS, acc);
 }
 
-// Adds the value of bucket g into `sum`.  A bucket wholly inside one accumulate segment was written
-// to `buckets`; one that straddles segments is stitched from tails / heads / tile sums; an empty
-// bucket contributes nothing.
-template <class Cv, class Ops>
-NMSM_HD void add_bucket(typename Cv::G::Acc& sum, uint32_t g, const uint32_t* offsets, const MsmPlan& plan,
-                        const uint32_t* buckets, const uint32_t* heads, const uint32_t* tails,
-                        const uint32_t* tile1, const uint32_t* tile2) {
-  using G = typename Cv::G;
-  const uint32_t b0 = offsets[g], b1 = offsets[g + 1];
-  if (b0 == b1) return;
-  const uint32_t ts = b0 / plan.L, te = (b1 - 1) / plan.L;
-  if (ts == te) {
-    Ops::add(sum, load_acc<G>(buckets + (size_t)g * G::ACC_WORDS));
-    return;
-  }
-  Ops::add(sum, load_acc<G>(tails + (size_t)ts * G::ACC_WORDS));
-  constexpr uint32_t F1 = STITCH_FAN, F2 = STITCH_FAN * STITCH_FAN;
-  uint32_t t = ts + 1;
-  while (t <= te) {
-    if ((t % F2) == 0 && te - t >= F2 - 1) {
-      Ops::add(sum, load_acc<G>(tile2 + (size_t)(t / F2) * G::ACC_WORDS));
-      t += F2;
-    } else if ((t % F1) == 0 && te - t >= F1 - 1) {
-      Ops::add(sum, load_acc<G>(tile1 + (size_t)(t / F1) * G::ACC_WORDS));
-      t += F1;
-    } else {
-      Ops::add(sum, load_acc<G>(heads + (size_t)t * G::ACC_WORDS));
-      t++;
-    }
-  }
-}
-
+// The value of bucket g: a bucket wholly inside one accumulate segment was written to `buckets`; one that
+// straddles segments ts..te is tails[ts] + heads[ts+1..te], with aligned runs of 32 / 1024 heads replaced by
+// their tile sums; an empty bucket contributes nothing.
 // Thread (w, k): chunk of K buckets of window w ->
 //   sums[id]  = sum_{b in chunk} B_b
 //   wsums[id] = sum_{b in chunk} (b - kK + 1) * B_b          (running-sum trick, curve.ts:897-900)
 // so that  sum_b (b+1) B_b = sum_k wsums_k + K * sum_k k * sums_k  (second level: reduce2).
+//
+// The walk is written as ONE loop with ONE addition per iteration — either `sum += next partial of the current
+// bucket` or, when the bucket is exhausted, `wsum += sum` — selected by pointers.  A point addition occupies the
+// multiply pipe for the whole warp whatever the number of active lanes, so the lanes of a warp must reach the same
+// call site in the same iteration: with one call site the warp executes max-over-lanes of (partials + K)
+// additions instead of one per distinct branch taken by any lane.
 template <class Cv, class Ops>
 NMSM_HD void reduce1_body(uint32_t id, const uint32_t* offsets, const uint32_t* buckets, const uint32_t* heads,
                           const uint32_t* tails, const uint32_t* tile1, const uint32_t* tile2, const MsmPlan& plan,
                           uint32_t* sums, uint32_t* wsums) {
   using G = typename Cv::G;
+  using Acc = typename G::Acc;
   const uint32_t w = id / plan.chunks, k = id % plan.chunks;
   const uint32_t g0 = w * plan.B + k * plan.K;
-  typename G::Acc sum = G::identity(), wsum = G::identity();
-  for (int b = plan.K - 1; b >= 0; b--) {
-    add_bucket<Cv, Ops>(sum, g0 + b, offsets, plan, buckets, heads, tails, tile1, tile2);
-    Ops::add(wsum, sum);
+  constexpr uint32_t F1 = STITCH_FAN, F2 = STITCH_FAN * STITCH_FAN;
+  Acc acc[2] = {G::identity(), G::identity()};  // [0] = sum, [1] = wsum
+  Acc part;
+  int b = plan.K - 1;
+  bool open = false;
+  uint32_t g = 0, t = 1, ts = 0, te = 0;  // t > te: no partial left in the current bucket
+  for (;;) {
+    if (!open) {
+      if (b < 0) break;
+      g = g0 + (uint32_t)b;
+      const uint32_t b0 = offsets[g], b1 = offsets[g + 1];
+      ts = 0;
+      te = 0;
+      t = 1;
+      if (b0 != b1) {
+        ts = b0 / plan.L;
+        te = (b1 - 1) / plan.L;
+        t = ts;
+      }
+      open = true;
+    }
+    const bool fold = t > te;  // bucket exhausted (or empty): wsum += sum and move to the next bucket
+    if (!fold) {
+      const uint32_t* src;
+      uint32_t step = 1;
+      if (t == ts) {
+        src = (ts == te) ? buckets + (size_t)g * G::ACC_WORDS : tails + (size_t)ts * G::ACC_WORDS;
+      } else if ((t % F2) == 0 && te - t >= F2 - 1) {
+        src = tile2 + (size_t)(t / F2) * G::ACC_WORDS;
+        step = F2;
+      } else if ((t % F1) == 0 && te - t >= F1 - 1) {
+        src = tile1 + (size_t)(t / F1) * G::ACC_WORDS;
+        step = F1;
+      } else {
+        src = heads + (size_t)t * G::ACC_WORDS;
+      }
+      part = load_acc<G>(src);
+      t += step;
+    }
+    Ops::add(acc[fold ? 1 : 0], fold ? acc[0] : part);
+    if (fold) {
+      open = false;
+      b--;
+    }
   }
-  save_acc<G>(sums + (size_t)id * G::ACC_WORDS, sum);
-  save_acc<G>(wsums + (size_t)id * G::ACC_WORDS, wsum);
+  save_acc<G>(sums + (size_t)id * G::ACC_WORDS, acc[0]);
+  save_acc<G>(wsums + (size_t)id * G::ACC_WORDS, acc[1]);
 }
 
 // Serial statement of the second level for one window (what k_reduce2 computes cooperatively):

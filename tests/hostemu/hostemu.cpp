@@ -21,7 +21,7 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
                      uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out, int table_c = 0) {
   using G = typename Cv::G;
   // table_c != 0: fixed-base table route (nmsm_points_precompute + nmsm_msm_points)
-  MsmPlan plan = table_c ? make_table_plan<Cv>(n, table_c, 148) : make_plan<Cv>(n, forced_c, 148);
+  MsmPlan plan = table_c ? make_table_plan<Cv>(n, canonical_table_bits<Cv>(table_c), 148) : make_plan<Cv>(n, forced_c, 148);
   if (forced_L > 0) plan.L = forced_L;
   plan_out[0] = plan.c; plan_out[1] = plan.W; plan_out[2] = plan.B; plan_out[3] = plan.L;
   const size_t terms = (size_t)n * (Cv::GLV ? 2 : 1);
@@ -34,7 +34,7 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
     for (int j = 1; j < plan.D; j++)
       for (uint32_t i = 0; i < terms; i++)
         table_level_body<Cv>(i, aff.data() + (size_t)(j - 1) * terms * G::AFF_WORDS,
-                             aff.data() + (size_t)j * terms * G::AFF_WORDS, plan.c);
+                             aff.data() + (size_t)j * terms * G::AFF_WORDS, digit_width(plan, j - 1));
   for (uint32_t i = 0; i < n; i++) digits_body<Cv, false>(i, n, scalars, plan, counts.data(), nullptr, err);
   uint32_t run = 0;
   for (int g = 0; g < plan.G; g++) { offsets[g] = run; cursor[g] = run; run += counts[g]; }

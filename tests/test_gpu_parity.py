@@ -359,7 +359,7 @@ def test_fixed_base_table_small(nmsm, name):
     for c in (0, 4, 11, 16, 19, 22):
         ps = nmsm.PointSet(cid, pb, n)
         got_c, levels = ps.precompute(c)
-        assert (c == 0 or got_c == c) and levels >= 1
+        assert (c == 0 or got_c <= c) and levels >= 1  # c bounds the digit width; widths are balanced
         for _ in range(2):  # the table is reused
             out, inf = ps.msm(sb, n)
             assert (*H.unpack_point(name, out), inf) == exp, (name, c)

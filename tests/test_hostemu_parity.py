@@ -94,7 +94,7 @@ def test_msm_fixed_base_table_route(name):
         exp = H.expected_tuple(name, R.pippenger(P, pts[:size], scalars[:size]))
         got, err, plan = H.emu_msm(name, pb[: size * step], sb[: size * 32], size, 0, L, table_c=c)
         assert err == (0xFFFFFFFF, 0xFFFFFFFF)
-        assert plan[0] == c and plan[1] == 1 and plan[2] == 1 << (c - 1)
+        assert plan[0] <= c and plan[1] == 1 and plan[2] == 1 << (plan[0] - 1)  # digit widths are balanced: max width <= c
         assert got == exp, (name, size, c, L)
 
 
