@@ -155,7 +155,8 @@ inline int choose_table_bits(uint64_t n_points, int sm_count, double mem_budget_
   const double fscale = limb_ratio * F::BASE_MULS;
   const double t_madd = 0.352e-6 * fscale * G::COST_MADD / 10.0;
   const double t_add_tp = 0.93e-6 * fscale * G::COST_ADD / 14.0;
-  const double t_add_lat = 0.030 * fscale * G::COST_ADD / 14.0;
+  const double t_add_lat = 0.006 * fscale * G::COST_ADD / 14.0;  // one dependent addition of a sparse k_reduce1 grid
+  const double t_level = 0.2 * fscale;                            // one more k_reduce2 pass (latency)
   int best_c = 4;
   double best = 1e300;
   for (int c0 = 4; c0 <= MAX_TABLE_BITS; c0++) {
@@ -174,7 +175,9 @@ inline int choose_table_bits(uint64_t n_points, int sm_count, double mem_budget_
     const double parts_top = 1.0 + load_low / L;
     const double kk = B < TABLE_REDUCE_CHUNK ? B : TABLE_REDUCE_CHUNK;
     const double t_r1a = (entries / L + 2.0 * B) * t_add_tp, t_r1b = kk * (1.0 + parts_top) * t_add_lat;
-    const double cost = entries * t_madd + (t_r1a > t_r1b ? t_r1a : t_r1b);
+    const double chunks = B / kk;
+    const int levels = chunks <= 4096.0 ? 1 : (chunks <= 524288.0 ? 2 : 3);
+    const double cost = entries * t_madd + (t_r1a > t_r1b ? t_r1a : t_r1b) + levels * t_level;
     if (cost < best) {
       best = cost;
       best_c = c;
