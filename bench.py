@@ -196,6 +196,9 @@ def main():
     torch.cuda.set_device(local_rank)
     nmsm.init(local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = nmsm._lib.load()
     if args.window:
