@@ -121,6 +121,17 @@ int nmsm_point_table_free(uint64_t handle);
 int nmsm_point_table_mul_batch(uint64_t handle, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
                                uint8_t* out_is_inf);
 
+/* NTT over the scalar field Fr of a pairing curve (next-row f4: the MSM's companion in SNARK provers): the batch
+ * form of FFT(rootsOfUnity(Fr, generator), Fr).direct / .inverse (/root/reference/src/abstract/fft.ts:518-575; root
+ * tables :230-312, loops :422-480).  `values`: 2^log_n elements of 32 bytes, canonical little-endian (< r),
+ * transformed in place.  curve: NMSM_BN254_G1/G2 (Fr of bn254, 2-adicity 28) or NMSM_BLS12_381_G1/G2 (2-adicity 32).
+ * generator: the non-residue G of rootsOfUnity (the reference's tests pass 7); 0 = findGenerator's choice
+ * (fft.ts:175-180: 5 for both fields).  inverse = 0: direct(values, brp_input, brp_output), out[k] = a(omega^k);
+ * inverse = 1: inverse(values, brp_input, brp_output) incl. the 1/n scaling.  An element >= r is reported as
+ * NMSM_ERR_SCALAR with its index and leaves `values` untouched. */
+int nmsm_ntt(int curve, uint8_t* values, int log_n, uint64_t generator, int inverse, int brp_input, int brp_output);
+int nmsm_ntt_device(int curve, void* d_values, int log_n, uint64_t generator, int inverse, int brp_input, int brp_output);
+
 /* Ed25519 batch verification (next-row f1).  The reference verifies one signature at a time
  * (/root/reference/src/abstract/edwards.ts:942-989, ZIP-215 decoding by default, src/ed25519.ts:168); this checks
  *   [8]( sum z_i*R_i + sum (z_i*k_i mod l)*A_i - (sum z_i*s_i mod l)*B ) == O ,  k_i = SHA-512(R_i||A_i||M_i) mod l

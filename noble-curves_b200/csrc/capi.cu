@@ -137,6 +137,9 @@ void nmsm_shutdown(void) {
     S.pend = Pending();
   }
   C.ed_scratch.release();
+  for (Buf* b : {&C.ntt_data, &C.ntt_work, &C.ntt_tmp, &C.ntt_roots, &C.ntt_aux}) b->release();
+  C.ntt_key_field = -1;
+  C.ntt_key_bits = -1;
   C.ready = false;
   C.device = -1;
 }
@@ -370,6 +373,22 @@ int nmsm_set_profiling(int enabled) {
   int prev = g_ctx.profiling ? 1 : 0;
   g_ctx.profiling = enabled != 0;
   return prev;
+}
+
+int nmsm_ntt(int curve, uint8_t* values, int log_n, uint64_t generator, int inverse, int brp_input, int brp_output) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
+  if (!values) return fail(NMSM_ERR_ARG, "null pointer");
+  return ntt_impl(curve, values, 0, log_n, generator, inverse, brp_input, brp_output);
+}
+
+int nmsm_ntt_device(int curve, void* d_values, int log_n, uint64_t generator, int inverse, int brp_input, int brp_output) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
+  if (!d_values) return fail(NMSM_ERR_ARG, "null pointer");
+  return ntt_impl(curve, d_values, 1, log_n, generator, inverse, brp_input, brp_output);
 }
 
 int nmsm_last_timing(float* ms, nmsm_plan_info* info) {

@@ -75,6 +75,9 @@ struct Context {
   Slot slot[NUM_SLOTS];
   int cur = 0;  // slot used by the call in progress (set by the C-ABI wrapper under the mutex)
   Buf ed_scratch;
+  Buf ntt_data, ntt_work, ntt_tmp, ntt_roots, ntt_aux;  // NTT staging / work / output / root table (ntt.cu)
+  int ntt_key_field = -1, ntt_key_bits = -1;            // which root table ntt_roots holds
+  uint64_t ntt_key_gen = 0;
   bool profiling = false;
   int forced_c = 0;
   float last_ms[NMSM_TIMING_SLOTS] = {};
@@ -135,6 +138,8 @@ struct EngineVTable {
 int ed25519_verify_batch_impl(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* msg_off,
                               uint64_t n, const uint8_t* z16, int* out_ok, long long* out_bad_index);
 int decode_points_impl(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_xy, uint8_t* out_status);
+int ntt_impl(int curve, void* values, int on_device, int log_n, uint64_t generator, int inverse, int brp_input,
+             int brp_output);
 const EngineVTable* engine_secp256k1();
 const EngineVTable* engine_ed25519();
 const EngineVTable* engine_bn254g1();

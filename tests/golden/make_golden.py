@@ -13,6 +13,8 @@ Sources (all under /root/reference/test/vectors, used by the reference tests cit
   bn254/eth-dump.js             test/bn254.test.ts:750-778       EIP-196 ECADD/ECMUL dumps
   bn254/seda.js                 test/bn254.test.ts:859-887       add / mul
   ed25519/vectors.txt           test/ed25519.test.ts:50-78       sk:pk:msg:sig (RFC 8032 / cr.yp.to)
+  (test source) test/fft.test.ts:155-215  fixed rootsOfUnity tables (roots(3), brp(3)) of bls12_381.fields.Fr and
+                                           bn254.fields.Fr with generator 7 -> fft.json
 """
 import json
 import os
@@ -90,7 +92,24 @@ def ed25519():
     dump("ed25519.json", {"vectors": rows, "zip215": zip215, "edge_cases": edge})
 
 
+def fft():
+    """The reference keeps its NTT known answers inline in test/fft.test.ts ('cache and fixed vectors'): the
+    8-entry root tables for generator 7.  Extracted by locating the eql(roots.roots(3) / roots.brp(3), [...]) blocks."""
+    src = open("/root/reference/test/fft.test.ts").read()
+    out = {}
+    for field in ("bls12_381", "bn254"):
+        a = src.index("roots = fft.rootsOfUnity(%s.fields.Fr, 7n);" % field)
+        seg = src[a:a + 6000]
+        for key in ("roots", "brp"):
+            m = re.search(r"roots\.%s\(3\),\s*\[(.*?)\]" % key, seg, re.S)
+            vals = [int(x) for x in re.findall(r"(\d+)n", m.group(1))]
+            assert len(vals) == 8, (field, key, len(vals))
+            out["%s_%s3" % (field, key)] = [str(v) for v in vals]
+    dump("fft.json", out)
+
+
 if __name__ == "__main__":
+    fft()
     secp256k1()
     bls()
     bn254()

@@ -704,3 +704,90 @@ def test_point_codec_roundtrip_object_api(nmsm):
     xb[0] |= 0x80 | (0x20 if (y * 2) // p else 0)
     with pytest.raises(ValueError, match="subgroup"):
         C.fromBytes(bytes(xb))
+
+
+# ------------------------------------------------------------------------------------------------
+# NTT over Fr (SURVEY §8 f4 companion): bit-exact against the oracle restatement of fft.ts
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("field", ["bls12_381", "bn254"])
+def test_ntt_matches_oracle_all_layouts(nmsm, field):
+    """FFT.direct / FFT.inverse for every boundary layout (fft.ts:538-575), generator 7 (the reference tests') and the
+    default generator, sizes 1 .. 2^13 (one tile, one partial tile, two passes), edge values 0 and r-1."""
+    from nmsm import fft as GF
+    from oracle import noble_fft as OF
+
+    p = OF.FR[field]
+    rnd = random.Random(99)
+    for gen in (7, None):
+        oracle = OF.FFT(OF.RootsOfUnity(p, gen))
+        gpu = GF.FFT(GF.rootsOfUnity(field, gen))
+        for bits in (0, 1, 2, 5, 10, 11, 12, 13):
+            n = 1 << bits
+            a = [rnd.randrange(p) for _ in range(n)]
+            a[0] = p - 1
+            if n > 2:
+                a[2] = 0
+            for bi in (False, True):
+                for bo in (False, True):
+                    assert gpu.direct(a, bi, bo) == oracle.direct(a, bi, bo), (field, gen, bits, bi, bo, "direct")
+                    assert gpu.inverse(a, bi, bo) == oracle.inverse(a, bi, bo), (field, gen, bits, bi, bo, "inverse")
+    g = load_golden("fft.json")
+    ones = GF.FFT(GF.rootsOfUnity(field, 7)).direct([0, 1, 0, 0, 0, 0, 0, 0])  # evaluates x at the 8 roots: the root table
+    assert [str(x) for x in ones] == g["%s_roots3" % field]
+
+
+@pytest.mark.parametrize("field,bits", [("bls12_381", 20), ("bn254", 22)])
+def test_ntt_large_properties(nmsm, field, bits):
+    """BASELINE-size transforms through size-independent properties (test/fft.test.ts:545-617): inverse(direct(a)) == a,
+    direct of a constant, additivity, and spot values against the DFT definition a(omega^k)."""
+    import numpy as np
+
+    from nmsm import fft as GF
+    from oracle import noble_fft as OF
+
+    p = OF.FR[field]
+    n = 1 << bits
+    rs = np.random.RandomState(7)
+    raw = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+    raw[:, 31] &= 0x0F  # < 2^252 < r
+    a_b = raw.tobytes()
+    d_b = GF.ntt_packed(field, a_b, bits, generator=7)
+    assert GF.ntt_packed(field, d_b, bits, inverse=True, generator=7) == a_b
+    # brp layouts at full size: direct(a, out=brp) then inverse(in=brp) returns a
+    d_brp = GF.ntt_packed(field, a_b, bits, brp_output=True, generator=7)
+    assert GF.ntt_packed(field, d_brp, bits, inverse=True, brp_input=True, generator=7) == a_b
+    # DFT definition on a sparse polynomial: a = c0 + c1 x + c5 x^5 (+ zeros) at a few roots
+    coeffs = {0: 12345, 1: p - 2, 5: 1 << 200, n - 1: 77}
+    sp = bytearray(n * 32)
+    for i, c in coeffs.items():
+        sp[i * 32:(i + 1) * 32] = c.to_bytes(32, "little")
+    out = GF.ntt_packed(field, bytes(sp), bits, generator=7)
+    w = OF.RootsOfUnity(p, 7).omega(bits)
+    for k in (0, 1, 2, n // 2, n - 1, 123457 % n):
+        wk = pow(w, k, p)
+        exp = sum(c * pow(wk, i, p) for i, c in coeffs.items()) % p
+        assert int.from_bytes(out[k * 32:(k + 1) * 32], "little") == exp, k
+    const = (5).to_bytes(32, "little") * n
+    oc = GF.ntt_packed(field, const, bits, generator=7)
+    assert int.from_bytes(oc[:32], "little") == 5 * n % p and not any(oc[32:])
+
+
+def test_ntt_errors(nmsm):
+    from nmsm import fft as GF
+    from oracle import noble_fft as OF
+
+    p = OF.FR["bn254"]
+    f = GF.FFT(GF.rootsOfUnity("bn254", 7))
+    with pytest.raises(ValueError, match="power of two"):
+        f.direct([1, 2, 3])
+    bad = [1, 2, p, 4]
+    with pytest.raises(ValueError, match="invalid field element at index 2"):
+        f.direct(bad)
+    assert f.direct([1, 2, 3, 4]) == OF.FFT(OF.RootsOfUnity(p, 7)).direct([1, 2, 3, 4])  # still usable afterwards
+    import ctypes
+
+    lib = nmsm._lib.load()
+    dummy = ctypes.create_string_buffer(64)
+    assert lib.nmsm_ntt(2, ctypes.cast(dummy, ctypes.c_void_p), 29, 7, 0, 0, 0) != 0  # bn254 Fr has 2-adicity 28
+    assert b"wrong bits 29 powerOfTwo=28" in lib.nmsm_last_error()
+    assert lib.nmsm_ntt(0, ctypes.cast(dummy, ctypes.c_void_p), 1, 7, 0, 0, 0) != 0   # secp256k1: no NTT field

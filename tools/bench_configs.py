@@ -162,6 +162,56 @@ def point_table_config(tag, name, logn, reps=3):
             "check": "table == generic batch bit-exact; oracle spot check" if ok else "MISMATCH"}
 
 
+def ntt_config(tag, field, logn, reps=5):
+    """Forward + inverse NTT over Fr, device-resident data (nmsm_ntt_device), CUDA-event time of the transform."""
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    from nmsm import fft as GF
+
+    n = 1 << logn
+    rs = np.random.RandomState(logn)
+    raw = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+    raw[:, 31] &= 0x0F
+    host = torch.from_numpy(raw.reshape(-1))
+    dev = host.cuda()
+    nmsm.set_profiling(True)
+    GF.ntt_device(field, dev.data_ptr(), logn, generator=7)             # builds the root table
+    t_roots = nmsm.last_timing()[0]["prepare"]
+    GF.ntt_device(field, dev.data_ptr(), logn, inverse=True, generator=7)
+    ok = bool(torch.equal(dev.cpu(), host))
+    fwd, inv = [], []
+    for _ in range(reps):
+        GF.ntt_device(field, dev.data_ptr(), logn, generator=7)
+        fwd.append(nmsm.last_timing()[0]["total"])
+        GF.ntt_device(field, dev.data_ptr(), logn, inverse=True, generator=7)
+        inv.append(nmsm.last_timing()[0]["total"])
+    ok &= bool(torch.equal(dev.cpu(), host))
+    brp = []
+    for _ in range(reps):
+        GF.ntt_device(field, dev.data_ptr(), logn, brp_output=True, generator=7)
+        brp.append(nmsm.last_timing()[0]["total"])
+        GF.ntt_device(field, dev.data_ptr(), logn, inverse=True, brp_input=True, generator=7)
+    ok &= bool(torch.equal(dev.cpu(), host))
+    t = min(fwd)
+    passes = (logn + 9) // 10
+    # algorithmic HBM bytes: ingest (r+w) + passes x (r+w) + emit (r+w) + copy back (r+w), 32 B elements
+    alg_bytes = (passes + 3) * 2 * n * 32
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)
+    except Exception:
+        peak = 6650.0
+    return {"config": tag, "what": "NTT over Fr(%s), 2^%d elements, device-resident (generator 7)" % (field, logn), "n": n,
+            "direct_ms": t, "inverse_ms": min(inv), "direct_brp_out_ms": min(brp), "root_table_ms": t_roots,
+            "elements_per_s": n / (t * 1e-3), "butterflies_per_s": (n // 2) * logn / (t * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg_bytes / (t * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg_bytes,
+                         "modmul_g_per_s": ((n // 2) * logn + 2 * n) / (t * 1e-3) / 1e9},
+            "check": "inverse(direct(a)) == a bit-exact (natural and brp layouts)" if ok else "MISMATCH"}
+
+
 def config0():
     P = R.CURVES["secp256k1"]
     rnd = random.Random(11)
@@ -218,7 +268,9 @@ def main():
         rows = (lambda: fixed_base_config("f4-a", "bls12_381_G1", 20), lambda: fixed_base_config("f4-b", "bls12_381_G1", 16),
                 lambda: fixed_base_config("f4-c", "bls12_381_G2", 18), lambda: fixed_base_config("f4-d", "bn254_G1", 20),
                 lambda: point_table_config("f4-e", "secp256k1", 20), lambda: point_table_config("f4-f", "ed25519", 20),
-                lambda: point_table_config("f4-g", "bls12_381_G1", 18))
+                lambda: point_table_config("f4-g", "bls12_381_G1", 18),
+                lambda: ntt_config("f4-h", "bls12_381", 20), lambda: ntt_config("f4-i", "bls12_381", 24),
+                lambda: ntt_config("f4-j", "bn254", 20))
     else:
         rows = (config0, lambda: msm_config(1, "bls12_381_G1", 16), lambda: msm_config(2, "bn254_G1", 20),
                 lambda: msm_config(3, "bls12_381_G2", 18), config4)
