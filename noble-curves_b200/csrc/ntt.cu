@@ -19,7 +19,7 @@ namespace nmsm {
 
 static constexpr int NTT_TILE_LOG = 11;               // elements per block tile (2048 x 32 B = 64 KB shared memory)
 static constexpr int NTT_MAX_STAGES = NTT_TILE_LOG - 1;  // stages per pass: leaves >= 2 adjacent columns per row
-static constexpr int NTT_THREADS = 1 << (NTT_TILE_LOG - 1);
+static constexpr int NTT_THREADS = 1 << (NTT_TILE_LOG - 2);  // 2 butterflies per thread per stage, 2 blocks per SM
 
 struct NttPass {
   int log_n;
@@ -59,7 +59,7 @@ __device__ __forceinline__ void ntt_store(uint32_t* p, const F& x) {
 
 // One pass: stages s_hi..s_lo (DIF, descending) or s_lo..s_hi (DIT, ascending) on a shared-memory tile.
 template <class P, bool DIT>
-__global__ void __launch_bounds__(NTT_THREADS, 1)
+__global__ void __launch_bounds__(NTT_THREADS, 2)
 k_ntt_pass(uint32_t* __restrict__ data, const uint32_t* __restrict__ roots, NttPass p) {
   using F = Fp<P>;
   extern __shared__ uint4 ntt_smem4[];
@@ -234,7 +234,7 @@ static int ntt_run(int field_key, int two_adicity, uint64_t default_gen, void* v
     p.tile_log = tile_log;
     p.inverse = inverse ? 1 : 0;
     const unsigned int tiles = n >> tile_log;
-    const int threads = tile_log ? (1 << (tile_log - 1)) : 1;
+    const int threads = tile_log >= 2 ? (1 << (tile_log - 2)) : 1;
     const size_t smem = (size_t)(1u << tile_log) * 32;
     if (dit) k_ntt_pass<P, true><<<tiles, threads, smem, st>>>(cur, roots, p);
     else k_ntt_pass<P, false><<<tiles, threads, smem, st>>>(cur, roots, p);
