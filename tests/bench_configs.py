@@ -2,7 +2,7 @@
 """Measure every BASELINE.json config on one B200 (parity-checked, CUDA-event kernel times where the MSM
 pipeline is used).  The headline (configs[1]/metric at 2^20) is bench.py; this writes the companion table.
 
-    python tools/bench_configs.py > profiles/r01_configs.jsonl
+    python tests/bench_configs.py > profiles/r01_configs.jsonl
 
 configs (BASELINE.json):
   0  secp256k1 Point.multiply batch of 1024 random scalars      (reference: CPU bigint; here also the GPU batch)
@@ -11,7 +11,8 @@ configs (BASELINE.json):
   3  BLS12-381 G2 MSM, 2^18
   4  ed25519 batch-verify 2^16 signatures
 Each line: {"config", "n", "gpu_ms" (best of K, wall through the C ABI incl. H2D), "per_s", "kernels_ms", "check"}.
-CPU comparison numbers use the oracle (tests-only code) on a bounded sample and are labelled.
+CPU comparison numbers use the oracle (tests-only code) on a bounded sample and are labelled.  The script lives under
+tests/ because it uses the oracle as its checker; pytest does not collect it.
 """
 import json
 import os
