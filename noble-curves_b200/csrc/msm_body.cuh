@@ -907,18 +907,37 @@ NMSM_HD void fold_body(const uint32_t* accs, int count, uint32_t* out, uint32_t*
   *out_inf = inf;
 }
 
-// k_i * P_i (Point.multiply / multiplyUnsafe, weierstrass.ts:900-928, edwards.ts:555-577): left-to-right
-// signed-binary (NAF) double-and-add with mixed additions, canonical affine out.  Public-input /
-// variable-time, like the reference's multiplyUnsafe; the value equals multiply()'s.
+// k_i * P_i (Point.multiply / multiplyUnsafe, weierstrass.ts:900-928, edwards.ts:555-577): fixed 4-bit signed
+// windows over a per-thread table {1..8} * P (the shape of the reference's uncached constant-time kernel,
+// curve.ts:707-729, without its blinding), canonical affine out.  Public-input / variable-time like multiplyUnsafe;
+// the value equals multiply()'s.  Why windows and not NAF: a point addition costs the whole warp its multiply-pipe
+// time whenever ANY lane needs it, so sparse per-lane digit patterns buy nothing under SIMT, while a window does one
+// table addition per 4 doublings for every lane at once.  On the GLV curves (secp256k1, bn254 G1, BLS12-381 G1;
+// weierstrass.ts:843-861 is the reference's use of the same endomorphism for secp256k1) k = k1 + k2 * lambda halves
+// the doublings: the second table is phi of the first, (beta * X, Y, ZZ, ZZZ).
+static constexpr int MUL_WBITS = 4;
+static constexpr int MUL_TABLE = 1 << (MUL_WBITS - 1);  // |digit| <= 8
+
+// digit w of the signed MUL_WBITS-bit recoding of m (nwords 32-bit words); `carry` threads through ascending w
+NMSM_HD int mul_window_digit(const uint32_t* m, int nwords, int w, uint32_t& carry) {
+  uint32_t v = scalar_bits(m, w * MUL_WBITS, MUL_WBITS, nwords) + carry;
+  carry = 0;
+  if (v > (uint32_t)MUL_TABLE) {
+    carry = 1;
+    return (int)v - (1 << MUL_WBITS);
+  }
+  return (int)v;
+}
+
 template <class Cv>
 NMSM_HD void mul_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, int allow_zero, uint32_t* out_xy,
                       uint32_t* out_inf, unsigned int* err) {
   using G = typename Cv::G;
+  using Acc = typename G::Acc;
   uint32_t in[G::IN_WORDS];
   load_words<G::IN_WORDS>(in, pts + (size_t)i * G::IN_WORDS);
-  uint32_t s[SCALAR_WORDS + 1];
+  uint32_t s[SCALAR_WORDS];
   load_words<SCALAR_WORDS>(s, scalars + (size_t)i * SCALAR_WORDS);
-  s[SCALAR_WORDS] = 0;
   bool bad_pt = !G::input_in_range(in);
   bool bad_sc = !scalar_in_range<typename Cv::Fn>(s);
   uint32_t nz = 0;
@@ -927,22 +946,66 @@ NMSM_HD void mul_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, 
   if (bad_pt) atomic_min_u32(&err[0], i);
   if (bad_sc) atomic_min_u32(&err[1], i);
   if (bad_pt || bad_sc) return;
-  typename G::Affine P = G::prepare(in);
-  typename G::Affine Pn = G::neg(P);
-  // NAF digit at position j-1 is h_j - k_j with h = 3k
-  uint32_t h[SCALAR_WORDS + 1];
-  {
-    uint32_t d[SCALAR_WORDS + 1];
-    for (int k = 0; k < SCALAR_WORDS + 1; k++) d[k] = (s[k] << 1) | (k ? (s[k - 1] >> 31) : 0);
-    h[0] = add_cc(s[0], d[0]);
-    for (int k = 1; k < SCALAR_WORDS; k++) h[k] = addc_cc(s[k], d[k]);
-    h[SCALAR_WORDS] = addc(s[SCALAR_WORDS], d[SCALAR_WORDS]);
+  const typename G::Affine P = G::prepare(in);
+  // table[d - 1] = d * P, d = 1..8
+  Acc table[MUL_TABLE];
+  table[0] = G::from_affine(P);
+  table[1] = table[0];
+  nl_dbl<G>(table[1]);
+  for (int d = 2; d < MUL_TABLE; d++) {
+    table[d] = table[d - 1];
+    nl_madd<G>(table[d], P);
   }
-  typename G::Acc acc = G::identity();
-  for (int j = 32 * SCALAR_WORDS + 1; j >= 1; j--) {
-    uint32_t hb = (h[j >> 5] >> (j & 31)) & 1, kb = (s[j >> 5] >> (j & 31)) & 1;
-    nl_dbl<G>(acc);
-    if (hb != kb) nl_madd<G>(acc, hb ? P : Pn);
+  Acc acc = G::identity();
+  if constexpr (Cv::GLV) {
+    constexpr int MW = Cv::GLV_KIND == 1 ? 4 : 5;       // words of a half-scalar magnitude
+    constexpr int HB = Cv::Glv::BITS;                    // |k1|, |k2| < 2^HB
+    constexpr int NW = (HB + 1 + MUL_WBITS - 1) / MUL_WBITS;
+    uint32_t m1[MW], m2[MW];
+    bool neg1, neg2;
+    if constexpr (Cv::GLV_KIND == 1) glv_split<typename Cv::Glv>(s, m1, neg1, m2, neg2);
+    else glv_split_lattice<typename Cv::Glv>(s, m1, neg1, m2, neg2);
+    typename G::Field beta;
+    for (int k = 0; k < G::Field::LIMBS; k++) beta.v[k] = Cv::Glv::BETA_MONT(k);
+    // digits, least significant first (the carries run upwards), consumed from the top
+    signed char d1[NW], d2[NW];
+    uint32_t c1 = 0, c2 = 0;
+    for (int w = 0; w < NW; w++) {
+      d1[w] = (signed char)mul_window_digit(m1, MW, w, c1);
+      d2[w] = (signed char)mul_window_digit(m2, MW, w, c2);
+    }
+    for (int w = NW - 1; w >= 0; w--) {
+      if (w != NW - 1)
+        for (int j = 0; j < MUL_WBITS; j++) nl_dbl<G>(acc);
+      if (d1[w] != 0) {
+        const int a = d1[w] < 0 ? -d1[w] : d1[w];
+        Acc t = table[a - 1];
+        if ((d1[w] < 0) != neg1) t = G::neg(t);
+        nl_add<G>(acc, t);
+      }
+      if (d2[w] != 0) {
+        const int a = d2[w] < 0 ? -d2[w] : d2[w];
+        Acc t = table[a - 1];
+        t.X = t.X * beta;  // phi on XYZZ coordinates: x = X / ZZ
+        if ((d2[w] < 0) != neg2) t = G::neg(t);
+        nl_add<G>(acc, t);
+      }
+    }
+  } else {
+    constexpr int NW = (Cv::Fn::BITS + 1 + MUL_WBITS - 1) / MUL_WBITS;
+    signed char dg[NW];
+    uint32_t c = 0;
+    for (int w = 0; w < NW; w++) dg[w] = (signed char)mul_window_digit(s, SCALAR_WORDS, w, c);
+    for (int w = NW - 1; w >= 0; w--) {
+      if (w != NW - 1)
+        for (int j = 0; j < MUL_WBITS; j++) nl_dbl<G>(acc);
+      if (dg[w] != 0) {
+        const int a = dg[w] < 0 ? -dg[w] : dg[w];
+        Acc t = table[a - 1];
+        if (dg[w] < 0) t = G::neg(t);
+        nl_add<G>(acc, t);
+      }
+    }
   }
   uint32_t xy[G::IN_WORDS];
   uint32_t inf;
