@@ -145,6 +145,7 @@ const EngineVTable* engine_ed25519();
 const EngineVTable* engine_bn254g1();
 const EngineVTable* engine_bn254g2();
 const EngineVTable* engine_bls381g1();
+const EngineVTable* engine_bls381g1_any();
 const EngineVTable* engine_bls381g2();
 
 }  // namespace nmsm

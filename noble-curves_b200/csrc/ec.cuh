@@ -437,6 +437,7 @@ struct CurveSecp256k1 {
   using Glv = Secp256k1Glv;
   using G = SwXyzz<Fp<FpSecp256k1>>;
   using Fn = Fn_secp256k1;
+  static constexpr bool COFACTOR_ONE = true;  // the endomorphism acts as lambda on the WHOLE group E(Fp)
   static constexpr int ID = 0;
 };
 struct CurveEd25519 {
@@ -444,6 +445,7 @@ struct CurveEd25519 {
   static constexpr int GLV_KIND = 0;
   using G = EdExt<Fp<FpEd25519>, Ed25519Consts>;
   using Fn = Fn_ed25519;
+  static constexpr bool COFACTOR_ONE = false;  // the endomorphism acts as lambda on the WHOLE group E(Fp)
   static constexpr int ID = 1;
 };
 struct CurveBn254G1 {
@@ -452,6 +454,7 @@ struct CurveBn254G1 {
   using Glv = Bn254G1Glv;
   using G = SwXyzz<Fp<FpBn254>>;
   using Fn = Fn_bn254;
+  static constexpr bool COFACTOR_ONE = true;  // the endomorphism acts as lambda on the WHOLE group E(Fp)
   static constexpr int ID = 2;
 };
 struct CurveBn254G2 {
@@ -459,6 +462,7 @@ struct CurveBn254G2 {
   static constexpr int GLV_KIND = 0;
   using G = SwXyzz<Fp2<FpBn254>>;
   using Fn = Fn_bn254;
+  static constexpr bool COFACTOR_ONE = false;  // the endomorphism acts as lambda on the WHOLE group E(Fp)
   static constexpr int ID = 3;
 };
 struct CurveBls381G1 {
@@ -469,13 +473,28 @@ struct CurveBls381G1 {
   using Glv = Bls381G1Glv;
   using G = SwXyzz<Fp<FpBls381>>;
   using Fn = Fn_bls12_381;
+  static constexpr bool COFACTOR_ONE = false;  // the endomorphism acts as lambda on the WHOLE group E(Fp)
   static constexpr int ID = 4;
+};
+// BLS12-381 G1 for ARBITRARY points of E(Fp) (cofactor h = 0x396c8c005555e1568c00aaab0000aaab): phi(P) = lambda * P only
+// holds on the prime-order subgroup, so this id runs the plain signed-window schedule (16 windows instead of 8).
+// The reference's pippenger is the group law and accepts any Point instance; NMSM_BLS12_381_G1 (GLV) matches it on
+// every point that passes the reference's assertValidity / fromBytes (on curve AND torsion-free,
+// weierstrass.ts:690-707), this id on every on-curve point.
+struct CurveBls381G1Any {
+  static constexpr bool GLV = false;
+  static constexpr int GLV_KIND = 0;
+  using G = SwXyzz<Fp<FpBls381>>;
+  using Fn = Fn_bls12_381;
+  static constexpr bool COFACTOR_ONE = false;
+  static constexpr int ID = 6;
 };
 struct CurveBls381G2 {
   static constexpr bool GLV = false;
   static constexpr int GLV_KIND = 0;
   using G = SwXyzz<Fp2<FpBls381>>;
   using Fn = Fn_bls12_381;
+  static constexpr bool COFACTOR_ONE = false;  // the endomorphism acts as lambda on the WHOLE group E(Fp)
   static constexpr int ID = 5;
 };
 

@@ -912,9 +912,11 @@ NMSM_HD void fold_body(const uint32_t* accs, int count, uint32_t* out, uint32_t*
 // curve.ts:707-729, without its blinding), canonical affine out.  Public-input / variable-time like multiplyUnsafe;
 // the value equals multiply()'s.  Why windows and not NAF: a point addition costs the whole warp its multiply-pipe
 // time whenever ANY lane needs it, so sparse per-lane digit patterns buy nothing under SIMT, while a window does one
-// table addition per 4 doublings for every lane at once.  On the GLV curves (secp256k1, bn254 G1, BLS12-381 G1;
+// table addition per 4 doublings for every lane at once.  On the cofactor-1 GLV curves (secp256k1, bn254 G1;
 // weierstrass.ts:843-861 is the reference's use of the same endomorphism for secp256k1) k = k1 + k2 * lambda halves
-// the doublings: the second table is phi of the first, (beta * X, Y, ZZ, ZZZ).
+// the doublings: the second table is phi of the first, (beta * X, Y, ZZ, ZZZ).  BLS12-381 G1 takes the plain route:
+// multiply() is what subgroup checks and cofactor clearing run on points OUTSIDE the prime-order subgroup, where
+// phi(P) != lambda * P.
 static constexpr int MUL_WBITS = 4;
 static constexpr int MUL_TABLE = 1 << (MUL_WBITS - 1);  // |digit| <= 8
 
@@ -957,7 +959,7 @@ NMSM_HD void mul_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, 
     nl_madd<G>(table[d], P);
   }
   Acc acc = G::identity();
-  if constexpr (Cv::GLV) {
+  if constexpr (Cv::GLV && Cv::COFACTOR_ONE) {  // multiply() must be right for every on-curve point (subgroup checks, cofactor clearing)
     constexpr int MW = Cv::GLV_KIND == 1 ? 4 : 5;       // words of a half-scalar magnitude
     constexpr int HB = Cv::Glv::BITS;                    // |k1|, |k2| < 2^HB
     constexpr int NW = (HB + 1 + MUL_WBITS - 1) / MUL_WBITS;

@@ -366,8 +366,13 @@ def _raise_mapped(e: NmsmError):
     raise ValueError(str(e)) from e
 
 
-def _msm_points(c, points, scalars):
-    out_xy, inf = msm_packed(c.CURVE_ID, _pack_points(points), _pack_scalars(scalars), len(points))
+# include/nmsm.h: NMSM_BLS12_381_G1 (4) assumes torsion-free points (GLV); NMSM_BLS12_381_G1_ANY (6) does not
+_ANY_POINT_ID = {4: 6}
+
+
+def _msm_points(c, points, scalars, assume_torsion_free=True):
+    cid = c.CURVE_ID if assume_torsion_free else _ANY_POINT_ID.get(c.CURVE_ID, c.CURVE_ID)
+    out_xy, inf = msm_packed(cid, _pack_points(points), _pack_scalars(scalars), len(points))
     return c.from_packed(out_xy, inf)
 
 
@@ -428,15 +433,18 @@ def msm_host_ptr(curve_id: int, h_pts: int, h_scalars: int, n: int):
     return out.raw, inf.value
 
 
-def pippenger(c, points, scalars):
-    """Drop-in for noble's pippenger (curve.ts:863-905): validates like the reference, runs on the GPU."""
+def pippenger(c, points, scalars, assume_torsion_free: bool = True):
+    """Drop-in for noble's pippenger (curve.ts:863-905): validates like the reference, runs on the GPU.
+    `assume_torsion_free` only matters for BLS12-381 G1: True (default) = the points pass the reference's
+    assertValidity / came from fromBytes, hash-to-curve or arithmetic on such points, and the GLV schedule is used;
+    False = any point of E(Fp) (the reference's pippenger is the plain group law), plain windows."""
     _validate_msm_points(points, c)
     _validate_msm_scalars(scalars, c.Fn)
     if len(points) != len(scalars):
         raise ValueError("arrays of points and scalars must have equal length")
     if len(points) == 0:
         return c.ZERO
-    return _msm_points(c, points, scalars)
+    return _msm_points(c, points, scalars, assume_torsion_free)
 
 
 def normalizeZ(c, points):

@@ -12,9 +12,35 @@ from oracle import noble_ref as R
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-CURVE_IDS = {"secp256k1": 0, "ed25519": 1, "bn254_G1": 2, "bn254_G2": 3, "bls12_381_G1": 4, "bls12_381_G2": 5}
-FP_BYTES = {"secp256k1": 32, "ed25519": 32, "bn254_G1": 32, "bn254_G2": 32, "bls12_381_G1": 48, "bls12_381_G2": 48}
-PARTS = {"secp256k1": 1, "ed25519": 1, "bn254_G1": 1, "bn254_G2": 2, "bls12_381_G1": 1, "bls12_381_G2": 2}
+# "bls12_381_G1_any" = NMSM_BLS12_381_G1_ANY: the same curve without the subgroup assumption (no GLV)
+CURVE_IDS = {"secp256k1": 0, "ed25519": 1, "bn254_G1": 2, "bn254_G2": 3, "bls12_381_G1": 4, "bls12_381_G2": 5,
+             "bls12_381_G1_any": 6}
+FP_BYTES = {"secp256k1": 32, "ed25519": 32, "bn254_G1": 32, "bn254_G2": 32, "bls12_381_G1": 48, "bls12_381_G2": 48,
+            "bls12_381_G1_any": 48}
+PARTS = {"secp256k1": 1, "ed25519": 1, "bn254_G1": 1, "bn254_G2": 2, "bls12_381_G1": 1, "bls12_381_G2": 2,
+         "bls12_381_G1_any": 1}
+
+
+def bls_g1_non_subgroup_points(count, seed=3):
+    """On-curve points of BLS12-381 E(Fp) that are NOT in the prime-order subgroup (cofactor part non-trivial):
+    what isTorsionFree rejects (weierstrass.ts:951-969) and what an MSM over unvalidated points can contain."""
+    import random
+
+    P = R.CURVES["bls12_381_G1"]
+    p, r = P.Fp.ORDER, P.Fn.ORDER
+    rnd = random.Random(seed)
+    out = []
+    while len(out) < count:
+        x = rnd.randrange(p)
+        y2 = (x * x * x + 4) % p
+        y = pow(y2, (p + 1) // 4, p)
+        if y * y % p != y2:
+            continue
+        cand = P.fromAffine({"x": x, "y": y})
+        if cand.multiplyUnsafe(r - 1).add(cand).is0():
+            continue  # happens with probability 1/h
+        out.append(cand)
+    return out
 # curve index in test/slow-curves.test.ts:186-194
 SOAK_INDEX = {"secp256k1": 0, "ed25519": 2, "bls12_381_G1": 3, "bls12_381_G2": 4, "bn254_G1": 5, "bn254_G2": 6}
 

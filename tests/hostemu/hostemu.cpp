@@ -147,6 +147,7 @@ static int emu_point_table_t(const uint32_t* point_xy, const uint32_t* scalars, 
     case 3: { using Cv = CurveBn254G2; return EXPR; }                \
     case 4: { using Cv = CurveBls381G1; return EXPR; }               \
     case 5: { using Cv = CurveBls381G2; return EXPR; }               \
+    case 6: { using Cv = CurveBls381G1Any; return EXPR; }            \
     default: return -1;                                              \
   }
 

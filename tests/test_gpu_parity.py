@@ -706,6 +706,52 @@ def test_point_codec_roundtrip_object_api(nmsm):
         C.fromBytes(bytes(xb))
 
 
+def test_bls12_381_g1_points_outside_the_subgroup(nmsm):
+    """pippenger / multiply are the plain group law in the reference.  Points of E(Fp) outside the prime-order
+    subgroup: NMSM_BLS12_381_G1_ANY matches the oracle (also through a fixed-base table), nmsm_mul_batch matches it
+    for both ids (isTorsionFree / clearCofactor depend on that), and on torsion-free points both ids agree."""
+    P = R.CURVES["bls12_381_G1"]
+    C = nmsm.CURVES["bls12_381_G1"]
+    rnd = random.Random(12)
+    bad = H.bls_g1_non_subgroup_points(40)
+    good = [P.BASE.multiplyUnsafe(rnd.randrange(1, P.Fn.ORDER)) for _ in range(24)]
+    pts = R.normalizeZ(P, bad + good)
+    rnd.shuffle(pts)
+    scalars = [rnd.randrange(P.Fn.ORDER) for _ in pts]
+    scalars[3] = P.Fn.ORDER - 1
+    n = len(pts)
+    exp = H.expected_tuple("bls12_381_G1", R.pippenger(P, pts, scalars))
+    pb, sb = H.pack_points("bls12_381_G1", pts), H.pack_scalars(scalars)
+    out, inf = nmsm.msm_packed(6, pb, sb, n)
+    assert (*H.unpack_point("bls12_381_G1", out), inf) == exp
+    ps = nmsm.PointSet(6, pb, n)
+    ps.precompute(0)
+    out, inf = ps.msm(sb, n)
+    assert (*H.unpack_point("bls12_381_G1", out), inf) == exp
+    ps.close()
+    cpts = [C.fromAffine(p.toAffine()) for p in pts]
+    got = nmsm.pippenger(C, cpts, scalars, assume_torsion_free=False)
+    assert (got.x, got.y, 1 if got.is0() else 0) == exp
+    # torsion-free inputs: the GLV id and the plain id give the same (reference) answer
+    gpts = R.normalizeZ(P, good)
+    gsc = scalars[: len(gpts)]
+    gexp = H.expected_tuple("bls12_381_G1", R.pippenger(P, gpts, gsc))
+    for cid in (4, 6):
+        o, f = nmsm.msm_packed(cid, H.pack_points("bls12_381_G1", gpts), H.pack_scalars(gsc), len(gpts))
+        assert (*H.unpack_point("bls12_381_G1", o), f) == gexp, cid
+    # Point.multiply on non-subgroup points
+    ks = [P.Fn.ORDER - 1, 0x396C8C005555E1568C00AAAB0000AAAB, 5, rnd.randrange(P.Fn.ORDER)]
+    bp = R.normalizeZ(P, bad[:4])
+    for cid in (4, 6):
+        o, f = nmsm.mul_batch_packed(cid, H.pack_points("bls12_381_G1", bp), H.pack_scalars(ks), 4, False)
+        for i in range(4):
+            assert (*H.unpack_point("bls12_381_G1", o[i * 96:(i + 1) * 96]), f[i]) == \
+                H.expected_tuple("bls12_381_G1", bp[i].multiplyUnsafe(ks[i])), (cid, i)
+    b0 = C.fromAffine(bad[0].toAffine())
+    assert not b0.isTorsionFree() and b0.clearCofactor().isTorsionFree()
+    assert C.fromAffine(good[0].toAffine()).isTorsionFree()
+
+
 # ------------------------------------------------------------------------------------------------
 # NTT over Fr (SURVEY §8 f4 companion): bit-exact against the oracle restatement of fft.ts
 # ------------------------------------------------------------------------------------------------

@@ -204,6 +204,37 @@ def test_point_table_multiply(name):
     assert res == [H.expected_tuple(name, P.ZERO)] * 2
 
 
+def test_bls12_381_g1_points_outside_the_subgroup():
+    """The reference's pippenger / multiply are the plain group law on E(Fp).  Points outside the prime-order subgroup:
+    NMSM_BLS12_381_G1_ANY (no GLV) and the multiply batch of either id must match the oracle; the GLV id is only
+    specified for torsion-free points (include/nmsm.h), where both ids agree."""
+    P = R.CURVES["bls12_381_G1"]
+    rng = R.Xorshift64(0xC0FAC7)
+    bad = H.bls_g1_non_subgroup_points(5)
+    good = [P.BASE.multiplyUnsafe(rng.rndBelow(P.Fn.ORDER - 1) + 1) for _ in range(4)]
+    pts = R.normalizeZ(P, bad + good)
+    scalars = [rng.rndBelow(P.Fn.ORDER) for _ in pts]
+    scalars[1] = P.Fn.ORDER - 1
+    exp = H.expected_tuple("bls12_381_G1", R.pippenger(P, pts, scalars))
+    pb, sb = H.pack_points("bls12_381_G1", pts), H.pack_scalars(scalars)
+    for c, L in ((0, 0), (5, 3)):
+        got, err, _ = H.emu_msm("bls12_381_G1_any", pb, sb, len(pts), c, L)
+        assert got == exp
+    got, _, _ = H.emu_msm("bls12_381_G1_any", pb, sb, len(pts), table_c=9)  # fixed-base table route, no GLV
+    assert got == exp
+    # subgroup points only: the GLV id and the plain id agree with the oracle
+    gp, gs = H.pack_points("bls12_381_G1", pts[5:]), H.pack_scalars(scalars[5:])
+    exp_g = H.expected_tuple("bls12_381_G1", R.pippenger(P, pts[5:], scalars[5:]))
+    assert H.emu_msm("bls12_381_G1", gp, gs, 4)[0] == exp_g == H.emu_msm("bls12_381_G1_any", gp, gs, 4)[0]
+    # Point.multiply on the non-subgroup points (what isTorsionFree / clearCofactor evaluate), both ids
+    ks = [P.Fn.ORDER - 1, 0x396C8C005555E1568C00AAAB0000AAAB, 5, rng.rndBelow(P.Fn.ORDER), 1]
+    for name in ("bls12_381_G1", "bls12_381_G1_any"):
+        res, err = H.emu_mul_batch(name, H.pack_points("bls12_381_G1", pts[:5]), H.pack_scalars(ks), 5, False)
+        assert err == (0xFFFFFFFF, 0xFFFFFFFF)
+        for pt, k, got in zip(pts[:5], ks, res):
+            assert got == H.expected_tuple("bls12_381_G1", pt.multiplyUnsafe(k)), (name, k)
+
+
 def test_glv_split_and_constants():
     """BLS12-381 G1 GLV: k = v1 + v2*lambda (mod r), |v| < 2^127, and phi(P) = (beta*x, y) = lambda*P."""
     import ctypes
