@@ -411,6 +411,25 @@ def main():
                          "which stays the general MSM with points passed per call"}
         lib.nmsm_points_free(h)
 
+    # ---- second companion: the same MSM under NMSM_BLS12_381_G1_ANY (no subgroup assumption, no GLV: 16 windows) ----
+    any_point = None
+    if world == 1 and not args.no_fixed_base:
+        ANY = 6
+        for _ in range(2):
+            nmsm._lib.check(lib.nmsm_msm_device(ANY, d_pts.data_ptr(), d_sc.data_ptr(), n_local,
+                                                ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf)))
+        assert out.raw == exp_xy and inf.value == exp_inf
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            nmsm._lib.check(lib.nmsm_msm_device(ANY, d_pts.data_ptr(), d_sc.data_ptr(), n_local,
+                                                ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf)))
+        torch.cuda.synchronize()
+        a_el = (time.perf_counter() - t0) / 5
+        any_point = {"latency_ms_single_msm": 1e3 * a_el, "value_serial": n_local / a_el, "unit": "points/s",
+                     "note": "curve id NMSM_BLS12_381_G1_ANY: valid for every on-curve point, not only the prime-order "
+                             "subgroup the headline id assumes (the bench points k_i*G are in it); serial calls"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -489,6 +508,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "fixed_base": fixed,
+        "any_point": any_point,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
