@@ -331,7 +331,7 @@ def main():
     h_sc = lib.nmsm_host_alloc(len(sc_b))
     ctypes.memmove(h_pts, pts_b, len(pts_b))
     ctypes.memmove(h_sc, sc_b, len(sc_b))
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, args.steps)  # the same K steps as the device-resident region
     e2e_bufs = ([(d_pts, d_sc)] + [(torch.empty_like(d_pts), torch.empty_like(d_sc)) for _ in range(NF - 1)]) if world > 1 else None
 
     def step_e2e():

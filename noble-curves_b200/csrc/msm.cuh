@@ -174,8 +174,9 @@ k_stitch_tiles(const uint32_t* __restrict__ offsets, MsmPlan plan, uint32_t span
 
 // One thread per chunk, out-of-line serial formulas: with >= 2 warps per SM sub-partition the multiply
 // pipe is shared anyway and the quad form only adds shuffle/select overhead (measured: 2.3 ms vs 1.5 ms).
+static constexpr int REDUCE1_THREADS = 64;
 template <class Cv>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(REDUCE1_THREADS)
 k_reduce1(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ buckets,
           const uint32_t* __restrict__ heads, const uint32_t* __restrict__ tails,
           const uint32_t* __restrict__ tile1, const uint32_t* __restrict__ tile2, MsmPlan plan,
