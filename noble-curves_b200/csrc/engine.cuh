@@ -129,7 +129,6 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   EV(6);
   {
     const uint64_t nchunks = (uint64_t)plan.W * plan.chunks;
-    // 64-thread blocks: with ~32k chunk threads, 512 blocks spread over the 148 SMs more evenly than 256 would
     k_reduce1<Cv><<<cdiv(nchunks, REDUCE1_THREADS), REDUCE1_THREADS, 0, st>>>(offsets, buckets, heads, tails, tile1, tile2,
                                                                              plan, sums, wsums);
   }

@@ -174,7 +174,7 @@ k_stitch_tiles(const uint32_t* __restrict__ offsets, MsmPlan plan, uint32_t span
 
 // One thread per chunk, out-of-line serial formulas: with >= 2 warps per SM sub-partition the multiply
 // pipe is shared anyway and the quad form only adds shuffle/select overhead (measured: 2.3 ms vs 1.5 ms).
-static constexpr int REDUCE1_THREADS = 64;
+static constexpr int REDUCE1_THREADS = 128;
 template <class Cv>
 __global__ void __launch_bounds__(REDUCE1_THREADS)
 k_reduce1(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ buckets,
