@@ -98,6 +98,12 @@ int nmsm_fold_partials_device(int curve, const void* d_accs, int count, uint8_t*
 int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero,
                    uint8_t* out_xy, uint8_t* out_is_inf);
 
+/* out_ok[i] = 1 iff n * pts[i] == O: the batch form of Point.isTorsionFree (/root/reference/src/abstract/
+ * weierstrass.ts:971-975, edwards.ts:584-586; bls12-381.ts:567-577,599-601 and bn254.ts:241 decide the same predicate
+ * with endomorphism shortcuts) — the subgroup check that follows decoding untrusted points (next-row f2).  The
+ * identity counts as torsion-free.  Works on any on-curve point (no GLV on curves with a cofactor). */
+int nmsm_points_torsion_free(int curve, const uint8_t* pts, uint64_t n, uint8_t* out_ok);
+
 /* Device-resident point sets: validate + convert a point array once, then run many MSMs against it
  * (fixed-base commitments).  The analogue of interleavedMSMUnsafe's captured tables
  * (/root/reference/src/abstract/curve.ts:937-959): fewer scalars than points use the first n points

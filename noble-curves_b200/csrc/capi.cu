@@ -204,6 +204,15 @@ int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64
   return E->mul_batch(pts, scalars, n, allow_zero, out_xy, out_is_inf);
 }
 
+int nmsm_points_torsion_free(int curve, const uint8_t* pts, uint64_t n, uint8_t* out_ok) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
+  if (n && (!pts || !out_ok)) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  return E->torsion_free(pts, n, out_ok);
+}
+
 // ---- device-resident point sets (fixed-base reuse) ---------------------------------------------
 struct PointSet {
   int curve;

@@ -134,6 +134,7 @@ struct EngineVTable {
   int (*collect)(uint8_t* out_xy, int* out_is_inf);
   int (*submit_prepared)(const uint32_t* d_prepared, uint64_t n_points, int table_c, const void* scalars, uint64_t n,
                          int scalars_on_device);
+  int (*torsion_free)(const uint8_t* pts, uint64_t n, uint8_t* out_ok);
 };
 int ed25519_verify_batch_impl(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* msg_off,
                               uint64_t n, const uint8_t* z16, int* out_ok, long long* out_bad_index);

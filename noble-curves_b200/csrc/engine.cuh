@@ -389,6 +389,31 @@ static int table_mul_batch(const uint32_t* tbl, const uint8_t* scalars, uint64_t
   return NMSM_OK;
 }
 
+// out_ok[i] = (n * P_i == O): the batch form of isTorsionFree
+static int run_torsion(const uint8_t* pts, uint64_t n, uint8_t* out_ok) {
+  Slot& C = g_ctx.slot[g_ctx.cur];
+  if (n == 0) return NMSM_OK;
+  if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
+  CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
+  CK(C.mul_out.ensure(n + 16));
+  CK(C.result.ensure(64));
+  unsigned int* d_err = (unsigned int*)C.result.p;
+  cudaStream_t st = C.stream;
+  CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(d_err, 0xff, 8, st));
+  EV(0);
+  k_torsion<Cv><<<cdiv(n, 128), 128, 0, st>>>((const uint32_t*)C.in_pts.p, (uint32_t)n, (uint8_t*)C.mul_out.p, d_err);
+  EV(1);
+  CK(cudaGetLastError());
+  unsigned int err[2];
+  CK(cudaMemcpyAsync(err, d_err, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_ok, C.mul_out.p, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  note_kernel_time(C);
+  if (err[0] != 0xffffffffu) return fail(NMSM_ERR_POINT, "invalid point at index " + std::to_string(err[0]), err[0]);
+  return NMSM_OK;
+}
+
 static int run_msm_dev(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
                        uint8_t* out_xy, int* out_is_inf) {
   return run_msm(d_pts, d_scalars, n, d_out_acc, out_xy, out_is_inf, nullptr);
@@ -465,7 +490,7 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
                                     &Engine<CURVE>::precompute_table,                              \
                                     &Engine<CURVE>::build_point_table, &Engine<CURVE>::table_mul_batch, \
                                     &Engine<CURVE>::submit_any,     &Engine<CURVE>::collect_msm,    \
-                                    &Engine<CURVE>::submit_prepared};                              \
+                                    &Engine<CURVE>::submit_prepared, &Engine<CURVE>::run_torsion};  \
     return &vt;                                                                                \
   }
 

@@ -441,4 +441,12 @@ k_mul_batch(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scala
   if (i < n) mul_body<Cv>(i, pts, scalars, allow_zero, out_xy, out_inf, err);
 }
 
+// n * P == O per point (nmsm_points_torsion_free)
+template <class Cv>
+__global__ void __launch_bounds__(128)
+k_torsion(const uint32_t* __restrict__ pts, uint32_t n, uint8_t* __restrict__ out_ok, unsigned int* err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) torsion_body<Cv>(i, pts, out_ok, err);
+}
+
 }  // namespace nmsm

@@ -931,24 +931,11 @@ NMSM_HD int mul_window_digit(const uint32_t* m, int nwords, int w, uint32_t& car
   return (int)v;
 }
 
+// s * P as an un-normalised accumulator (the core of mul_body / torsion_body); s < n, 8 words
 template <class Cv>
-NMSM_HD void mul_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, int allow_zero, uint32_t* out_xy,
-                      uint32_t* out_inf, unsigned int* err) {
+NMSM_HD typename Cv::G::Acc scalar_mul_acc(const typename Cv::G::Affine& P, const uint32_t* s) {
   using G = typename Cv::G;
   using Acc = typename G::Acc;
-  uint32_t in[G::IN_WORDS];
-  load_words<G::IN_WORDS>(in, pts + (size_t)i * G::IN_WORDS);
-  uint32_t s[SCALAR_WORDS];
-  load_words<SCALAR_WORDS>(s, scalars + (size_t)i * SCALAR_WORDS);
-  bool bad_pt = !G::input_in_range(in);
-  bool bad_sc = !scalar_in_range<typename Cv::Fn>(s);
-  uint32_t nz = 0;
-  for (int k = 0; k < SCALAR_WORDS; k++) nz |= s[k];
-  if (!allow_zero && nz == 0) bad_sc = true;
-  if (bad_pt) atomic_min_u32(&err[0], i);
-  if (bad_sc) atomic_min_u32(&err[1], i);
-  if (bad_pt || bad_sc) return;
-  const typename G::Affine P = G::prepare(in);
   // table[d - 1] = d * P, d = 1..8
   Acc table[MUL_TABLE];
   table[0] = G::from_affine(P);
@@ -1009,11 +996,52 @@ NMSM_HD void mul_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, 
       }
     }
   }
+  return acc;
+}
+
+template <class Cv>
+NMSM_HD void mul_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, int allow_zero, uint32_t* out_xy,
+                      uint32_t* out_inf, unsigned int* err) {
+  using G = typename Cv::G;
+  uint32_t in[G::IN_WORDS];
+  load_words<G::IN_WORDS>(in, pts + (size_t)i * G::IN_WORDS);
+  uint32_t s[SCALAR_WORDS];
+  load_words<SCALAR_WORDS>(s, scalars + (size_t)i * SCALAR_WORDS);
+  bool bad_pt = !G::input_in_range(in);
+  bool bad_sc = !scalar_in_range<typename Cv::Fn>(s);
+  uint32_t nz = 0;
+  for (int k = 0; k < SCALAR_WORDS; k++) nz |= s[k];
+  if (!allow_zero && nz == 0) bad_sc = true;
+  if (bad_pt) atomic_min_u32(&err[0], i);
+  if (bad_sc) atomic_min_u32(&err[1], i);
+  if (bad_pt || bad_sc) return;
+  const typename G::Acc acc = scalar_mul_acc<Cv>(G::prepare(in), s);
   uint32_t xy[G::IN_WORDS];
   uint32_t inf;
   nl_to_affine<G>(acc, xy, &inf);
   store_words<G::IN_WORDS>(out_xy + (size_t)i * G::IN_WORDS, xy);
   out_inf[i] = inf;
+}
+
+// isTorsionFree (weierstrass.ts:971-975, edwards.ts:584-586; the curve files' endomorphism shortcuts
+// bls12-381.ts:567-577,599-601 and bn254.ts:241 decide the same predicate): n * P == O, evaluated as
+// (n - 1) * P + P.  Every lane walks the same digits of n - 1, so the warp never diverges.
+template <class Cv>
+NMSM_HD void torsion_body(uint32_t i, const uint32_t* pts, uint8_t* out_ok, unsigned int* err) {
+  using G = typename Cv::G;
+  uint32_t in[G::IN_WORDS];
+  load_words<G::IN_WORDS>(in, pts + (size_t)i * G::IN_WORDS);
+  if (!G::input_in_range(in)) {
+    atomic_min_u32(&err[0], i);
+    return;
+  }
+  uint32_t s[SCALAR_WORDS];
+  for (int k = 0; k < SCALAR_WORDS; k++) s[k] = Cv::Fn::ORDER(k);
+  s[0] -= 1u;  // the group orders are odd
+  const typename G::Affine P = G::prepare(in);
+  typename G::Acc acc = scalar_mul_acc<Cv>(P, s);
+  nl_madd<G>(acc, P);
+  out_ok[i] = G::is_identity(acc) ? 1 : 0;
 }
 
 }  // namespace nmsm

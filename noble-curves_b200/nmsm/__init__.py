@@ -469,6 +469,23 @@ def mulAddUnsafe(c, points, scalars):
     return pippenger(c, points, scalars)
 
 
+def torsion_free_packed(curve_id: int, pts: bytes, n: int) -> bytes:
+    """Batch Point.isTorsionFree (nmsm_points_torsion_free): one byte per point, 1 = n*P == O."""
+    _lib.ensure_init()
+    lib = _lib.load()
+    pb = lib.nmsm_point_bytes(curve_id)
+    if len(pts) != n * pb:
+        raise ValueError("expected %d bytes per point" % pb)
+    out = ctypes.create_string_buffer(max(1, n))
+    rc = lib.nmsm_points_torsion_free(curve_id, ctypes.cast(ctypes.c_char_p(bytes(pts)), ctypes.c_void_p), n,
+                                      ctypes.cast(out, ctypes.c_void_p))
+    try:
+        _lib.check(rc)
+    except NmsmError as e:
+        _raise_mapped(e)
+    return out.raw[:n]
+
+
 class PointTable:
     """Device-resident multiplication table of ONE point (nmsm_point_table_create): d * 2^(16 j) * P."""
 

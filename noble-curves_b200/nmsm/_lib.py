@@ -25,7 +25,7 @@ EXPORTS = [
     "nmsm_acc_bytes", "nmsm_msm", "nmsm_msm_device", "nmsm_msm_partial_device", "nmsm_fold_partials_device",
     "nmsm_mul_batch", "nmsm_set_window_bits", "nmsm_set_profiling", "nmsm_last_timing", "nmsm_bench_modmul",
     "nmsm_host_alloc", "nmsm_host_free", "nmsm_points_upload", "nmsm_points_free", "nmsm_msm_points", "nmsm_points_precompute", "nmsm_msm_points_submit", "nmsm_point_table_create", "nmsm_point_table_free",
-    "nmsm_point_table_mul_batch", "nmsm_ntt", "nmsm_ntt_device",
+    "nmsm_point_table_mul_batch", "nmsm_ntt", "nmsm_ntt_device", "nmsm_points_torsion_free",
     "nmsm_ed25519_verify_batch", "nmsm_msm_submit", "nmsm_msm_collect", "nmsm_points_decode", "nmsm_msm_submit_partial",
 ]
 
@@ -118,6 +118,8 @@ def load() -> ctypes.CDLL:
         for f in (lib.nmsm_ntt, lib.nmsm_ntt_device):
             f.argtypes = [ctypes.c_int, u8p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
             f.restype = ctypes.c_int
+        lib.nmsm_points_torsion_free.argtypes = [ctypes.c_int, u8p, ctypes.c_uint64, u8p]
+        lib.nmsm_points_torsion_free.restype = ctypes.c_int
         lib.nmsm_point_table_create.argtypes = [ctypes.c_int, u8p, ctypes.POINTER(ctypes.c_uint64)]
         lib.nmsm_point_table_create.restype = ctypes.c_int
         lib.nmsm_point_table_free.argtypes = [ctypes.c_uint64]

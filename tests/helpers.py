@@ -178,6 +178,16 @@ def emu_point_table(name, point_b: bytes, scalars_b: bytes, n: int, allow_zero: 
     return res, (int(err[0]), int(err[1]))
 
 
+def emu_torsion(name, pts_b: bytes, n: int):
+    lib = hostemu()
+    pts = u32(pts_b)
+    ok = np.zeros(n, np.uint8)
+    err = np.zeros(2, np.uint32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    assert lib.emu_torsion(CURVE_IDS[name], p(pts), n, p(ok), p(err)) == 0
+    return [int(v) for v in ok], (int(err[0]), int(err[1]))
+
+
 def emu_mul_batch(name, pts_b: bytes, scalars_b: bytes, n: int, allow_zero: bool):
     lib = hostemu()
     cb = FP_BYTES[name] * PARTS[name]

@@ -139,6 +139,15 @@ static int emu_point_table_t(const uint32_t* point_xy, const uint32_t* scalars, 
   return 0;
 }
 
+template <class Cv>
+static int emu_torsion_t(const uint32_t* pts, uint32_t n, uint8_t* out_ok, uint32_t* err_out) {
+  unsigned int err[2] = {0xffffffffu, 0xffffffffu};
+  for (uint32_t i = 0; i < n; i++) torsion_body<Cv>(i, pts, out_ok, err);
+  err_out[0] = err[0];
+  err_out[1] = err[1];
+  return 0;
+}
+
 #define DISPATCH(curve, EXPR)                                        \
   switch (curve) {                                                   \
     case 0: { using Cv = CurveSecp256k1; return EXPR; }              \
@@ -229,6 +238,9 @@ int emu_point_table(int curve, int table_bits, const uint32_t* point_xy, const u
     DISPATCH(curve, (emu_point_table_t<Cv, 5>(point_xy, scalars, n, allow_zero, out_xy, out_inf, err_out)));
   }
   DISPATCH(curve, (emu_point_table_t<Cv, 8>(point_xy, scalars, n, allow_zero, out_xy, out_inf, err_out)));
+}
+int emu_torsion(int curve, const uint32_t* pts, uint32_t n, uint8_t* out_ok, uint32_t* err_out) {
+  DISPATCH(curve, emu_torsion_t<Cv>(pts, n, out_ok, err_out));
 }
 int emu_msm_table(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, int table_c, int forced_L,
                   uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out) {

@@ -747,6 +747,10 @@ def test_bls12_381_g1_points_outside_the_subgroup(nmsm):
         for i in range(4):
             assert (*H.unpack_point("bls12_381_G1", o[i * 96:(i + 1) * 96]), f[i]) == \
                 H.expected_tuple("bls12_381_G1", bp[i].multiplyUnsafe(ks[i])), (cid, i)
+    # batch isTorsionFree (nmsm_points_torsion_free)
+    flags = nmsm.torsion_free_packed(4, pb, n)
+    assert list(flags) == [1 if p.multiplyUnsafe(P.Fn.ORDER - 1).add(p).is0() else 0 for p in pts]
+    assert sum(flags) == len(good) and nmsm.torsion_free_packed(6, pb, n) == flags
     b0 = C.fromAffine(bad[0].toAffine())
     assert not b0.isTorsionFree() and b0.clearCofactor().isTorsionFree()
     assert C.fromAffine(good[0].toAffine()).isTorsionFree()

@@ -235,6 +235,35 @@ def test_bls12_381_g1_points_outside_the_subgroup():
             assert got == H.expected_tuple("bls12_381_G1", pt.multiplyUnsafe(k)), (name, k)
 
 
+def test_torsion_free_batch():
+    """nmsm_points_torsion_free body (isTorsionFree, weierstrass.ts:971-975 / edwards.ts:584-586) against the oracle's
+    n*P == O on subgroup points, points outside the subgroup, small-order points and the identity."""
+    G1 = R.CURVES["bls12_381_G1"]
+    rng = R.Xorshift64(0x7045)
+    pts = H.bls_g1_non_subgroup_points(3) + [G1.BASE.multiplyUnsafe(rng.rndBelow(G1.Fn.ORDER - 1) + 1) for _ in range(3)] + [G1.ZERO]
+    pts = R.normalizeZ(G1, pts)
+    exp = [1 if p.multiplyUnsafe(G1.Fn.ORDER - 1).add(p).is0() else 0 for p in pts]
+    assert exp == [0, 0, 0, 1, 1, 1, 1]
+    for name in ("bls12_381_G1", "bls12_381_G1_any"):
+        got, err = H.emu_torsion(name, H.pack_points("bls12_381_G1", pts), len(pts))
+        assert got == exp and err[0] == 0xFFFFFFFF
+    ED = R.CURVES["ed25519"]
+    p = ED.Fp.ORDER
+    t2 = ED.fromAffine({"x": 0, "y": p - 1})  # order 2
+    base = ED.BASE.multiplyUnsafe(12345)
+    epts = R.normalizeZ(ED, [base, t2, base.add(t2), ED.ZERO, ED.BASE])
+    got, _ = H.emu_torsion("ed25519", H.pack_points("ed25519", epts), len(epts))
+    assert got == [1, 0, 0, 1, 1]
+    S = R.CURVES["secp256k1"]
+    spts = R.normalizeZ(S, [S.BASE, S.BASE.multiplyUnsafe(77), S.ZERO])
+    got, _ = H.emu_torsion("secp256k1", H.pack_points("secp256k1", spts), 3)
+    assert got == [1, 1, 1]
+    bad = bytearray(H.pack_points("secp256k1", spts))
+    bad[64:96] = b"\xff" * 32
+    _, err = H.emu_torsion("secp256k1", bytes(bad), 3)
+    assert err[0] == 1
+
+
 def test_glv_split_and_constants():
     """BLS12-381 G1 GLV: k = v1 + v2*lambda (mod r), |v| < 2^127, and phi(P) = (beta*x, y) = lambda*P."""
     import ctypes
