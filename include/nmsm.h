@@ -159,9 +159,11 @@ int nmsm_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pubkeys, const
 
 /* Batched wire-format decoding on the GPU (next-row f2): encodings -> canonical affine points in the packing
  * above, ready for nmsm_msm.  secp256k1: 33-byte SEC1 compressed (weierstrass.ts:565-588); BLS12-381 G1: 48-byte
- * Zcash-flag compressed (bls12-381.ts:377-468); ed25519: 32-byte RFC 8032 with ZIP-215 acceptance (edwards.ts:405-436).
- * out_status[i]: 0 = invalid encoding, 1 = point, 2 = point at infinity.  Mirrors the reference's decode step only
- * (no subgroup check).  Other curves: NMSM_ERR_ARG. */
+ * Zcash-flag compressed (bls12-381.ts:377-468); BLS12-381 G2: 96-byte Zcash-flag compressed, x = c1 || c0
+ * (bls12-381.ts:354-367,488-491; Fp2 square root tower.ts:476-498); ed25519: 32-byte RFC 8032 with ZIP-215
+ * acceptance (edwards.ts:405-436).  out_status[i]: 0 = invalid encoding, 1 = point, 2 = point at infinity.  Mirrors
+ * the reference's decode step only; the subgroup check its fromBytes adds is nmsm_points_torsion_free.  Other
+ * curves: NMSM_ERR_ARG. */
 int nmsm_points_decode(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_xy, uint8_t* out_status);
 
 /* Tuning / introspection ------------------------------------------------------------------- */

@@ -11,6 +11,7 @@ k_decode(const uint8_t* __restrict__ enc, uint32_t n, uint32_t* __restrict__ out
   if (i >= n) return;
   if (CURVE == NMSM_SECP256K1) status[i] = (uint8_t)sec1_decode_secp256k1(enc + (size_t)i * 33, out_xy + (size_t)i * 16);
   if (CURVE == NMSM_BLS12_381_G1) status[i] = (uint8_t)zcash_decode_bls12_381_g1(enc + (size_t)i * 48, out_xy + (size_t)i * 24);
+  if (CURVE == NMSM_BLS12_381_G2) status[i] = (uint8_t)zcash_decode_bls12_381_g2(enc + (size_t)i * 96, out_xy + (size_t)i * 48);
   if (CURVE == NMSM_ED25519) status[i] = (uint8_t)ed25519_decode(enc + (size_t)i * 32, out_xy + (size_t)i * 16);
 }
 
@@ -21,8 +22,9 @@ int decode_points_impl(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_x
   switch (curve) {
     case NMSM_SECP256K1: enc_bytes = 33; pt_bytes = 64; break;
     case NMSM_BLS12_381_G1: enc_bytes = 48; pt_bytes = 96; break;
+    case NMSM_BLS12_381_G2: enc_bytes = 96; pt_bytes = 192; break;
     case NMSM_ED25519: enc_bytes = 32; pt_bytes = 64; break;
-    default: return fail(NMSM_ERR_ARG, "nmsm_points_decode: no decoder for this curve (secp256k1, ed25519, BLS12-381 G1 only)");
+    default: return fail(NMSM_ERR_ARG, "nmsm_points_decode: no decoder for this curve (secp256k1, ed25519, BLS12-381 G1/G2 only)");
   }
   if (n == 0) return NMSM_OK;
   if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
@@ -35,6 +37,7 @@ int decode_points_impl(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_x
   const unsigned int blocks = (unsigned int)((n + 127) / 128);
   if (curve == NMSM_SECP256K1) k_decode<NMSM_SECP256K1><<<blocks, 128, 0, st>>>((const uint8_t*)C.in_pts.p, (uint32_t)n, d_xy, d_st);
   if (curve == NMSM_BLS12_381_G1) k_decode<NMSM_BLS12_381_G1><<<blocks, 128, 0, st>>>((const uint8_t*)C.in_pts.p, (uint32_t)n, d_xy, d_st);
+  if (curve == NMSM_BLS12_381_G2) k_decode<NMSM_BLS12_381_G2><<<blocks, 128, 0, st>>>((const uint8_t*)C.in_pts.p, (uint32_t)n, d_xy, d_st);
   if (curve == NMSM_ED25519) k_decode<NMSM_ED25519><<<blocks, 128, 0, st>>>((const uint8_t*)C.in_pts.p, (uint32_t)n, d_xy, d_st);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out_xy, d_xy, n * pt_bytes, cudaMemcpyDeviceToHost, st));

@@ -2,6 +2,7 @@
 // so callers can hand the encodings the reference's `fromBytes` consumes instead of bigints.
 //   secp256k1  SEC1 compressed, 33 B      /root/reference/src/abstract/weierstrass.ts:565-588 (pointFromBytes)
 //   BLS12-381 G1  Zcash-flag compressed, 48 B   src/bls12-381.ts:377-468 (coder.decode, parseMask/validateMask)
+//   BLS12-381 G2  Zcash-flag compressed, 96 B   same coder over Fp2 (c1 || c0, bls12-381.ts:354-367,488-491), Fp2 sqrt tower.ts:476-498
 //   ed25519    RFC 8032 / ZIP-215, 32 B   src/abstract/edwards.ts:405-436  (ed25519_verify.cuh ed_decompress)
 // Only the decode step is mirrored (coordinates from bytes); the reference's `Point.fromBytes` additionally runs
 // assertValidity (subgroup membership for cofactor > 1), which is a scalar multiplication of its own.
@@ -109,6 +110,99 @@ NMSM_HD int zcash_decode_bls12_381_g1(const uint8_t* enc, uint32_t* out_xy) {
   for (int k = 0; k < 12; k++) {
     out_xy[k] = xw[k];
     out_xy[12 + k] = yw[k];
+  }
+  return 1;
+}
+
+// Square root in Fp2 = Fp[u]/(u^2 + 1), p = 3 (mod 4): the reference's complex method (tower.ts:476-498).  Returns
+// false when `n` is not a square; which of the two roots comes back is irrelevant to the caller, the wire format's
+// sort bit selects the sign afterwards.
+template <class P>
+NMSM_HD bool fp2_sqrt(const Fp2<P>& n, Fp2<P>& out) {
+  using B = Fp<P>;
+  bool ok;
+  if (n.c1.is_zero()) {
+    B r = fp_sqrt_3mod4<P>(n.c0, ok);  // c0 a residue: (sqrt(c0), 0)
+    if (ok) {
+      out = Fp2<P>{r, B::zero()};
+      return true;
+    }
+    r = fp_sqrt_3mod4<P>(-n.c0, ok);   // else c0 / (-1) is one: (0, sqrt(-c0))
+    out = Fp2<P>{B::zero(), r};
+    return ok;
+  }
+  const B a = fp_sqrt_3mod4<P>(sqr(n.c0) + sqr(n.c1), ok);  // sqrt of the norm c0^2 - c1^2 * (-1)
+  if (!ok) return false;
+  uint32_t hw[P::N];  // (p + 1) / 2 = 1/2 mod p
+  {
+    uint32_t t[P::N];
+    t[0] = add_cc(P::P(0), 1u);
+    for (int k = 1; k < P::N; k++) t[k] = addc_cc(P::P(k), 0u);
+    const uint32_t top = addc(0, 0);
+    for (int k = 0; k < P::N - 1; k++) hw[k] = (t[k] >> 1) | (t[k + 1] << 31);
+    hw[P::N - 1] = (t[P::N - 1] >> 1) | (top << 31);
+  }
+  const B half = B::from_canonical(hw);
+  B d = (a + n.c0) * half;
+  B a0 = fp_sqrt_3mod4<P>(d, ok);
+  if (!ok) {  // legendre(d) == -1 (tower.ts:489)
+    d = d - a;
+    a0 = fp_sqrt_3mod4<P>(d, ok);
+    if (!ok) return false;
+  }
+  out = Fp2<P>{a0, n.c1 * half * inv(a0)};
+  const Fp2<P> chk = out * out;
+  return chk == n;
+}
+
+// BLS12-381 G2, 96-byte compressed: x = c1 || c0 big-endian (bls12-381.ts:354-367), flags in the top three bits,
+// y = sqrt(x^3 + 4(1 + u)) with the sort bit taken over [y.c1, y.c0] (bls12-381.ts:347-352,488-491).
+// out: x.c0, x.c1, y.c0, y.c1 as 12 little-endian words each (the C-ABI packing of a G2 point).
+NMSM_HD int zcash_decode_bls12_381_g2(const uint8_t* enc, uint32_t* out_xy) {
+  using B = Fp<FpBls381>;
+  using F2 = Fp2<FpBls381>;
+  const bool compressed = (enc[0] >> 7) & 1, infinity = (enc[0] >> 6) & 1, sort = (enc[0] >> 5) & 1;
+  if (!compressed) return 0;                    // this entry point takes the 96-byte compressed form only
+  if (compressed && infinity && sort) return 0;  // validateMask: 0xe0
+  uint8_t v[96];
+  for (int k = 0; k < 96; k++) v[k] = enc[k];
+  v[0] &= 0x1f;
+  if (infinity) {
+    for (int k = 0; k < 96; k++)
+      if (v[k]) return 0;  // non-canonical zero
+    for (int k = 0; k < 48; k++) out_xy[k] = 0;
+    return 2;
+  }
+  uint32_t xw[24];
+  words_from_be_bytes<48>(xw + 12, v);      // c1 comes first on the wire
+  words_from_be_bytes<48>(xw, v + 48);      // then c0
+  if (!B::canonical_in_range(xw) || !B::canonical_in_range(xw + 12)) return 0;
+  const F2 x = F2::from_canonical(xw);
+  uint32_t four[12] = {4, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const B b4 = B::from_canonical(four);
+  const F2 rhs = x * x * x + F2{b4, b4};
+  F2 y;
+  if (!fp2_sqrt<FpBls381>(rhs, y)) return 0;
+  uint32_t yw[24];
+  y.to_canonical(yw);
+  // sortBit over [c1, c0]: the first non-zero part decides, larger iff 2 * part >= p
+  const uint32_t* part = yw + 12;
+  bool c1_zero = true;
+  for (int k = 0; k < 12; k++) c1_zero &= (yw[12 + k] == 0);
+  if (c1_zero) part = yw;
+  uint32_t d2[12];
+  for (int k = 11; k >= 1; k--) d2[k] = (part[k] << 1) | (part[k - 1] >> 31);
+  d2[0] = part[0] << 1;
+  bool all_zero = true;
+  for (int k = 0; k < 12; k++) all_zero &= (part[k] == 0);
+  const bool larger = !all_zero && !B::canonical_in_range(d2);
+  if (larger != sort) {
+    y = -y;
+    y.to_canonical(yw);
+  }
+  for (int k = 0; k < 24; k++) {
+    out_xy[k] = xw[k];
+    out_xy[24 + k] = yw[k];
   }
   return 1;
 }

@@ -220,14 +220,14 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
         def fromBytes(b: bytes):
             """Point.fromBytes (weierstrass.ts:720-724, edwards.ts:405-436): decode on the GPU (nmsm_points_decode),
             then the reference's validity check (subgroup membership where the cofactor is not 1)."""
-            enc_len = {"secp256k1": 33, "bls12_381_G1": 48, "ed25519": 32}.get(name)
+            enc_len = {"secp256k1": 33, "bls12_381_G1": 48, "bls12_381_G2": 96, "ed25519": 32}.get(name)
             if enc_len is None or len(b) != enc_len:
                 raise ValueError("bad point: got length %d, expected compressed=%s" % (len(b), enc_len))
             out, st = points_decode(curve_id, bytes(b), 1)
             if st[0] == 0:
                 raise ValueError("bad point: is not on curve" if not edwards else "bad point: invalid y coordinate")
             P_ = Point.from_packed(out, 1 if st[0] == 2 else 0)
-            if name == "bls12_381_G1" and not P_.isTorsionFree():
+            if name in ("bls12_381_G1", "bls12_381_G2") and not P_.isTorsionFree():
                 raise ValueError("bad point: not in prime-order subgroup")
             return P_
 
@@ -699,7 +699,7 @@ def ed25519_verify_batch(signatures, messages, public_keys, z: bytes | None = No
 
 
 def points_decode(curve_id: int, encodings: bytes, n: int):
-    """Batched `fromBytes` decode step on the GPU (secp256k1 SEC1-33, BLS12-381 G1 Zcash-48, ed25519-32):
+    """Batched `fromBytes` decode step on the GPU (secp256k1 SEC1-33, BLS12-381 G1 Zcash-48 / G2 Zcash-96, ed25519-32):
     returns (packed points, status bytes: 0 invalid / 1 point / 2 infinity)."""
     _lib.ensure_init()
     lib = _lib.load()

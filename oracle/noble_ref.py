@@ -222,6 +222,44 @@ class Field2:
             power >>= 1
         return res
 
+    def sqrt(self, num):
+        """tower.ts:476-498 (complex method, Fp_NONRESIDUE = -1); raises ValueError('Cannot find square root').
+        The base-field root is modular.ts sqrt3mod4 (p = 3 mod 4 for BLS12-381 and bn254)."""
+        Fp = self.Fp
+        p = Fp.ORDER
+        assert p % 4 == 3
+
+        def fsqrt(n):
+            r = pow(n, (p + 1) // 4, p)
+            if r * r % p != n % p:
+                raise ValueError("Cannot find square root")
+            return r
+
+        def legendre(n):
+            t = pow(n, (p - 1) // 2, p)
+            return -1 if t == p - 1 else t
+
+        nonres = p - 1
+        div2 = pow(2, -1, p)
+        c0, c1 = num
+        if c1 == 0:
+            if legendre(c0) == 1:
+                return (fsqrt(c0), 0)
+            return (0, fsqrt(c0 * pow(nonres, -1, p) % p))
+        a = fsqrt((c0 * c0 - c1 * c1 * nonres) % p)
+        d = (a + c0) * div2 % p
+        if legendre(d) == -1:
+            d = (d - a) % p
+        a0 = fsqrt(d)
+        cand = (a0, c1 * div2 % p * pow(a0, -1, p) % p)
+        if self.sqr(cand) != (c0 % p, c1 % p):
+            raise ValueError("Cannot find square root")
+        x1, x2 = cand, self.neg(cand)
+        (re1, im1), (re2, im2) = x1, x2
+        if im1 > im2 or (im1 == im2 and re1 > re2):
+            return x1
+        return x2
+
 
 # --------------------------------------------------------------------------------------
 # curve.ts — recoding helpers and the generic algorithms
@@ -1243,6 +1281,52 @@ def secp256k1_decode_sec1(b: bytes):
             raise ValueError("bad point: is not on curve")
         return x, y
     raise ValueError("bad point: got length %d" % len(b))
+
+
+def bls12_381_g2_decode(b: bytes):
+    """src/bls12-381.ts:377-468 `coder('G2').decode` (allowUncompressed): x, y in Fp2 as (c0, c1) tuples, wire order
+    c1 || c0 (:354-367), sort bit over [y.c1, y.c0] (:347-352,:488-491); ((0,0),(0,0)) for infinity."""
+    P = BLS12_381_G1_CURVE["p"]
+    F2 = Field2(Field(P))
+    mask = b[0] & 0xE0
+    compressed, infinity, sort = bool(mask >> 7 & 1), bool(mask >> 6 & 1), bool(mask >> 5 & 1)
+    if (not compressed and not infinity and sort) or (not compressed and infinity and sort) or (compressed and infinity and sort):
+        raise ValueError("invalid encoding flag")
+    v = bytes([b[0] & 0x1F]) + b[1:]
+    ln = 96 if compressed else 192
+    if len(v) != ln:
+        raise ValueError("invalid G2 point: expected %d bytes" % ln)
+    if infinity:
+        if any(v):
+            raise ValueError("invalid G2 point: non-canonical zero")
+        return (0, 0), (0, 0)
+
+    def dec(chunk):
+        c1, c0 = int.from_bytes(chunk[:48], "big"), int.from_bytes(chunk[48:], "big")
+        if not (0 <= c0 < P and 0 <= c1 < P):
+            raise ValueError("invalid field element")
+        return (c0, c1)
+
+    x = dec(v[:96])
+    if compressed:
+        rhs = F2.add(F2.mul(F2.sqr(x), x), BLS12_381_G2_CURVE["b"])
+        try:
+            y = F2.sqrt(rhs)
+        except ValueError:
+            raise ValueError("invalid G2 point: compressed")
+        parts = [y[1], y[0]]
+        bit = False
+        for part in parts:
+            if part != 0:
+                bit = bool((part * 2) // P)
+                break
+        if bit != sort:
+            y = F2.neg(y)
+    else:
+        y = dec(v[96:])
+        if x == (0, 0) and y == (0, 0):
+            raise ValueError("invalid G2 point: uncompressed")
+    return x, y
 
 
 def bls12_381_g1_decode(b: bytes):

@@ -59,6 +59,7 @@ def bls():
         "G1_Uncompressed": d["G1_Uncompressed"][:1000],
         "G2_Uncompressed": d["G2_Uncompressed"][:256],
         "G1_Compressed": d["G1_Compressed"][:1000],  # test/bls12-381.test.ts:1463-1500 (Zcash-flag codec)
+        "G2_Compressed": d["G2_Compressed"][:256],   # test/bls12-381.test.ts:1500-1533
     }
     dump("bls12_381.json", out)
 

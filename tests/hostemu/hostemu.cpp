@@ -209,9 +209,17 @@ int emu_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pks, const uint
                              const uint8_t* z16, int* out_ok, long long* out_bad) {
   return emu_ed_verify(sigs, pks, msgs, off, n, z16, out_ok, out_bad);
 }
+// Fp2 square root over BLS12-381 Fp (codec.cuh fp2_sqrt): canonical c0 || c1 words in and out; returns 1 if a root exists
+int emu_fp2_sqrt(const uint32_t* in, uint32_t* out) {
+  Fp2<FpBls381> n = Fp2<FpBls381>::from_canonical(in), r;
+  if (!fp2_sqrt<FpBls381>(n, r)) return 0;
+  r.to_canonical(out);
+  return 1;
+}
 int emu_decode(int curve, const uint8_t* enc, uint32_t* out_xy) {
   if (curve == 0) return sec1_decode_secp256k1(enc, out_xy);
   if (curve == 4) return zcash_decode_bls12_381_g1(enc, out_xy);
+  if (curve == 5) return zcash_decode_bls12_381_g2(enc, out_xy);
   if (curve == 1) return ed25519_decode(enc, out_xy);
   return -1;
 }

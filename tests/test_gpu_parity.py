@@ -653,6 +653,33 @@ def test_point_decoders_gpu(nmsm):
     tot = sum(i * s for i, s in enumerate(sc)) % G1.Fn.ORDER
     assert gpu_msm(nmsm, "bls12_381_G1", pts, H.pack_scalars(sc), len(encs)) == H.expected_tuple(
         "bls12_381_G1", G1.BASE.multiplyUnsafe(tot))
+    # G2, 96-byte compressed (Fp2 square roots on the GPU), then subgroup checks and an MSM over the decoded points
+    encs2 = [bytes.fromhex(c) for c in gb["G2_Compressed"]]
+    bad2 = [bytes([0x80]) + bytes(94) + bytes([k]) for k in range(1, 9)]  # x = (k, 0): some on the twist, never in G2
+    pts2, st2 = nmsm.points_decode(5, b"".join(encs2 + bad2), len(encs2) + len(bad2))
+    assert st2[0] == 2 and all(s == 1 for s in st2[1:len(encs2)])
+    for i in (1, 2, 100, 255):
+        x, y = R.bls12_381_g2_decode(encs2[i])
+        assert H.unpack_point("bls12_381_G2", pts2[i * 192:(i + 1) * 192]) == (x, y)
+    for j, e in enumerate(bad2):
+        try:
+            exp_pt = R.bls12_381_g2_decode(e)
+            assert st2[len(encs2) + j] == 1
+            assert H.unpack_point("bls12_381_G2", pts2[(len(encs2) + j) * 192:(len(encs2) + j + 1) * 192]) == exp_pt
+        except ValueError:
+            assert st2[len(encs2) + j] == 0
+    G2 = R.CURVES["bls12_381_G2"]
+    ok_idx = [i for i, s in enumerate(st2) if s != 0]
+    packed = b"".join(pts2[i * 192:(i + 1) * 192] for i in ok_idx)
+    flags = nmsm.torsion_free_packed(5, packed, len(ok_idx))
+    for k, i in enumerate(ok_idx):
+        assert flags[k] == (1 if i < len(encs2) else 0), i  # i*G2 is in the subgroup; the small-x twist points are not
+    sc2 = [rnd.randrange(G2.Fn.ORDER) for _ in encs2]
+    tot2 = sum(i * s for i, s in enumerate(sc2)) % G2.Fn.ORDER
+    assert gpu_msm(nmsm, "bls12_381_G2", pts2[: len(encs2) * 192], H.pack_scalars(sc2), len(encs2)) == H.expected_tuple(
+        "bls12_381_G2", G2.BASE.multiplyUnsafe(tot2))
+    C2 = nmsm.CURVES["bls12_381_G2"]
+    assert C2.fromBytes(encs2[5]).equals(C2.BASE.multiply(5))
     s = load_golden("secp256k1.json")["isPoint33"]
     pts, st = nmsm.points_decode(0, b"".join(bytes.fromhex(e) for e, _ in s), len(s))
     for i, (e, exp) in enumerate(s):

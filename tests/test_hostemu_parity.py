@@ -427,6 +427,52 @@ def test_point_decoders_match_oracle():
             assert (st, x, y) == ((2 if (ex, ey) == (0, 0) else 1), ex, ey), enc.hex()
         except ValueError:
             assert st == 0, enc.hex()
+    # G2, 96-byte compressed: reference vectors + flag / range / non-residue cases + c1 == 0 roots
+    g2 = load_golden("bls12_381.json")["G2_Compressed"]
+
+    def emu_g2(enc):
+        out = np.zeros(48, np.uint32)
+        st = lib.emu_decode(5, enc, out.ctypes.data_as(ctypes.c_void_p))
+        w = [int.from_bytes(out[12 * k:12 * (k + 1)].tobytes(), "little") for k in range(4)]
+        return st, (w[0], w[1]), (w[2], w[3])
+
+    cases2 = [bytes.fromhex(c) for c in g2[:24]] + [bytes.fromhex(g2[200])]
+    cases2 += [bytes([0xC0] + [0] * 95), bytes([0xE0] + [0] * 95), bytes([0xC0] + [0] * 94 + [1]), bytes([0x40] + [0] * 95),
+               bytes([0x80]) + bytes(95), bytes([0x9F] + [0xFF] * 95),
+               bytes([0x80]) + bytes(47) + p.to_bytes(48, "big"),   # c0 == p: out of range
+               (p | (1 << 383)).to_bytes(48, "big") + bytes(48)]    # c1 == p
+    for xv in range(1, 14):  # small x = (xv, 0) and (0, xv): squares and non-squares, both sort bits
+        for enc_x in (bytes(48) + xv.to_bytes(48, "big"), xv.to_bytes(48, "big") + bytes(48)):
+            for flag in (0x80, 0xA0):
+                cases2.append(bytes([enc_x[0] | flag]) + enc_x[1:])
+    n_ok = 0
+    for enc in cases2:
+        st, x, y = emu_g2(enc)
+        try:
+            ex, ey = R.bls12_381_g2_decode(enc)
+            if not (enc[0] & 0x80):
+                raise ValueError("uncompressed form not taken by this entry point")
+            assert (st, x, y) == ((2 if (ex, ey) == ((0, 0), (0, 0)) else 1), ex, ey), enc.hex()
+            n_ok += 1
+        except ValueError:
+            assert st == 0, enc.hex()
+    assert n_ok > 40
+    # fp2_sqrt directly, incl. the c1 == 0 branches the decoder rarely reaches (tower.ts:481-485)
+    F2 = R.Field2(R.Field(p))
+    rnd_ = __import__("random").Random(4)
+    vals = [(4, 0), (5, 0), (p - 4, 0), (0, 9), (0, 0), (3, 7)] + [(rnd_.randrange(p), rnd_.randrange(p)) for _ in range(6)]
+    for v in vals + [F2.sqr(v) for v in vals]:
+        inp = np.frombuffer(v[0].to_bytes(48, "little") + v[1].to_bytes(48, "little"), dtype=np.uint32).copy()
+        out = np.zeros(24, np.uint32)
+        ok = lib.emu_fp2_sqrt(inp.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+        try:
+            exp = F2.sqrt(v)
+        except ValueError:
+            exp = None
+        assert bool(ok) == (exp is not None), v
+        if ok:
+            r = (int.from_bytes(out[:12].tobytes(), "little"), int.from_bytes(out[12:].tobytes(), "little"))
+            assert r in (exp, F2.neg(exp)), v
     s = load_golden("secp256k1.json")["isPoint33"]
     sample = s[:80] + [c for c in s if not c[1]]
     pk = R.SECP256K1_CURVE["p"]

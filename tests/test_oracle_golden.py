@@ -223,6 +223,21 @@ def test_codec_oracle_against_reference_vectors():
         assert R.bls12_381_g1_decode(bytes.fromhex(c)) == R.bls12_381_g1_decode(bytes.fromhex(u)), i
         if i:
             assert R.bls12_381_g1_decode(bytes.fromhex(c)) == R.affine_tuple(G1, g1_decode_uncompressed(u))
+    # G2: 96-byte compressed (c1 || c0, sort bit over [y.c1, y.c0]) against the uncompressed list, incl. Fp2 sqrt
+    for i, (c, u) in enumerate(zip(g["G2_Compressed"], g["G2_Uncompressed"])):
+        if i % 4 and i > 16:
+            continue
+        dc = R.bls12_381_g2_decode(bytes.fromhex(c))
+        assert dc == R.bls12_381_g2_decode(bytes.fromhex(u)), i
+        if i:
+            assert dc == R.affine_tuple(G2, g2_decode_uncompressed(u))
+    F2 = R.Field2(R.Field(G1.Fp.ORDER))
+    for v in ((4, 0), (0, 9), (5, 0), (3, 7)):
+        sq = F2.sqr(v)
+        r = F2.sqrt(sq)
+        assert F2.sqr(r) == sq and r in (v, F2.neg(v))
+    with pytest.raises(ValueError):
+        F2.sqrt((1, 1))  # (1 + u) is a non-residue in Fp2 (the sextic-twist constant's base)
     s = load_golden("secp256k1.json")
     assert len(s["isPoint33"]) > 1000
     for enc, exp in s["isPoint33"]:

@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_v15.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_v15.log
+tail -3 gpurun_out/pytest_gpu_v15.log
