@@ -868,3 +868,27 @@ def test_ntt_errors(nmsm):
     assert lib.nmsm_ntt(2, ctypes.cast(dummy, ctypes.c_void_p), 29, 7, 0, 0, 0) != 0  # bn254 Fr has 2-adicity 28
     assert b"wrong bits 29 powerOfTwo=28" in lib.nmsm_last_error()
     assert lib.nmsm_ntt(0, ctypes.cast(dummy, ctypes.c_void_p), 1, 7, 0, 0, 0) != 0   # secp256k1: no NTT field
+
+
+def test_ntt_output_feeds_msm_on_device(nmsm):
+    """The prover-loop composition without host round trips: coefficients -> nmsm_ntt_device (evaluations, canonical
+    32-byte scalars) -> nmsm_msm_device over the same device buffer; equals the oracle's pippenger over the oracle's FFT."""
+    import torch
+
+    from nmsm import fft as GF
+    from oracle import noble_fft as OF
+
+    G1 = R.CURVES["bls12_381_G1"]
+    p = OF.FR["bls12_381"]
+    n, bits = 256, 8
+    rnd = random.Random(21)
+    coeffs = [rnd.randrange(p) for _ in range(n)]
+    evals = OF.FFT(OF.RootsOfUnity(p, 7)).direct(coeffs)
+    P, pts, _, _ = H.soak_inputs("bls12_381_G1", n, seed_offset=3)
+    exp = H.expected_tuple("bls12_381_G1", R.pippenger(P, pts, evals))
+    d_sc = torch.frombuffer(bytearray(b"".join(c.to_bytes(32, "little") for c in coeffs)), dtype=torch.uint8).cuda()
+    d_pts = torch.frombuffer(bytearray(H.pack_points("bls12_381_G1", pts)), dtype=torch.uint8).cuda()
+    GF.ntt_device("bls12_381", d_sc.data_ptr(), bits, generator=7)
+    assert bytes(d_sc.cpu().numpy().tobytes()) == b"".join(e.to_bytes(32, "little") for e in evals)
+    out, inf = nmsm.msm_device(4, d_pts.data_ptr(), d_sc.data_ptr(), n)
+    assert (*H.unpack_point("bls12_381_G1", out), inf) == exp
