@@ -300,6 +300,23 @@ def test_config_ed25519_131073_terms(nmsm):
     _large_case(nmsm, "ed25519", 2 * (1 << 16) + 1, 5)
 
 
+@pytest.mark.parametrize("name,n", [("bls12_381_G1", 100003), ("bn254_G1", 77777), ("secp256k1", 54321),
+                                    ("bls12_381_G1_any", 40001), ("bn254_G2", 9973), ("ed25519", 65537)])
+def test_msm_ragged_sizes(nmsm, name, n):
+    """Sizes that are not powers of two (odd tails in every kernel's grid), every 13th scalar zero."""
+    if name == "bls12_381_G1_any":
+        P = R.CURVES["bls12_381_G1"]
+        rnd = random.Random(n)
+        ks = [rnd.randrange(1, P.Fn.ORDER) for _ in range(n)]
+        sc = [0 if i % 13 == 0 else rnd.randrange(P.Fn.ORDER) for i in range(n)]
+        pts_b, _ = nmsm.mul_batch_packed(4, H.point_bytes("bls12_381_G1", P.BASE) * n, H.pack_scalars(ks), n, False)
+        total = sum(k * s for k, s in zip(ks, sc)) % P.Fn.ORDER
+        out, inf = nmsm.msm_packed(6, pts_b, H.pack_scalars(sc), n)
+        assert (*H.unpack_point("bls12_381_G1", out), inf) == H.expected_tuple("bls12_381_G1", H.expected_from_total(P, total))
+    else:
+        _large_case(nmsm, name, n, 1000 + n, zero_every=13)
+
+
 def test_config_secp256k1_multiply_1024(nmsm):
     """configs[0] GPU counterpart: Point.multiply on 1024 random scalars of a non-base point vs the oracle."""
     P = R.CURVES["secp256k1"]
