@@ -3,14 +3,17 @@
 // Replaces FFT(rootsOfUnity(Fr, G), Fr).direct / .inverse, /root/reference/src/abstract/fft.ts:518-575 (loops
 // :422-480, root tables :230-312).  The reference walks one butterfly at a time over bigint arrays; here a
 // transform of N = 2^n elements is ceil(n / 10) passes over HBM: every block keeps a tile of 2048 elements in shared
-// memory and runs up to 10 butterfly stages on it, one butterfly per thread per stage, twiddles gathered from an
-// L2-resident table of the N roots (Montgomery form).  Field arithmetic is exact, so any correct schedule is
-// bit-identical to the reference's DIT/DIF loops; the schedule per boundary layout:
+// memory and runs up to 10 butterfly stages on it, twiddles gathered from an L2-resident table of the N roots.
+// The table is in Montgomery form and the DATA stays canonical: mont_mul(x, w * R) = x * w, so the one multiplication
+// of a butterfly needs no conversion of the data on the way in or out (additions and subtractions do not care).
+// Field arithmetic is exact, so any correct schedule is bit-identical to the reference's DIT/DIF loops; the
+// schedule per boundary layout:
 //   natural in,  natural out : DIF passes, bit-reversal folded into the store          (fft.ts:551 `dit: true, brp: true`)
 //   natural in,  brp out     : DIF passes                                               (fft.ts:550)
 //   brp in,      natural out : DIT passes                                               (fft.ts:549)
 //   brp in,      brp out     : permute, DIF passes                                      (fft.ts:544-548)
-// Bound: the modular multiplications (one per butterfly) and the HBM passes are both small; see DESIGN.md.
+// Bound (ncu, profiles/): the integer multiply pipe — one 256-bit Montgomery multiplication per butterfly; the
+// fmaheavy pipe is ~62 % active in k_ntt_pass while DRAM throughput stays below 5 % of peak.
 #include "context.h"
 #include "field.cuh"
 #include "curve_consts.cuh"
@@ -139,8 +142,8 @@ k_ntt_roots(const uint32_t* __restrict__ aux, uint32_t n, uint32_t* __restrict__
   ntt_store<F>(roots + (size_t)i * 8, acc);
 }
 
-// canonical -> Montgomery into the work buffer, range check (element >= r: first bad index to err); `reverse`
-// folds the bit-reversal permutation of a brp-ordered input into the copy (fft.ts:544-548)
+// copy into the work buffer with the range check (element >= r: first bad index to err); `reverse` folds the
+// bit-reversal permutation of a brp-ordered input into the copy (fft.ts:544-548)
 template <class P>
 __global__ void __launch_bounds__(256)
 k_ntt_ingest(const uint32_t* __restrict__ in, uint32_t* __restrict__ work, int log_n, int reverse, unsigned int* err) {
@@ -153,10 +156,11 @@ k_ntt_ingest(const uint32_t* __restrict__ in, uint32_t* __restrict__ work, int l
     return;
   }
   const uint32_t j = reverse ? (log_n ? (__brev(i) >> (32 - log_n)) : 0u) : i;
-  ntt_store<F>(work + (size_t)j * 8, F::from_canonical(raw.v));
+  ntt_store<F>(work + (size_t)j * 8, raw);
 }
 
-// Montgomery -> canonical, optional 1/N scaling (fft.ts:566-568), optional bit-reversed destination
+// copy out with the optional 1/N scaling (fft.ts:566-568; 1/N is held in Montgomery form, so the product is
+// canonical again) and the optional bit-reversed destination
 template <class P>
 __global__ void __launch_bounds__(256)
 k_ntt_emit(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int log_n, const uint32_t* __restrict__ aux,
@@ -166,10 +170,8 @@ k_ntt_emit(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int log
   if (i >= (1u << log_n)) return;
   F x = ntt_load<F>(src + (size_t)i * 8);
   if (scale) x = x * ntt_load<F>(aux + 8);
-  F out;
-  x.to_canonical(out.v);
   const uint32_t j = reverse ? (log_n ? (__brev(i) >> (32 - log_n)) : 0u) : i;
-  ntt_store<F>(dst + (size_t)j * 8, out);
+  ntt_store<F>(dst + (size_t)j * 8, x);
 }
 
 template <class P>
