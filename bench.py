@@ -196,9 +196,9 @@ def main():
     torch.cuda.set_device(local_rank)
     nmsm.init(local_rank)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner / warnings to stdout (at NCCL_DEBUG=VERSION or WARN, which some launch
+        # environments set); stdout carries exactly one JSON line, so send NCCL's log to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = nmsm._lib.load()
     if args.window:
