@@ -145,7 +145,7 @@ def cpu_reference(n_sample, seed, max_seconds=30.0):
     return cpu_baseline.time_bls_g1_msm(n_sample, seed, max_seconds)
 
 
-def run_reference(args):
+def run_reference(args, real_stdout):
     """`--impl reference`: the reference's algorithm on this box's host cores (rank 0 only under torchrun).
     Inputs are generated once; each step is one timed run of the C port on the same workload."""
     rank = int(os.environ.get("RANK", "0"))
@@ -171,16 +171,32 @@ def run_reference(args):
                          "sample": res["sample"]},
         "e2e": {"value": pts_per_s, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(real_stdout, line)
 
 
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but native libraries write there too (NCCL prints its version banner
+    to fd 1 when the launch environment sets NCCL_DEBUG=VERSION/WARN).  Point fd 1 at stderr for the whole run and keep
+    the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_stdout_fd, line: dict):
+    sys.stdout.flush()
+    os.write(real_stdout_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse_args()
+    real_stdout = _claim_stdout()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, real_stdout)
         return
 
     import torch
@@ -196,9 +212,6 @@ def main():
     torch.cuda.set_device(local_rank)
     nmsm.init(local_rank)
     if world > 1:
-        # NCCL writes its version banner / warnings to stdout (at NCCL_DEBUG=VERSION or WARN, which some launch
-        # environments set); stdout carries exactly one JSON line, so send NCCL's log to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = nmsm._lib.load()
     if args.window:
@@ -510,7 +523,7 @@ def main():
         "fixed_base": fixed,
         "any_point": any_point,
     }
-    print(json.dumps(line), flush=True)
+    _emit(real_stdout, line)
     if world > 1:
         dist.destroy_process_group()
 
