@@ -317,32 +317,13 @@ NMSM_NL void nl_to_affine(const typename G::Acc& p, uint32_t* xy, uint32_t* inf)
   G::to_affine_canonical(p, xy, inf);
 }
 
-// Group-operation policies for the reduction bodies: one logical thread per lane (out-of-line serial
-// formulas) or one logical thread per quad of lanes (ec.cuh Par4; device only).
+// Group-operation policy of reduce1_body: one logical thread per lane, out-of-line serial formulas (a quad-per-thread
+// policy was measured slower there: msm.cuh k_reduce1).
 template <class G>
 struct SerialOps {
   NMSM_HD static void add(typename G::Acc& p, const typename G::Acc& q) { nl_add<G>(p, q); }
   NMSM_HD static void dbl(typename G::Acc& p) { nl_dbl<G>(p); }
 };
-#if defined(__CUDACC__)
-template <class G>
-struct QuadOps {
-  NMSM_HD static void add(typename G::Acc& p, const typename G::Acc& q) {
-#if defined(__CUDA_ARCH__)
-    G::template par_add<false>(p, q);
-#else
-    (void)p; (void)q;
-#endif
-  }
-  NMSM_HD static void dbl(typename G::Acc& p) {
-#if defined(__CUDA_ARCH__)
-    G::template par_dbl<false>(p);
-#else
-    (void)p;
-#endif
-  }
-};
-#endif
 
 // c bits of a 256-bit little-endian scalar starting at bit `off`
 NMSM_HD uint32_t scalar_bits(const uint32_t* s, int off, int c, int nwords = SCALAR_WORDS) {
