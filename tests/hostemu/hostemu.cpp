@@ -148,6 +148,17 @@ static int emu_torsion_t(const uint32_t* pts, uint32_t n, uint8_t* out_ok, uint3
   return 0;
 }
 
+// plan introspection for tests: out = {c, W, B, L, K, chunks, D, wb, r, stride, auto_c}
+template <class Cv>
+static int emu_plan_t(uint32_t n, int table_c_req, uint32_t* out) {
+  MsmPlan p = table_c_req ? make_table_plan<Cv>(n, canonical_table_bits<Cv>(table_c_req), 148) : make_plan<Cv>(n, 0, 148);
+  out[0] = p.c; out[1] = p.W; out[2] = p.B; out[3] = p.L; out[4] = p.K; out[5] = p.chunks; out[6] = p.D;
+  out[7] = p.wb; out[8] = p.r; out[9] = p.stride;
+  out[10] = choose_table_bits<Cv>(n, 148, 64e9);
+  out[11] = glv_bits<Cv>() + 1;
+  return 0;
+}
+
 #define DISPATCH(curve, EXPR)                                        \
   switch (curve) {                                                   \
     case 0: { using Cv = CurveSecp256k1; return EXPR; }              \
@@ -250,6 +261,7 @@ int emu_point_table(int curve, int table_bits, const uint32_t* point_xy, const u
 int emu_torsion(int curve, const uint32_t* pts, uint32_t n, uint8_t* out_ok, uint32_t* err_out) {
   DISPATCH(curve, emu_torsion_t<Cv>(pts, n, out_ok, err_out));
 }
+int emu_plan(int curve, uint32_t n, int table_c_req, uint32_t* out) { DISPATCH(curve, emu_plan_t<Cv>(n, table_c_req, out)); }
 int emu_msm_table(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, int table_c, int forced_L,
                   uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out) {
   DISPATCH(curve, emu_msm_t<Cv>(pts, scalars, n, 0, forced_L, out_xy, out_inf, err_out, plan_out, table_c));
