@@ -28,11 +28,11 @@ def _is_pow2(n: int) -> bool:
 
 def ntt_packed(field: str, values: bytes, log_n: int, inverse=False, brp_input=False, brp_output=False, generator=0) -> bytes:
     """2^log_n canonical little-endian 32-byte elements in, transformed elements out."""
-    _lib.ensure_init()
-    lib = _lib.load()
     n = 1 << log_n
     if len(values) != n * 32:
         raise ValueError("FFT: wrong Polynomial length")
+    _lib.ensure_init()
+    lib = _lib.load()
     buf = ctypes.create_string_buffer(bytes(values), n * 32)
     rc = lib.nmsm_ntt(FIELD_CURVE[field], ctypes.cast(buf, ctypes.c_void_p), log_n, int(generator), 1 if inverse else 0,
                       1 if brp_input else 0, 1 if brp_output else 0)

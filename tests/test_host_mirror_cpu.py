@@ -1,0 +1,106 @@
+"""Host-side logic of the reference-facing mirror (noble-curves_b200/nmsm) that runs before any GPU call: the argument
+validation and error text of pippenger / multiply / FFT (curve.ts:390-404,863-878; weierstrass.ts:900-928;
+edwards.ts:555-577; fft.ts:518-575), the wire encodings of toBytes, packing helpers.  No device is needed: every case
+here must be decided on the host, and anything that reaches the library must fail loudly (no CPU fallback)."""
+import pytest
+
+import nmsm
+from nmsm import fft as GF
+from oracle import noble_ref as R
+
+from conftest import load_golden
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "ed25519", "bls12_381_G1", "bn254_G2"])
+def test_pippenger_validation_messages(name):
+    C = nmsm.CURVES[name]
+    G = C.BASE
+    n = C.Fn.ORDER
+    with pytest.raises(ValueError, match="arrays of points and scalars must have equal length"):
+        nmsm.pippenger(C, [G, G], [1])
+    with pytest.raises(ValueError, match="invalid point at index 1"):
+        nmsm.pippenger(C, [G, object()], [1, 2])
+    with pytest.raises(ValueError, match="invalid scalar at index 2"):
+        nmsm.pippenger(C, [G, G, G], [1, 2, n])
+    with pytest.raises(ValueError, match="invalid scalar at index 0"):
+        nmsm.pippenger(C, [G], [-1])
+    with pytest.raises(ValueError, match="array of scalars expected"):
+        nmsm.pippenger(C, [G], 5)
+    with pytest.raises(TypeError):
+        nmsm.pippenger(C, "GG", [1, 2])
+    # points are validated before scalars, as in the reference (curve.ts:871-872)
+    with pytest.raises(ValueError, match="invalid point at index 0"):
+        nmsm.pippenger(C, [None], [n])
+    assert nmsm.pippenger(C, [], []).is0()  # curve.ts:878: empty input is the identity, no device needed
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "ed25519", "bls12_381_G1"])
+def test_multiply_range_messages(name):
+    C = nmsm.CURVES[name]
+    n = C.Fn.ORDER
+    edw = name == "ed25519"
+    msg1 = "invalid scalar: expected 1 <= sc < curve.n" if edw else "invalid scalar: out of range"
+    msg0 = "invalid scalar: expected 0 <= sc < curve.n" if edw else "invalid scalar: out of range"
+    for bad in (0, n, -3):
+        with pytest.raises(ValueError, match=msg1.replace("(", "\\(").replace(")", "\\)")):
+            C.BASE.multiply(bad)
+    for bad in (n, -1):
+        with pytest.raises(ValueError, match=msg0):
+            C.BASE.multiplyUnsafe(bad)
+    with pytest.raises(ValueError, match="invalid window size"):
+        C.BASE.precompute(0)
+    assert nmsm.multiply_many(C, [], []) == []
+
+
+def test_wire_encodings_match_reference_vectors_on_the_host():
+    """toBytes is pure byte packing on the host (weierstrass.ts:541-563, bls12-381.ts:377-402): check it against the
+    reference's encodings without touching the device."""
+    g = load_golden("bls12_381.json")
+    C = nmsm.CURVES["bls12_381_G1"]
+    O = R.CURVES["bls12_381_G1"]
+    for i in (1, 2, 77, 999):
+        a = O.BASE.multiplyUnsafe(i).toAffine()
+        P = C.fromAffine(a)
+        assert P.toBytes(True).hex() == g["G1_Compressed"][i] and P.toBytes(False).hex() == g["G1_Uncompressed"][i]
+    assert C.ZERO.toBytes(True).hex() == g["G1_Compressed"][0]
+    S = nmsm.CURVES["secp256k1"]
+    for k, x, y in load_golden("secp256k1.json")["privates2"][:5]:
+        P = S.fromAffine({"x": int(x, 16), "y": int(y, 16)})
+        assert P.toBytes(False).hex() == "04" + x + y and P.toBytes(True)[1:].hex() == x
+    E = nmsm.CURVES["ed25519"]
+    OE = R.CURVES["ed25519"]
+    v = load_golden("ed25519.json")["vectors"][0]
+    pk = bytes.fromhex(v["pk"])
+    a = R.ed25519_point_from_bytes(pk, True).toAffine()
+    assert E.fromAffine(a).toBytes() == pk and OE is not None
+
+
+def test_fft_wrapper_validation():
+    f = GF.FFT(GF.rootsOfUnity("bls12_381", 7))
+    with pytest.raises(ValueError, match="power of two"):
+        f.direct([1, 2, 3])
+    with pytest.raises(ValueError, match="power of two"):
+        f.inverse([])
+    with pytest.raises(ValueError, match="scalar fields of bn254 and bls12_381 only"):
+        GF.rootsOfUnity("secp256k1")
+    with pytest.raises(TypeError):
+        GF.rootsOfUnity("bn254", 7.0)
+    r = GF.rootsOfUnity("bn254")
+    assert r.info["powerOfTwo"] == 28 and r.info["G"] == 5 and (r.info["oddFactor"] << 28) + 1 == GF.FR_ORDER["bn254"]
+    with pytest.raises(ValueError, match="wrong Polynomial length"):
+        GF.ntt_packed("bn254", b"\x00" * 31, 0)
+
+
+def test_compute_entry_points_refuse_without_a_device():
+    """There is no CPU fallback: on this box (no GPU) everything that needs the device raises."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    C = nmsm.CURVES["secp256k1"]
+    with pytest.raises(Exception, match="CUDA|cuda|device"):
+        nmsm.pippenger(C, [C.BASE], [5])
+    with pytest.raises(Exception, match="CUDA|cuda|device"):
+        GF.FFT(GF.rootsOfUnity("bn254", 7)).direct([1, 2, 3, 4])
+    with pytest.raises(Exception, match="CUDA|cuda|device"):
+        nmsm.points_decode(0, bytes(33), 1)
