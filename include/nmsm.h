@@ -10,6 +10,14 @@
  *   nmsm_msm_partial_device / nmsm_fold_partials_device           (multi-GPU split of the same MSM; MSM is
  *                                                                 linear in its term set, curve.ts:863)
  *   nmsm_last_error     <- the thrown Error messages              curve.ts:390-404,875
+ * and, for the callers and data formats either side of that path:
+ *   nmsm_msm_submit / _collect / nmsm_msm_points_submit           asynchronous halves (several MSMs in flight)
+ *   nmsm_points_upload / _precompute / nmsm_msm_points            interleavedMSMUnsafe, Point.precompute  curve.ts:532-577,937-959
+ *   nmsm_point_table_*  <- P.precompute(W) + cached P.multiply(k) curve.ts:532-606 (BASE.multiply at rate)
+ *   nmsm_points_decode / nmsm_points_torsion_free  <- Point.fromBytes: decode + isTorsionFree
+ *                                                                 weierstrass.ts:541-605,971-975, bls12-381.ts:377-468
+ *   nmsm_ed25519_verify_batch <- ed25519.verify over a batch      edwards.ts:942-989
+ *   nmsm_ntt            <- FFT(rootsOfUnity(Fr, G), Fr).direct / .inverse   src/abstract/fft.ts:518-575
  *
  * Data formats (all little-endian, plain bytes, caller-owned):
  *   point   : canonical affine (x, y); each base-field coordinate is FpBytes little-endian bytes
