@@ -13,6 +13,7 @@
 #include "msm_body.cuh"
 #include "ed25519_verify.cuh"
 #include "codec.cuh"
+#include "inv_divsteps.cuh"
 
 using namespace nmsm;
 
@@ -183,6 +184,8 @@ static void field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) 
     case 4: z = Fp<P>::from_canonical(a); break;
     case 5: x.to_canonical(z.v); break;
     case 6: z = sqr(x); break;
+    case 8: z = DivstepsInv<P>::inverse(x); break;                                  // Montgomery in / out
+    case 9: if (!DivstepsInv<P>::inverse_words(a, z.v)) z = Fp<P>::zero(); break;    // plain integers
     default: z = -x; break;
   }
   for (int i = 0; i < P::N; i++) r[i] = z.v[i];

@@ -61,6 +61,28 @@ def test_field_ops_match_bigint(field):
         assert _fop(field, 3, (a * Rm) % p) == exp
 
 
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
+def test_divsteps_inverse(field):
+    """csrc/inv_divsteps.cuh (experimental, not yet used by the kernels): batched division-step inversion equals
+    pow(x, -1, p) on plain integers and equals field.cuh's inv in Montgomery form, on edge values and random ones."""
+    import random as _r
+
+    p = FIELDS[field]
+    n = 12 if field == 3 else 8
+    Rm = pow(2, 32 * n, p)
+    rnd = _r.Random(field)
+    vals = [1, 2, 3, p - 1, p - 2, (p + 1) // 2, (p - 1) // 2, 1 << 30, (1 << 30) - 1, 1 << 60, (1 << 255) % p,
+            (1 << (p.bit_length() - 1)) - 1, 0x55555555555555555555555555555555 % p, pow(3, 200, p)]
+    vals += [rnd.randrange(1, p) for _ in range(300)]
+    vals += [rnd.randrange(1, 1 << k) for k in (8, 31, 61, 64, 90, 200) for _ in range(5)]
+    for x in vals:
+        assert _fop(field, 9, x) == pow(x, -1, p), hex(x)
+    for x in vals[:60]:
+        xm = x * Rm % p
+        assert _fop(field, 8, xm) == _fop(field, 3, xm) == pow(x, -1, p) * Rm % p
+    assert _fop(field, 8, 0) == 0
+
+
 @pytest.mark.parametrize("name", ALL)
 def test_msm_soak(name):
     """test/slow-curves.test.ts:185-252 construction (every 17th scalar zero), several window sizes."""
