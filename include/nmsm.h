@@ -168,18 +168,36 @@ int nmsm_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pubkeys, const
 /* Batched wire-format decoding on the GPU (next-row f2): encodings -> canonical affine points in the packing
  * above, ready for nmsm_msm.  secp256k1: 33-byte SEC1 compressed (weierstrass.ts:565-588); BLS12-381 G1: 48-byte
  * Zcash-flag compressed (bls12-381.ts:377-468); BLS12-381 G2: 96-byte Zcash-flag compressed, x = c1 || c0
- * (bls12-381.ts:354-367,488-491; Fp2 square root tower.ts:476-498); ed25519: 32-byte RFC 8032 with ZIP-215
- * acceptance (edwards.ts:405-436).  out_status[i]: 0 = invalid encoding, 1 = point, 2 = point at infinity.  Mirrors
+ * (bls12-381.ts:354-367,488-491; Fp2 square root tower.ts:476-498); ed25519: 32-byte RFC 8032, strict like the
+ * reference's fromBytes default (edwards.ts:405-436; ZIP-215 acceptance: nmsm_points_decode_ex).  out_status[i]: 0 = invalid encoding, 1 = point, 2 = point at infinity.  Mirrors
  * the reference's decode step only; the subgroup check its fromBytes adds is nmsm_points_torsion_free.  Other
  * curves: NMSM_ERR_ARG. */
 int nmsm_points_decode(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_xy, uint8_t* out_status);
+/* Same with flags.  nmsm_points_decode == flags 0 == the reference's defaults: for ed25519 that is the strict RFC 8032
+ * decoding of `Point.fromBytes(bytes, zip215 = false)` (/root/reference/src/abstract/edwards.ts:405-436: y >= p
+ * rejected, x = 0 with the sign bit set rejected); NMSM_DECODE_ZIP215 selects the ZIP-215 acceptance rules that
+ * ed25519.verify (and nmsm_ed25519_verify_batch) decode with.  Invalid encodings return status 0 and zeroed bytes. */
+#define NMSM_DECODE_ZIP215 1
+int nmsm_points_decode_ex(int curve, const uint8_t* enc, uint64_t n, int flags, uint8_t* out_xy, uint8_t* out_status);
+
+/* out_ok[i] = 1 iff pts[i] has in-range coordinates and satisfies the curve equation: the `isValidXY` half of the
+ * reference's assertValidity (/root/reference/src/abstract/weierstrass.ts:617-624,766; edwards.ts:461-480) in batch
+ * form; together with nmsm_points_torsion_free it is what Point.assertValidity checks.  The affine identity encoding
+ * counts as on the curve.  pippenger itself never validates ("Does NOT validate", weierstrass.ts:695,711). */
+int nmsm_points_on_curve(int curve, const uint8_t* pts, uint64_t n, uint8_t* out_ok);
 
 /* Tuning / introspection ------------------------------------------------------------------- */
 /* Force the window size c (0 = automatic cost model).  Returns the previous value. */
 int nmsm_set_window_bits(int c);
+/* Force the number of window groups an MSM is pipelined over (1..8; 0 = automatic: one group for small inputs, one
+ * group per window (at most 8) once the accumulation is long enough to hide the bucket reduction and the Horner
+ * doublings of the finished groups underneath it).  Results never depend on it.  Returns the previous value. */
+int nmsm_set_window_groups(int groups);
 
-/* Plan + per-kernel device times (ms, CUDA events on the library stream) of the last MSM call.
- * `ms` receives NMSM_TIMING_SLOTS floats; see the NMSM_T_* indices. */
+/* Plan + device times (ms, CUDA events on the library's streams) of the last MSM call.  `ms` receives
+ * NMSM_TIMING_SLOTS floats, see the NMSM_T_* indices.  NMSM_T_TOTAL (first kernel to the inversion, the whole MSM
+ * on the device) is always measured; the per-kernel entries only while profiling is on, which also forces the
+ * linear one-group pipeline (per-kernel times of overlapping launches would not add up). */
 enum {
   NMSM_T_PREPARE = 0, NMSM_T_COUNT, NMSM_T_SCAN, NMSM_T_SCATTER, NMSM_T_ACCUMULATE, NMSM_T_STITCH,
   NMSM_T_REDUCE1, NMSM_T_REDUCE23, NMSM_T_FINAL, NMSM_T_TOTAL, NMSM_TIMING_SLOTS
@@ -189,6 +207,7 @@ typedef struct {
   uint64_t sorted_entries;      /* non-zero digits = mixed additions issued + bucket starts       */
   uint64_t modmul_equiv;        /* field multiplications executed by the plan (SURVEY §8d formula) */
   int launches;                 /* kernels launched by the call                                   */
+  int window_groups;            /* window groups the call was pipelined over (1 = linear pipeline) */
 } nmsm_plan_info;
 int nmsm_set_profiling(int enabled);
 int nmsm_last_timing(float* ms, nmsm_plan_info* info);

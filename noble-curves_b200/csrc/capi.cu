@@ -111,11 +111,22 @@ int nmsm_init(int device) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   C.sm_count = prop.multiProcessorCount;
+  int prio_lo = 0, prio_hi = 0;  // numerically lower = more urgent
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (Slot& S : C.slot) {
     CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    for (auto& st : S.acc_stream) CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_lo));
+    for (auto& st : S.tail_stream) CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&S.horner_stream, cudaStreamNonBlocking, prio_hi));
     CK(cudaMallocHost((void**)&S.h_result, 1024));
     for (auto& ev : S.ev) CK(cudaEventCreate(&ev));
     CK(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&S.ev_horner, cudaEventDisableTiming));
+    for (auto& ev : S.ev_acc) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : S.ev_tail) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventCreate(&S.ev_t0));
+    CK(cudaEventCreate(&S.ev_t1));
   }
   C.device = device;
   C.ready = true;
@@ -128,12 +139,20 @@ void nmsm_shutdown(void) {
   if (!C.ready) return;
   for (Slot& S : C.slot) {
     cudaStreamSynchronize(S.stream);
+    for (auto st : S.acc_stream) cudaStreamSynchronize(st);
+    for (auto st : S.tail_stream) cudaStreamSynchronize(st);
+    cudaStreamSynchronize(S.horner_stream);
     for (Buf* b : {&S.in_pts, &S.in_scalars, &S.aff, &S.counts, &S.offsets, &S.cursor, &S.sorted, &S.buckets, &S.heads,
-                   &S.tails, &S.chunk_out, &S.window_out, &S.tile_sums, &S.blk, &S.tiles, &S.result, &S.mul_out})
+                   &S.tails, &S.chunk_out, &S.window_out, &S.tile_sums, &S.blk, &S.tiles, &S.result, &S.mul_out, &S.hacc})
       b->release();
     for (auto& ev : S.ev) cudaEventDestroy(ev);
-    cudaEventDestroy(S.done);
+    for (auto& ev : S.ev_acc) cudaEventDestroy(ev);
+    for (auto& ev : S.ev_tail) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {S.done, S.ev_fork, S.ev_horner, S.ev_t0, S.ev_t1}) cudaEventDestroy(ev);
     cudaFreeHost(S.h_result);
+    for (auto st : S.acc_stream) cudaStreamDestroy(st);
+    for (auto st : S.tail_stream) cudaStreamDestroy(st);
+    cudaStreamDestroy(S.horner_stream);
     cudaStreamDestroy(S.stream);
     S.pend = Pending();
   }
@@ -145,8 +164,16 @@ void nmsm_shutdown(void) {
   C.device = -1;
 }
 
-const char* nmsm_last_error(void) { return g_ctx.last_error.c_str(); }
-long long nmsm_last_error_index(void) { return g_ctx.last_error_index; }
+const char* nmsm_last_error(void) {
+  static thread_local std::string copy;  // the caller's pointer stays valid while other threads keep calling in
+  std::lock_guard<std::mutex> lk(g_mu);
+  copy = g_ctx.last_error;
+  return copy.c_str();
+}
+long long nmsm_last_error_index(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_ctx.last_error_index;
+}
 
 int nmsm_point_bytes(int curve) {
   ENGINE(curve);
@@ -365,21 +392,44 @@ int nmsm_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pubkeys, const
   return ed25519_verify_batch_impl(sigs, pubkeys, msgs, msg_off, n, z16, out_ok, out_bad_index);
 }
 
-int nmsm_points_decode(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_xy, uint8_t* out_status) {
+int nmsm_points_decode_ex(int curve, const uint8_t* enc, uint64_t n, int flags, uint8_t* out_xy, uint8_t* out_status) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
   if (n && (!enc || !out_xy || !out_status)) return fail(NMSM_ERR_ARG, "null pointer");
-  return decode_points_impl(curve, enc, n, out_xy, out_status);
+  if (flags & ~NMSM_DECODE_ZIP215) return fail(NMSM_ERR_ARG, "nmsm_points_decode_ex: unknown flag");
+  return decode_points_impl(curve, enc, n, flags, out_xy, out_status);
+}
+
+int nmsm_points_decode(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_xy, uint8_t* out_status) {
+  return nmsm_points_decode_ex(curve, enc, n, 0, out_xy, out_status);
+}
+
+int nmsm_points_on_curve(int curve, const uint8_t* pts, uint64_t n, uint8_t* out_ok) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
+  if (n && (!pts || !out_ok)) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  return E->on_curve(pts, n, out_ok);
 }
 
 int nmsm_set_window_bits(int c) {
+  std::lock_guard<std::mutex> lk(g_mu);
   int prev = g_ctx.forced_c;
   g_ctx.forced_c = (c >= 1 && c <= 16) ? c : 0;
   return prev;
 }
 
+int nmsm_set_window_groups(int groups) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int prev = g_ctx.forced_groups;
+  g_ctx.forced_groups = (groups >= 1 && groups <= MAX_GROUPS) ? groups : 0;
+  return prev;
+}
+
 int nmsm_set_profiling(int enabled) {
+  std::lock_guard<std::mutex> lk(g_mu);
   int prev = g_ctx.profiling ? 1 : 0;
   g_ctx.profiling = enabled != 0;
   return prev;
@@ -402,6 +452,7 @@ int nmsm_ntt_device(int curve, void* d_values, int log_n, uint64_t generator, in
 }
 
 int nmsm_last_timing(float* ms, nmsm_plan_info* info) {
+  std::lock_guard<std::mutex> lk(g_mu);
   if (ms) memcpy(ms, g_ctx.last_ms, sizeof(g_ctx.last_ms));
   if (info) *info = g_ctx.last_info;
   return NMSM_OK;

@@ -207,6 +207,10 @@ NMSM_HD int zcash_decode_bls12_381_g2(const uint8_t* enc, uint32_t* out_xy) {
   return 1;
 }
 
-NMSM_HD int ed25519_decode(const uint8_t* enc, uint32_t* out_xy) { return ed_decompress(enc, out_xy) ? 1 : 0; }
+// zip215 = false: the reference's default `fromBytes(bytes, zip215 = false)` (edwards.ts:405-436): y must be < p and
+// x = 0 with the sign bit set is rejected; zip215 = true: the ZIP-215 acceptance rules ed25519.verify uses by default.
+NMSM_HD int ed25519_decode(const uint8_t* enc, uint32_t* out_xy, bool zip215 = false) {
+  return ed_decompress(enc, out_xy, zip215) ? 1 : 0;
+}
 
 }  // namespace nmsm

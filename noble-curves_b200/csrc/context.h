@@ -16,6 +16,7 @@
 namespace nmsm {
 struct MsmPlanLite {  // mirror of MsmPlan (msm_body.cuh) so this header stays free of device code
   int c, W, B, G, L, K, chunks, D;
+  uint32_t TPW;
 };
 }  // namespace nmsm
 
@@ -54,11 +55,22 @@ struct Pending {
   uint64_t n = 0;
   bool partial = false;   // raw accumulator requested instead of an affine result
   bool empty = false;     // n == 0
+  bool profiled = false;  // per-kernel events were recorded at submit (nmsm_set_profiling was on then)
+  int groups = 1;         // window groups the pipeline was split into
+  int launches = 0;       // kernels launched for this MSM
 };
+static constexpr int MAX_GROUPS = 8;       // window groups per MSM (engine.cuh submit_msm)
+static constexpr int ACC_STREAMS = 2, TAIL_STREAMS = 2;
 struct Slot {
   cudaStream_t stream = nullptr;
+  // Window-group pipelining: the per-group accumulate launches alternate between two low-priority streams (the
+  // next group's blocks fill the SMs as the previous group's drain), every finished group's bucket reduction runs
+  // on a high-priority tail stream, and the Horner steps on their own high-priority stream.
+  cudaStream_t acc_stream[ACC_STREAMS] = {}, tail_stream[TAIL_STREAMS] = {}, horner_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_acc[MAX_GROUPS] = {}, ev_tail[MAX_GROUPS] = {}, ev_horner = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // whole-MSM device time, always recorded
   Buf in_pts, in_scalars, aff, counts, offsets, cursor, sorted, buckets, heads, tails, chunk_out, window_out, tile_sums,
-      blk, tiles, result, mul_out;
+      blk, tiles, result, mul_out, hacc;
   uint32_t* h_result = nullptr;  // pinned staging for (xy | inf | err0 | err1 | entries)
   cudaEvent_t ev[NMSM_TIMING_SLOTS + 2] = {};
   cudaEvent_t done = nullptr;
@@ -80,6 +92,7 @@ struct Context {
   uint64_t ntt_key_gen = 0;
   bool profiling = false;
   int forced_c = 0;
+  int forced_groups = 0;  // 0 = automatic (nmsm_set_window_groups)
   float last_ms[NMSM_TIMING_SLOTS] = {};
   nmsm_plan_info last_info = {};
   std::string last_error;
@@ -135,10 +148,11 @@ struct EngineVTable {
   int (*submit_prepared)(const uint32_t* d_prepared, uint64_t n_points, int table_c, const void* scalars, uint64_t n,
                          int scalars_on_device);
   int (*torsion_free)(const uint8_t* pts, uint64_t n, uint8_t* out_ok);
+  int (*on_curve)(const uint8_t* pts, uint64_t n, uint8_t* out_ok);
 };
 int ed25519_verify_batch_impl(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* msg_off,
                               uint64_t n, const uint8_t* z16, int* out_ok, long long* out_bad_index);
-int decode_points_impl(int curve, const uint8_t* enc, uint64_t n, uint8_t* out_xy, uint8_t* out_status);
+int decode_points_impl(int curve, const uint8_t* enc, uint64_t n, int flags, uint8_t* out_xy, uint8_t* out_status);
 int ntt_impl(int curve, void* values, int on_device, int log_n, uint64_t generator, int inverse, int brp_input,
              int brp_output);
 const EngineVTable* engine_secp256k1();

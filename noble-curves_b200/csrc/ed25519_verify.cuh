@@ -54,10 +54,12 @@ NMSM_HD EdF ed_sqrt_m1() {
   return r;
 }
 
-// Point.fromBytes(bytes, zip215 = true) (edwards.ts:405-436): any 255-bit y is accepted and reduced,
-// x = 0 with the sign bit set is accepted.  Writes canonical (x, y) little-endian words; false if
-// y^2 - 1 / (d y^2 + 1) is not a square.
-NMSM_HD bool ed_decompress(const uint8_t* enc, uint32_t* out_xy) {
+// Point.fromBytes(bytes, zip215) (edwards.ts:405-436).  zip215 = true: any 255-bit y is accepted and reduced,
+// x = 0 with the sign bit set is accepted (what ed25519.verify decodes with by default, ed25519.ts:168).
+// zip215 = false (RFC 8032 / the reference's fromBytes default): y >= p is rejected (`aInRange('point.y', y, 0, p)`
+// :421) and so is x = 0 with the sign bit set (:431-433).  Writes canonical (x, y) little-endian words; false if
+// rejected or y^2 - 1 / (d y^2 + 1) is not a square.
+NMSM_HD bool ed_decompress(const uint8_t* enc, uint32_t* out_xy, bool zip215 = true) {
   uint32_t yw[8];
   for (int k = 0; k < 8; k++)
     yw[k] = (uint32_t)enc[4 * k] | ((uint32_t)enc[4 * k + 1] << 8) | ((uint32_t)enc[4 * k + 2] << 16) |
@@ -65,6 +67,7 @@ NMSM_HD bool ed_decompress(const uint8_t* enc, uint32_t* out_xy) {
   const bool sign = (yw[7] >> 31) != 0;
   yw[7] &= 0x7fffffffu;
   if (!EdF::canonical_in_range(yw)) {  // y in [p, 2^255): reduce (ZIP-215 allows unreduced encodings)
+    if (!zip215) return false;
     yw[0] = sub_cc(yw[0], FpEd25519::P(0));
     for (int k = 1; k < 8; k++) yw[k] = subc_cc(yw[k], FpEd25519::P(k));
   }
@@ -94,6 +97,7 @@ NMSM_HD bool ed_decompress(const uint8_t* enc, uint32_t* out_xy) {
     x.to_canonical(xc);
     x_odd = (xc[0] & 1u) != 0;  // false unless x == 0 (then still false)
   }
+  if (!zip215 && sign && x.is_zero()) return false;  // edwards.ts:431-433 "bad point: x=0 and x_0=1"
   if (sign != x_odd) {
     x = -x;
     x.to_canonical(xc);

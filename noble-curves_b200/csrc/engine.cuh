@@ -32,7 +32,29 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   return collect_msm(out_xy, out_is_inf);
 }
 
-// Enqueue the whole pipeline (and the small result D2H) on the current slot's stream; no host sync.
+// How many window groups to pipeline: worth it once the accumulation is long enough to hide a group's reduction
+// and Horner chain underneath it; small MSMs run as one group (fewest launches).
+static int choose_groups(const MsmPlan& plan, uint64_t max_entries) {
+  if (plan.W <= 1) return 1;
+  int ng = max_entries >= (3ull << 20) ? (plan.W < MAX_GROUPS ? plan.W : MAX_GROUPS) : 1;
+  if (g_ctx.forced_groups) ng = g_ctx.forced_groups < plan.W ? g_ctx.forced_groups : plan.W;
+  if (g_ctx.profiling) ng = 1;  // per-kernel event times only mean something on a linear pipeline
+  return ng;
+}
+
+// Enqueue the whole pipeline (and the small result D2H); no host sync.
+//
+//   main stream   : prepare, digit count, scan, scatter                                   -> ev_fork
+//   group g = 0.. : windows [w_lo, w_hi), top windows first
+//       acc_stream[g % 2]  (low priority)  k_accumulate of the group                      -> ev_acc[g]
+//       tail_stream[g % 2] (high priority) stitch tiles, k_reduce1, k_reduce2, k_reduce3  -> ev_tail[g]
+//       horner_stream      (high priority) k_horner_step: hacc = 2^(c * windows) * hacc + group sum
+//   main stream   : waits for the last Horner step, k_combine (inversion to affine), D2H   -> done
+// The accumulate launches of consecutive groups sit on alternating streams, so the blocks of group g+1 fill the SMs as
+// the blocks of group g drain (no wave-quantisation gap between launches), while the latency-bound reduction and the
+// doubling chain of every finished group run underneath.  Only the last group's reduction, one Horner step of
+// c * (windows per group) doublings and the inversion remain on the critical path.  With one group (small inputs,
+// profiling) everything is issued on the main stream.
 static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
                       const uint32_t* d_prepared, int table_c = 0, uint64_t table_points = 0) {
   Slot& C = g_ctx.slot[g_ctx.cur];
@@ -71,7 +93,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
     if (sp <= REDUCE2_MAX_SPLITS) break;
     m = sp;
   }
-  const uint64_t max_threads = (max_entries + plan.L - 1) / plan.L;
+  const uint64_t nseg = (uint64_t)plan.W * plan.TPW;  // accumulate segments, TPW per window
 
   if (!d_prepared) CK(C.aff.ensure(n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
   CK(C.counts.ensure((size_t)(plan.G + 1) * 4));
@@ -79,14 +101,15 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   CK(C.cursor.ensure((size_t)(plan.G + 1) * 4));
   CK(C.sorted.ensure(max_entries * 4));
   CK(C.buckets.ensure((size_t)plan.G * G::ACC_WORDS * 4));
-  CK(C.heads.ensure(max_threads * G::ACC_WORDS * 4));
-  CK(C.tails.ensure(max_threads * G::ACC_WORDS * 4));
+  CK(C.heads.ensure(nseg * G::ACC_WORDS * 4));
+  CK(C.tails.ensure(nseg * G::ACC_WORDS * 4));
   CK(C.chunk_out.ensure((size_t)plan.W * plan.chunks * G::ACC_WORDS * 4 * 2));
   CK(C.tile_sums.ensure((size_t)(plan.G / SCAN_TILE + 2) * 4));
-  const uint64_t ntile1 = max_threads / STITCH_FAN + 1, ntile2 = ntile1 / STITCH_FAN + 1;
+  const uint64_t ntile1 = nseg / STITCH_FAN, ntile2 = ntile1 / STITCH_FAN;  // nseg is a multiple of 1024
   CK(C.tiles.ensure((ntile1 + ntile2) * G::ACC_WORDS * 4));
   CK(C.blk.ensure((size_t)plan.W * blk_entries * G::ACC_WORDS * 4 * 2));
   CK(C.window_out.ensure((size_t)plan.W * G::ACC_WORDS * 4));
+  CK(C.hacc.ensure((size_t)G::ACC_WORDS * 4));
 
   uint32_t* aff = d_prepared ? const_cast<uint32_t*>(d_prepared) : (uint32_t*)C.aff.p;
   unsigned int* counts = (unsigned int*)C.counts.p;
@@ -102,71 +125,120 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   uint32_t* tile1 = (uint32_t*)C.tiles.p;
   uint32_t* tile2 = tile1 + ntile1 * G::ACC_WORDS;
   uint32_t* window_out = (uint32_t*)C.window_out.p;
+  uint32_t* hacc = (uint32_t*)C.hacc.p;
   cudaStream_t st = C.stream;
   const uint32_t n32 = (uint32_t)n;
+  const int NG = choose_groups(plan, max_entries);
+  const bool prof = g_ctx.profiling;
+  int launches = 0;
+#define PEV(slot)                                   \
+  do {                                              \
+    if (prof) cudaEventRecord(C.ev[slot], st);      \
+  } while (0)
 
-  EV(0);
+  CK(cudaEventRecord(C.ev_t0, st));
+  PEV(0);
   CK(cudaMemsetAsync(d_err, 0xff, 8, st));
   CK(cudaMemsetAsync(counts, 0, (size_t)(plan.G + 1) * 4, st));
-  if (!d_prepared) k_prepare<Cv><<<cdiv(n, 128), 128, 0, st>>>(d_pts, n32, aff, d_err);
-  EV(1);
+  if (!d_prepared) { k_prepare<Cv><<<cdiv(n, 128), 128, 0, st>>>(d_pts, n32, aff, d_err); launches++; }
+  PEV(1);
   k_digits<Cv, false><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, counts, nullptr, d_err);
-  EV(2);
+  PEV(2);
   {
     const unsigned int tiles = cdiv(plan.G, SCAN_TILE);
     k_scan_tiles<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)plan.G, tile_sums);
     k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)plan.G, tile_sums, offsets, cursor);
   }
-  EV(3);
+  PEV(3);
   k_digits<Cv, true><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, cursor, sorted, d_err);
-  EV(4);
-  k_accumulate<Cv><<<cdiv(max_threads, 128), 128, 0, st>>>(aff, sorted, offsets, plan, buckets, heads, tails);
-  EV(5);
-  // tile sums for buckets spanning many accumulate segments (no-ops for ordinary inputs)
-  k_stitch_tiles<Cv><<<cdiv(ntile1 * 32, 128), 128, 0, st>>>(offsets, plan, STITCH_FAN, (uint32_t)ntile1, heads, tile1);
-  k_stitch_tiles<Cv><<<cdiv(ntile2 * 32, 128), 128, 0, st>>>(offsets, plan, STITCH_FAN * STITCH_FAN, (uint32_t)ntile2,
-                                                              tile1, tile2);
-  EV(6);
-  {
-    const uint64_t nchunks = (uint64_t)plan.W * plan.chunks;
-    k_reduce1<Cv><<<cdiv(nchunks, REDUCE1_THREADS), REDUCE1_THREADS, 0, st>>>(offsets, buckets, heads, tails, tile1, tile2,
-                                                                             plan, sums, wsums);
-  }
-  EV(7);
-  {
-    // msm.cuh "Bucket reduction": P/Q of one level are the T/S of the next (chunks := splits, K := K * Mb)
-    const size_t smem2 = (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4;
-    MsmPlan pl = plan;
-    const uint32_t *S = sums, *T = wsums;
-    uint32_t* base = (uint32_t*)C.blk.p;
-    for (;;) {
-      const int splits = (pl.chunks + REDUCE2_CHUNKS_PER_BLOCK - 1) / REDUCE2_CHUNKS_PER_BLOCK;
-      uint32_t* blkP = base;
-      uint32_t* blkQ = base + (size_t)plan.W * splits * G::ACC_WORDS;
-      base = blkQ + (size_t)plan.W * splits * G::ACC_WORDS;
-      k_reduce2<Cv><<<dim3(splits, plan.W), REDUCE2_THREADS, smem2, st>>>(S, T, pl, REDUCE2_R, blkP, blkQ);
-      if (splits <= REDUCE2_MAX_SPLITS) {
-        k_reduce3<Cv><<<plan.W, 32, 0, st>>>(blkP, blkQ, pl, splits, REDUCE2_R, window_out);
-        break;
-      }
-      S = blkQ;
-      T = blkP;
-      pl.chunks = splits;
-      pl.K *= REDUCE2_CHUNKS_PER_BLOCK;
+  launches += 4;
+  PEV(4);
+  if (NG > 1) CK(cudaEventRecord(C.ev_fork, st));
+
+  const int per = (plan.W + NG - 1) / NG;  // windows per group
+  int g = 0;
+  for (int w_hi = plan.W; w_hi > 0; w_hi -= per, g++) {
+    const int w_lo = w_hi > per ? w_hi - per : 0;
+    const uint32_t nw = (uint32_t)(w_hi - w_lo);
+    cudaStream_t sa = NG > 1 ? C.acc_stream[g % ACC_STREAMS] : st;
+    cudaStream_t stl = NG > 1 ? C.tail_stream[g % TAIL_STREAMS] : st;
+    cudaStream_t sh = NG > 1 ? C.horner_stream : st;
+    if (NG > 1) CK(cudaStreamWaitEvent(sa, C.ev_fork, 0));
+    k_accumulate<Cv><<<cdiv((uint64_t)nw * plan.TPW, 128), 128, 0, sa>>>(aff, sorted, offsets, plan, (uint32_t)w_lo, buckets,
+                                                                         heads, tails);
+    if (NG > 1) {
+      CK(cudaEventRecord(C.ev_acc[g], sa));
+      CK(cudaStreamWaitEvent(stl, C.ev_acc[g], 0));
     }
+    PEV(5);
+    {  // tile sums for buckets spanning many accumulate segments (no-ops for ordinary inputs)
+      const uint32_t a0 = (uint32_t)((uint64_t)w_lo * plan.TPW / STITCH_FAN), a1 = (uint32_t)((uint64_t)w_hi * plan.TPW / STITCH_FAN);
+      k_stitch_tiles<Cv><<<cdiv((uint64_t)(a1 - a0) * 32, 128), 128, 0, stl>>>(offsets, plan, STITCH_FAN, a0, a1, heads, tile1);
+      const uint32_t b0 = a0 / STITCH_FAN, b1 = a1 / STITCH_FAN;
+      k_stitch_tiles<Cv><<<cdiv((uint64_t)(b1 - b0) * 32, 128), 128, 0, stl>>>(offsets, plan, STITCH_FAN * STITCH_FAN, b0, b1,
+                                                                              tile1, tile2);
+    }
+    PEV(6);
+    {
+      const uint32_t id0 = (uint32_t)w_lo * plan.chunks, id1 = (uint32_t)w_hi * plan.chunks;
+      k_reduce1<Cv><<<cdiv(id1 - id0, REDUCE1_THREADS), REDUCE1_THREADS, 0, stl>>>(offsets, buckets, heads, tails, tile1, tile2,
+                                                                                  plan, id0, id1, sums, wsums);
+    }
+    PEV(7);
+    launches += 4;
+    {
+      // msm.cuh "Bucket reduction": P/Q of one level are the T/S of the next (chunks := splits, K := K * Mb)
+      const size_t smem2 = (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4;
+      MsmPlan pl = plan;
+      const uint32_t *S = sums, *T = wsums;
+      uint32_t* base = (uint32_t*)C.blk.p;
+      for (;;) {
+        const int splits = (pl.chunks + REDUCE2_CHUNKS_PER_BLOCK - 1) / REDUCE2_CHUNKS_PER_BLOCK;
+        uint32_t* blkP = base;
+        uint32_t* blkQ = base + (size_t)plan.W * splits * G::ACC_WORDS;
+        base = blkQ + (size_t)plan.W * splits * G::ACC_WORDS;
+        k_reduce2<Cv><<<dim3(splits, nw), REDUCE2_THREADS, smem2, stl>>>(S, T, pl, REDUCE2_R, (uint32_t)w_lo, blkP, blkQ);
+        launches++;
+        if (splits <= REDUCE2_MAX_SPLITS) {
+          k_reduce3<Cv><<<nw, 32, 0, stl>>>(blkP, blkQ, pl, splits, REDUCE2_R, (uint32_t)w_lo, window_out);
+          launches++;
+          break;
+        }
+        S = blkQ;
+        T = blkP;
+        pl.chunks = splits;
+        pl.K *= REDUCE2_CHUNKS_PER_BLOCK;
+      }
+    }
+    PEV(8);
+    if (NG > 1) {
+      CK(cudaEventRecord(C.ev_tail[g], stl));
+      CK(cudaStreamWaitEvent(sh, C.ev_tail[g], 0));
+    }
+    k_horner_step<Cv><<<1, 32, 0, sh>>>(window_out, plan, w_lo, w_hi, g == 0 ? 1 : 0, 0, hacc);
+    launches++;
   }
-  EV(8);
+  if (NG > 1) {
+    CK(cudaEventRecord(C.ev_horner, C.horner_stream));
+    CK(cudaStreamWaitEvent(st, C.ev_horner, 0));
+  }
   if (d_out_acc)
-    k_final<Cv, false><<<1, 32, 0, st>>>(window_out, plan, d_out_acc, nullptr);
+    k_combine<Cv, false><<<1, 32, 0, st>>>(hacc, 1, d_out_acc, nullptr);
   else
-    k_final<Cv, true><<<1, 32, 0, st>>>(window_out, plan, d_res, d_res + G::IN_WORDS);
-  EV(9);
+    k_combine<Cv, true><<<1, 32, 0, st>>>(hacc, 1, d_res, d_res + G::IN_WORDS);
+  launches++;
+  PEV(9);
+#undef PEV
+  CK(cudaEventRecord(C.ev_t1, st));
   CK(cudaGetLastError());
   // one small D2H: result + error slots (+ entry count for accounting)
   CK(cudaMemcpyAsync(C.h_result, d_res, RES_WORDS * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(C.h_result + RES_WORDS, offsets + plan.G, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(C.done, st));
-  C.pend.plan = MsmPlanLite{plan.c, plan.W, plan.B, plan.G, plan.L, plan.K, plan.chunks, plan.D};
+  C.pend.plan = MsmPlanLite{plan.c, plan.W, plan.B, plan.G, plan.L, plan.K, plan.chunks, plan.D, plan.TPW};
+  C.pend.profiled = prof;
+  C.pend.groups = g;
+  C.pend.launches = launches;
   C.pend.active = true;
   return NMSM_OK;
 }
@@ -204,11 +276,14 @@ static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
   C.last_info.reduce_chunk = plan.K;
   C.last_info.sorted_entries = entries;
   C.last_info.modmul_equiv = plan_modmuls<Cv>(plan, entries);
-  C.last_info.launches = 12;  // prepare, count, scan x2, scatter, accumulate, stitch x2, reduce1, reduce2, reduce3, final
-  if (g_ctx.profiling) {
-    for (int k = 0; k < 9; k++) cudaEventElapsedTime(&C.last_ms[k], C.ev[k], C.ev[k + 1]);
-    cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev[0], C.ev[9]);
-  }
+  C.last_info.launches = C.pend.launches;
+  C.last_info.window_groups = C.pend.groups;
+  memset(C.last_ms, 0, sizeof(C.last_ms));
+  if (C.pend.profiled)  // events were recorded at submit (not: whatever the profiling switch says now)
+    for (int k = 0; k < 9; k++)
+      if (cudaEventElapsedTime(&C.last_ms[k], C.ev[k], C.ev[k + 1]) != cudaSuccess) C.last_ms[k] = 0;
+  if (cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev_t0, C.ev_t1) != cudaSuccess) C.last_ms[NMSM_T_TOTAL] = 0;
+  (void)cudaGetLastError();
   memcpy(g_ctx.last_ms, C.last_ms, sizeof(C.last_ms));
   g_ctx.last_info = C.last_info;
   if (!partial) {
@@ -220,9 +295,9 @@ static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
 
 // single-kernel calls (multiply batches): device time of the kernel between ev[0] and ev[1] -> NMSM_T_TOTAL
 static void note_kernel_time(Slot& C) {
-  if (!g_ctx.profiling) return;
+  if (!g_ctx.profiling) return;  // same lock-protected call that recorded ev[0] / ev[1]
   memset(C.last_ms, 0, sizeof(C.last_ms));
-  cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev[0], C.ev[1]);
+  if (cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev[0], C.ev[1]) != cudaSuccess) (void)cudaGetLastError();
   memcpy(g_ctx.last_ms, C.last_ms, sizeof(C.last_ms));
 }
 
@@ -414,6 +489,22 @@ static int run_torsion(const uint8_t* pts, uint64_t n, uint8_t* out_ok) {
   return NMSM_OK;
 }
 
+// out_ok[i] = 1 iff pts[i] satisfies the curve equation (assertValidity's isValidXY)
+static int run_on_curve(const uint8_t* pts, uint64_t n, uint8_t* out_ok) {
+  Slot& C = g_ctx.slot[g_ctx.cur];
+  if (n == 0) return NMSM_OK;
+  if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
+  CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
+  CK(C.mul_out.ensure(n + 16));
+  cudaStream_t st = C.stream;
+  CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, st));
+  k_on_curve<Cv><<<cdiv(n, 128), 128, 0, st>>>((const uint32_t*)C.in_pts.p, (uint32_t)n, (uint8_t*)C.mul_out.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_ok, C.mul_out.p, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return NMSM_OK;
+}
+
 static int run_msm_dev(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
                        uint8_t* out_xy, int* out_is_inf) {
   return run_msm(d_pts, d_scalars, n, d_out_acc, out_xy, out_is_inf, nullptr);
@@ -490,7 +581,8 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
                                     &Engine<CURVE>::precompute_table,                              \
                                     &Engine<CURVE>::build_point_table, &Engine<CURVE>::table_mul_batch, \
                                     &Engine<CURVE>::submit_any,     &Engine<CURVE>::collect_msm,    \
-                                    &Engine<CURVE>::submit_prepared, &Engine<CURVE>::run_torsion};  \
+                                    &Engine<CURVE>::submit_prepared, &Engine<CURVE>::run_torsion,  \
+                                    &Engine<CURVE>::run_on_curve};  \
     return &vt;                                                                                \
   }
 

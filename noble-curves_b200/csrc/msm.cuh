@@ -19,8 +19,10 @@
 //   k_reduce2      second level: suffix scan + reduction of chunk sums inside blocks of
 //                  32 quads (registers -> quad/warp shuffles -> shared memory)             (W x splits blocks)
 //   k_reduce3      folds the <= 32 block results of every window                           (W warps)
-//   k_final        Horner over windows (c doublings each) + one inversion to affine;
-//                  one warp, lanes share each formula's independent multiplications      (1 warp)
+//   k_horner_step  Horner over the windows of one group (c doublings each), one warp whose lanes
+//                  share each formula's independent multiplications; k_combine: inversion to affine (1 warp)
+// The windows form groups that are accumulated top-first as separate launches; the reduction and Horner
+// chains of finished groups run on high-priority side streams underneath the accumulation of the rest.
 //
 // No atomics touch curve points, so degenerate inputs (all scalars equal, all points equal —
 // test/point.test.ts:842-853, benchmark/msm_timings.ts:45-63) stay correct; they only lengthen the
@@ -30,6 +32,7 @@
 #include <stdint.h>
 
 #include "msm_body.cuh"
+#include "validate.cuh"
 
 namespace nmsm {
 
@@ -127,9 +130,11 @@ k_scan_apply(const unsigned int* __restrict__ counts, uint32_t G, const uint32_t
 template <class Cv>
 __global__ void __launch_bounds__(128, (sizeof(typename Cv::G::Acc) > 256 ? NMSM_ACC_MINBLOCKS_WIDE : NMSM_ACC_MINBLOCKS))
 k_accumulate(const uint32_t* __restrict__ aff, const uint32_t* __restrict__ sorted,
-             const uint32_t* __restrict__ offsets, MsmPlan plan, uint32_t* __restrict__ buckets,
+             const uint32_t* __restrict__ offsets, MsmPlan plan, uint32_t w0, uint32_t* __restrict__ buckets,
              uint32_t* __restrict__ heads, uint32_t* __restrict__ tails) {
-  accumulate_body<Cv>(blockIdx.x * blockDim.x + threadIdx.x, aff, sorted, offsets, plan, buckets, heads, tails);
+  // grid = (windows of the group) * TPW threads; TPW is a multiple of the block size, so a block never straddles windows
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  accumulate_body<Cv>(w0 + gid / plan.TPW, gid % plan.TPW, aff, sorted, offsets, plan, buckets, heads, tails);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -158,11 +163,11 @@ __device__ __forceinline__ typename G::Acc shfl_down_acc(const typename G::Acc& 
 // which is every tile for ordinary inputs; see msm_body.cuh "stitching".
 template <class Cv>
 __global__ void __launch_bounds__(128)
-k_stitch_tiles(const uint32_t* __restrict__ offsets, MsmPlan plan, uint32_t span, uint32_t ntiles,
+k_stitch_tiles(const uint32_t* __restrict__ offsets, MsmPlan plan, uint32_t span, uint32_t j0, uint32_t j1,
                const uint32_t* __restrict__ in, uint32_t* __restrict__ out) {
   using G = typename Cv::G;
-  const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (j >= ntiles) return;
+  const uint32_t j = j0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;  // tiles [j0, j1)
+  if (j >= j1) return;
   if (!tile_is_uniform(offsets, plan, (uint64_t)j * span, span)) return;  // warp-uniform
   typename G::Acc acc = load_acc<G>(in + ((size_t)j * STITCH_FAN + lane) * G::ACC_WORDS);
   for (int d = 16; d >= 1; d >>= 1) {
@@ -179,12 +184,11 @@ template <class Cv>
 __global__ void __launch_bounds__(REDUCE1_THREADS)
 k_reduce1(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ buckets,
           const uint32_t* __restrict__ heads, const uint32_t* __restrict__ tails,
-          const uint32_t* __restrict__ tile1, const uint32_t* __restrict__ tile2, MsmPlan plan,
-          uint32_t* __restrict__ sums, uint32_t* __restrict__ wsums) {
+          const uint32_t* __restrict__ tile1, const uint32_t* __restrict__ tile2, MsmPlan plan, uint32_t id0,
+          uint32_t id1, uint32_t* __restrict__ sums, uint32_t* __restrict__ wsums) {
   using G = typename Cv::G;
-  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id < (uint32_t)plan.W * plan.chunks)
-    reduce1_body<Cv, SerialOps<G>>(id, offsets, buckets, heads, tails, tile1, tile2, plan, sums, wsums);
+  const uint32_t id = id0 + blockIdx.x * blockDim.x + threadIdx.x;  // chunks [id0, id1) = the windows of one group
+  if (id < id1) reduce1_body<Cv, SerialOps<G>>(id, offsets, buckets, heads, tails, tile1, tile2, plan, sums, wsums);
 }
 
 // shuffle by `dq` logical lanes (quads); every lane of the warp must be converged here
@@ -219,12 +223,12 @@ static constexpr int REDUCE2_CHUNKS_PER_BLOCK = REDUCE2_LOGICAL * REDUCE2_R;
 // grid (splits, W).  Logical thread lt owns R consecutive chunks; see the formulas above.
 template <class Cv>
 __global__ void __launch_bounds__(REDUCE2_THREADS)
-k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums, MsmPlan plan, int R,
+k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums, MsmPlan plan, int R, uint32_t w0,
           uint32_t* __restrict__ blkP, uint32_t* __restrict__ blkQ) {
   using G = typename Cv::G;
   using Acc = typename G::Acc;
   extern __shared__ uint32_t smem[];  // one accumulator per warp
-  const uint32_t s = blockIdx.x, w = blockIdx.y, splits = gridDim.x;
+  const uint32_t s = blockIdx.x, w = w0 + blockIdx.y, splits = gridDim.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ql = lane >> 2;
   const uint32_t lt = threadIdx.x >> 2;
   constexpr uint32_t NW = REDUCE2_THREADS / 32;
@@ -283,10 +287,10 @@ k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums,
 template <class Cv>
 __global__ void __launch_bounds__(32)
 k_reduce3(const uint32_t* __restrict__ blkP, const uint32_t* __restrict__ blkQ, MsmPlan plan, int splits, int R,
-          uint32_t* __restrict__ window_out) {
+          uint32_t w0, uint32_t* __restrict__ window_out) {
   using G = typename Cv::G;
   using Acc = typename G::Acc;
-  const uint32_t w = blockIdx.x, lane = threadIdx.x, ql = lane >> 2;
+  const uint32_t w = w0 + blockIdx.x, lane = threadIdx.x, ql = lane >> 2;
   const uint32_t R3 = (uint32_t)(splits + 7) / 8;  // splits is a power of two: R3 in {1, 2, 4}
   const uint32_t lo = ql * R3;
   Acc PT = G::identity(), QS = G::identity(), QL = G::identity();
@@ -326,19 +330,34 @@ k_reduce3(const uint32_t* __restrict__ blkP, const uint32_t* __restrict__ blkQ, 
   }
 }
 
-// Horner over the window sums (curve.ts:901-902) by ONE warp whose lanes hold replicated state and
-// split the independent multiplications of every point formula between them (ec.cuh Par4).
-template <class Cv, bool AFFINE_OUT>
+// One Horner step over the window sums of a window group (msm_body.cuh horner_step_body; curve.ts:901-902) by ONE warp
+// whose lanes hold replicated state and split the independent multiplications of every point formula between them
+// (ec.cuh Par4).  Runs on its own high-priority stream: the doubling chains of the upper windows overlap the
+// accumulation of the lower ones (engine.cuh submit_msm).
+template <class Cv>
 __global__ void __launch_bounds__(32)
-k_final(const uint32_t* __restrict__ window_out, MsmPlan plan, uint32_t* __restrict__ out,
-        uint32_t* __restrict__ out_inf) {
+k_horner_step(const uint32_t* __restrict__ window_out, MsmPlan plan, int w_lo, int w_hi, int first, int shift,
+              uint32_t* __restrict__ hacc) {
   using G = typename Cv::G;
-  typename G::Acc acc = G::identity();
-  for (int w = plan.W - 1; w >= 0; w--) {
-    if (w != plan.W - 1)
+  typename G::Acc acc = first ? G::identity() : load_acc<G>(hacc);
+  for (int w = w_hi - 1; w >= w_lo; w--) {
+    if (!(first && w == w_hi - 1))
       for (int j = 0; j < plan.c; j++) G::template par_dbl<true>(acc);
     G::template par_add<true>(acc, load_acc<G>(window_out + (size_t)w * G::ACC_WORDS));
   }
+  if (shift)
+    for (int j = 0; j < plan.c * w_lo; j++) G::template par_dbl<true>(acc);
+  if (threadIdx.x == 0) save_acc<G>(hacc, acc);
+}
+
+// Sum of the `count` group accumulators; AFFINE_OUT: canonical affine + infinity flag, else the raw accumulator
+// (multi-GPU partial, folded later by k_fold).
+template <class Cv, bool AFFINE_OUT>
+__global__ void __launch_bounds__(32)
+k_combine(const uint32_t* __restrict__ accs, int count, uint32_t* __restrict__ out, uint32_t* __restrict__ out_inf) {
+  using G = typename Cv::G;
+  typename G::Acc acc = G::identity();
+  for (int i = 0; i < count; i++) G::template par_add<true>(acc, load_acc<G>(accs + (size_t)i * G::ACC_WORDS));
   if (AFFINE_OUT) {
     uint32_t xy[G::IN_WORDS];
     uint32_t inf;
@@ -447,6 +466,14 @@ __global__ void __launch_bounds__(128)
 k_torsion(const uint32_t* __restrict__ pts, uint32_t n, uint8_t* __restrict__ out_ok, unsigned int* err) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) torsion_body<Cv>(i, pts, out_ok, err);
+}
+
+// curve-equation check per point (nmsm_points_on_curve)
+template <class Cv>
+__global__ void __launch_bounds__(128)
+k_on_curve(const uint32_t* __restrict__ pts, uint32_t n, uint8_t* __restrict__ out_ok) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out_ok[i] = (uint8_t)point_on_curve<Cv>(pts + (size_t)i * Cv::G::IN_WORDS);
 }
 
 }  // namespace nmsm

@@ -41,7 +41,16 @@ struct MsmPlan {
   int wb, r;        // digit w is  wb + (w < r)  bits wide and starts at bit  w * wb + min(w, r).  Ordinary plans:
                     // wb = c, r = 0.  Table plans spread the bits+1 scalar bits evenly over the D digits so that no
                     // digit is much narrower than the others (a narrow digit piles its terms onto few buckets)
+  uint32_t TPW;     // accumulate segments (= threads) reserved per bucket window, a multiple of SEG_ALIGN.  Segment
+                    // (w, t) owns the sorted entries [offsets[w*B] + t*L, + L) of window w, so no segment straddles
+                    // two windows and the windows can be accumulated and reduced as independent launches
 };
+static constexpr uint32_t SEG_ALIGN = 1024;  // two stitch-tile levels of fan 32 never straddle a window
+// entries a single window can receive at most: one per term and digit routed to it
+NMSM_HD uint32_t plan_tpw(uint64_t max_window_entries, int L) {
+  const uint64_t t = (max_window_entries + (uint32_t)L - 1) / (uint32_t)L;
+  return (uint32_t)((t + SEG_ALIGN - 1) / SEG_ALIGN * SEG_ALIGN);
+}
 NMSM_HD int digit_width(const MsmPlan& p, int w) { return p.wb + (w < p.r ? 1 : 0); }
 NMSM_HD int digit_offset(const MsmPlan& p, int w) { return w * p.wb + (w < p.r ? w : p.r); }
 
@@ -120,6 +129,7 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
   p.stride = 0;
   p.wb = p.c;
   p.r = 0;
+  p.TPW = plan_tpw((uint64_t)terms, p.L);
   return p;
 }
 
@@ -208,6 +218,7 @@ inline MsmPlan make_table_plan(uint64_t n_points, int c, int sm_count) {
 #endif
   p.K = p.B < Kc ? p.B : Kc;
   p.chunks = p.B / p.K;
+  p.TPW = plan_tpw((uint64_t)terms * p.D, p.L);
   return p;
 }
 
@@ -679,20 +690,23 @@ NMSM_HD void digits_body(uint32_t i, uint32_t n, const uint32_t* scalars, const 
   }
 }
 
-// Balanced bucket accumulation: thread t owns sorted[t*L, (t+1)*L).  Constant work per thread
-// whatever the bucket sizes; a bucket that is wholly inside the segment is written straight to
-// `buckets`, a bucket cut by the segment start goes to heads[t], one cut by the end to tails[t].
+// Balanced bucket accumulation: segment (w, t) owns L consecutive sorted entries of window w (see MsmPlan::TPW).
+// Constant work per thread whatever the bucket sizes; a bucket that is wholly inside the segment is written straight
+// to `buckets`, a bucket cut by the segment start goes to heads[sid], one cut by the end to tails[sid], with
+// sid = w * TPW + t the global segment id.
 template <class Cv>
-NMSM_HD void accumulate_body(uint32_t t, const uint32_t* aff, const uint32_t* sorted, const uint32_t* offsets,
+NMSM_HD void accumulate_body(uint32_t w, uint32_t t, const uint32_t* aff, const uint32_t* sorted, const uint32_t* offsets,
                              const MsmPlan& plan, uint32_t* buckets, uint32_t* heads, uint32_t* tails) {
   using G = typename Cv::G;
-  const uint32_t T = offsets[plan.G];
-  const uint64_t seg64 = (uint64_t)t * (uint32_t)plan.L;
+  const uint32_t g_lo = w * (uint32_t)plan.B, g_hi = g_lo + (uint32_t)plan.B;
+  const uint32_t base = offsets[g_lo], T = offsets[g_hi];  // this window's slice of the sorted array
+  const uint64_t seg64 = (uint64_t)base + (uint64_t)t * (uint32_t)plan.L;
   if (seg64 >= T) return;
   const uint32_t seg = (uint32_t)seg64;
   const uint32_t end = (T - seg > (uint32_t)plan.L) ? seg + plan.L : T;
-  // bucket containing `seg`: the last g with offsets[g] <= seg
-  uint32_t lo = 0, hi = plan.G;
+  const size_t sid = (size_t)w * plan.TPW + t;
+  // bucket containing `seg`: the last g of this window with offsets[g] <= seg
+  uint32_t lo = g_lo, hi = g_hi;
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
     if (offsets[mid] <= seg) lo = mid; else hi = mid;
@@ -704,7 +718,7 @@ NMSM_HD void accumulate_body(uint32_t t, const uint32_t* aff, const uint32_t* so
     if (pos == bend) {
       // bucket g is finished inside this segment
       if (bstart >= seg) save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, acc);
-      else save_acc<G>(heads + (size_t)t * G::ACC_WORDS, acc);
+      else save_acc<G>(heads + sid * G::ACC_WORDS, acc);
       acc = G::identity();
       do { g++; } while (offsets[g + 1] <= pos);
       bstart = offsets[g];
@@ -718,8 +732,8 @@ NMSM_HD void accumulate_body(uint32_t t, const uint32_t* aff, const uint32_t* so
   const bool head_open = bstart < seg;
   const bool tail_open = bend > end;
   if (!head_open && !tail_open) save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, acc);
-  else if (head_open) save_acc<G>(heads + (size_t)t * G::ACC_WORDS, acc);
-  else save_acc<G>(tails + (size_t)t * G::ACC_WORDS, acc);
+  else if (head_open) save_acc<G>(heads + sid * G::ACC_WORDS, acc);
+  else save_acc<G>(tails + sid * G::ACC_WORDS, acc);
 }
 
 // Adds the value of bucket g into `sum`.  A bucket wholly inside one accumulate segment was written
@@ -735,21 +749,24 @@ NMSM_HD void accumulate_body(uint32_t t, const uint32_t* aff, const uint32_t* so
 // each defined only when all of its segments lie inside ONE bucket's (ts, te] range.
 static constexpr uint32_t STITCH_FAN = 32;
 
-// bucket containing sorted entry e: the last g with offsets[g] <= e
-NMSM_HD uint32_t bucket_of_entry(const uint32_t* offsets, uint32_t G, uint32_t e) {
-  uint32_t lo = 0, hi = G;
+// bucket of window w containing sorted entry e: the last g in [w*B, (w+1)*B) with offsets[g] <= e
+NMSM_HD uint32_t bucket_of_entry(const uint32_t* offsets, const MsmPlan& plan, uint32_t w, uint32_t e) {
+  uint32_t lo = w * (uint32_t)plan.B, hi = lo + (uint32_t)plan.B;
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
     if (offsets[mid] <= e) lo = mid; else hi = mid;
   }
   return lo;
 }
-// Do segments [t0, t0 + span) all hold a head partial of one and the same bucket?
+// Do the segments with global ids [t0, t0 + span) all hold a head partial of one and the same bucket?  (t0 is a
+// multiple of span and span divides SEG_ALIGN, so the run lies inside one window.)
 NMSM_HD bool tile_is_uniform(const uint32_t* offsets, const MsmPlan& plan, uint64_t t0, uint32_t span) {
-  const uint32_t T = offsets[plan.G];
-  const uint64_t e0 = t0 * (uint32_t)plan.L, e_last = (t0 + span - 1) * (uint32_t)plan.L;
+  const uint32_t w = (uint32_t)(t0 / plan.TPW), tl = (uint32_t)(t0 % plan.TPW);
+  if (w >= (uint32_t)plan.W) return false;
+  const uint32_t base = offsets[w * (uint32_t)plan.B], T = offsets[(w + 1) * (uint32_t)plan.B];
+  const uint64_t e0 = (uint64_t)base + (uint64_t)tl * (uint32_t)plan.L, e_last = e0 + (uint64_t)(span - 1) * (uint32_t)plan.L;
   if (e_last >= T) return false;
-  const uint32_t g = bucket_of_entry(offsets, plan.G, (uint32_t)e0);
+  const uint32_t g = bucket_of_entry(offsets, plan, w, (uint32_t)e0);
   return offsets[g] < e0 && offsets[g + 1] > e_last;
 }
 // serial statement of one tile sum (the kernel uses a warp-shuffle tree over the 32 inputs)
@@ -784,6 +801,8 @@ NMSM_HD void reduce1_body(uint32_t id, const uint32_t* offsets, const uint32_t* 
   using Acc = typename G::Acc;
   const uint32_t w = id / plan.chunks, k = id % plan.chunks;
   const uint32_t g0 = w * plan.B + k * plan.K;
+  const uint32_t wbase = offsets[w * (uint32_t)plan.B];  // first sorted entry of this window
+  const uint32_t sid0 = w * plan.TPW;                    // its first segment id
   constexpr uint32_t F1 = STITCH_FAN, F2 = STITCH_FAN * STITCH_FAN;
   Acc acc[2] = {G::identity(), G::identity()};  // [0] = sum, [1] = wsum
   Acc part;
@@ -799,8 +818,8 @@ NMSM_HD void reduce1_body(uint32_t id, const uint32_t* offsets, const uint32_t* 
       te = 0;
       t = 1;
       if (b0 != b1) {
-        ts = b0 / plan.L;
-        te = (b1 - 1) / plan.L;
+        ts = sid0 + (b0 - wbase) / plan.L;
+        te = sid0 + (b1 - 1 - wbase) / plan.L;
         t = ts;
       }
       open = true;
@@ -873,6 +892,26 @@ NMSM_HD void final_body(const uint32_t* window_out, const MsmPlan& plan, uint32_
   } else {
     save_acc<G>(out, acc);
   }
+}
+
+// One step of the Horner evaluation over window groups (curve.ts:901-902 walks the windows MSB -> LSB the same way):
+//   hacc = first ? sum_{w in [w_lo, w_hi)} 2^(c (w - w_lo)) S_w : 2^(c (w_hi - w_lo)) * hacc + (that sum)
+// Groups arrive top windows first, so the doubling chains of the upper windows run while the lower windows are still
+// being accumulated and reduced (engine.cuh submit_msm); after the last group hacc is the MSM result.
+// shift != 0 (multi-GPU window owners): afterwards hacc *= 2^(c * w_lo), the group's absolute weight.
+template <class Cv>
+NMSM_HD void horner_step_body(const uint32_t* window_out, const MsmPlan& plan, int w_lo, int w_hi, bool first, bool shift,
+                              uint32_t* hacc) {
+  using G = typename Cv::G;
+  typename G::Acc acc = first ? G::identity() : load_acc<G>(hacc);
+  for (int w = w_hi - 1; w >= w_lo; w--) {
+    if (!(first && w == w_hi - 1))
+      for (int j = 0; j < plan.c; j++) nl_dbl<G>(acc);
+    nl_add<G>(acc, load_acc<G>(window_out + (size_t)w * G::ACC_WORDS));
+  }
+  if (shift)
+    for (int j = 0; j < plan.c * w_lo; j++) nl_dbl<G>(acc);
+  save_acc<G>(hacc, acc);
 }
 
 // Fold `count` raw accumulators (e.g. one per GPU) and emit canonical affine.

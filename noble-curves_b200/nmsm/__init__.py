@@ -75,16 +75,22 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
     class Point:
         """Affine host handle of a curve point; every group operation runs on the GPU."""
 
-        __slots__ = ("x", "y", "_inf")
+        __slots__ = ("x", "y", "_inf", "_valid")
         CURVE_ID = curve_id
         NAME = name
 
-        def __init__(self, x, y, _inf: bool = False):
+        def __init__(self, x, y, _inf: bool = False, _valid: bool = False):
+            """Like the reference's constructor (weierstrass.ts:695-704, edwards.ts:377-385) this does NOT validate
+            curve or subgroup membership.  `_valid` is the host mirror of the reference's validityCache
+            (weierstrass.ts:760-771): set by assertValidity / fromBytes / BASE / ZERO and inherited by the results
+            of group operations on valid inputs.  pippenger only takes the endomorphism schedule on BLS12-381 G1
+            when every input carries it (phi(P) = lambda*P needs the prime-order subgroup)."""
             if not Fp.isValid(x):
                 raise ValueError("bad point coordinate x")
-            if not Fp.isValid(y):
+            # weierstrass.ts:698-701: a finite point with y = 0 is 2-torsion and is rejected by the constructor
+            if not Fp.isValid(y) or (not edwards and not _inf and y == zero_coord):
                 raise ValueError("bad point coordinate y")
-            self.x, self.y, self._inf = x, y, bool(_inf)
+            self.x, self.y, self._inf, self._valid = x, y, bool(_inf), bool(_valid)
 
         # -- noble's projective accessors (weierstrass.ts:687-704 / edwards.ts:370-385), Z = 1 ----
         @property
@@ -127,10 +133,10 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
             if self._inf:
                 return self
             if edwards:  # -(x, y) = (-x, y)   edwards.ts:497-500
-                return Point((-self.x) % p, self.y)
+                return Point((-self.x) % p, self.y, False, self._valid)
             if parts == 1:  # weierstrass.ts:785-787
-                return Point(self.x, (-self.y) % p)
-            return Point(self.x, ((-self.y[0]) % p, (-self.y[1]) % p))
+                return Point(self.x, (-self.y) % p, False, self._valid)
+            return Point(self.x, ((-self.y[0]) % p, (-self.y[1]) % p), False, self._valid)
 
         def add(self, other):
             if not isinstance(other, Point):
@@ -142,6 +148,21 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
 
         def double(self):
             return _msm_points(Point, [self], [2])
+
+        def assertValidity(self) -> None:
+            """weierstrass.ts:752-771 / edwards.ts:461-480: on-curve + prime-order-subgroup check (both on the GPU:
+            the curve equation through nmsm_points_on_curve, n*P == O through nmsm_points_torsion_free)."""
+            if self._inf:
+                if name.startswith("bls12_381") or edwards:  # allowInfinityPoint (bls12-381.ts) / Edwards identity
+                    return
+                raise ValueError("bad point: ZERO")
+            if self._valid:
+                return
+            if points_on_curve(curve_id, self.to_packed(), 1)[0] != 1:
+                raise ValueError("bad point: equation left != right")
+            if h != 1 and torsion_free_packed(_ANY_POINT_ID.get(curve_id, curve_id), self.to_packed(), 1)[0] != 1:
+                raise ValueError("bad point: not in prime-order subgroup")
+            self._valid = True
 
         def multiply(self, scalar):
             """weierstrass.ts:900-907 / edwards.ts:555-564: 1 <= scalar < n."""
@@ -217,29 +238,37 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
             return b"\x04" + xb + self.y.to_bytes(fp_bytes, "big")
 
         @staticmethod
-        def fromBytes(b: bytes):
-            """Point.fromBytes (weierstrass.ts:720-724, edwards.ts:405-436): decode on the GPU (nmsm_points_decode),
-            then the reference's validity check (subgroup membership where the cofactor is not 1)."""
+        def fromBytes(b: bytes, zip215: bool = False):
+            """Point.fromBytes (weierstrass.ts:720-724; edwards.ts:405-436 `fromBytes(bytes, zip215 = false)`): decode on
+            the GPU (nmsm_points_decode_ex), then the reference's validity check (subgroup membership where the
+            cofactor is not 1).  Edwards: the default is the strict RFC 8032 decoding (y < p, no x = 0 with the sign
+            bit set) exactly like the reference; zip215=True accepts the non-canonical encodings ZIP-215 allows.
+            Like the reference, Edwards fromBytes does not run a subgroup check (edwards.ts:436)."""
             enc_len = {"secp256k1": 33, "bls12_381_G1": 48, "bls12_381_G2": 96, "ed25519": 32}.get(name)
             if enc_len is None or len(b) != enc_len:
                 raise ValueError("bad point: got length %d, expected compressed=%s" % (len(b), enc_len))
-            out, st = points_decode(curve_id, bytes(b), 1)
+            if not isinstance(zip215, bool):
+                raise TypeError('"zip215" expected boolean')
+            out, st = points_decode(curve_id, bytes(b), 1, zip215=bool(zip215) and edwards)
             if st[0] == 0:
                 raise ValueError("bad point: is not on curve" if not edwards else "bad point: invalid y coordinate")
             P_ = Point.from_packed(out, 1 if st[0] == 2 else 0)
             if name in ("bls12_381_G1", "bls12_381_G2") and not P_.isTorsionFree():
                 raise ValueError("bad point: not in prime-order subgroup")
+            if not edwards:
+                P_._valid = True  # decodePoint checks the equation, assertValidity the subgroup (weierstrass.ts:720-724)
             return P_
 
         def to_packed(self) -> bytes:
             return _coord_to_bytes(self.x, fp_bytes, parts) + _coord_to_bytes(self.y, fp_bytes, parts)
 
         @staticmethod
-        def from_packed(b: bytes, is_inf: int):
+        def from_packed(b: bytes, is_inf: int, valid: bool = False):
             cb = fp_bytes * parts
             if is_inf:
                 return Point.ZERO
-            return Point(_coord_from_bytes(b[:cb], fp_bytes, parts), _coord_from_bytes(b[cb:2 * cb], fp_bytes, parts))
+            return Point(_coord_from_bytes(b[:cb], fp_bytes, parts), _coord_from_bytes(b[cb:2 * cb], fp_bytes, parts),
+                         False, valid)
 
         def __repr__(self):
             return f"<{name}.Point {'ZERO' if self._inf else self.toAffine()}>"
@@ -252,13 +281,13 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
     Point.POINT_BYTES = 2 * fp_bytes * parts
     Point.IS_EDWARDS = edwards
     Point.cofactor = h
-    Point.BASE = Point(Gx, Gy)
-    Point.ZERO = Point(0, 1, True) if edwards else Point(zero_coord, zero_coord, True)
+    Point.BASE = Point(Gx, Gy, False, True)
+    Point.ZERO = Point(0, 1, True, True) if edwards else Point(zero_coord, zero_coord, True, True)
     return Point
 
 
 # Parameter blocks: SURVEY §8 a17 (src/secp256k1.ts:48-56, src/ed25519.ts:49-63, src/bn254.ts:80-90,207-223,
-# src/bls12-381.ts:134-148,321-345).  tests/test_consts.py cross-checks them against the oracle's copies.
+# src/bls12-381.ts:134-148,321-345).  tests/test_abi.py cross-checks them against the oracle's copies.
 _BLS_P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
 _BLS_N = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 _BN_P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
@@ -370,10 +399,27 @@ def _raise_mapped(e: NmsmError):
 _ANY_POINT_ID = {4: 6}
 
 
-def _msm_points(c, points, scalars, assume_torsion_free=True):
-    cid = c.CURVE_ID if assume_torsion_free else _ANY_POINT_ID.get(c.CURVE_ID, c.CURVE_ID)
+def _all_valid(points) -> bool:
+    return all(p._valid for p in points)
+
+
+def _curve_id_for(c, points, assume_torsion_free=None) -> int:
+    """Curve id of the C ABI for an MSM over `points`.  BLS12-381 G1 has a cofactor, and the endomorphism schedule of
+    id 4 is only the group law on the prime-order subgroup; the reference's pippenger is the plain group law on ANY
+    Point instance (its constructor / fromAffine do not validate, weierstrass.ts:695-718).  So id 4 is taken only
+    when every input is known valid (assertValidity / fromBytes / BASE / results of arithmetic on such points), or
+    when the caller vouches for it; otherwise the plain-window id 6."""
+    if c.CURVE_ID not in _ANY_POINT_ID:
+        return c.CURVE_ID
+    ok = _all_valid(points) if assume_torsion_free is None else bool(assume_torsion_free)
+    return c.CURVE_ID if ok else _ANY_POINT_ID[c.CURVE_ID]
+
+
+def _msm_points(c, points, scalars, assume_torsion_free=None):
+    cid = _curve_id_for(c, points, assume_torsion_free)
     out_xy, inf = msm_packed(cid, _pack_points(points), _pack_scalars(scalars), len(points))
-    return c.from_packed(out_xy, inf)
+    # the group generated by valid points consists of valid points
+    return c.from_packed(out_xy, inf, _all_valid(points))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -433,11 +479,13 @@ def msm_host_ptr(curve_id: int, h_pts: int, h_scalars: int, n: int):
     return out.raw, inf.value
 
 
-def pippenger(c, points, scalars, assume_torsion_free: bool = True):
+def pippenger(c, points, scalars, assume_torsion_free=None):
     """Drop-in for noble's pippenger (curve.ts:863-905): validates like the reference, runs on the GPU.
-    `assume_torsion_free` only matters for BLS12-381 G1: True (default) = the points pass the reference's
-    assertValidity / came from fromBytes, hash-to-curve or arithmetic on such points, and the GLV schedule is used;
-    False = any point of E(Fp) (the reference's pippenger is the plain group law), plain windows."""
+    With default arguments the result equals the reference's for EVERY Point instance: on BLS12-381 G1 the
+    endomorphism schedule (id 4) is used only when all inputs are known members of the prime-order subgroup (the
+    `_valid` bit: assertValidity / fromBytes / BASE / arithmetic on valid points), otherwise plain windows (id 6).
+    `assume_torsion_free=True` lets a caller who knows its fromAffine-built points are subgroup members (e.g. an
+    SRS) opt into the fast schedule; False forces the plain one."""
     _validate_msm_points(points, c)
     _validate_msm_scalars(scalars, c.Fn)
     if len(points) != len(scalars):
@@ -449,9 +497,10 @@ def pippenger(c, points, scalars, assume_torsion_free: bool = True):
 
 def normalizeZ(c, points):
     """curve.ts:311-326: batch projective -> affine.  Host handles are already canonical affine (every
-    GPU result is normalised on the device), so this validates and returns fresh equal points."""
+    GPU result is normalised on the device — k_mul_batch / k_table_mul share ONE inversion per warp, the device form
+    of FpInvertBatch modular.ts:734-760), so this validates and returns fresh equal points."""
     _validate_msm_points(points, c)
-    return [c.from_packed(p.to_packed(), 1 if p.is0() else 0) for p in points]
+    return [c.from_packed(p.to_packed(), 1 if p.is0() else 0, p._valid) for p in points]
 
 
 def aggregate_points(c, points):
@@ -464,9 +513,43 @@ def aggregate_points(c, points):
     return _msm_points(c, points, [1] * len(points))
 
 
-def mulAddUnsafe(c, points, scalars):
-    """curve.ts:820-836 — same value as the Strauss–Shamir walk, evaluated as a (small) MSM."""
-    return pippenger(c, points, scalars)
+def mulAddUnsafe(c, points, scalars, allowOversized: bool = False):
+    """curve.ts:820-836 — same value as the Strauss–Shamir walk, evaluated as a (small) MSM on the GPU.
+    allowOversized replaces the `s < Fn.ORDER` check by the `Fn.ORDER^4` cap (curve.ts:829-830).  Oversized scalars
+    must NOT be reduced mod ORDER (the reference uses them for torsion checks `ORDER*P == O` on points that may lie
+    outside the prime-order subgroup), so s is cut into digits of Fn.BITS-1 bits, s = sum_j d_j 2^(b j), and the term
+    becomes sum_j d_j * (2^(b j) * P) with every d_j and 2^b in the accelerated range — exact for any point."""
+    _validate_msm_points(points, c)
+    if not isinstance(allowOversized, bool):
+        raise TypeError('"allowOversized" expected boolean')
+    if not allowOversized:
+        _validate_msm_scalars(scalars, c.Fn)
+    else:
+        if not isinstance(scalars, (list, tuple)):
+            raise ValueError("array of scalars expected")
+        cap = c.Fn.ORDER ** 4
+        for i, s_ in enumerate(scalars):
+            if not (isinstance(s_, int) and not isinstance(s_, bool) and 0 <= s_ < cap):
+                raise ValueError("invalid scalar at index " + str(i))
+    if len(points) != len(scalars):
+        raise ValueError("arrays of points and scalars must have equal length")
+    if len(points) == 0:
+        return c.ZERO
+    if all(s_ < c.Fn.ORDER for s_ in scalars):
+        return _msm_points(c, points, scalars)
+    b = c.Fn.BITS - 1
+    step, mask = 1 << b, (1 << b) - 1
+    pts2, sc2 = [], []
+    for P_, s_ in zip(points, scalars):
+        Q = P_
+        while True:
+            pts2.append(Q)
+            sc2.append(s_ & mask)
+            s_ >>= b
+            if s_ == 0:
+                break
+            Q = multiply_many(c, [Q], [step], unsafe=True)[0]  # 2^b * Q, plain double-and-add on any point
+    return _msm_points(c, pts2, sc2)
 
 
 def torsion_free_packed(curve_id: int, pts: bytes, n: int) -> bytes:
@@ -566,7 +649,7 @@ def multiply_many(c, points, scalars, unsafe: bool = False) -> List:
     else:
         out_xy, infs = mul_batch_packed(c.CURVE_ID, _pack_points(points), _pack_scalars(scalars), n, unsafe)
     pb = c.POINT_BYTES
-    return [c.from_packed(out_xy[i * pb:(i + 1) * pb], infs[i]) for i in range(n)]
+    return [c.from_packed(out_xy[i * pb:(i + 1) * pb], infs[i], points[i]._valid) for i in range(n)]
 
 
 def mul_batch_packed(curve_id: int, pts: bytes, scalars: bytes, n: int, allow_zero: bool):
@@ -635,16 +718,18 @@ class PointSet:
             pass
 
 
-def interleavedMSMUnsafe(c, points, windowSize: int = 4, precompute: bool = True):
+def interleavedMSMUnsafe(c, points, windowSize: int = 4, precompute: bool = True, assume_torsion_free=None):
     """curve.ts:937-959: captures a FIXED point set once and returns `scalars -> sum s_i*P_i`.  Here the
     captured state is the device-resident prepared array plus (precompute=True, like the reference's per-point
     tables built at capture time) the fixed-base table of nmsm_points_precompute; `windowSize` is accepted for
-    signature compatibility (the GPU schedule picks its own window).  Fewer scalars than points are zero-padded."""
+    signature compatibility (the GPU schedule picks its own window).  Fewer scalars than points are zero-padded.
+    BLS12-381 G1: the endomorphism id is used only for sets of known-valid points (see pippenger)."""
     if not (isinstance(windowSize, int) and 2 <= windowSize <= c.Fn.BITS):
         raise ValueError("invalid window size, expected [2..%d], got W=%s" % (c.Fn.BITS, windowSize))
     _validate_msm_points(points, c)
     n = len(points)
-    ps = PointSet(c.CURVE_ID, _pack_points(points), n) if n else None
+    valid = _all_valid(points)
+    ps = PointSet(_curve_id_for(c, points, assume_torsion_free), _pack_points(points), n) if n else None
     if ps is not None and precompute:
         ps.precompute(0)
 
@@ -656,7 +741,7 @@ def interleavedMSMUnsafe(c, points, windowSize: int = 4, precompute: bool = True
             return c.ZERO
         padded = list(scalars) + [0] * (n - len(scalars))
         out, inf = ps.msm(_pack_scalars(padded), n)
-        return c.from_packed(out, inf)
+        return c.from_packed(out, inf, valid)
 
     return run
 
@@ -698,16 +783,39 @@ def ed25519_verify_batch(signatures, messages, public_keys, z: bytes | None = No
     return bool(ok.value), int(bad.value)
 
 
-def points_decode(curve_id: int, encodings: bytes, n: int):
+DECODE_ZIP215 = 1  # include/nmsm.h NMSM_DECODE_ZIP215
+
+
+def points_on_curve(curve_id: int, pts: bytes, n: int) -> bytes:
+    """Batch curve-equation check (nmsm_points_on_curve; weierstrass.ts:617-624 isValidXY, edwards.ts:461-480): one
+    byte per point, 1 = coordinates in range and on the curve (the affine identity encoding counts as on-curve)."""
+    _lib.ensure_init()
+    lib = _lib.load()
+    pb = lib.nmsm_point_bytes(curve_id)
+    if len(pts) != n * pb:
+        raise ValueError("expected %d bytes per point" % pb)
+    out = ctypes.create_string_buffer(max(1, n))
+    rc = lib.nmsm_points_on_curve(curve_id, ctypes.cast(ctypes.c_char_p(bytes(pts)), ctypes.c_void_p), n,
+                                  ctypes.cast(out, ctypes.c_void_p))
+    try:
+        _lib.check(rc)
+    except NmsmError as e:
+        _raise_mapped(e)
+    return out.raw[:n]
+
+
+def points_decode(curve_id: int, encodings: bytes, n: int, zip215: bool = False):
     """Batched `fromBytes` decode step on the GPU (secp256k1 SEC1-33, BLS12-381 G1 Zcash-48 / G2 Zcash-96, ed25519-32):
-    returns (packed points, status bytes: 0 invalid / 1 point / 2 infinity)."""
+    returns (packed points, status bytes: 0 invalid / 1 point / 2 infinity).  ed25519: strict RFC 8032 by default
+    (the reference's `fromBytes(bytes, zip215 = false)`), ZIP-215 acceptance with zip215=True."""
     _lib.ensure_init()
     lib = _lib.load()
     pb = lib.nmsm_point_bytes(curve_id)
     out = ctypes.create_string_buffer(max(1, n * pb))
     st = ctypes.create_string_buffer(max(1, n))
-    rc = lib.nmsm_points_decode(curve_id, ctypes.cast(ctypes.c_char_p(bytes(encodings)), ctypes.c_void_p), n,
-                                ctypes.cast(out, ctypes.c_void_p), ctypes.cast(st, ctypes.c_void_p))
+    rc = lib.nmsm_points_decode_ex(curve_id, ctypes.cast(ctypes.c_char_p(bytes(encodings)), ctypes.c_void_p), n,
+                                   DECODE_ZIP215 if zip215 else 0,
+                                   ctypes.cast(out, ctypes.c_void_p), ctypes.cast(st, ctypes.c_void_p))
     try:
         _lib.check(rc)
     except NmsmError as e:
@@ -730,6 +838,11 @@ def set_profiling(enabled: bool) -> None:
 
 def set_window_bits(c: int) -> int:
     return _lib.load().nmsm_set_window_bits(c)
+
+
+def set_window_groups(groups: int) -> int:
+    """Force the number of window groups the MSM pipeline overlaps (0 = automatic); results never depend on it."""
+    return _lib.load().nmsm_set_window_groups(groups)
 
 
 def bench_modmul(field: int, blocks_per_sm: int = 8, threads: int = 128, iters: int = 2000, ilp: int = 1) -> float:

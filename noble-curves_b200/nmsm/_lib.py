@@ -27,6 +27,7 @@ EXPORTS = [
     "nmsm_host_alloc", "nmsm_host_free", "nmsm_points_upload", "nmsm_points_free", "nmsm_msm_points", "nmsm_points_precompute", "nmsm_msm_points_submit", "nmsm_point_table_create", "nmsm_point_table_free",
     "nmsm_point_table_mul_batch", "nmsm_ntt", "nmsm_ntt_device", "nmsm_points_torsion_free",
     "nmsm_ed25519_verify_batch", "nmsm_msm_submit", "nmsm_msm_collect", "nmsm_points_decode", "nmsm_msm_submit_partial",
+    "nmsm_points_decode_ex", "nmsm_points_on_curve", "nmsm_set_window_groups",
 ]
 
 
@@ -40,6 +41,7 @@ class PlanInfo(ctypes.Structure):
         ("sorted_entries", ctypes.c_uint64),
         ("modmul_equiv", ctypes.c_uint64),
         ("launches", ctypes.c_int),
+        ("window_groups", ctypes.c_int),
     ]
 
 
@@ -94,6 +96,8 @@ def load() -> ctypes.CDLL:
         lib.nmsm_mul_batch.restype = ctypes.c_int
         lib.nmsm_set_window_bits.argtypes = [ctypes.c_int]
         lib.nmsm_set_window_bits.restype = ctypes.c_int
+        lib.nmsm_set_window_groups.argtypes = [ctypes.c_int]
+        lib.nmsm_set_window_groups.restype = ctypes.c_int
         lib.nmsm_set_profiling.argtypes = [ctypes.c_int]
         lib.nmsm_set_profiling.restype = ctypes.c_int
         lib.nmsm_last_timing.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(PlanInfo)]
@@ -135,6 +139,10 @@ def load() -> ctypes.CDLL:
         lib.nmsm_msm_collect.restype = ctypes.c_int
         lib.nmsm_points_decode.argtypes = [ctypes.c_int, u8p, ctypes.c_uint64, u8p, u8p]
         lib.nmsm_points_decode.restype = ctypes.c_int
+        lib.nmsm_points_decode_ex.argtypes = [ctypes.c_int, u8p, ctypes.c_uint64, ctypes.c_int, u8p, u8p]
+        lib.nmsm_points_decode_ex.restype = ctypes.c_int
+        lib.nmsm_points_on_curve.argtypes = [ctypes.c_int, u8p, ctypes.c_uint64, u8p]
+        lib.nmsm_points_on_curve.restype = ctypes.c_int
         lib.nmsm_msm_submit_partial.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_uint64, u8p, ctypes.c_int]
         lib.nmsm_msm_submit_partial.restype = ctypes.c_int
         _lib = lib

@@ -136,8 +136,9 @@ def u32(b: bytes):
     return np.frombuffer(b, dtype=np.uint32).copy()
 
 
-def emu_msm(name, pts_b: bytes, scalars_b: bytes, n: int, forced_c=0, forced_L=0, table_c=0):
-    """table_c != 0: the fixed-base table route (levels 2^(c*j)*P, one bucket window)."""
+def emu_msm(name, pts_b: bytes, scalars_b: bytes, n: int, forced_c=0, forced_L=0, table_c=0, groups=1):
+    """table_c != 0: the fixed-base table route (levels 2^(c*j)*P, one bucket window).  groups: window groups the
+    pipeline is split into (engine.cuh submit_msm), top windows first."""
     lib = hostemu()
     cb = FP_BYTES[name] * PARTS[name]
     pts = u32(pts_b) if n else np.zeros(4, np.uint32)
@@ -149,6 +150,8 @@ def emu_msm(name, pts_b: bytes, scalars_b: bytes, n: int, forced_c=0, forced_L=0
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     if table_c:
         rc = lib.emu_msm_table(CURVE_IDS[name], p(pts), p(sc), n, table_c, forced_L, p(out), p(inf), p(err), p(plan))
+    elif groups != 1:
+        rc = lib.emu_msm_groups(CURVE_IDS[name], p(pts), p(sc), n, forced_c, forced_L, groups, p(out), p(inf), p(err), p(plan))
     else:
         rc = lib.emu_msm(CURVE_IDS[name], p(pts), p(sc), n, forced_c, forced_L, p(out), p(inf), p(err), p(plan))
     assert rc == 0, rc

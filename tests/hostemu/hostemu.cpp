@@ -13,17 +13,22 @@
 #include "msm_body.cuh"
 #include "ed25519_verify.cuh"
 #include "codec.cuh"
+#include "validate.cuh"
 #include "inv_divsteps.cuh"
 
 using namespace nmsm;
 
 template <class Cv>
 static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, int forced_c, int forced_L,
-                     uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out, int table_c = 0) {
+                     uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out, int table_c = 0,
+                     int groups = 1) {
   using G = typename Cv::G;
   // table_c != 0: fixed-base table route (nmsm_points_precompute + nmsm_msm_points)
   MsmPlan plan = table_c ? make_table_plan<Cv>(n, canonical_table_bits<Cv>(table_c), 148) : make_plan<Cv>(n, forced_c, 148);
-  if (forced_L > 0) plan.L = forced_L;
+  if (forced_L > 0) {
+    plan.L = forced_L;
+    plan.TPW = plan_tpw((uint64_t)n * (Cv::GLV ? 2 : 1) * (table_c ? plan.D : 1), plan.L);
+  }
   plan_out[0] = plan.c; plan_out[1] = plan.W; plan_out[2] = plan.B; plan_out[3] = plan.L;
   const size_t terms = (size_t)n * (Cv::GLV ? 2 : 1);
   std::vector<uint32_t> aff(terms * G::AFF_WORDS * (table_c ? plan.D : 1));
@@ -43,26 +48,58 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
   const uint32_t T = run;
   std::vector<uint32_t> sorted(T ? T : 1);
   for (uint32_t i = 0; i < n; i++) digits_body<Cv, true>(i, n, scalars, plan, cursor.data(), sorted.data(), err);
-  const uint32_t nthreads = (T + plan.L - 1) / plan.L;
+  (void)T;
+  // segments: TPW per window (the launch geometry of k_accumulate: every (w, t) with t < TPW runs, most exit at once)
+  const size_t nseg = (size_t)plan.W * plan.TPW;
   std::vector<uint32_t> buckets((size_t)plan.G * G::ACC_WORDS, 0xdeadbeefu);
-  std::vector<uint32_t> heads((size_t)(nthreads + STITCH_FAN + 1) * G::ACC_WORDS, 0xdeadbeefu), tails((size_t)(nthreads + 1) * G::ACC_WORDS, 0xdeadbeefu);
-  // launch geometry rounds the thread count up to whole blocks, so run a few idle threads too
-  for (uint32_t t = 0; t < nthreads + 3; t++)
-    accumulate_body<Cv>(t, aff.data(), sorted.data(), offsets.data(), plan, buckets.data(), heads.data(), tails.data());
+  std::vector<uint32_t> heads(nseg * G::ACC_WORDS, 0xdeadbeefu), tails(nseg * G::ACC_WORDS, 0xdeadbeefu);
   const size_t nchunks = (size_t)plan.W * plan.chunks;
   std::vector<uint32_t> sums(nchunks * G::ACC_WORDS), wsums(nchunks * G::ACC_WORDS);
-  const uint32_t ntile1 = nthreads / STITCH_FAN + 1, ntile2 = ntile1 / STITCH_FAN + 1;
-  std::vector<uint32_t> tile1((size_t)ntile1 * G::ACC_WORDS, 0xdeadbeefu), tile2((size_t)ntile2 * G::ACC_WORDS, 0xdeadbeefu);
-  for (uint32_t j = 0; j < ntile1; j++) stitch_tile_serial<Cv>(j, STITCH_FAN, offsets.data(), plan, heads.data(), tile1.data());
-  for (uint32_t j = 0; j < ntile2; j++) stitch_tile_serial<Cv>(j, STITCH_FAN * STITCH_FAN, offsets.data(), plan, tile1.data(), tile2.data());
-  for (uint32_t id = 0; id < nchunks; id++)
-    reduce1_body<Cv, SerialOps<G>>(id, offsets.data(), buckets.data(), heads.data(), tails.data(), tile1.data(), tile2.data(), plan, sums.data(), wsums.data());
-  std::vector<uint32_t> window_out((size_t)plan.W * G::ACC_WORDS);
-  for (int w = 0; w < plan.W; w++)  // serial statement of what k_reduce2 computes cooperatively
-    reduce2_serial<Cv>(w, sums.data(), wsums.data(), plan, window_out.data());
-  final_body<Cv, true>(window_out.data(), plan, out_xy, out_inf);
+  const uint32_t ntile1 = (uint32_t)(nseg / STITCH_FAN), ntile2 = ntile1 / STITCH_FAN;
+  std::vector<uint32_t> tile1((size_t)ntile1 * G::ACC_WORDS, 0xdeadbeefu), tile2((size_t)(ntile2 + 1) * G::ACC_WORDS, 0xdeadbeefu);
+  std::vector<uint32_t> window_out((size_t)plan.W * G::ACC_WORDS), hacc(G::ACC_WORDS);
+  // window groups, top windows first, exactly as engine.cuh submit_msm issues them
+  if (groups < 1) groups = 1;
+  if (groups > plan.W) groups = plan.W;
+  const int per = (plan.W + groups - 1) / groups;
+  bool first = true;
+  for (int w_hi = plan.W; w_hi > 0; w_hi -= per) {
+    const int w_lo = w_hi > per ? w_hi - per : 0;
+    for (int w = w_lo; w < w_hi; w++)
+      for (uint32_t t = 0; t < plan.TPW; t++) {
+        // skip the (many) idle segments quickly: same early exit the body takes
+        if ((uint64_t)offsets[(size_t)w * plan.B] + (uint64_t)t * plan.L >= offsets[(size_t)(w + 1) * plan.B] && t > 2) break;
+        accumulate_body<Cv>(w, t, aff.data(), sorted.data(), offsets.data(), plan, buckets.data(), heads.data(), tails.data());
+      }
+    const uint32_t a0 = (uint32_t)((uint64_t)w_lo * plan.TPW / STITCH_FAN), a1 = (uint32_t)((uint64_t)w_hi * plan.TPW / STITCH_FAN);
+    for (uint32_t j = a0; j < a1; j++) stitch_tile_serial<Cv>(j, STITCH_FAN, offsets.data(), plan, heads.data(), tile1.data());
+    for (uint32_t j = a0 / STITCH_FAN; j < a1 / STITCH_FAN; j++)
+      stitch_tile_serial<Cv>(j, STITCH_FAN * STITCH_FAN, offsets.data(), plan, tile1.data(), tile2.data());
+    for (uint32_t id = (uint32_t)w_lo * plan.chunks; id < (uint32_t)w_hi * plan.chunks; id++)
+      reduce1_body<Cv, SerialOps<G>>(id, offsets.data(), buckets.data(), heads.data(), tails.data(), tile1.data(), tile2.data(), plan, sums.data(), wsums.data());
+    for (int w = w_lo; w < w_hi; w++)  // serial statement of what k_reduce2 computes cooperatively
+      reduce2_serial<Cv>(w, sums.data(), wsums.data(), plan, window_out.data());
+    horner_step_body<Cv>(window_out.data(), plan, w_lo, w_hi, first, false, hacc.data());
+    first = false;
+  }
+  fold_body<Cv>(hacc.data(), 1, out_xy, out_inf);  // k_combine<AFFINE_OUT>: fold of one accumulator + to-affine
   err_out[0] = err[0];
   err_out[1] = err[1];
+  // cross-check 1: the classic single Horner over all windows (final_body) must agree
+  {
+    std::vector<uint32_t> xy1(G::IN_WORDS);
+    uint32_t inf1 = 7;
+    final_body<Cv, true>(window_out.data(), plan, xy1.data(), &inf1);
+    if (inf1 != *out_inf || memcmp(xy1.data(), out_xy, G::IN_WORDS * 4) != 0) return -101;
+  }
+  // cross-check 2: shifted per-window results (what multi-GPU window owners compute) summed by the fold
+  {
+    std::vector<uint32_t> parts((size_t)plan.W * G::ACC_WORDS), xy1(G::IN_WORDS);
+    uint32_t inf1 = 7;
+    for (int w = 0; w < plan.W; w++) horner_step_body<Cv>(window_out.data(), plan, w, w + 1, true, true, parts.data() + (size_t)w * G::ACC_WORDS);
+    fold_body<Cv>(parts.data(), plan.W, xy1.data(), &inf1);
+    if (plan.stride == 0 && (inf1 != *out_inf || memcmp(xy1.data(), out_xy, G::IN_WORDS * 4) != 0)) return -102;
+  }
   // also exercise the partial + fold route (multi-GPU path): must give the same answer
   std::vector<uint32_t> raw(2 * G::ACC_WORDS);
   final_body<Cv, false>(window_out.data(), plan, raw.data(), nullptr);
@@ -273,6 +310,12 @@ int emu_msm(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n,
             uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out) {
   DISPATCH(curve, emu_msm_t<Cv>(pts, scalars, n, forced_c, forced_L, out_xy, out_inf, err_out, plan_out));
 }
+int emu_msm_groups(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, int forced_c, int forced_L, int groups,
+                   uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out) {
+  DISPATCH(curve, emu_msm_t<Cv>(pts, scalars, n, forced_c, forced_L, out_xy, out_inf, err_out, plan_out, 0, groups));
+}
+int emu_ed25519_decompress_strict(const uint8_t* enc, uint32_t* out_xy) { return ed_decompress(enc, out_xy, false) ? 1 : 0; }
+int emu_on_curve(int curve, const uint32_t* xy) { DISPATCH(curve, point_on_curve<Cv>(xy)); }
 int emu_mul_batch(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, int allow_zero,
                   uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out) {
   DISPATCH(curve, emu_mul_t<Cv>(pts, scalars, n, allow_zero, out_xy, out_inf, err_out));

@@ -104,3 +104,40 @@ def test_compute_entry_points_refuse_without_a_device():
         GF.FFT(GF.rootsOfUnity("bn254", 7)).direct([1, 2, 3, 4])
     with pytest.raises(Exception, match="CUDA|cuda|device"):
         nmsm.points_decode(0, bytes(33), 1)
+
+
+def test_round2_host_validation_without_device():
+    """Constructor / mulAddUnsafe / fromBytes argument checks that never reach the GPU (weierstrass.ts:698-701,
+    curve.ts:826-832, edwards.ts:405-410)."""
+    import nmsm
+
+    C = nmsm.CURVES["secp256k1"]
+    with pytest.raises(ValueError, match="bad point coordinate y"):
+        C(1, 0)
+    assert C.BASE._valid and C.ZERO._valid and not C(1, 1)._valid
+    assert C.BASE.negate()._valid
+    G2 = nmsm.CURVES["bls12_381_G2"]
+    with pytest.raises(ValueError, match="bad point coordinate y"):
+        G2((1, 2), (0, 0))
+    E = nmsm.CURVES["ed25519"]
+    assert E(0, 1, True).is0()  # Edwards: y = 0 is not special, identity is (0, 1)
+    E(5, 0)
+    n = C.Fn.ORDER
+    with pytest.raises(ValueError, match="invalid scalar at index 1"):
+        nmsm.mulAddUnsafe(C, [C.BASE, C.BASE], [1, n])
+    with pytest.raises(ValueError, match="invalid scalar at index 0"):
+        nmsm.mulAddUnsafe(C, [C.BASE], [n ** 4], True)
+    with pytest.raises(TypeError):
+        nmsm.mulAddUnsafe(C, [C.BASE], [1], 1)
+    with pytest.raises(ValueError, match="equal length"):
+        nmsm.mulAddUnsafe(C, [C.BASE], [1, 2], True)
+    assert nmsm.mulAddUnsafe(C, [], [], True).is0()
+    with pytest.raises(TypeError):
+        E.fromBytes(bytes(32), 1)
+    # curve id selection for BLS12-381 G1 (id 4 only for known-valid inputs)
+    B = nmsm.CURVES["bls12_381_G1"]
+    unv = B.fromAffine({"x": B.BASE.x, "y": B.BASE.y})
+    assert nmsm._curve_id_for(B, [B.BASE, B.BASE.negate()]) == 4
+    assert nmsm._curve_id_for(B, [B.BASE, unv]) == 6
+    assert nmsm._curve_id_for(B, [unv], True) == 4 and nmsm._curve_id_for(B, [B.BASE], False) == 6
+    assert nmsm._curve_id_for(C, [C(1, 1)]) == 0

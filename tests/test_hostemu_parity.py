@@ -545,3 +545,62 @@ def test_glv_lattice_split(cid, name, lam, bits):
         if name == "secp256k1":
             k1neg, k1, k2neg, k2 = R.split_endo_scalar(k, R.SECP256K1_ENDO["basises"], n)
             assert (m1, m2) == (k1, k2) and (not m1 or bool(out[10]) == k1neg) and (not m2 or bool(out[11]) == k2neg)
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "ed25519", "bn254_G2", "bls12_381_G1", "bls12_381_G1_any"])
+def test_window_groups_hostemu(name):
+    """Window-group pipelining (engine.cuh submit_msm) on the device bodies: per-window accumulate segments, per-group
+    stitch / reduce, Horner steps across groups — every group count gives the oracle's pippenger, also for inputs
+    whose buckets span many segments (small L) and for degenerate scalars."""
+    cname = "bls12_381_G1" if name.endswith("_any") else name
+    n = 160
+    P, pts, scalars, _ = H.soak_inputs(cname, n, seed_offset=11)
+    scalars[5] = P.Fn.ORDER - 1
+    exp = H.expected_tuple(cname, R.pippenger(P, pts, scalars))
+    pb, sb = H.pack_points(cname, pts), H.pack_scalars(scalars)
+    for groups, c, L in ((2, 0, 0), (3, 5, 1), (8, 4, 2), (64, 3, 3)):
+        got, err, plan = H.emu_msm(name, pb, sb, n, forced_c=c, forced_L=L, groups=groups)
+        assert err == (0xFFFFFFFF, 0xFFFFFFFF)
+        assert got == exp, (name, groups, c, L, plan)
+    same = [(P.Fn.ORDER - 1) // 5] * n
+    exp2 = H.expected_tuple(cname, R.pippenger(P, pts, same))
+    got, _, _ = H.emu_msm(name, pb, H.pack_scalars(same), n, forced_c=6, forced_L=1, groups=4)
+    assert got == exp2
+
+
+def test_strict_ed25519_decode_and_on_curve_hostemu():
+    """ed_decompress(zip215 = false) = the reference's fromBytes default (edwards.ts:405-436); point_on_curve =
+    isValidXY (weierstrass.ts:617-624)."""
+    import ctypes
+
+    import numpy as np
+
+    from conftest import load_golden
+
+    lib = H.hostemu()
+    g = load_golden("ed25519.json")
+    p = R.ED25519_CURVE["p"]
+    encs = [bytes.fromhex(v["pk"]) for v in g["vectors"][:8]] + [bytes.fromhex(v["vk_bytes"]) for v in g["zip215"][:60]]
+    encs += [p.to_bytes(32, "little"), (p + 1).to_bytes(32, "little"), ((1 << 255) | 1).to_bytes(32, "little"),
+             ((1 << 255) | (p - 1)).to_bytes(32, "little"), (1).to_bytes(32, "little")]
+    rejected = 0
+    for e in encs:
+        out = np.zeros(16, np.uint32)
+        ok = lib.emu_ed25519_decompress_strict(e, out.ctypes.data_as(ctypes.c_void_p))
+        try:
+            a = R.ed25519_point_from_bytes(e, False).toAffine()
+            assert ok == 1, e.hex()
+            assert int.from_bytes(out[:8].tobytes(), "little") == a["x"] and int.from_bytes(out[8:].tobytes(), "little") == a["y"]
+        except ValueError:
+            rejected += 1
+            assert ok == 0, e.hex()
+    assert rejected >= 4
+    for name in ("secp256k1", "ed25519", "bn254_G1", "bn254_G2", "bls12_381_G1", "bls12_381_G2"):
+        P, pts, _, _ = H.soak_inputs(name, 6)
+        for i, q in enumerate(pts):
+            b = bytearray(H.point_bytes(name, q))
+            arr = np.frombuffer(bytes(b), dtype=np.uint32).copy()
+            assert lib.emu_on_curve(H.CURVE_IDS[name], arr.ctypes.data_as(ctypes.c_void_p)) == 1, name
+            b[len(b) // 2] ^= 2
+            arr = np.frombuffer(bytes(b), dtype=np.uint32).copy()
+            assert lib.emu_on_curve(H.CURVE_IDS[name], arr.ctypes.data_as(ctypes.c_void_p)) == 0, name

@@ -1,0 +1,84 @@
+// Microbenchmark of the latency-bound primitives of the bucket-reduction / Horner tails (one warp, dependent chains).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 [-DNMSM_MUL_NOINLINE] -I noble-curves_b200/csrc
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdint.h>
+#include "ec.cuh"
+using namespace nmsm;
+using F = Fp<FpBls381>;
+using G = SwXyzz<F>;
+
+__device__ F mk(uint32_t s) {
+  F x;
+  for (int k = 0; k < 12; k++) x.v[k] = FpBls381::R2(k) ^ (s * 2654435761u >> (k & 7));
+  x.v[11] &= 0x0fffffffu;
+  return x;
+}
+__device__ G::Acc mkp(uint32_t s) {
+  // a real curve point is not needed for timing: formulas are branch-free except for the exceptional cases
+  return G::Acc{mk(s), mk(s + 1), mk(s + 2), mk(s + 3)};
+}
+
+template <int OP>
+__global__ void k(uint32_t* out, long long* cyc, int iters, uint32_t seed) {
+  F a = mk(seed + (OP >= 100 ? 0 : 0)), b = mk(seed + 7);
+  G::Acc p = mkp(seed + 11), q = mkp(seed + 23);
+  long long t0 = clock64();
+  for (int i = 0; i < iters; i++) {
+    if (OP == 0) a = a * b;
+    if (OP == 1) a = sqr(a);
+    if (OP == 2) a = a + b;
+    if (OP == 3) a = a - b;
+    if (OP == 4) G::template par_dbl<true>(p);
+    if (OP == 5) G::template par_add<true>(p, q);
+    if (OP == 6) G::dbl(p);
+    if (OP == 7) G::add(p, q);
+    if (OP == 8) G::template par_dbl<false>(p);
+    if (OP == 9) G::template par_add<false>(p, q);
+    if (OP == 10) { F r; mont_mul<FpBls381>(r.v, a.v, b.v); a = r; }
+  }
+  long long t1 = clock64();
+  uint32_t acc = 0;
+  for (int k2 = 0; k2 < 12; k2++) acc ^= a.v[k2] ^ p.X.v[k2] ^ p.Y.v[k2] ^ p.ZZ.v[k2] ^ p.ZZZ.v[k2];
+  if (threadIdx.x == 0 && blockIdx.x == 0) { cyc[0] = t1 - t0; }
+  if (acc == 0x1234567u) out[threadIdx.x] = acc;
+}
+
+template <int OP>
+void run(const char* name, int threads, int blocks, int iters) {
+  uint32_t* d; long long* c;
+  cudaMalloc(&d, 4096 * 4); cudaMalloc(&c, 64);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e9; long long cy = 0;
+  for (int r = 0; r < 3; r++) {
+    cudaEventRecord(e0);
+    k<OP><<<blocks, threads>>>(d, c, iters, 12345u + r);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+    cudaMemcpy(&cy, c, 8, cudaMemcpyDeviceToHost);
+  }
+  printf("{\"op\": \"%s\", \"threads\": %d, \"blocks\": %d, \"iters\": %d, \"us_per_op\": %.4f, \"cycles_per_op\": %.1f, \"err\": \"%s\"}\n",
+         name, threads, blocks, iters, best * 1e3 / iters, (double)cy / iters, cudaGetErrorString(cudaGetLastError()));
+  cudaFree(d); cudaFree(c);
+}
+
+int main() {
+  const int IT = 512;
+  for (int thr : {32, 64, 128}) {
+    for (int blocks : {1, 148 * 4}) {
+      run<0>("mul", thr, blocks, IT);
+      run<10>("mul_inline", thr, blocks, IT);
+      run<1>("sqr", thr, blocks, IT);
+      run<2>("fadd", thr, blocks, IT * 8);
+      run<3>("fsub", thr, blocks, IT * 8);
+      run<4>("par_dbl_fw", thr, blocks, IT);
+      run<5>("par_add_fw", thr, blocks, IT);
+      run<6>("dbl_serial", thr, blocks, IT);
+      run<7>("add_serial", thr, blocks, IT);
+      run<8>("par_dbl_quad", thr, blocks, IT);
+      run<9>("par_add_quad", thr, blocks, IT);
+    }
+  }
+  return 0;
+}
