@@ -101,6 +101,30 @@ int nmsm_msm_submit_partial(int curve, const void* d_pts, const void* d_scalars,
 int nmsm_msm_partial_device(int curve, const void* d_pts, const void* d_scalars, uint64_t n, void* d_out_acc);
 int nmsm_fold_partials_device(int curve, const void* d_accs, int count, uint8_t* out_xy, int* out_is_inf);
 
+/* Multi-GPU MSM with a bucket exchange (BASELINE north_star: "a single NCCL allreduce over NVLink of the
+ * per-window bucket accumulators").  One process per GPU.  The (point, scalar) array is split across the ranks; every
+ * rank accumulates its shard into the full W x B bucket array with the window size of the WHOLE MSM (n_total), window w
+ * belongs to rank w % world: after a window's accumulation its dense bucket array goes to the owner (ncclSend/ncclRecv
+ * on the library's own stream, overlapping the accumulation of the next windows), the owner folds the partial buckets
+ * (EC addition is not an ncclRedOp_t, hence exchange + fold kernel), reduces ONE window's buckets and applies the
+ * window weight 2^(c w); a final ncclAllGather of the weighted window sums (a few hundred bytes per rank) and one fold
+ * give every rank the same affine result.  No host synchronisation between the shard's kernels and the exchange.
+ *   nmsm_dist_unique_id : rank 0 creates the NCCL id (128 bytes) and hands it to the other ranks by any channel
+ *                         (torch.distributed broadcast in the Python mirror, nmsm/dist.py)
+ *   nmsm_dist_init      : every rank, after nmsm_init(local device)
+ *   nmsm_msm_sharded    : collective call — every rank passes ITS shard [shard_offset, shard_offset + n_local) of the
+ *                         n_total terms (n_local may be 0) and receives the full result.  Invalid points / scalars on
+ *                         any rank are reported on every rank with their GLOBAL index, points before scalars.
+ *   nmsm_msm_sharded_submit + nmsm_msm_collect: the asynchronous halves (ranks must submit in the same order). */
+#define NMSM_DIST_ID_BYTES 128
+int nmsm_dist_unique_id(uint8_t* out128);
+int nmsm_dist_init(int rank, int world, const uint8_t* id128);
+int nmsm_dist_info(int* out_rank, int* out_world, int* out_nccl_version);
+int nmsm_msm_sharded(int curve, const void* pts, const void* scalars, uint64_t n_local, uint64_t n_total,
+                     uint64_t shard_offset, int inputs_on_device, uint8_t* out_xy, int* out_is_inf);
+int nmsm_msm_sharded_submit(int curve, const void* pts, const void* scalars, uint64_t n_local, uint64_t n_total,
+                            uint64_t shard_offset, int inputs_on_device, int slot);
+
 /* out[i] = scalars[i] * pts[i] for i < n (host buffers).  allow_zero = 0: Point.multiply range
  * (1 <= k < n); allow_zero = 1: Point.multiplyUnsafe range (0 <= k < n).  out_is_inf: n bytes. */
 int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero,

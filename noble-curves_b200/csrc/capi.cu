@@ -2,6 +2,9 @@
 // The per-curve engines are instantiated in inst_*.cu (compiled in parallel); this file holds the
 // process-wide context, the Montgomery-multiplication microbenchmark and the extern "C" surface.
 // There is deliberately no CPU path: every entry point needs a CUDA device.
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the entry points are resolved with dlsym (no link-time dependency)
+
 #include "context.h"
 #include "curve_consts.cuh"
 #include "field.cuh"
@@ -10,6 +13,66 @@ namespace nmsm {
 
 Context g_ctx;
 std::mutex g_mu;
+DistState g_dist;
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, resolved at run time
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  int (*GetVersion)(int*) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.handle) return NMSM_OK;
+  void* h = nullptr;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(NMSM_ERR_CUDA, std::string("NCCL is not available: ") + (dlerror() ? dlerror() : "dlopen failed"));
+#define NCCL_SYM(field, sym)                                                            \
+  *(void**)(&g_nccl.field) = dlsym(h, sym);                                             \
+  if (!g_nccl.field) return fail(NMSM_ERR_CUDA, std::string("NCCL symbol missing: ") + sym)
+  NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+  NCCL_SYM(CommInitRank, "ncclCommInitRank");
+  NCCL_SYM(CommDestroy, "ncclCommDestroy");
+  NCCL_SYM(Send, "ncclSend");
+  NCCL_SYM(Recv, "ncclRecv");
+  NCCL_SYM(AllGather, "ncclAllGather");
+  NCCL_SYM(GroupStart, "ncclGroupStart");
+  NCCL_SYM(GroupEnd, "ncclGroupEnd");
+  NCCL_SYM(GetErrorString, "ncclGetErrorString");
+  NCCL_SYM(GetVersion, "ncclGetVersion");
+#undef NCCL_SYM
+  g_nccl.handle = h;
+  return NMSM_OK;
+}
+static int nccl_check(ncclResult_t r, const char* what) {
+  if (r == ncclSuccess) return NMSM_OK;
+  return fail(NMSM_ERR_CUDA, std::string("NCCL error in ") + what + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+}
+int nccl_send(const void* buf, size_t bytes, int peer, cudaStream_t st) {
+  return nccl_check(g_nccl.Send(buf, bytes, ncclUint8, peer, (ncclComm_t)g_dist.comm, st), "ncclSend");
+}
+int nccl_recv(void* buf, size_t bytes, int peer, cudaStream_t st) {
+  return nccl_check(g_nccl.Recv(buf, bytes, ncclUint8, peer, (ncclComm_t)g_dist.comm, st), "ncclRecv");
+}
+int nccl_group_start() { return nccl_check(g_nccl.GroupStart(), "ncclGroupStart"); }
+int nccl_group_end() { return nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd"); }
+int nccl_all_gather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t st) {
+  return nccl_check(g_nccl.AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t)g_dist.comm, st), "ncclAllGather");
+}
 
 static const EngineVTable* engine_for(int curve) {
   switch (curve) {
@@ -127,6 +190,11 @@ int nmsm_init(int device) {
     for (auto& ev : S.ev_tail) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CK(cudaEventCreate(&S.ev_t0));
     CK(cudaEventCreate(&S.ev_t1));
+    CK(cudaStreamCreateWithPriority(&S.comm_stream, cudaStreamNonBlocking, prio_hi));
+    CK(cudaEventCreateWithFlags(&S.ev_gather, cudaEventDisableTiming));
+    for (auto& ev : S.ev_fin) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : S.ev_xchg) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaMallocHost((void**)&S.h_gather, 64 * 1024));
   }
   C.device = device;
   C.ready = true;
@@ -137,14 +205,26 @@ void nmsm_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   Context& C = g_ctx;
   if (!C.ready) return;
+  if (g_dist.ready) {
+    for (Slot& S : C.slot) cudaStreamSynchronize(S.comm_stream);
+    g_nccl.CommDestroy((ncclComm_t)g_dist.comm);
+    g_dist = DistState();
+  }
   for (Slot& S : C.slot) {
     cudaStreamSynchronize(S.stream);
+    cudaStreamSynchronize(S.comm_stream);
     for (auto st : S.acc_stream) cudaStreamSynchronize(st);
     for (auto st : S.tail_stream) cudaStreamSynchronize(st);
     cudaStreamSynchronize(S.horner_stream);
     for (Buf* b : {&S.in_pts, &S.in_scalars, &S.aff, &S.counts, &S.offsets, &S.cursor, &S.sorted, &S.buckets, &S.heads,
-                   &S.tails, &S.chunk_out, &S.window_out, &S.tile_sums, &S.blk, &S.tiles, &S.result, &S.mul_out, &S.hacc})
+                   &S.tails, &S.chunk_out, &S.window_out, &S.tile_sums, &S.blk, &S.tiles, &S.result, &S.mul_out, &S.hacc,
+                   &S.recv, &S.gsend, &S.grecv})
       b->release();
+    for (auto& ev : S.ev_fin) cudaEventDestroy(ev);
+    for (auto& ev : S.ev_xchg) cudaEventDestroy(ev);
+    cudaEventDestroy(S.ev_gather);
+    cudaFreeHost(S.h_gather);
+    cudaStreamDestroy(S.comm_stream);
     for (auto& ev : S.ev) cudaEventDestroy(ev);
     for (auto& ev : S.ev_acc) cudaEventDestroy(ev);
     for (auto& ev : S.ev_tail) cudaEventDestroy(ev);
@@ -356,7 +436,7 @@ int nmsm_msm_submit(int curve, const void* pts, const void* scalars, uint64_t n,
   if (n && (!pts || !scalars)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   g_ctx.cur = slot;
-  return E->submit(pts, scalars, n, inputs_on_device, nullptr);
+  return E->submit(pts, scalars, n, inputs_on_device, nullptr, nullptr);
 }
 
 int nmsm_msm_submit_partial(int curve, const void* d_pts, const void* d_scalars, uint64_t n, void* d_out_acc, int slot) {
@@ -366,7 +446,67 @@ int nmsm_msm_submit_partial(int curve, const void* d_pts, const void* d_scalars,
   if (!d_out_acc || (n && (!d_pts || !d_scalars))) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   g_ctx.cur = slot;
-  return E->submit(d_pts, d_scalars, n, 1, d_out_acc);
+  return E->submit(d_pts, d_scalars, n, 1, d_out_acc, nullptr);
+}
+
+// ---- multi-GPU: one process per GPU, NCCL communicator owned by the library ------------------------------------
+int nmsm_dist_unique_id(uint8_t* out128) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out128) return fail(NMSM_ERR_ARG, "null pointer");
+  if (int r = nccl_load()) return r;
+  ncclUniqueId id;
+  if (int r = nccl_check(g_nccl.GetUniqueId(&id), "ncclGetUniqueId")) return r;
+  static_assert(sizeof(id) == NMSM_DIST_ID_BYTES, "NCCL unique id size");
+  memcpy(out128, &id, sizeof(id));
+  return NMSM_OK;
+}
+
+int nmsm_dist_init(int rank, int world, const uint8_t* id128) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (g_dist.ready) {
+    if (g_dist.rank == rank && g_dist.world == world) return NMSM_OK;
+    return fail(NMSM_ERR_ARG, "nmsm_dist_init: already initialised with another rank / world size");
+  }
+  if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(NMSM_ERR_ARG, "nmsm_dist_init: bad argument");
+  if (int r = nccl_load()) return r;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  if (int r = nccl_check(g_nccl.CommInitRank(&comm, world, id, rank), "ncclCommInitRank")) return r;
+  g_dist.comm = (NcclComm*)comm;
+  g_dist.rank = rank;
+  g_dist.world = world;
+  g_dist.ready = true;
+  return NMSM_OK;
+}
+
+int nmsm_dist_info(int* out_rank, int* out_world, int* out_nccl_version) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_dist.ready) return fail(NMSM_ERR_ARG, "nmsm_dist_init has not been called");
+  if (out_rank) *out_rank = g_dist.rank;
+  if (out_world) *out_world = g_dist.world;
+  if (out_nccl_version) g_nccl.GetVersion(out_nccl_version);
+  return NMSM_OK;
+}
+
+int nmsm_msm_sharded_submit(int curve, const void* pts, const void* scalars, uint64_t n_local, uint64_t n_total,
+                            uint64_t shard_offset, int inputs_on_device, int slot) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  if (slot < 0 || slot >= NUM_SLOTS) return fail(NMSM_ERR_ARG, "slot out of range (0..3)");
+  if (n_local && (!pts || !scalars)) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  g_ctx.cur = slot;
+  ShardArgs sa{n_total, shard_offset};
+  return E->submit(pts, scalars, n_local, inputs_on_device, nullptr, &sa);
+}
+
+int nmsm_msm_sharded(int curve, const void* pts, const void* scalars, uint64_t n_local, uint64_t n_total,
+                     uint64_t shard_offset, int inputs_on_device, uint8_t* out_xy, int* out_is_inf) {
+  if (!out_xy || !out_is_inf) return fail(NMSM_ERR_ARG, "null pointer");
+  if (int r = nmsm_msm_sharded_submit(curve, pts, scalars, n_local, n_total, shard_offset, inputs_on_device, 0)) return r;
+  return nmsm_msm_collect(0, out_xy, out_is_inf);
 }
 
 int nmsm_msm_collect(int slot, uint8_t* out_xy, int* out_is_inf) {

@@ -55,11 +55,14 @@ struct Pending {
   uint64_t n = 0;
   bool partial = false;   // raw accumulator requested instead of an affine result
   bool empty = false;     // n == 0
+  bool sharded = false;   // multi-GPU bucket-exchange MSM: errors of every rank arrive in h_gather
+  int gather_words = 0;   // words per rank in h_gather
   bool profiled = false;  // per-kernel events were recorded at submit (nmsm_set_profiling was on then)
   int groups = 1;         // window groups the pipeline was split into
   int launches = 0;       // kernels launched for this MSM
 };
-static constexpr int MAX_GROUPS = 8;       // window groups per MSM (engine.cuh submit_msm)
+static constexpr int MAX_GROUPS = 8;       // window groups per single-GPU MSM (engine.cuh submit_msm)
+static constexpr int MAX_WINDOWS = 34;     // sharded MSMs run one group per window: 16-bit windows over <= 256+1 bits, c >= 8
 static constexpr int ACC_STREAMS = 2, TAIL_STREAMS = 2;
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -67,7 +70,12 @@ struct Slot {
   // next group's blocks fill the SMs as the previous group's drain), every finished group's bucket reduction runs
   // on a high-priority tail stream, and the Horner steps on their own high-priority stream.
   cudaStream_t acc_stream[ACC_STREAMS] = {}, tail_stream[TAIL_STREAMS] = {}, horner_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_acc[MAX_GROUPS] = {}, ev_tail[MAX_GROUPS] = {}, ev_horner = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_acc[MAX_WINDOWS] = {}, ev_tail[MAX_WINDOWS] = {}, ev_horner = nullptr;
+  // multi-GPU bucket exchange (nmsm_msm_sharded_*): NCCL calls are issued on comm_stream
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_fin[MAX_WINDOWS] = {}, ev_xchg[MAX_WINDOWS] = {}, ev_gather = nullptr;
+  uint32_t* h_gather = nullptr;  // pinned copy of the gathered window results + error words
+  Buf recv, gsend, grecv;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // whole-MSM device time, always recorded
   Buf in_pts, in_scalars, aff, counts, offsets, cursor, sorted, buckets, heads, tails, chunk_out, window_out, tile_sums,
       blk, tiles, result, mul_out, hacc;
@@ -97,6 +105,25 @@ struct Context {
   nmsm_plan_info last_info = {};
   std::string last_error;
   long long last_error_index = -1;
+};
+
+// NCCL entry points resolved at run time (dlopen "libnccl.so.2": inside a torch process that is the copy torch already
+// loaded), so libnmsm.so has no link-time dependency on NCCL and loads on machines without it.
+struct NcclComm;
+struct DistState {
+  bool ready = false;
+  int rank = 0, world = 1;
+  NcclComm* comm = nullptr;
+};
+int nccl_send(const void* buf, size_t bytes, int peer, cudaStream_t st);
+int nccl_recv(void* buf, size_t bytes, int peer, cudaStream_t st);
+int nccl_group_start();
+int nccl_group_end();
+int nccl_all_gather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t st);
+extern DistState g_dist;
+
+struct ShardArgs {  // sharded MSM: this GPU holds n_local of the n_total terms, starting at global index `offset`
+  uint64_t n_total, offset;
 };
 
 extern Context g_ctx;
@@ -143,7 +170,7 @@ struct EngineVTable {
   int (*table_mul_batch)(const uint32_t* tbl, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
                          uint8_t* out_is_inf);
   // asynchronous halves on the slot g_ctx.cur: enqueue (optionally H2D from host pointers) / wait + read back
-  int (*submit)(const void* pts, const void* scalars, uint64_t n, int inputs_on_device, void* d_out_acc);
+  int (*submit)(const void* pts, const void* scalars, uint64_t n, int inputs_on_device, void* d_out_acc, const ShardArgs* shard);
   int (*collect)(uint8_t* out_xy, int* out_is_inf);
   int (*submit_prepared)(const uint32_t* d_prepared, uint64_t n_points, int table_c, const void* scalars, uint64_t n,
                          int scalars_on_device);

@@ -43,6 +43,8 @@ struct Par4 {
     for (int k = 0; k < WORDS; k++) d[k] = __shfl_sync(qmask, s[k], qbase + src);
     return r;
   }
+  // lane-dependent operand choice by masks: a ternary chain here compiles to divergent branches (one BSSY/BSYNC region
+  // per word — measured: 2x the cost of the multiplication it feeds), and the quad's lanes must not diverge
   __device__ static __forceinline__ F pick(int l, const F& a0, const F& a1, const F& a2, const F& a3) {
     F r;
     const uint32_t* p0 = reinterpret_cast<const uint32_t*>(&a0);
@@ -50,8 +52,10 @@ struct Par4 {
     const uint32_t* p2 = reinterpret_cast<const uint32_t*>(&a2);
     const uint32_t* p3 = reinterpret_cast<const uint32_t*>(&a3);
     uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+    const uint32_t m0 = 0u - (uint32_t)(l == 0), m1 = 0u - (uint32_t)(l == 1), m2 = 0u - (uint32_t)(l == 2),
+                   m3 = 0u - (uint32_t)(l == 3);
 #pragma unroll
-    for (int k = 0; k < WORDS; k++) d[k] = l == 0 ? p0[k] : (l == 1 ? p1[k] : (l == 2 ? p2[k] : p3[k]));
+    for (int k = 0; k < WORDS; k++) d[k] = (p0[k] & m0) | (p1[k] & m1) | (p2[k] & m2) | (p3[k] & m3);
     return r;
   }
   // r_k = a_k * b_k for k < 4, one product per lane, every lane receives all four

@@ -55,11 +55,26 @@ static int choose_groups(const MsmPlan& plan, uint64_t max_entries) {
 // doubling chain of every finished group run underneath.  Only the last group's reduction, one Horner step of
 // c * (windows per group) doublings and the inversion remain on the critical path.  With one group (small inputs,
 // profiling) everything is issued on the main stream.
+//
+// Sharded (multi-GPU) MSM, `shard` != nullptr (BASELINE north_star "allreduce of the per-window bucket
+// accumulators"): every GPU accumulates its n_local terms into the full W x B bucket array with the GLOBAL window
+// size; window w is owned by rank w % world.  One group per window, top window first; after a window's accumulate:
+//       tail stream   k_stitch_tiles, k_bucket_finalize (dense bucket array of the window)     -> ev_fin[w]
+//       comm stream   ncclSend of the window's buckets to its owner / ncclRecv from every peer  -> ev_xchg[w]
+//       owner only    k_bucket_fold (EC addition is not an NCCL reduction operator: exchange + fold), k_reduce1_dense,
+//                     k_reduce2, k_reduce3, k_horner_step with the window's weight 2^(c w)      -> ev_tail[w]
+//   comm stream: ncclAllGather of every rank's weighted window sums (+ its validation words); k_combine folds them.
+// The exchange of window w overlaps the accumulation of windows w-1..0; every rank ends with the same affine result.
 static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
-                      const uint32_t* d_prepared, int table_c = 0, uint64_t table_points = 0) {
+                      const uint32_t* d_prepared, int table_c = 0, uint64_t table_points = 0,
+                      const ShardArgs* shard = nullptr) {
   Slot& C = g_ctx.slot[g_ctx.cur];
   if (C.pend.active) return fail(NMSM_ERR_ARG, "slot busy: collect the previous MSM first");
   if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
+  if (shard && (!g_dist.ready || d_out_acc || d_prepared))
+    return fail(NMSM_ERR_ARG, shard && !g_dist.ready ? "nmsm_dist_init has not been called" : "sharded MSM: unsupported combination");
+  const uint64_t n_plan = shard ? shard->n_total : n;
+  if (shard && (n_plan >= (1ull << 31) || shard->offset + n > n_plan)) return fail(NMSM_ERR_ARG, "sharded MSM: bad shard bounds");
   const int RES_WORDS = G::IN_WORDS + 4;  // xy | inf | err_pt | err_sc | pad
   CK(C.result.ensure(RES_WORDS * 4));
   uint32_t* d_res = (uint32_t*)C.result.p;
@@ -69,7 +84,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   C.pend.curve = Cv::ID;
   C.pend.n = n;
   C.pend.partial = d_out_acc != nullptr;
-  if (n == 0) {  // curve.ts:878 — empty input returns the identity
+  if (n_plan == 0) {  // curve.ts:878 — empty input returns the identity (sharded: empty on every rank, no exchange)
     if (d_out_acc) {
       typename G::Acc id = G::identity();
       CK(cudaMemcpyAsync(d_out_acc, &id, sizeof(id), cudaMemcpyHostToDevice, C.stream));
@@ -81,8 +96,9 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   }
 
   MsmPlan plan = table_c ? make_table_plan<Cv>(table_points, table_c, g_ctx.sm_count)
-                         : make_plan<Cv>(n, g_ctx.forced_c, g_ctx.sm_count);
-  const uint64_t max_entries = n * (uint64_t)plan.D * (Cv::GLV ? 2 : 1);
+                         : make_plan<Cv>(n_plan, g_ctx.forced_c, g_ctx.sm_count, shard ? (n ? n : 1) : 0);
+  if (plan.W > MAX_WINDOWS) return fail(NMSM_ERR_ARG, "window count exceeds MAX_WINDOWS");
+  const uint64_t max_entries = (n ? n : 1) * (uint64_t)plan.D * (Cv::GLV ? 2 : 1);
   if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
   // bucket reduction levels: every k_reduce2 pass shrinks the per-window chunk count by REDUCE2_CHUNKS_PER_BLOCK
   // until <= REDUCE2_MAX_SPLITS block results per window remain for k_reduce3 (one pass for the ordinary plans)
@@ -95,7 +111,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   }
   const uint64_t nseg = (uint64_t)plan.W * plan.TPW;  // accumulate segments, TPW per window
 
-  if (!d_prepared) CK(C.aff.ensure(n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
+  if (!d_prepared) CK(C.aff.ensure((n ? n : 1) * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
   CK(C.counts.ensure((size_t)(plan.G + 1) * 4));
   CK(C.offsets.ensure((size_t)(plan.G + 1) * 4));
   CK(C.cursor.ensure((size_t)(plan.G + 1) * 4));
@@ -128,8 +144,22 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   uint32_t* hacc = (uint32_t*)C.hacc.p;
   cudaStream_t st = C.stream;
   const uint32_t n32 = (uint32_t)n;
-  const int NG = choose_groups(plan, max_entries);
-  const bool prof = g_ctx.profiling;
+  const int NG = shard ? plan.W : choose_groups(plan, max_entries);
+  const bool prof = g_ctx.profiling && !shard;
+  // sharded: which windows this rank owns, where their peers' buckets land, and the gather layout
+  const int world = shard ? g_dist.world : 1, rank = shard ? g_dist.rank : 0;
+  const int slots = (plan.W + world - 1) / world;                    // owned windows per rank (upper bound)
+  const size_t WB = (size_t)plan.B * G::ACC_WORDS;                   // words of one window's dense bucket array
+  const int gather_words = slots * G::ACC_WORDS + 4;                 // per rank: weighted window sums | err_pt err_sc off_lo off_hi
+  uint32_t *recv = nullptr, *gsend = nullptr, *grecv = nullptr;
+  if (shard) {
+    CK(C.recv.ensure((size_t)slots * (world - 1) * WB * 4 + 16));
+    CK(C.gsend.ensure((size_t)gather_words * 4));
+    CK(C.grecv.ensure((size_t)gather_words * 4 * world));
+    recv = (uint32_t*)C.recv.p;
+    gsend = (uint32_t*)C.gsend.p;
+    grecv = (uint32_t*)C.grecv.p;
+  }
   int launches = 0;
 #define PEV(slot)                                   \
   do {                                              \
@@ -140,9 +170,9 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   PEV(0);
   CK(cudaMemsetAsync(d_err, 0xff, 8, st));
   CK(cudaMemsetAsync(counts, 0, (size_t)(plan.G + 1) * 4, st));
-  if (!d_prepared) { k_prepare<Cv><<<cdiv(n, 128), 128, 0, st>>>(d_pts, n32, aff, d_err); launches++; }
+  if (!d_prepared && n) { k_prepare<Cv><<<cdiv(n, 128), 128, 0, st>>>(d_pts, n32, aff, d_err); launches++; }
   PEV(1);
-  k_digits<Cv, false><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, counts, nullptr, d_err);
+  if (n) k_digits<Cv, false><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, counts, nullptr, d_err);
   PEV(2);
   {
     const unsigned int tiles = cdiv(plan.G, SCAN_TILE);
@@ -150,9 +180,10 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
     k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)plan.G, tile_sums, offsets, cursor);
   }
   PEV(3);
-  k_digits<Cv, true><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, cursor, sorted, d_err);
+  if (n) k_digits<Cv, true><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, cursor, sorted, d_err);
   launches += 4;
   PEV(4);
+  if (shard) { k_set_identity<Cv><<<1, 32, 0, st>>>(gsend, slots); launches++; }
   if (NG > 1) CK(cudaEventRecord(C.ev_fork, st));
 
   const int per = (plan.W + NG - 1) / NG;  // windows per group
@@ -179,13 +210,45 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
                                                                               tile1, tile2);
     }
     PEV(6);
-    {
+    bool owner = true;
+    if (shard) {  // one window per group: finalize its dense buckets, exchange with the owner, fold
+      const int w = w_lo, own_rank = w % world, slot = w / world;
+      owner = own_rank == rank;
+      uint32_t* wb = buckets + (size_t)w * WB;
+      uint32_t* wrecv = recv + (size_t)slot * (world - 1) * WB;
+      k_bucket_finalize<Cv><<<cdiv(plan.B, 128), 128, 0, stl>>>(offsets, buckets, heads, tails, tile1, tile2, plan,
+                                                               (uint32_t)w * plan.B, (uint32_t)(w + 1) * plan.B);
+      launches++;
+      if (world > 1) {
+        CK(cudaEventRecord(C.ev_fin[g], stl));
+        CK(cudaStreamWaitEvent(C.comm_stream, C.ev_fin[g], 0));
+        if (nccl_group_start()) return NMSM_ERR_CUDA;
+        if (owner) {
+          for (int r = 0, k = 0; r < world; r++)
+            if (r != rank && nccl_recv(wrecv + (size_t)(k++) * WB, WB * 4, r, C.comm_stream)) return NMSM_ERR_CUDA;
+        } else if (nccl_send(wb, WB * 4, own_rank, C.comm_stream)) {
+          return NMSM_ERR_CUDA;
+        }
+        if (nccl_group_end()) return NMSM_ERR_CUDA;
+        if (owner) {
+          CK(cudaEventRecord(C.ev_xchg[g], C.comm_stream));
+          CK(cudaStreamWaitEvent(stl, C.ev_xchg[g], 0));
+          k_bucket_fold<Cv><<<cdiv(plan.B, 128), 128, 0, stl>>>(wb, wrecv, world - 1, WB, (uint32_t)plan.B);
+          launches++;
+        }
+      }
+    }
+    if (owner) {
       const uint32_t id0 = (uint32_t)w_lo * plan.chunks, id1 = (uint32_t)w_hi * plan.chunks;
-      k_reduce1<Cv><<<cdiv(id1 - id0, REDUCE1_THREADS), REDUCE1_THREADS, 0, stl>>>(offsets, buckets, heads, tails, tile1, tile2,
-                                                                                  plan, id0, id1, sums, wsums);
+      if (shard)
+        k_reduce1_dense<Cv><<<cdiv(id1 - id0, REDUCE1_THREADS), REDUCE1_THREADS, 0, stl>>>(buckets, plan, id0, id1, sums, wsums);
+      else
+        k_reduce1<Cv><<<cdiv(id1 - id0, REDUCE1_THREADS), REDUCE1_THREADS, 0, stl>>>(offsets, buckets, heads, tails, tile1,
+                                                                                    tile2, plan, id0, id1, sums, wsums);
     }
     PEV(7);
     launches += 4;
+    if (owner)
     {
       // msm.cuh "Bucket reduction": P/Q of one level are the T/S of the next (chunks := splits, K := K * Mb)
       const size_t smem2 = (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4;
@@ -211,6 +274,14 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
       }
     }
     PEV(8);
+    if (shard) {  // owner: weighted window sum 2^(c w) S_w straight into its gather slot
+      if (owner) {
+        k_horner_step<Cv><<<1, 32, 0, stl>>>(window_out, plan, w_lo, w_hi, 1, 1, gsend + (size_t)(w_lo / world) * G::ACC_WORDS);
+        launches++;
+      }
+      if (NG > 1) CK(cudaEventRecord(C.ev_tail[g], stl));
+      continue;
+    }
     if (NG > 1) {
       CK(cudaEventRecord(C.ev_tail[g], stl));
       CK(cudaStreamWaitEvent(sh, C.ev_tail[g], 0));
@@ -218,15 +289,36 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
     k_horner_step<Cv><<<1, 32, 0, sh>>>(window_out, plan, w_lo, w_hi, g == 0 ? 1 : 0, 0, hacc);
     launches++;
   }
-  if (NG > 1) {
-    CK(cudaEventRecord(C.ev_horner, C.horner_stream));
-    CK(cudaStreamWaitEvent(st, C.ev_horner, 0));
+  if (shard) {
+    cudaStream_t sc = world > 1 ? C.comm_stream : st;
+    if (NG > 1)
+      for (int k = 0; k < g; k++) CK(cudaStreamWaitEvent(sc, C.ev_tail[k], 0));
+    k_pack_shard_tail<<<1, 32, 0, sc>>>(gsend + (size_t)slots * G::ACC_WORDS, d_err, shard->offset);
+    if (world > 1) {
+      if (nccl_all_gather(gsend, grecv, (size_t)gather_words * 4, sc)) return NMSM_ERR_CUDA;
+      CK(cudaEventRecord(C.ev_gather, sc));
+      CK(cudaStreamWaitEvent(st, C.ev_gather, 0));
+    } else {
+      CK(cudaMemcpyAsync(grecv, gsend, (size_t)gather_words * 4, cudaMemcpyDeviceToDevice, sc));
+      if (sc != st) {
+        CK(cudaEventRecord(C.ev_gather, sc));
+        CK(cudaStreamWaitEvent(st, C.ev_gather, 0));
+      }
+    }
+    k_combine<Cv, true><<<1, 32, 0, st>>>(grecv, world * slots, slots, gather_words, d_res, d_res + G::IN_WORDS);
+    launches += 2;
+    CK(cudaMemcpyAsync(C.h_gather, grecv, (size_t)gather_words * 4 * world, cudaMemcpyDeviceToHost, st));
+  } else {
+    if (NG > 1) {
+      CK(cudaEventRecord(C.ev_horner, C.horner_stream));
+      CK(cudaStreamWaitEvent(st, C.ev_horner, 0));
+    }
+    if (d_out_acc)
+      k_combine<Cv, false><<<1, 32, 0, st>>>(hacc, 1, 1, 0, d_out_acc, nullptr);
+    else
+      k_combine<Cv, true><<<1, 32, 0, st>>>(hacc, 1, 1, 0, d_res, d_res + G::IN_WORDS);
+    launches++;
   }
-  if (d_out_acc)
-    k_combine<Cv, false><<<1, 32, 0, st>>>(hacc, 1, d_out_acc, nullptr);
-  else
-    k_combine<Cv, true><<<1, 32, 0, st>>>(hacc, 1, d_res, d_res + G::IN_WORDS);
-  launches++;
   PEV(9);
 #undef PEV
   CK(cudaEventRecord(C.ev_t1, st));
@@ -237,6 +329,8 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   CK(cudaEventRecord(C.done, st));
   C.pend.plan = MsmPlanLite{plan.c, plan.W, plan.B, plan.G, plan.L, plan.K, plan.chunks, plan.D, plan.TPW};
   C.pend.profiled = prof;
+  C.pend.sharded = shard != nullptr;
+  C.pend.gather_words = gather_words;
   C.pend.groups = g;
   C.pend.launches = launches;
   C.pend.active = true;
@@ -263,10 +357,22 @@ static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
   plan.L = C.pend.plan.L; plan.K = C.pend.plan.K; plan.chunks = C.pend.plan.chunks; plan.D = C.pend.plan.D;
   const bool partial = C.pend.partial;
 
-  const uint32_t err_pt = C.h_result[G::IN_WORDS + 1], err_sc = C.h_result[G::IN_WORDS + 2];
+  uint64_t err_pt = C.h_result[G::IN_WORDS + 1], err_sc = C.h_result[G::IN_WORDS + 2];
+  if (err_pt == 0xffffffffu) err_pt = ~0ull;
+  if (err_sc == 0xffffffffu) err_sc = ~0ull;
+  if (C.pend.sharded) {  // every rank's validation words came with the gather: report the smallest GLOBAL index
+    err_pt = err_sc = ~0ull;
+    const int slots_words = C.pend.gather_words - 4;
+    for (int r = 0; r < g_dist.world; r++) {
+      const uint32_t* t = C.h_gather + (size_t)r * C.pend.gather_words + slots_words;
+      const uint64_t off = (uint64_t)t[2] | ((uint64_t)t[3] << 32);
+      if (t[0] != 0xffffffffu && off + t[0] < err_pt) err_pt = off + t[0];
+      if (t[1] != 0xffffffffu && off + t[1] < err_sc) err_sc = off + t[1];
+    }
+  }
   // the reference validates all points before any scalar (curve.ts:871-872)
-  if (err_pt != 0xffffffffu) return fail(NMSM_ERR_POINT, "invalid point at index " + std::to_string(err_pt), err_pt);
-  if (err_sc != 0xffffffffu) return fail(NMSM_ERR_SCALAR, "invalid scalar at index " + std::to_string(err_sc), err_sc);
+  if (err_pt != ~0ull) return fail(NMSM_ERR_POINT, "invalid point at index " + std::to_string(err_pt), (long long)err_pt);
+  if (err_sc != ~0ull) return fail(NMSM_ERR_SCALAR, "invalid scalar at index " + std::to_string(err_sc), (long long)err_sc);
 
   const uint64_t entries = C.h_result[RES_WORDS];
   C.last_info.c = plan.c;
@@ -302,17 +408,18 @@ static void note_kernel_time(Slot& C) {
 }
 
 // C-ABI asynchronous halves (nmsm_msm_submit / nmsm_msm_collect)
-static int submit_any(const void* pts, const void* scalars, uint64_t n, int inputs_on_device, void* d_out_acc) {
+static int submit_any(const void* pts, const void* scalars, uint64_t n, int inputs_on_device, void* d_out_acc,
+                      const ShardArgs* shard) {
   Slot& C = g_ctx.slot[g_ctx.cur];
   if (C.pend.active) return fail(NMSM_ERR_ARG, "slot busy: collect the previous MSM first");
   if (d_out_acc && !inputs_on_device) return fail(NMSM_ERR_ARG, "raw-accumulator output needs device-resident inputs");
   if (inputs_on_device || n == 0)
-    return submit_msm((const uint32_t*)pts, (const uint32_t*)scalars, n, (uint32_t*)d_out_acc, nullptr);
+    return submit_msm((const uint32_t*)pts, (const uint32_t*)scalars, n, (uint32_t*)d_out_acc, nullptr, 0, 0, shard);
   CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
   CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
   CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
   CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
-  return submit_msm((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p, n, nullptr, nullptr);
+  return submit_msm((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p, n, nullptr, nullptr, 0, 0, shard);
 }
 
 // Upload + validate + prepare a point set once (fixed-base reuse; the device-resident analogue of the

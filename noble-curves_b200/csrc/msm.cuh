@@ -191,6 +191,44 @@ k_reduce1(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ buc
   if (id < id1) reduce1_body<Cv, SerialOps<G>>(id, offsets, buckets, heads, tails, tile1, tile2, plan, sums, wsums);
 }
 
+// ---- multi-GPU bucket exchange (engine.cuh submit_msm, dist mode) -------------------------------------------
+template <class Cv>
+__global__ void __launch_bounds__(128)
+k_bucket_finalize(const uint32_t* __restrict__ offsets, uint32_t* __restrict__ buckets, const uint32_t* __restrict__ heads,
+                  const uint32_t* __restrict__ tails, const uint32_t* __restrict__ tile1, const uint32_t* __restrict__ tile2,
+                  MsmPlan plan, uint32_t g0, uint32_t g1) {
+  const uint32_t g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < g1) bucket_finalize_body<Cv>(g, offsets, buckets, heads, tails, tile1, tile2, plan);
+}
+template <class Cv>
+__global__ void __launch_bounds__(128)
+k_bucket_fold(uint32_t* __restrict__ own, const uint32_t* __restrict__ recv, int npeers, size_t stride_words, uint32_t B) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) bucket_fold_body<Cv>(b, own, recv, npeers, stride_words);
+}
+template <class Cv>
+__global__ void __launch_bounds__(REDUCE1_THREADS)
+k_reduce1_dense(const uint32_t* __restrict__ buckets, MsmPlan plan, uint32_t id0, uint32_t id1, uint32_t* __restrict__ sums,
+                uint32_t* __restrict__ wsums) {
+  const uint32_t id = id0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (id < id1) reduce1_dense_body<Cv>(id, buckets, plan, sums, wsums);
+}
+// tail of a rank's gather block: err_pt | err_sc (local indices, 0xffffffff = none) | shard offset (lo, hi)
+static __global__ void k_pack_shard_tail(uint32_t* __restrict__ tail, const unsigned int* __restrict__ err, uint64_t offset) {
+  if (threadIdx.x == 0) {
+    tail[0] = err[0];
+    tail[1] = err[1];
+    tail[2] = (uint32_t)offset;
+    tail[3] = (uint32_t)(offset >> 32);
+  }
+}
+template <class Cv>
+__global__ void __launch_bounds__(32)
+k_set_identity(uint32_t* __restrict__ accs, int count) {
+  using G = typename Cv::G;
+  if ((int)threadIdx.x < count) save_acc<G>(accs + (size_t)threadIdx.x * G::ACC_WORDS, G::identity());
+}
+
 // shuffle by `dq` logical lanes (quads); every lane of the warp must be converged here
 template <class G>
 __device__ __forceinline__ typename G::Acc shfl_down_quads(const typename G::Acc& a, int dq) {
@@ -352,12 +390,16 @@ k_horner_step(const uint32_t* __restrict__ window_out, MsmPlan plan, int w_lo, i
 
 // Sum of the `count` group accumulators; AFFINE_OUT: canonical affine + infinity flag, else the raw accumulator
 // (multi-GPU partial, folded later by k_fold).
+// The accumulators sit in blocks of `per_block` consecutive ones, `block_stride` words apart (the all-gathered layout of
+// a sharded MSM: every rank's weighted window sums followed by its validation words).
 template <class Cv, bool AFFINE_OUT>
 __global__ void __launch_bounds__(32)
-k_combine(const uint32_t* __restrict__ accs, int count, uint32_t* __restrict__ out, uint32_t* __restrict__ out_inf) {
+k_combine(const uint32_t* __restrict__ accs, int count, int per_block, int block_stride, uint32_t* __restrict__ out,
+          uint32_t* __restrict__ out_inf) {
   using G = typename Cv::G;
   typename G::Acc acc = G::identity();
-  for (int i = 0; i < count; i++) G::template par_add<true>(acc, load_acc<G>(accs + (size_t)i * G::ACC_WORDS));
+  for (int i = 0; i < count; i++)
+    G::template par_add<true>(acc, load_acc<G>(accs + (size_t)(i / per_block) * block_stride + (size_t)(i % per_block) * G::ACC_WORDS));
   if (AFFINE_OUT) {
     uint32_t xy[G::IN_WORDS];
     uint32_t inf;

@@ -71,8 +71,10 @@ constexpr int glv_bits() {
 //                parts_top partials per bucket
 //   reduce2/3    ~0.75 ms latency,  final  ~6.2 us per Horner doubling
 // ---------------------------------------------------------------------------------------------
+// n: term count the window size is chosen for (the GLOBAL count of a sharded MSM, so that every GPU uses the same
+// windows and buckets); n_local (0 = n): terms this GPU accumulates, which sizes the accumulate segments.
 template <class Cv>
-inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
+inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_local = 0) {
   using G = typename Cv::G;
   using F = typename G::Field;
   // with GLV every scalar becomes two signed halves of at most 127 bits, each attached to its own point
@@ -116,7 +118,8 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
   p.W = (bits + 1 + c - 1) / c;
   p.B = 1 << (c - 1);
   p.G = p.W * p.B;
-  p.L = seg_len(terms * p.W);
+  const double terms_local = n_local ? (double)n_local * (Cv::GLV ? 2 : 1) : terms;
+  p.L = seg_len(terms_local * p.W);
   // reduce chunk: 8 buckets per thread keeps >= 1 warp per SM sub-partition busy down to ~150k buckets
   int Kc = K;
 #if !defined(__CUDA_ARCH__)
@@ -129,7 +132,7 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count) {
   p.stride = 0;
   p.wb = p.c;
   p.r = 0;
-  p.TPW = plan_tpw((uint64_t)terms, p.L);
+  p.TPW = plan_tpw((uint64_t)terms_local, p.L);
   return p;
 }
 
@@ -850,6 +853,70 @@ NMSM_HD void reduce1_body(uint32_t id, const uint32_t* offsets, const uint32_t* 
   }
   save_acc<G>(sums + (size_t)id * G::ACC_WORDS, acc[0]);
   save_acc<G>(wsums + (size_t)id * G::ACC_WORDS, acc[1]);
+}
+
+// ---- dense buckets (multi-GPU bucket exchange) ---------------------------------------------------
+// bucket_finalize_body: after it, buckets[g] holds the complete value of bucket g for every g of the window range —
+// straddling buckets are stitched from tails / heads / tile sums, empty buckets become the identity — so a window's
+// B accumulators form one contiguous array that can be sent to the GPU that owns the window.
+template <class Cv>
+NMSM_HD void bucket_finalize_body(uint32_t g, const uint32_t* offsets, uint32_t* buckets, const uint32_t* heads,
+                                  const uint32_t* tails, const uint32_t* tile1, const uint32_t* tile2, const MsmPlan& plan) {
+  using G = typename Cv::G;
+  using Acc = typename G::Acc;
+  constexpr uint32_t F1 = STITCH_FAN, F2 = STITCH_FAN * STITCH_FAN;
+  const uint32_t w = g / (uint32_t)plan.B;
+  const uint32_t wbase = offsets[w * (uint32_t)plan.B], sid0 = w * plan.TPW;
+  const uint32_t b0 = offsets[g], b1 = offsets[g + 1];
+  if (b0 == b1) {
+    save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, G::identity());
+    return;
+  }
+  const uint32_t ts = sid0 + (b0 - wbase) / plan.L, te = sid0 + (b1 - 1 - wbase) / plan.L;
+  if (ts == te) return;  // wholly inside one segment: k_accumulate wrote it
+  Acc acc = load_acc<G>(tails + (size_t)ts * G::ACC_WORDS);
+  for (uint32_t t = ts + 1; t <= te;) {
+    const uint32_t* src;
+    uint32_t step = 1;
+    if ((t % F2) == 0 && te - t >= F2 - 1) {
+      src = tile2 + (size_t)(t / F2) * G::ACC_WORDS;
+      step = F2;
+    } else if ((t % F1) == 0 && te - t >= F1 - 1) {
+      src = tile1 + (size_t)(t / F1) * G::ACC_WORDS;
+      step = F1;
+    } else {
+      src = heads + (size_t)t * G::ACC_WORDS;
+    }
+    nl_add<G>(acc, load_acc<G>(src));
+    t += step;
+  }
+  save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, acc);
+}
+
+// bucket b of an owned window: own partial += the partials received from the `npeers` other GPUs (peer arrays are
+// `stride_words` apart).  The EC fold of the "allreduce of bucket accumulators": point addition is not an NCCL
+// reduction operator, so the exchange is send/recv + this kernel.
+template <class Cv>
+NMSM_HD void bucket_fold_body(uint32_t b, uint32_t* own, const uint32_t* recv, int npeers, size_t stride_words) {
+  using G = typename Cv::G;
+  typename G::Acc acc = load_acc<G>(own + (size_t)b * G::ACC_WORDS);
+  for (int r = 0; r < npeers; r++) nl_add<G>(acc, load_acc<G>(recv + (size_t)r * stride_words + (size_t)b * G::ACC_WORDS));
+  save_acc<G>(own + (size_t)b * G::ACC_WORDS, acc);
+}
+
+// reduce1 over dense buckets: chunk running sums without any stitching (curve.ts:897-900)
+template <class Cv>
+NMSM_HD void reduce1_dense_body(uint32_t id, const uint32_t* buckets, const MsmPlan& plan, uint32_t* sums, uint32_t* wsums) {
+  using G = typename Cv::G;
+  const uint32_t w = id / plan.chunks, k = id % plan.chunks;
+  const uint32_t g0 = w * plan.B + k * plan.K;
+  typename G::Acc sum = G::identity(), wsum = G::identity();
+  for (int b = plan.K - 1; b >= 0; b--) {
+    nl_add<G>(sum, load_acc<G>(buckets + (size_t)(g0 + (uint32_t)b) * G::ACC_WORDS));
+    nl_add<G>(wsum, sum);
+  }
+  save_acc<G>(sums + (size_t)id * G::ACC_WORDS, sum);
+  save_acc<G>(wsums + (size_t)id * G::ACC_WORDS, wsum);
 }
 
 // Serial statement of the second level for one window (what k_reduce2 computes cooperatively):

@@ -112,6 +112,65 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
   return 0;
 }
 
+// ---- sharded MSM with bucket exchange (engine.cuh submit_msm, shard != nullptr) ---------------------------------
+// Stage 1 on every rank: local terms -> DENSE buckets of all windows, planned for the global term count.
+template <class Cv>
+static int emu_shard_buckets_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n_local, uint32_t n_total,
+                               uint32_t* buckets_out, uint32_t* plan_out, uint32_t* err_out) {
+  using G = typename Cv::G;
+  MsmPlan plan = make_plan<Cv>(n_total, 0, 148, n_local ? n_local : 1);
+  plan_out[0] = plan.c; plan_out[1] = plan.W; plan_out[2] = plan.B; plan_out[3] = G::ACC_WORDS;
+  if (!buckets_out) return 0;  // plan query
+  const size_t terms = (size_t)(n_local ? n_local : 1) * (Cv::GLV ? 2 : 1);
+  std::vector<uint32_t> aff(terms * G::AFF_WORDS);
+  std::vector<unsigned int> counts(plan.G + 1, 0), cursor(plan.G + 1, 0);
+  std::vector<uint32_t> offsets(plan.G + 1, 0);
+  unsigned int err[2] = {0xffffffffu, 0xffffffffu};
+  for (uint32_t i = 0; i < n_local; i++) prepare_body<Cv>(i, n_local, pts, aff.data(), err);
+  for (uint32_t i = 0; i < n_local; i++) digits_body<Cv, false>(i, n_local, scalars, plan, counts.data(), nullptr, err);
+  uint32_t run = 0;
+  for (int g = 0; g < plan.G; g++) { offsets[g] = run; cursor[g] = run; run += counts[g]; }
+  offsets[plan.G] = run;
+  std::vector<uint32_t> sorted(run ? run : 1);
+  for (uint32_t i = 0; i < n_local; i++) digits_body<Cv, true>(i, n_local, scalars, plan, cursor.data(), sorted.data(), err);
+  const size_t nseg = (size_t)plan.W * plan.TPW;
+  std::vector<uint32_t> heads(nseg * G::ACC_WORDS, 0xdeadbeefu), tails(nseg * G::ACC_WORDS, 0xdeadbeefu);
+  const uint32_t ntile1 = (uint32_t)(nseg / STITCH_FAN), ntile2 = ntile1 / STITCH_FAN;
+  std::vector<uint32_t> tile1((size_t)ntile1 * G::ACC_WORDS, 0xdeadbeefu), tile2((size_t)(ntile2 + 1) * G::ACC_WORDS, 0xdeadbeefu);
+  for (size_t k = 0; k < (size_t)plan.G * G::ACC_WORDS; k++) buckets_out[k] = 0xdeadbeefu;
+  for (int w = 0; w < plan.W; w++)
+    for (uint32_t t = 0; t < plan.TPW; t++) {
+      if ((uint64_t)offsets[(size_t)w * plan.B] + (uint64_t)t * plan.L >= offsets[(size_t)(w + 1) * plan.B] && t > 2) break;
+      accumulate_body<Cv>(w, t, aff.data(), sorted.data(), offsets.data(), plan, buckets_out, heads.data(), tails.data());
+    }
+  for (uint32_t j = 0; j < ntile1; j++) stitch_tile_serial<Cv>(j, STITCH_FAN, offsets.data(), plan, heads.data(), tile1.data());
+  for (uint32_t j = 0; j < ntile2; j++) stitch_tile_serial<Cv>(j, STITCH_FAN * STITCH_FAN, offsets.data(), plan, tile1.data(), tile2.data());
+  for (uint32_t g = 0; g < (uint32_t)plan.G; g++)
+    bucket_finalize_body<Cv>(g, offsets.data(), buckets_out, heads.data(), tails.data(), tile1.data(), tile2.data(), plan);
+  err_out[0] = err[0];
+  err_out[1] = err[1];
+  return 0;
+}
+// Stage 2 on the owner of window w: fold the peers' partial buckets, reduce the window, weight it by 2^(c w).
+// `own` = this rank's dense buckets of window w (B accumulators, modified in place), `recv` = npeers such arrays.
+template <class Cv>
+static int emu_owner_window_t(uint32_t n_total, int w, uint32_t* own, const uint32_t* recv, int npeers, uint32_t* out_acc) {
+  using G = typename Cv::G;
+  MsmPlan plan = make_plan<Cv>(n_total, 0, 148, 1);
+  const size_t WB = (size_t)plan.B * G::ACC_WORDS;
+  for (uint32_t b = 0; b < (uint32_t)plan.B; b++) bucket_fold_body<Cv>(b, own, recv, npeers, WB);
+  // the kernels index buckets / chunks / window sums globally: stage the window at its global position
+  std::vector<uint32_t> all((size_t)plan.W * WB, 0xdeadbeefu);
+  memcpy(all.data() + (size_t)w * WB, own, WB * 4);
+  const size_t nchunks = (size_t)plan.W * plan.chunks;
+  std::vector<uint32_t> sums(nchunks * G::ACC_WORDS), wsums(nchunks * G::ACC_WORDS), window_out((size_t)plan.W * G::ACC_WORDS);
+  for (uint32_t id = (uint32_t)w * plan.chunks; id < (uint32_t)(w + 1) * plan.chunks; id++)
+    reduce1_dense_body<Cv>(id, all.data(), plan, sums.data(), wsums.data());
+  reduce2_serial<Cv>(w, sums.data(), wsums.data(), plan, window_out.data());
+  horner_step_body<Cv>(window_out.data(), plan, w, w + 1, true, true, out_acc);
+  return 0;
+}
+
 // multi-GPU building blocks: raw accumulator of a shard, and the fold of several accumulators
 template <class Cv>
 static int emu_partial_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, uint32_t* out_acc) {
@@ -322,6 +381,13 @@ int emu_mul_batch(int curve, const uint32_t* pts, const uint32_t* scalars, uint3
 }
 int emu_msm_partial(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n, uint32_t* out_acc) {
   DISPATCH(curve, emu_partial_t<Cv>(pts, scalars, n, out_acc));
+}
+int emu_shard_buckets(int curve, const uint32_t* pts, const uint32_t* scalars, uint32_t n_local, uint32_t n_total,
+                      uint32_t* buckets_out, uint32_t* plan_out, uint32_t* err_out) {
+  DISPATCH(curve, emu_shard_buckets_t<Cv>(pts, scalars, n_local, n_total, buckets_out, plan_out, err_out));
+}
+int emu_owner_window(int curve, uint32_t n_total, int w, uint32_t* own, const uint32_t* recv, int npeers, uint32_t* out_acc) {
+  DISPATCH(curve, emu_owner_window_t<Cv>(n_total, w, own, recv, npeers, out_acc));
 }
 int emu_fold(int curve, const uint32_t* accs, int count, uint32_t* out_xy, uint32_t* out_inf) {
   DISPATCH(curve, emu_fold_t<Cv>(accs, count, out_xy, out_inf));
