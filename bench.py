@@ -5,14 +5,18 @@
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
 
 One "step" = one complete MSM (curve.ts:863-905 `pippenger` semantics) over one batch of synthetic
-(point, scalar) terms:  points P_i = k_i*G, scalars uniform in [0, n).  At N GPUs the term array is
-sharded across ranks, each rank reduces its shard to one raw accumulator, the accumulators are
-exchanged with one NCCL all-gather and folded (MSM is linear in its term set).  Default "scaling": "weak":
-every GPU holds 2^20 terms of ONE MSM with N*2^20 terms; `--scaling strong` splits 2^20 terms over the GPUs.
+(point, scalar) terms:  points P_i = k_i*G, scalars uniform in [0, n).  SURVEY §8(d): points/s = N / wall time of ONE
+MSM, so the timed region runs the K steps one after the other (each call returns the affine result before the next
+starts); the throughput with several MSMs in flight is a named companion (`pipelined`), not the headline.
+At N GPUs (default "scaling": "strong" = the metric's configuration: 2^20 terms IN TOTAL) the term array is sharded
+across the ranks and one step is one nmsm_msm_sharded call: every rank accumulates its shard into the full bucket array,
+window w's buckets go to rank w % N (NCCL send/recv inside the library), the owner folds + reduces its windows, one small
+all-gather + fold finishes (nmsm/dist.py).  `--scaling weak` (2^logn terms PER GPU, one MSM of N*2^logn terms) is kept
+as a companion mode.
 
 Timed numbers:
-  value  — whole-job points/s with inputs already resident in HBM (CUDA path via nmsm_msm_device)
-  e2e    — same metric through the host-buffer entry point nmsm_msm (pinned host inputs, H2D inside)
+  value  — whole-job points/s with inputs already resident in HBM (nmsm_msm_device / nmsm_msm_sharded), serial steps
+  e2e    — same metric through the host-buffer entry points (pinned host inputs, H2D inside), serial steps
   roofline — modmul-bound integer roofline of the dominant kernel (k_accumulate): executed field
              multiplications / CUDA-event time, against the register-resident Montgomery-multiply
              microbenchmark measured in the same run; HBM figures alongside
@@ -28,6 +32,7 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before any CUDA context exists (see nmsm/_lib.py)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "noble-curves_b200"))
 sys.path.insert(0, ROOT)
@@ -47,11 +52,13 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--logn", type=int, default=20, help="log2 of the MSM size (headline: 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fixed-base", action="store_true", help="skip the fixed-base table companion measurement")
+    ap.add_argument("--no-fixed-base", action="store_true", help="skip the fixed-base table and any-point companion measurements")
+    ap.add_argument("--no-pipelined", action="store_true", help="skip the MSMs-in-flight companion measurement")
     ap.add_argument("--window", type=int, default=0, help="force window bits c (0 = cost model)")
-    ap.add_argument("--in-flight", type=int, default=4, choices=[1, 2, 3, 4], help="MSMs kept in flight in the timed region")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N>1: weak = 2^logn terms PER GPU (one MSM of N*2^logn terms); strong = 2^logn terms in total")
+    ap.add_argument("--in-flight", type=int, default=4, choices=[2, 3, 4], help="MSMs kept in flight in the `pipelined` companion")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N>1: strong (default, the metric's config) = 2^logn terms in total; weak = 2^logn terms PER GPU")
+    ap.add_argument("--groups", type=int, default=0, help="force the window-group count of the pipeline (0 = automatic)")
     return ap.parse_args()
 
 
@@ -163,7 +170,7 @@ def run_reference(args, real_stdout):
         "impl": "reference",
         "metric": "BLS12-381 G1 MSM points/sec at 2^%d scalars" % args.logn,
         "value": pts_per_s, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * n_full / pts_per_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * n_full / pts_per_s, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64-limb integer (381-bit Fp, Montgomery)", "data": "synthetic",
         "config": {"workload": "BLS12-381 G1 MSM, 2^%d terms, reference algorithm (curve.ts:863-905) on host cores; "
                                "host-only: the same single-box workload at every --gpus" % args.logn},
@@ -203,6 +210,7 @@ def main():
     import torch.distributed as dist
 
     import nmsm
+    from nmsm import dist as nd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -211,27 +219,28 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the MSM path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     nmsm.init(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
+        nd.init()
     lib = nmsm._lib.load()
     if args.window:
         nmsm.set_window_bits(args.window)
+    if args.groups:
+        nmsm.set_window_groups(args.groups)
 
-    # weak scaling (default): every GPU holds a 2^logn-term shard of ONE MSM with world*2^logn terms, so per-GPU
-    # work is fixed; strong: the 2^logn terms are split across the GPUs.  Either way: one all-gather + fold.
-    scaling = args.scaling if world > 1 else "weak"
-    n_local = (1 << args.logn) if scaling == "weak" else (1 << args.logn) // world
-    n_total = n_local * world
+    # strong (default): the 2^logn terms of ONE MSM are split across the GPUs; weak: 2^logn terms per GPU
+    scaling = args.scaling if world > 1 else "strong"
+    n_total = (1 << args.logn) * (world if scaling == "weak" else 1)
+    lo, hi = nd.shard_bounds(n_total, world, rank)
+    n_local = hi - lo
     # every rank generates only its own shard; seeds make shards disjoint and reproducible
     pts_b, sc_b, total_local = make_terms(nmsm, n_local, 1000 + rank)
-    dev = torch.device("cuda", local_rank)
     d_pts = torch.frombuffer(bytearray(pts_b), dtype=torch.uint8).to(dev)
     d_sc = torch.frombuffer(bytearray(sc_b), dtype=torch.uint8).to(dev)
-    acc_bytes = lib.nmsm_acc_bytes(BLS_G1)
-    d_acc = torch.zeros(acc_bytes, dtype=torch.uint8, device=dev)
-    d_all = torch.zeros(acc_bytes * world, dtype=torch.uint8, device=dev)
     out = ctypes.create_string_buffer(POINT_BYTES)
     inf = ctypes.c_int(0)
+    vp = lambda b: ctypes.cast(b, ctypes.c_void_p)  # noqa: E731
 
     if world > 1:
         totals = [None] * world
@@ -241,55 +250,101 @@ def main():
         total = total_local
     exp_xy, exp_inf = expected_point(nmsm, total)
 
-    def step_device():
+    def check_result(o=out, f=inf):
+        assert o.raw == exp_xy and f.value == exp_inf, "MSM result does not match (sum k_i s_i)*G"
+
+    def step_device():  # ONE complete MSM, inputs resident in HBM
         if world == 1:
-            nmsm._lib.check(lib.nmsm_msm_device(BLS_G1, d_pts.data_ptr(), d_sc.data_ptr(), n_local,
-                                                ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf)))
+            nmsm._lib.check(lib.nmsm_msm_device(BLS_G1, d_pts.data_ptr(), d_sc.data_ptr(), n_local, vp(out), ctypes.byref(inf)))
         else:
-            nmsm._lib.check(lib.nmsm_msm_partial_device(BLS_G1, d_pts.data_ptr(), d_sc.data_ptr(), n_local,
-                                                        d_acc.data_ptr()))
-            dist.all_gather_into_tensor(d_all, d_acc)
-            torch.cuda.current_stream().synchronize()
-            nmsm._lib.check(lib.nmsm_fold_partials_device(BLS_G1, d_all.data_ptr(), world,
-                                                          ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf)))
+            nmsm._lib.check(lib.nmsm_msm_sharded(BLS_G1, d_pts.data_ptr(), d_sc.data_ptr(), n_local, n_total, lo, 1, vp(out),
+                                                 ctypes.byref(inf)))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident: (1) serial steps -> latency + per-kernel CUDA-event times -------------
-    nmsm.set_profiling(True)
-    for _ in range(max(args.warmup, 3)):
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W = max(args.warmup, 3)
+    # ---- (1) profiling pass (single GPU): linear pipeline, per-kernel CUDA-event times, executed-addition counts ----
+    kern_ms, acc_ms, lin_ms, prof_info = {}, [], [], None
+    if world == 1:
+        nmsm.set_profiling(True)
+        for _ in range(W):
+            step_device()
+        check_result()
+        for _ in range(args.steps):
+            step_device()
+            ms, prof_info = nmsm.last_timing()
+            acc_ms.append(ms["accumulate"])
+            lin_ms.append(ms["total"])
+            for k, v in ms.items():
+                kern_ms[k] = kern_ms.get(k, 0.0) + v / args.steps
+        nmsm.set_profiling(False)
+
+    # ---- (2) THE TIMED REGION: K serial steps, one complete MSM each (N / wall time of one MSM) -----------
+    for _ in range(W):
         step_device()
-    assert out.raw == exp_xy and inf.value == exp_inf, "MSM result does not match (sum k_i s_i)*G"
-    acc_ms, tot_ms, kern_ms = [], [], {}
+    check_result()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_ms = []
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
-        ms, info = nmsm.last_timing()
-        acc_ms.append(ms["accumulate"])
-        tot_ms.append(ms["total"])
-        for k, v in ms.items():
-            kern_ms[k] = kern_ms.get(k, 0.0) + v / args.steps
+        dev_ms.append(nmsm.last_timing()[0]["total"])
     barrier()
-    serial_elapsed = time.perf_counter() - t0
-    assert out.raw == exp_xy and inf.value == exp_inf
-    nmsm.set_profiling(False)
+    elapsed = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    check_result()
+    main_info = nmsm.last_timing()[1]
+    device_ms = max_over_ranks(sum(dev_ms) / len(dev_ms))
+    value = n_total * args.steps / elapsed
 
-    # ---- (2) the timed region: K steps, --in-flight MSMs in flight (submit/collect round-robin over the slots) -----------
-    # At N > 1 the shard reduction of step i overlaps the all-gather + fold of step i-1 the same way.
-    pipelined = True
+    # ---- (3) end to end: the same serial steps through the host-buffer entry points (pinned inputs, H2D inside) -------
+    h_pts = lib.nmsm_host_alloc(max(16, len(pts_b)))
+    h_sc = lib.nmsm_host_alloc(max(16, len(sc_b)))
+    ctypes.memmove(h_pts, pts_b, len(pts_b))
+    ctypes.memmove(h_sc, sc_b, len(sc_b))
+
+    def step_e2e():
+        if world == 1:
+            nmsm._lib.check(lib.nmsm_msm(BLS_G1, h_pts, h_sc, n_local, vp(out), ctypes.byref(inf)))
+        else:
+            nmsm._lib.check(lib.nmsm_msm_sharded(BLS_G1, h_pts, h_sc, n_local, n_total, lo, 0, vp(out), ctypes.byref(inf)))
+
+    for _ in range(W):
+        step_e2e()
+    check_result()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
+    check_result()
+    e2e_value = n_total * args.steps / e2e_elapsed
+
+    # ---- (4) companion: several MSMs in flight (nmsm_msm_submit / collect over the slots) ----------------------------
     NF = args.in_flight
-    d_accs = [torch.zeros(acc_bytes, dtype=torch.uint8, device=dev) for _ in range(NF)]
+    pipelined = None
 
     def run_pipelined(steps, submit):
         outs = [ctypes.create_string_buffer(POINT_BYTES) for _ in range(NF)]
         infs = [ctypes.c_int(0) for _ in range(NF)]
+
         def take(s):
-            collect(s, outs[s], infs[s])
-            assert outs[s].raw == exp_xy and infs[s].value == exp_inf
+            nmsm._lib.check(lib.nmsm_msm_collect(s, vp(outs[s]), ctypes.byref(infs[s])))
+            check_result(outs[s], infs[s])
 
         for i in range(steps):
             s = i % NF
@@ -299,97 +354,34 @@ def main():
         for j in range(max(0, steps - NF), steps):
             take(j % NF)
 
-    def submit_device(slot, pts_t=None, sc_t=None):
-        pts_t = d_pts if pts_t is None else pts_t
-        sc_t = d_sc if sc_t is None else sc_t
+    def submit_device(slot):
         if world == 1:
-            nmsm._lib.check(lib.nmsm_msm_submit(BLS_G1, pts_t.data_ptr(), sc_t.data_ptr(), n_local, 1, slot))
+            nmsm._lib.check(lib.nmsm_msm_submit(BLS_G1, d_pts.data_ptr(), d_sc.data_ptr(), n_local, 1, slot))
         else:
-            nmsm._lib.check(lib.nmsm_msm_submit_partial(BLS_G1, pts_t.data_ptr(), sc_t.data_ptr(), n_local,
-                                                        d_accs[slot].data_ptr(), slot))
-
-    def collect(slot, o, f):
-        if world == 1:
-            nmsm._lib.check(lib.nmsm_msm_collect(slot, ctypes.cast(o, ctypes.c_void_p), ctypes.byref(f)))
-        else:  # shard done -> one all-gather of the raw accumulators -> fold
-            nmsm._lib.check(lib.nmsm_msm_collect(slot, None, None))
-            dist.all_gather_into_tensor(d_all, d_accs[slot])
-            torch.cuda.current_stream().synchronize()
-            nmsm._lib.check(lib.nmsm_fold_partials_device(BLS_G1, d_all.data_ptr(), world, ctypes.cast(o, ctypes.c_void_p),
-                                                          ctypes.byref(f)))
-
-    sampler = ClockSampler(local_rank)
-    if pipelined:
-        run_pipelined(2 * NF + 1, submit_device)  # touches every slot (workspace allocation) before the timed region
-    if rank == 0:
-        sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    if pipelined:
-        run_pipelined(args.steps, submit_device)
-    else:
-        for _ in range(args.steps):
-            step_device()
-    barrier()
-    elapsed = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
-    value = n_total * args.steps / elapsed
-
-    # ---- end-to-end through the host-buffer entry point (pinned host inputs) --------------
-    h_pts = lib.nmsm_host_alloc(len(pts_b))
-    h_sc = lib.nmsm_host_alloc(len(sc_b))
-    ctypes.memmove(h_pts, pts_b, len(pts_b))
-    ctypes.memmove(h_sc, sc_b, len(sc_b))
-    e2e_steps = max(3, args.steps)  # the same K steps as the device-resident region
-    e2e_bufs = ([(d_pts, d_sc)] + [(torch.empty_like(d_pts), torch.empty_like(d_sc)) for _ in range(NF - 1)]) if world > 1 else None
-
-    def step_e2e():
-        if world == 1:
-            nmsm._lib.check(lib.nmsm_msm(BLS_G1, h_pts, h_sc, n_local, ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf)))
-        else:
-            d_pts.copy_(torch.frombuffer((ctypes.c_uint8 * len(pts_b)).from_address(h_pts), dtype=torch.uint8), non_blocking=True)
-            d_sc.copy_(torch.frombuffer((ctypes.c_uint8 * len(sc_b)).from_address(h_sc), dtype=torch.uint8), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            step_device()
+            nmsm._lib.check(lib.nmsm_msm_sharded_submit(BLS_G1, d_pts.data_ptr(), d_sc.data_ptr(), n_local, n_total, lo, 1, slot))
 
     def submit_host(slot):
         if world == 1:
             nmsm._lib.check(lib.nmsm_msm_submit(BLS_G1, h_pts, h_sc, n_local, 0, slot))
-        else:  # multi-GPU e2e: H2D on torch's stream into this slot's device buffers, then the sharded step
-            tp, ts = e2e_bufs[slot]
-            tp.copy_(torch.frombuffer((ctypes.c_uint8 * len(pts_b)).from_address(h_pts), dtype=torch.uint8), non_blocking=True)
-            ts.copy_(torch.frombuffer((ctypes.c_uint8 * len(sc_b)).from_address(h_sc), dtype=torch.uint8), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            submit_device(slot, tp, ts)
+        else:
+            nmsm._lib.check(lib.nmsm_msm_sharded_submit(BLS_G1, h_pts, h_sc, n_local, n_total, lo, 0, slot))
 
-    step_e2e()
-    if pipelined:
-        run_pipelined(NF + 1, submit_host)
-    barrier()
-    t0 = time.perf_counter()
-    if pipelined:
-        run_pipelined(e2e_steps, submit_host)
-    else:
-        for _ in range(e2e_steps):
-            step_e2e()
-    barrier()
-    e2e_elapsed = time.perf_counter() - t0
-    assert out.raw == exp_xy and inf.value == exp_inf
-    if world > 1:
-        t = torch.tensor([e2e_elapsed], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_elapsed = float(t.item())
-    e2e_value = n_total * e2e_steps / e2e_elapsed
+    if not args.no_pipelined:
+        pipelined = {"in_flight": NF}
+        for key, submit in (("device", submit_device), ("e2e", submit_host)):
+            run_pipelined(2 * NF + 1, submit)  # touches every slot (workspace allocation) before the timed loop
+            barrier()
+            t0 = time.perf_counter()
+            run_pipelined(args.steps, submit)
+            barrier()
+            el = max_over_ranks(time.perf_counter() - t0)
+            pipelined[key] = {"value": n_total * args.steps / el, "unit": "points/s", "ms_per_step": 1e3 * el / args.steps}
+        pipelined["note"] = ("companion, NOT the headline: the same K MSMs with several kept in flight on separate slots "
+                             "(nmsm_msm_submit / nmsm_msm_collect); throughput of a prover that has independent MSMs to run")
     lib.nmsm_host_free(h_pts)
     lib.nmsm_host_free(h_sc)
-    main_timing = nmsm.last_timing()  # plan + kernel times of the general MSM, before the fixed-base pass below
 
-    # ---- companion number (not the headline): the same MSM over a device-resident point set with a fixed-base
-    # table (nmsm_points_precompute): scalars resident on the device, same pipelined loop ----------
+    # ---- companion: the same MSM over a device-resident point set with a fixed-base table -------------
     fixed = None
     if world == 1 and not args.no_fixed_base:
         h, tc, lv = ctypes.c_uint64(0), ctypes.c_int(0), ctypes.c_int(0)
@@ -398,97 +390,110 @@ def main():
         nmsm._lib.check(lib.nmsm_points_precompute(h, 0, ctypes.byref(tc), ctypes.byref(lv)))
         t_pre = time.perf_counter() - t0
 
-        def submit_fixed(slot):
-            nmsm._lib.check(lib.nmsm_msm_points_submit(h, d_sc.data_ptr(), n_local, 1, slot))
+        def step_fixed():
+            nmsm._lib.check(lib.nmsm_msm_points_submit(h, d_sc.data_ptr(), n_local, 1, 0))
+            nmsm._lib.check(lib.nmsm_msm_collect(0, vp(out), ctypes.byref(inf)))
 
         nmsm.set_profiling(True)
         for _ in range(3):
-            submit_fixed(0)
-            collect(0, out, inf)
-            assert out.raw == exp_xy and inf.value == exp_inf
+            step_fixed()
+        check_result()
         fms, finfo = nmsm.last_timing()
         nmsm.set_profiling(False)
-        run_pipelined(2 * NF + 1, submit_fixed)
+        for _ in range(3):
+            step_fixed()
         barrier()
         t0 = time.perf_counter()
-        run_pipelined(args.steps, submit_fixed)
+        for _ in range(args.steps):
+            step_fixed()
         barrier()
         f_el = time.perf_counter() - t0
+        check_result()
         fixed = {"value": n_local * args.steps / f_el, "unit": "points/s", "ms_per_step": 1e3 * f_el / args.steps,
-                 "latency_ms_single_msm": fms["total"], "in_flight": NF,
                  "table": {"window_bits": tc.value, "levels": lv.value, "bytes": lv.value * 2 * n_local * 96,
                            "precompute_ms": t_pre * 1e3},
                  "plan": {"c": finfo.c, "windows": finfo.windows, "sorted_entries": finfo.sorted_entries},
-                 "kernel_ms_breakdown": {k: round(v, 4) for k, v in fms.items()},
-                 "note": "device-resident point set + table 2^(c*j)*P (nmsm_points_precompute); companion to `value`, "
-                         "which stays the general MSM with points passed per call"}
+                 "kernel_ms_breakdown_linear": {k: round(v, 4) for k, v in fms.items()},
+                 "note": "device-resident point set + table 2^(c*j)*P (nmsm_points_precompute), serial steps; companion to "
+                         "`value`, which stays the general MSM with points passed per call"}
         lib.nmsm_points_free(h)
 
-    # ---- second companion: the same MSM under NMSM_BLS12_381_G1_ANY (no subgroup assumption, no GLV: 16 windows) ----
+    # ---- companion: the same MSM under NMSM_BLS12_381_G1_ANY (what nmsm.pippenger selects for unvalidated points) -----
     any_point = None
     if world == 1 and not args.no_fixed_base:
         ANY = 6
-        for _ in range(2):
-            nmsm._lib.check(lib.nmsm_msm_device(ANY, d_pts.data_ptr(), d_sc.data_ptr(), n_local,
-                                                ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf)))
-        assert out.raw == exp_xy and inf.value == exp_inf
+        for _ in range(3):
+            nmsm._lib.check(lib.nmsm_msm_device(ANY, d_pts.data_ptr(), d_sc.data_ptr(), n_local, vp(out), ctypes.byref(inf)))
+        check_result()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(5):
-            nmsm._lib.check(lib.nmsm_msm_device(ANY, d_pts.data_ptr(), d_sc.data_ptr(), n_local,
-                                                ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf)))
+        for _ in range(args.steps):
+            nmsm._lib.check(lib.nmsm_msm_device(ANY, d_pts.data_ptr(), d_sc.data_ptr(), n_local, vp(out), ctypes.byref(inf)))
         torch.cuda.synchronize()
-        a_el = (time.perf_counter() - t0) / 5
-        any_point = {"latency_ms_single_msm": 1e3 * a_el, "value_serial": n_local / a_el, "unit": "points/s",
-                     "note": "curve id NMSM_BLS12_381_G1_ANY: valid for every on-curve point, not only the prime-order "
-                             "subgroup the headline id assumes (the bench points k_i*G are in it); serial calls"}
+        a_el = (time.perf_counter() - t0) / args.steps
+        any_point = {"value": n_local / a_el, "unit": "points/s", "ms_per_step": 1e3 * a_el,
+                     "note": "curve id NMSM_BLS12_381_G1_ANY (no endomorphism, 16 windows): valid for EVERY on-curve point; "
+                             "the host mirror's pippenger picks it unless all inputs are known subgroup members (the bench "
+                             "points k_i*G are, so the headline uses id 4); serial steps"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel ------------------------------------------------------
-    ms, info = main_timing
+    # ---- roofline ---------------------------------------------------------------------------------------------------
     peak = 0.0
     for (bps, thr, ilp) in ((4, 128, 1), (8, 128, 1), (4, 256, 1), (4, 128, 2), (8, 128, 2), (2, 256, 2)):
         peak = max(peak, nmsm.bench_modmul(1, bps, thr, 3000, ilp))
-    acc_t = sum(acc_ms) / len(acc_ms) * 1e-3
-    madd_modmuls = info.sorted_entries * 10  # madd-2008-s: 8M + 2S per mixed addition
-    achieved = madd_modmuls / acc_t
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    # algorithmic bytes of k_accumulate per launch: every sorted entry gathers one 96-byte affine point + its
-    # 4-byte index; every bucket (and partial) is written once (192 B)
-    acc_bytes_alg = info.sorted_entries * (96 + 4) + (info.windows * info.buckets_per_window) * 192
-    roofline = {
-        "bound": "int-modmul", "kernel": "k_accumulate<BLS12-381 G1>",
-        "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Gmodmul/s (381-bit Montgomery)",
-        "frac": achieved / peak if peak > 0 else None,
-        "peak_source": "nmsm_bench_modmul: register-resident mont_mul<FpBls381> microbenchmark, same run",
-        "modmul_per_launch": madd_modmuls, "kernel_ms": acc_t * 1e3,
-        "whole_msm": {"modmul_equiv": info.modmul_equiv, "ms": sum(tot_ms) / len(tot_ms),
-                      "frac": (info.modmul_equiv / (sum(tot_ms) / len(tot_ms) * 1e-3)) / peak if peak > 0 else None,
-                      # same work against the pipelined step time of this GPU (MSMs overlapped on separate streams)
-                      "frac_pipelined": (info.modmul_equiv / (elapsed / args.steps)) / peak if peak > 0 else None},
-        "hbm": {"achieved_gbs": acc_bytes_alg / acc_t / 1e9, "peak_gbs": hbm_peak,
-                "frac": acc_bytes_alg / acc_t / 1e9 / hbm_peak, "algorithmic_bytes": acc_bytes_alg,
-                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
-        "traffic": None,
-        "plan": {"c": info.c, "windows": info.windows, "buckets_per_window": info.buckets_per_window,
-                 "entries_per_thread": info.entries_per_thread, "sorted_entries": info.sorted_entries},
-        "kernel_ms_breakdown": {k: round(v, 4) for k, v in kern_ms.items()},
-    }
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_k_accumulate.json")
-    if os.path.exists(traffic_file):
-        try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    info = prof_info if prof_info is not None else main_info
+    roofline = {"bound": "int-modmul", "kernel": "k_accumulate<BLS12-381 G1>", "unit": "Gmodmul/s (381-bit Montgomery)",
+                "peak": peak / 1e9,
+                "peak_source": "nmsm_bench_modmul: register-resident dependent mont_mul<FpBls381> chains on all SMs, same run",
+                "plan": {"c": info.c, "windows": info.windows, "buckets_per_window": info.buckets_per_window,
+                         "entries_per_thread": info.entries_per_thread, "sorted_entries": info.sorted_entries,
+                         "window_groups_timed_region": main_info.window_groups}}
+    if world == 1:
+        acc_t = sum(acc_ms) / len(acc_ms) * 1e-3
+        # executed mixed additions: every sorted entry except those that START an accumulator (a copy, no multiplications)
+        madds = info.sorted_entries - info.bucket_starts
+        madd_modmuls = madds * 10  # madd-2008-s: 8M + 2S
+        achieved = madd_modmuls / acc_t
+        # whole MSM, executed: mixed additions + bucket reduction (2 additions per bucket of 12M+2S) + Horner doublings (6M+3S)
+        W_, B_ = info.windows, info.buckets_per_window
+        whole_modmuls = madd_modmuls + W_ * 2 * B_ * 14 + (W_ - 1) * info.c * 9
+        # algorithmic bytes of k_accumulate per launch: per sorted entry one 96-byte gathered affine point + its 4-byte index;
+        # per accumulator start one 192-byte XYZZ accumulator written (buckets, heads, tails)
+        acc_bytes_alg = info.sorted_entries * (96 + 4) + info.bucket_starts * 192
+        one_ms = 1e3 * elapsed / args.steps
+        roofline.update({
+            "achieved": achieved / 1e9, "frac": achieved / peak if peak > 0 else None,
+            "mixed_additions_executed": madds, "accumulator_starts": info.bucket_starts,
+            "modmul_per_launch": madd_modmuls, "kernel_ms": acc_t * 1e3,
+            "whole_msm": {"modmul_executed": whole_modmuls, "ms": one_ms,
+                          "frac": (whole_modmuls / (one_ms * 1e-3)) / peak if peak > 0 else None,
+                          "ms_linear_pipeline": sum(lin_ms) / len(lin_ms),
+                          "note": "executed field multiplications of one MSM / wall time of one serial step / peak"},
+            "hbm": {"achieved_gbs": acc_bytes_alg / acc_t / 1e9, "peak_gbs": hbm_peak,
+                    "frac": acc_bytes_alg / acc_t / 1e9 / hbm_peak, "algorithmic_bytes": acc_bytes_alg,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
+            "traffic": None,
+            "kernel_ms_breakdown_linear": {k: round(v, 4) for k, v in kern_ms.items()},
+        })
+        traffic_file = os.path.join(ROOT, "profiles", "traffic_k_accumulate.json")
+        if os.path.exists(traffic_file):
+            try:
+                roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+    else:
+        roofline.update({"achieved": None, "frac": None, "traffic": None,
+                         "note": "per-kernel profile is taken at N=1 (profiling forces the linear pipeline); at N>1 see device_ms_per_step"})
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -499,27 +504,34 @@ def main():
         except Exception as e:  # never lose the GPU line because the CPU leg failed
             cpu = {"value": None, "unit": "points/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 
+    nccl_ver = None
+    if world > 1:
+        v = ctypes.c_int(0)
+        lib.nmsm_dist_info(None, None, ctypes.byref(v))
+        nccl_ver = v.value
     line = {
         "metric": "BLS12-381 G1 MSM points/sec at 2^%d scalars" % args.logn,
-        "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": 1e3 * elapsed / args.steps, "latency_ms_single_msm": 1e3 * serial_elapsed / args.steps,
-        "in_flight": NF, "higher_is_better": True, "scaling": scaling,
+        "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": 1e3 * elapsed / args.steps, "device_ms_per_step": device_ms,
+        "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "u32-limb integer (381-bit Fp, Montgomery)", "data": "synthetic",
-        "config": {"workload": ("BLS12-381 G1 Pippenger MSM, 2^%d random terms (points k_i*G, uniform scalars) per GPU; "
-                                "at N GPUs one MSM of N*2^%d terms" % (args.logn, args.logn)) if scaling == "weak" else
-                               "BLS12-381 G1 Pippenger MSM, 2^%d terms in total split over the GPUs" % args.logn,
-                   "terms": n_total, "terms_per_gpu": n_local, "parallelism": "term-sharded x%d, 1 all-gather of raw accumulators" % world,
-                   "l2": "inputs+workspace (>=450 MB/GPU at N=2^20) exceed the 126 MB L2; no flush needed",
-                   "pipelining": ("timed steps keep several MSMs in flight (see in_flight) on separate CUDA streams (nmsm_msm_submit/collect): the "
-                                  "latency-bound tail of one overlaps the copy + wide kernels of the next; "
-                                  "latency_ms_single_msm and the roofline block come from a serial pass")
-                   + ("; at N>1 the all-gather + fold of step i-1 overlaps the shard reduction of step i" if world > 1 else "")},
-        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": len(pts_b) + len(sc_b),
-                "d2h_bytes_per_step": POINT_BYTES + 20, "steps": e2e_steps},
-        "gpu_launches": info.launches * args.steps * world,  # kernels of the timed K steps (serial pass not counted)
+        "config": {"workload": ("BLS12-381 G1 Pippenger MSM, 2^%d random terms (points k_i*G, uniform scalars) IN TOTAL" % args.logn)
+                   if scaling == "strong" else
+                   ("BLS12-381 G1 Pippenger MSM, 2^%d terms per GPU: one MSM of %d*2^%d terms" % (args.logn, world, args.logn)),
+                   "terms": n_total, "terms_per_gpu": n_local,
+                   "parallelism": "1 GPU" if world == 1 else
+                   ("term-sharded x%d; per-window bucket exchange (NCCL send/recv to the window owner w %% N, issued by the "
+                    "library on its own stream), owner fold + reduce, all-gather of %d-byte weighted window sums" % (world, 192)),
+                   "steps_are": "serial: one complete MSM per step, result on the host before the next step starts",
+                   "l2": "inputs + workspace (>= 450 MB at 2^20 terms) exceed the 126 MB L2; no flush needed",
+                   "nccl_version": nccl_ver},
+        "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": 1e3 * e2e_elapsed / args.steps,
+                "h2d_bytes_per_step": len(pts_b) + len(sc_b), "d2h_bytes_per_step": POINT_BYTES + 24, "steps": args.steps},
+        "gpu_launches": main_info.launches * args.steps * world,  # our kernels inside the timed region (every rank runs its own)
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "pipelined": pipelined,
         "fixed_base": fixed,
         "any_point": any_point,
     }

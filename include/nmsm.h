@@ -232,6 +232,8 @@ typedef struct {
   uint64_t modmul_equiv;        /* field multiplications executed by the plan (SURVEY §8d formula) */
   int launches;                 /* kernels launched by the call                                   */
   int window_groups;            /* window groups the call was pipelined over (1 = linear pipeline) */
+  uint64_t bucket_starts;       /* of sorted_entries: copies into an empty accumulator (no multiplications); counted
+                                   while profiling is on, else 0.  executed mixed additions = sorted_entries - this */
 } nmsm_plan_info;
 int nmsm_set_profiling(int enabled);
 int nmsm_last_timing(float* ms, nmsm_plan_info* info);

@@ -156,6 +156,11 @@ using namespace nmsm;
 #define ENGINE(curve)                                      \
   const EngineVTable* E = engine_for(curve);               \
   if (!E) return fail(NMSM_ERR_ARG, "unknown curve id")
+// The synchronous entry points run on slot 0's stream, workspace and pinned staging: refuse while an MSM submitted on
+// slot 0 has not been collected (its result would be overwritten) instead of silently sharing them.
+#define SLOT0_FREE()                                                                                         \
+  if (g_ctx.slot[0].pend.active)                                                                             \
+  return fail(NMSM_ERR_ARG, "slot 0 holds an MSM that has not been collected: collect it before a synchronous call")
 
 extern "C" {
 
@@ -164,6 +169,10 @@ int nmsm_init(int device) {
   Context& C = g_ctx;
   if (C.ready && C.device == device) return NMSM_OK;
   if (C.ready) return fail(NMSM_ERR_ARG, "nmsm_init: context already bound to another device");
+  // The MSM pipeline overlaps kernels on several streams per slot; with the default of 8 hardware work queues unrelated
+  // streams share a queue and serialise.  Only effective if this process has not created its CUDA context yet (the
+  // Python mirror and bench.py also set it before importing torch); never overrides the user's choice.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -190,6 +199,13 @@ int nmsm_init(int device) {
     for (auto& ev : S.ev_tail) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CK(cudaEventCreate(&S.ev_t0));
     CK(cudaEventCreate(&S.ev_t1));
+    if (getenv("NMSM_TRACE")) {
+      C.trace = true;
+      CK(cudaEventCreate(&S.tr_fork));
+      for (auto& ev : S.tr_acc) CK(cudaEventCreate(&ev));
+      for (auto& ev : S.tr_tail) CK(cudaEventCreate(&ev));
+      for (auto& ev : S.tr_h) CK(cudaEventCreate(&ev));
+    }
     CK(cudaStreamCreateWithPriority(&S.comm_stream, cudaStreamNonBlocking, prio_hi));
     CK(cudaEventCreateWithFlags(&S.ev_gather, cudaEventDisableTiming));
     for (auto& ev : S.ev_fin) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -268,6 +284,7 @@ int nmsm_msm(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, 
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (!out_xy || !out_is_inf || (n && (!pts || !scalars))) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   return E->msm_host(pts, scalars, n, out_xy, out_is_inf);
@@ -278,6 +295,7 @@ int nmsm_msm_device(int curve, const void* d_pts, const void* d_scalars, uint64_
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (!out_xy || !out_is_inf || (n && (!d_pts || !d_scalars))) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   return E->msm_device((const uint32_t*)d_pts, (const uint32_t*)d_scalars, n, nullptr, out_xy, out_is_inf);
@@ -287,6 +305,7 @@ int nmsm_msm_partial_device(int curve, const void* d_pts, const void* d_scalars,
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (!d_out_acc || (n && (!d_pts || !d_scalars))) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   return E->msm_device((const uint32_t*)d_pts, (const uint32_t*)d_scalars, n, (uint32_t*)d_out_acc, nullptr, nullptr);
@@ -296,6 +315,7 @@ int nmsm_fold_partials_device(int curve, const void* d_accs, int count, uint8_t*
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (!d_accs || count < 0 || !out_xy || !out_is_inf) return fail(NMSM_ERR_ARG, "bad argument");
   ENGINE(curve);
   return E->fold((const uint32_t*)d_accs, count, out_xy, out_is_inf);
@@ -306,6 +326,7 @@ int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (n && (!pts || !scalars || !out_xy || !out_is_inf)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   return E->mul_batch(pts, scalars, n, allow_zero, out_xy, out_is_inf);
@@ -315,6 +336,7 @@ int nmsm_points_torsion_free(int curve, const uint8_t* pts, uint64_t n, uint8_t*
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (n && (!pts || !out_ok)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   return E->torsion_free(pts, n, out_ok);
@@ -333,6 +355,7 @@ int nmsm_points_upload(int curve, const uint8_t* pts, uint64_t n, uint64_t* out_
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (!pts || !out_handle) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   uint32_t* d = nullptr;
@@ -355,6 +378,7 @@ int nmsm_msm_points(uint64_t handle, const uint8_t* scalars, uint64_t n, uint8_t
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   PointSet* ps = (PointSet*)(uintptr_t)handle;
   if (!ps || !out_xy || !out_is_inf || (n && !scalars)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(ps->curve);
@@ -376,6 +400,7 @@ int nmsm_points_precompute(uint64_t handle, int window_bits, int* out_window_bit
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   PointSet* ps = (PointSet*)(uintptr_t)handle;
   if (!ps) return fail(NMSM_ERR_ARG, "null handle");
   if (ps->table_c) return fail(NMSM_ERR_ARG, "point set already carries a table");
@@ -400,6 +425,7 @@ int nmsm_point_table_create(int curve, const uint8_t* point_xy, uint64_t* out_ha
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (!point_xy || !out_handle) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   uint32_t* d = nullptr;
@@ -423,6 +449,7 @@ int nmsm_point_table_mul_batch(uint64_t handle, const uint8_t* scalars, uint64_t
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   PointTable* pt = (PointTable*)(uintptr_t)handle;
   if (!pt || (n && (!scalars || !out_xy || !out_is_inf))) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(pt->curve);
@@ -526,6 +553,7 @@ int nmsm_ed25519_verify_batch(const uint8_t* sigs, const uint8_t* pubkeys, const
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (!out_ok || !out_bad_index || (n && (!sigs || !pubkeys || !msg_off || !z16)))
     return fail(NMSM_ERR_ARG, "null pointer");
   if (n && msg_off[n] && !msgs) return fail(NMSM_ERR_ARG, "null pointer");
@@ -536,6 +564,7 @@ int nmsm_points_decode_ex(int curve, const uint8_t* enc, uint64_t n, int flags, 
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (n && (!enc || !out_xy || !out_status)) return fail(NMSM_ERR_ARG, "null pointer");
   if (flags & ~NMSM_DECODE_ZIP215) return fail(NMSM_ERR_ARG, "nmsm_points_decode_ex: unknown flag");
   return decode_points_impl(curve, enc, n, flags, out_xy, out_status);
@@ -549,6 +578,7 @@ int nmsm_points_on_curve(int curve, const uint8_t* pts, uint64_t n, uint8_t* out
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (n && (!pts || !out_ok)) return fail(NMSM_ERR_ARG, "null pointer");
   ENGINE(curve);
   return E->on_curve(pts, n, out_ok);
@@ -579,6 +609,7 @@ int nmsm_ntt(int curve, uint8_t* values, int log_n, uint64_t generator, int inve
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (!values) return fail(NMSM_ERR_ARG, "null pointer");
   return ntt_impl(curve, values, 0, log_n, generator, inverse, brp_input, brp_output);
 }
@@ -587,6 +618,7 @@ int nmsm_ntt_device(int curve, void* d_values, int log_n, uint64_t generator, in
   std::lock_guard<std::mutex> lk(g_mu);
   if (int r = ensure_init()) return r;
   g_ctx.cur = 0;
+  SLOT0_FREE();
   if (!d_values) return fail(NMSM_ERR_ARG, "null pointer");
   return ntt_impl(curve, d_values, 1, log_n, generator, inverse, brp_input, brp_output);
 }

@@ -63,7 +63,7 @@ struct Pending {
 };
 static constexpr int MAX_GROUPS = 8;       // window groups per single-GPU MSM (engine.cuh submit_msm)
 static constexpr int MAX_WINDOWS = 34;     // sharded MSMs run one group per window: 16-bit windows over <= 256+1 bits, c >= 8
-static constexpr int ACC_STREAMS = 2, TAIL_STREAMS = 2;
+static constexpr int ACC_STREAMS = 2, TAIL_STREAMS = 4;
 struct Slot {
   cudaStream_t stream = nullptr;
   // Window-group pipelining: the per-group accumulate launches alternate between two low-priority streams (the
@@ -77,6 +77,8 @@ struct Slot {
   uint32_t* h_gather = nullptr;  // pinned copy of the gathered window results + error words
   Buf recv, gsend, grecv;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // whole-MSM device time, always recorded
+  // NMSM_TRACE=1 (debugging aid): timing events at the end of every group's accumulate / reduction / Horner step
+  cudaEvent_t tr_fork = nullptr, tr_acc[MAX_WINDOWS] = {}, tr_tail[MAX_WINDOWS] = {}, tr_h[MAX_WINDOWS] = {};
   Buf in_pts, in_scalars, aff, counts, offsets, cursor, sorted, buckets, heads, tails, chunk_out, window_out, tile_sums,
       blk, tiles, result, mul_out, hacc;
   uint32_t* h_result = nullptr;  // pinned staging for (xy | inf | err0 | err1 | entries)
@@ -99,6 +101,7 @@ struct Context {
   int ntt_key_field = -1, ntt_key_bits = -1;            // which root table ntt_roots holds
   uint64_t ntt_key_gen = 0;
   bool profiling = false;
+  bool trace = false;
   int forced_c = 0;
   int forced_groups = 0;  // 0 = automatic (nmsm_set_window_groups)
   float last_ms[NMSM_TIMING_SLOTS] = {};

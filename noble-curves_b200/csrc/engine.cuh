@@ -32,11 +32,29 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   return collect_msm(out_xy, out_is_inf);
 }
 
-// How many window groups to pipeline: worth it once the accumulation is long enough to hide a group's reduction
-// and Horner chain underneath it; small MSMs run as one group (fewest launches).
+// chunks per logical thread of k_reduce2: 4, or up to 16 when that lets ONE pass leave <= REDUCE2_MAX_SPLITS block results
+// per window (a second pass costs a whole latency-bound launch)
+static int reduce2_r(uint64_t chunks) {
+  int r = REDUCE2_R;
+  while (r < 16 && (chunks + (uint64_t)REDUCE2_LOGICAL * r - 1) / ((uint64_t)REDUCE2_LOGICAL * r) > (uint64_t)REDUCE2_MAX_SPLITS &&
+         chunks <= (uint64_t)REDUCE2_LOGICAL * 16 * REDUCE2_MAX_SPLITS)
+    r *= 2;
+  return r;
+}
+
+static constexpr int SHARD_MIN_C = 8;  // sharded MSMs: at most ceil(257 / 8) = 33 windows (MAX_WINDOWS), one group each
+
+// How many window groups to pipeline.  Measured on B200 (2^20 BLS12-381 G1 terms, profiles/r02_trace_window_groups.txt):
+// overlapping the bucket reduction and Horner chains of finished groups with the accumulation of the rest does NOT
+// shorten one MSM — the latency-bound tail kernels share every SM sub-partition with 4 accumulate warps and run 3-5x
+// slower, the accumulation loses the pipe time they take (5.9 -> 6.6 ms), and the last group's tail stays on the
+// critical path: 8.36 ms with 8 groups vs 8.38 ms with one.  So one group is the default; nmsm_set_window_groups keeps
+// the pipelined form available, and sharded MSMs use one group per window because that is what lets a window's bucket
+// exchange overlap the accumulation of the next windows.
 static int choose_groups(const MsmPlan& plan, uint64_t max_entries) {
+  (void)max_entries;
   if (plan.W <= 1) return 1;
-  int ng = max_entries >= (3ull << 20) ? (plan.W < MAX_GROUPS ? plan.W : MAX_GROUPS) : 1;
+  int ng = 1;
   if (g_ctx.forced_groups) ng = g_ctx.forced_groups < plan.W ? g_ctx.forced_groups : plan.W;
   if (g_ctx.profiling) ng = 1;  // per-kernel event times only mean something on a linear pipeline
   return ng;
@@ -75,8 +93,8 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
     return fail(NMSM_ERR_ARG, shard && !g_dist.ready ? "nmsm_dist_init has not been called" : "sharded MSM: unsupported combination");
   const uint64_t n_plan = shard ? shard->n_total : n;
   if (shard && (n_plan >= (1ull << 31) || shard->offset + n > n_plan)) return fail(NMSM_ERR_ARG, "sharded MSM: bad shard bounds");
-  const int RES_WORDS = G::IN_WORDS + 4;  // xy | inf | err_pt | err_sc | pad
-  CK(C.result.ensure(RES_WORDS * 4));
+  const int RES_WORDS = G::IN_WORDS + 4;  // xy | inf | err_pt | err_sc | pad   (then 2 words: accumulator starts, profiling)
+  CK(C.result.ensure((RES_WORDS + 2) * 4));
   uint32_t* d_res = (uint32_t*)C.result.p;
   unsigned int* d_err = (unsigned int*)(d_res + G::IN_WORDS + 1);
 
@@ -96,15 +114,15 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   }
 
   MsmPlan plan = table_c ? make_table_plan<Cv>(table_points, table_c, g_ctx.sm_count)
-                         : make_plan<Cv>(n_plan, g_ctx.forced_c, g_ctx.sm_count, shard ? (n ? n : 1) : 0);
-  if (plan.W > MAX_WINDOWS) return fail(NMSM_ERR_ARG, "window count exceeds MAX_WINDOWS");
+                         : make_plan<Cv>(n_plan, g_ctx.forced_c, g_ctx.sm_count, shard ? (n ? n : 1) : 0, shard ? SHARD_MIN_C : 2);
+  if (shard && plan.W > MAX_WINDOWS) return fail(NMSM_ERR_ARG, "window count exceeds MAX_WINDOWS");
   const uint64_t max_entries = (n ? n : 1) * (uint64_t)plan.D * (Cv::GLV ? 2 : 1);
   if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
   // bucket reduction levels: every k_reduce2 pass shrinks the per-window chunk count by REDUCE2_CHUNKS_PER_BLOCK
   // until <= REDUCE2_MAX_SPLITS block results per window remain for k_reduce3 (one pass for the ordinary plans)
   size_t blk_entries = 0;
   for (uint64_t m = plan.chunks;;) {
-    const uint64_t sp = (m + REDUCE2_CHUNKS_PER_BLOCK - 1) / REDUCE2_CHUNKS_PER_BLOCK;
+    const uint64_t sp = (m + (uint64_t)REDUCE2_LOGICAL * reduce2_r(m) - 1) / ((uint64_t)REDUCE2_LOGICAL * reduce2_r(m));
     blk_entries += sp;
     if (sp <= REDUCE2_MAX_SPLITS) break;
     m = sp;
@@ -145,6 +163,8 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   cudaStream_t st = C.stream;
   const uint32_t n32 = (uint32_t)n;
   const int NG = shard ? plan.W : choose_groups(plan, max_entries);
+  static const bool quad_env = getenv("NMSM_QUAD_REDUCE1") ? atoi(getenv("NMSM_QUAD_REDUCE1")) != 0 : false;  // tuning experiment
+  const bool quad_reduce1 = quad_env && NG > 1;
   const bool prof = g_ctx.profiling && !shard;
   // sharded: which windows this rank owns, where their peers' buckets land, and the gather layout
   const int world = shard ? g_dist.world : 1, rank = shard ? g_dist.rank : 0;
@@ -183,24 +203,40 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   if (n) k_digits<Cv, true><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, cursor, sorted, d_err);
   launches += 4;
   PEV(4);
+  if (prof) {  // accounting only (not part of the timed kernels: between the scatter and the accumulate events)
+    CK(cudaMemsetAsync(d_res + RES_WORDS, 0, 8, st));
+    const uint64_t items = nseg > (uint64_t)plan.G ? nseg : (uint64_t)plan.G;
+    k_count_starts<<<cdiv(items, 256), 256, 0, st>>>(offsets, plan, (unsigned long long*)(d_res + RES_WORDS));
+    cudaEventRecord(C.ev[4], st);  // restart the accumulate interval after the counting kernel
+  }
   if (shard) { k_set_identity<Cv><<<1, 32, 0, st>>>(gsend, slots); launches++; }
   if (NG > 1) CK(cudaEventRecord(C.ev_fork, st));
+  const bool trace = g_ctx.trace && NG > 1 && !shard;
+  if (trace) cudaEventRecord(C.tr_fork, st);
 
   const int per = (plan.W + NG - 1) / NG;  // windows per group
+  // Pass 1: every group's accumulate launch, top windows first.  They are issued before any tail work so that, should
+  // two of the library's streams share a hardware work queue (CUDA_DEVICE_MAX_CONNECTIONS), an accumulate launch never
+  // sits behind a tail kernel that is still waiting for an earlier group.
+  int ngroups = 0;
+  for (int w_hi = plan.W; w_hi > 0; w_hi -= per, ngroups++) {
+    const int w_lo = w_hi > per ? w_hi - per : 0;
+    const uint32_t nw = (uint32_t)(w_hi - w_lo);
+    cudaStream_t sa = NG > 1 ? C.acc_stream[ngroups % ACC_STREAMS] : st;
+    if (NG > 1 && ngroups < ACC_STREAMS) CK(cudaStreamWaitEvent(sa, C.ev_fork, 0));
+    k_accumulate<Cv><<<cdiv((uint64_t)nw * plan.TPW, 128), 128, 0, sa>>>(aff, sorted, offsets, plan, (uint32_t)w_lo, buckets,
+                                                                         heads, tails);
+    if (NG > 1) CK(cudaEventRecord(C.ev_acc[ngroups], sa));
+    if (trace) cudaEventRecord(C.tr_acc[ngroups], sa);
+  }
+  // Pass 2: per group, the bucket reduction and Horner step (single GPU) or the bucket exchange + owner reduction (sharded)
   int g = 0;
   for (int w_hi = plan.W; w_hi > 0; w_hi -= per, g++) {
     const int w_lo = w_hi > per ? w_hi - per : 0;
     const uint32_t nw = (uint32_t)(w_hi - w_lo);
-    cudaStream_t sa = NG > 1 ? C.acc_stream[g % ACC_STREAMS] : st;
     cudaStream_t stl = NG > 1 ? C.tail_stream[g % TAIL_STREAMS] : st;
     cudaStream_t sh = NG > 1 ? C.horner_stream : st;
-    if (NG > 1) CK(cudaStreamWaitEvent(sa, C.ev_fork, 0));
-    k_accumulate<Cv><<<cdiv((uint64_t)nw * plan.TPW, 128), 128, 0, sa>>>(aff, sorted, offsets, plan, (uint32_t)w_lo, buckets,
-                                                                         heads, tails);
-    if (NG > 1) {
-      CK(cudaEventRecord(C.ev_acc[g], sa));
-      CK(cudaStreamWaitEvent(stl, C.ev_acc[g], 0));
-    }
+    if (NG > 1) CK(cudaStreamWaitEvent(stl, C.ev_acc[g], 0));
     PEV(5);
     {  // tile sums for buckets spanning many accumulate segments (no-ops for ordinary inputs)
       const uint32_t a0 = (uint32_t)((uint64_t)w_lo * plan.TPW / STITCH_FAN), a1 = (uint32_t)((uint64_t)w_hi * plan.TPW / STITCH_FAN);
@@ -242,9 +278,12 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
       const uint32_t id0 = (uint32_t)w_lo * plan.chunks, id1 = (uint32_t)w_hi * plan.chunks;
       if (shard)
         k_reduce1_dense<Cv><<<cdiv(id1 - id0, REDUCE1_THREADS), REDUCE1_THREADS, 0, stl>>>(buckets, plan, id0, id1, sums, wsums);
+      else if (quad_reduce1 && w_lo == 0)  // last group: its chain is the critical path, run it in the latency form
+        k_reduce1<Cv, true><<<cdiv((uint64_t)(id1 - id0) * 4, REDUCE1_THREADS), REDUCE1_THREADS, 0, stl>>>(
+            offsets, buckets, heads, tails, tile1, tile2, plan, id0, id1, sums, wsums);
       else
-        k_reduce1<Cv><<<cdiv(id1 - id0, REDUCE1_THREADS), REDUCE1_THREADS, 0, stl>>>(offsets, buckets, heads, tails, tile1,
-                                                                                    tile2, plan, id0, id1, sums, wsums);
+        k_reduce1<Cv, false><<<cdiv(id1 - id0, REDUCE1_THREADS), REDUCE1_THREADS, 0, stl>>>(offsets, buckets, heads, tails,
+                                                                                           tile1, tile2, plan, id0, id1, sums, wsums);
     }
     PEV(7);
     launches += 4;
@@ -256,21 +295,22 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
       const uint32_t *S = sums, *T = wsums;
       uint32_t* base = (uint32_t*)C.blk.p;
       for (;;) {
-        const int splits = (pl.chunks + REDUCE2_CHUNKS_PER_BLOCK - 1) / REDUCE2_CHUNKS_PER_BLOCK;
+        const int R2 = reduce2_r(pl.chunks), per_block = REDUCE2_LOGICAL * R2;
+        const int splits = (pl.chunks + per_block - 1) / per_block;
         uint32_t* blkP = base;
         uint32_t* blkQ = base + (size_t)plan.W * splits * G::ACC_WORDS;
         base = blkQ + (size_t)plan.W * splits * G::ACC_WORDS;
-        k_reduce2<Cv><<<dim3(splits, nw), REDUCE2_THREADS, smem2, stl>>>(S, T, pl, REDUCE2_R, (uint32_t)w_lo, blkP, blkQ);
+        k_reduce2<Cv><<<dim3(splits, nw), REDUCE2_THREADS, smem2, stl>>>(S, T, pl, R2, (uint32_t)w_lo, blkP, blkQ);
         launches++;
         if (splits <= REDUCE2_MAX_SPLITS) {
-          k_reduce3<Cv><<<nw, 32, 0, stl>>>(blkP, blkQ, pl, splits, REDUCE2_R, (uint32_t)w_lo, window_out);
+          k_reduce3<Cv><<<nw, 32, 0, stl>>>(blkP, blkQ, pl, splits, R2, (uint32_t)w_lo, window_out);
           launches++;
           break;
         }
         S = blkQ;
         T = blkP;
         pl.chunks = splits;
-        pl.K *= REDUCE2_CHUNKS_PER_BLOCK;
+        pl.K *= per_block;
       }
     }
     PEV(8);
@@ -286,7 +326,9 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
       CK(cudaEventRecord(C.ev_tail[g], stl));
       CK(cudaStreamWaitEvent(sh, C.ev_tail[g], 0));
     }
+    if (trace) cudaEventRecord(C.tr_tail[g], stl);
     k_horner_step<Cv><<<1, 32, 0, sh>>>(window_out, plan, w_lo, w_hi, g == 0 ? 1 : 0, 0, hacc);
+    if (trace) cudaEventRecord(C.tr_h[g], sh);
     launches++;
   }
   if (shard) {
@@ -326,6 +368,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   // one small D2H: result + error slots (+ entry count for accounting)
   CK(cudaMemcpyAsync(C.h_result, d_res, RES_WORDS * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(C.h_result + RES_WORDS, offsets + plan.G, 4, cudaMemcpyDeviceToHost, st));
+  if (prof) CK(cudaMemcpyAsync(C.h_result + RES_WORDS + 2, d_res + RES_WORDS, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(C.done, st));
   C.pend.plan = MsmPlanLite{plan.c, plan.W, plan.B, plan.G, plan.L, plan.K, plan.chunks, plan.D, plan.TPW};
   C.pend.profiled = prof;
@@ -382,6 +425,7 @@ static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
   C.last_info.reduce_chunk = plan.K;
   C.last_info.sorted_entries = entries;
   C.last_info.modmul_equiv = plan_modmuls<Cv>(plan, entries);
+  C.last_info.bucket_starts = C.pend.profiled ? ((uint64_t)C.h_result[RES_WORDS + 2] | ((uint64_t)C.h_result[RES_WORDS + 3] << 32)) : 0;
   C.last_info.launches = C.pend.launches;
   C.last_info.window_groups = C.pend.groups;
   memset(C.last_ms, 0, sizeof(C.last_ms));
@@ -390,6 +434,19 @@ static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
       if (cudaEventElapsedTime(&C.last_ms[k], C.ev[k], C.ev[k + 1]) != cudaSuccess) C.last_ms[k] = 0;
   if (cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev_t0, C.ev_t1) != cudaSuccess) C.last_ms[NMSM_T_TOTAL] = 0;
   (void)cudaGetLastError();
+  if (g_ctx.trace && C.pend.groups > 1 && !C.pend.sharded) {
+    float f = 0, a = 0, t = 0, h = 0, tot = C.last_ms[NMSM_T_TOTAL];
+    cudaEventElapsedTime(&f, C.ev_t0, C.tr_fork);
+    fprintf(stderr, "[nmsm trace] fork %.3f total %.3f |", f, tot);
+    for (int k = 0; k < C.pend.groups; k++) {
+      cudaEventElapsedTime(&a, C.ev_t0, C.tr_acc[k]);
+      cudaEventElapsedTime(&t, C.ev_t0, C.tr_tail[k]);
+      cudaEventElapsedTime(&h, C.ev_t0, C.tr_h[k]);
+      fprintf(stderr, " g%d acc %.3f tail %.3f horner %.3f |", k, a, t, h);
+    }
+    fprintf(stderr, "\n");
+    (void)cudaGetLastError();
+  }
   memcpy(g_ctx.last_ms, C.last_ms, sizeof(C.last_ms));
   g_ctx.last_info = C.last_info;
   if (!partial) {

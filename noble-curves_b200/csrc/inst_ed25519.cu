@@ -74,6 +74,10 @@ int ed25519_verify_batch_impl(const uint8_t* sigs, const uint8_t* pks, const uin
     return NMSM_OK;
   }
   if (2 * n + 1 >= (1ull << 31)) return fail(NMSM_ERR_ARG, "batch too large");
+  // the offsets drive device reads of `msgs`: they must start at 0 and never decrease
+  if (msg_off[0] != 0) return fail(NMSM_ERR_ARG, "msg_off[0] must be 0");
+  for (uint64_t i = 0; i < n; i++)
+    if (msg_off[i + 1] < msg_off[i]) return fail(NMSM_ERR_ARG, "msg_off must be non-decreasing (index " + std::to_string(i + 1) + ")", (long long)(i + 1));
   const uint64_t msg_bytes = msg_off[n];
   const uint64_t terms = 2 * n + 1;
   // scratch layout in one buffer (16-byte aligned pieces)

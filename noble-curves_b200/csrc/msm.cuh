@@ -177,18 +177,30 @@ k_stitch_tiles(const uint32_t* __restrict__ offsets, MsmPlan plan, uint32_t span
   if (lane == 0) save_acc<G>(out + (size_t)j * G::ACC_WORDS, acc);
 }
 
-// One thread per chunk, out-of-line serial formulas: with >= 2 warps per SM sub-partition the multiply
-// pipe is shared anyway and the quad form only adds shuffle/select overhead (measured: 2.3 ms vs 1.5 ms).
+// Two forms of the first reduction level.  Serial (one thread per chunk, out-of-line formulas): the throughput form —
+// with >= 2 warps per SM sub-partition the multiply pipe is shared anyway.  Quad (one chunk per 4 lanes, ec.cuh Par4):
+// the latency form for a group whose chain is on the critical path (the last window group: nothing left to overlap it
+// with) — 4 multiplication levels per addition instead of 14 dependent multiplications.
 static constexpr int REDUCE1_THREADS = 128;
-template <class Cv>
+#if defined(__CUDACC__)
+template <class G>
+struct QuadOps {
+  __device__ static void add(typename G::Acc& p, const typename G::Acc& q) { G::template par_add<false>(p, q); }
+  __device__ static void dbl(typename G::Acc& p) { G::template par_dbl<false>(p); }
+};
+#endif
+template <class Cv, bool QUAD>
 __global__ void __launch_bounds__(REDUCE1_THREADS)
 k_reduce1(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ buckets,
           const uint32_t* __restrict__ heads, const uint32_t* __restrict__ tails,
           const uint32_t* __restrict__ tile1, const uint32_t* __restrict__ tile2, MsmPlan plan, uint32_t id0,
           uint32_t id1, uint32_t* __restrict__ sums, uint32_t* __restrict__ wsums) {
   using G = typename Cv::G;
-  const uint32_t id = id0 + blockIdx.x * blockDim.x + threadIdx.x;  // chunks [id0, id1) = the windows of one group
-  if (id < id1) reduce1_body<Cv, SerialOps<G>>(id, offsets, buckets, heads, tails, tile1, tile2, plan, sums, wsums);
+  const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t id = id0 + (QUAD ? gt >> 2 : gt);  // chunks [id0, id1) = the windows of one group
+  if (id >= id1) return;  // whole quads leave together
+  if (QUAD) reduce1_body<Cv, QuadOps<G>>(id, offsets, buckets, heads, tails, tile1, tile2, plan, sums, wsums);
+  else reduce1_body<Cv, SerialOps<G>>(id, offsets, buckets, heads, tails, tile1, tile2, plan, sums, wsums);
 }
 
 // ---- multi-GPU bucket exchange (engine.cuh submit_msm, dist mode) -------------------------------------------
@@ -493,13 +505,25 @@ k_table_mul(const uint32_t* __restrict__ tbl, const uint32_t* __restrict__ scala
   out_inf[i] = inf;
 }
 
+// out[i] = scalars[i] * pts[i].  The to-affine step is the reference's normalizeZ (curve.ts:311-326: one inversion for
+// a whole batch by Montgomery's trick, FpInvertBatch modular.ts:734-760): here ONE inversion per warp shared through
+// prefix / suffix products over the lanes (warp_batch_inverse), instead of a ~770-step binary xgcd in every thread.
 template <class Cv>
 __global__ void __launch_bounds__(128)
 k_mul_batch(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars, uint32_t n,
             int allow_zero, uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_inf,
             unsigned int* err) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) mul_body<Cv>(i, pts, scalars, allow_zero, out_xy, out_inf, err);
+  using G = typename Cv::G;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  typename G::Acc acc = G::identity();
+  const bool ok = i < n && mul_acc_body<Cv>(i, pts, scalars, allow_zero, acc, err);
+  const typename G::Field iz = warp_batch_inverse(G::inv_target(acc));  // whole warp, also the idle lanes
+  if (!ok) return;
+  uint32_t xy[G::IN_WORDS];
+  uint32_t inf;
+  G::to_affine_canonical_with_inv(acc, iz, xy, &inf);
+  store_words<G::IN_WORDS>(out_xy + (size_t)i * G::IN_WORDS, xy);
+  out_inf[i] = inf;
 }
 
 // n * P == O per point (nmsm_points_torsion_free)
@@ -508,6 +532,27 @@ __global__ void __launch_bounds__(128)
 k_torsion(const uint32_t* __restrict__ pts, uint32_t n, uint8_t* __restrict__ out_ok, unsigned int* err) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) torsion_body<Cv>(i, pts, out_ok, err);
+}
+
+// Profiling only: how many of the sorted entries START an accumulator (a copy, no field multiplications) instead of
+// being added to one — one per non-empty bucket plus one per accumulate segment that begins inside a bucket.  The
+// roofline accounting subtracts them from the entry count: executed mixed additions = entries - starts.
+static __global__ void k_count_starts(const uint32_t* __restrict__ offsets, MsmPlan plan, unsigned long long* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int c = 0;
+  if (i < (uint32_t)plan.G && offsets[i + 1] > offsets[i]) c++;
+  const uint64_t nseg = (uint64_t)plan.W * plan.TPW;
+  if (i < nseg) {  // segment (w, t): does it begin strictly inside a bucket?
+    const uint32_t w = i / plan.TPW, t = i % plan.TPW;
+    const uint32_t base = offsets[w * (uint32_t)plan.B], T = offsets[(w + 1) * (uint32_t)plan.B];
+    const uint64_t seg = (uint64_t)base + (uint64_t)t * (uint32_t)plan.L;
+    if (seg < T && t > 0) {
+      const uint32_t g = bucket_of_entry(offsets, plan, w, (uint32_t)seg);
+      if (offsets[g] < seg) c++;
+    }
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
 }
 
 // curve-equation check per point (nmsm_points_on_curve)

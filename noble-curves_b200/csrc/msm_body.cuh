@@ -45,6 +45,16 @@ struct MsmPlan {
                     // (w, t) owns the sorted entries [offsets[w*B] + t*L, + L) of window w, so no segment straddles
                     // two windows and the windows can be accumulated and reduced as independent launches
 };
+// Entries per accumulate thread: whole waves of the grid (4 blocks of 128 threads per SM) with at most 64 entries per
+// thread.  Longer segments mean fewer bucket partials for k_reduce1 to stitch (measured on B200, 2^20 BLS12-381 G1 terms:
+// L = 32 -> 56 takes reduce1 from 0.88 to 0.65 ms, the whole MSM from 8.40 to 8.28 ms), and sizing them to fill the last
+// wave keeps k_accumulate's tail short.
+NMSM_HD int plan_seg_len(double entries, int sm_count) {
+  const double wave = (double)sm_count * 4.0 * 128.0;  // threads of one full wave
+  const double waves = ceil(entries / (64.0 * wave));
+  int L = (int)ceil(entries / ((waves < 1.0 ? 1.0 : waves) * wave));
+  return L < 4 ? 4 : (L > 64 ? 64 : L);
+}
 static constexpr uint32_t SEG_ALIGN = 1024;  // two stitch-tile levels of fan 32 never straddle a window
 // entries a single window can receive at most: one per term and digit routed to it
 NMSM_HD uint32_t plan_tpw(uint64_t max_window_entries, int L) {
@@ -74,7 +84,7 @@ constexpr int glv_bits() {
 // n: term count the window size is chosen for (the GLOBAL count of a sharded MSM, so that every GPU uses the same
 // windows and buckets); n_local (0 = n): terms this GPU accumulates, which sizes the accumulate segments.
 template <class Cv>
-inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_local = 0) {
+inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_local = 0, int min_c = 2) {
   using G = typename Cv::G;
   using F = typename G::Field;
   // with GLV every scalar becomes two signed halves of at most 127 bits, each attached to its own point
@@ -87,13 +97,10 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_loca
   const double t_add_lat = 0.030 * fscale * G::COST_ADD / 14.0;          // ms, dependent chain (2 warps / sub-partition)
   const double t_dbl_par = 0.0062 * fscale;                              // ms per Horner doubling (lane-parallel)
   const int K = 8;
-  auto seg_len = [&](double entries) {
-    int L = (int)ceil(entries / ((double)sm_count * 1024.0));
-    return L < 4 ? 4 : (L > 32 ? 32 : L);
-  };
-  int best_c = 2;
+  auto seg_len = [&](double entries) { return plan_seg_len(entries, sm_count); };
+  int best_c = min_c;
   double best = 1e300;
-  for (int c = 2; c <= MAX_WINDOW_BITS; c++) {
+  for (int c = min_c; c <= MAX_WINDOW_BITS; c++) {  // min_c: sharded MSMs run one launch group per window, keep W small
     const int W = (bits + 1 + c - 1) / c;
     const double B = (double)(1u << (c - 1));
     const double entries = terms * W;
@@ -113,6 +120,7 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_loca
     }
   }
   int c = (forced_c >= 1 && forced_c <= MAX_WINDOW_BITS) ? forced_c : best_c;
+  if (c < min_c) c = min_c;
   MsmPlan p;
   p.c = c;
   p.W = (bits + 1 + c - 1) / c;
@@ -180,8 +188,7 @@ inline int choose_table_bits(uint64_t n_points, int sm_count, double mem_budget_
     const int wb = T / D, r = T % D;
     const double B = (double)(1u << (c - 1));
     const double entries = terms * D;
-    int L = (int)ceil(entries / ((double)sm_count * 1024.0));
-    L = L < 4 ? 4 : (L > 32 ? 32 : L);
+    const int L = plan_seg_len(entries, sm_count);
     // r digits are c bits wide, D - r only c - 1: the lower half of the buckets receives all D digits
     const double load_low = r ? terms * ((double)(D - r) / (double)(1u << (wb - 1)) + (double)r / (double)(1u << wb))
                               : entries / B;
@@ -213,8 +220,7 @@ inline MsmPlan make_table_plan(uint64_t n_points, int c, int sm_count) {
   p.B = 1 << (p.c - 1);
   p.G = p.B;
   p.stride = (uint32_t)(n_points * (Cv::GLV ? 2 : 1));
-  int L = (int)ceil(terms * p.D / ((double)sm_count * 1024.0));
-  p.L = L < 4 ? 4 : (L > 32 ? 32 : L);
+  p.L = plan_seg_len(terms * p.D, sm_count);
   int Kc = TABLE_REDUCE_CHUNK;
 #if !defined(__CUDA_ARCH__)
   if (const char* e = getenv("NMSM_TK")) { int v = atoi(e); if (v >= 1 && (v & (v - 1)) == 0) Kc = v; }  // tuning experiments
@@ -887,7 +893,10 @@ NMSM_HD void bucket_finalize_body(uint32_t g, const uint32_t* offsets, uint32_t*
     } else {
       src = heads + (size_t)t * G::ACC_WORDS;
     }
-    nl_add<G>(acc, load_acc<G>(src));
+    // G::add inline, not nl_add: ptxas 12.9 clones the out-of-line nl_add into this kernel with its operand
+    // addresses in uniform registers and reads one of them uninitialised (compute-sanitizer: invalid __local__ read)
+    const Acc part = load_acc<G>(src);
+    G::add(acc, part);
     t += step;
   }
   save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, acc);
@@ -900,7 +909,10 @@ template <class Cv>
 NMSM_HD void bucket_fold_body(uint32_t b, uint32_t* own, const uint32_t* recv, int npeers, size_t stride_words) {
   using G = typename Cv::G;
   typename G::Acc acc = load_acc<G>(own + (size_t)b * G::ACC_WORDS);
-  for (int r = 0; r < npeers; r++) nl_add<G>(acc, load_acc<G>(recv + (size_t)r * stride_words + (size_t)b * G::ACC_WORDS));
+  for (int r = 0; r < npeers; r++) {
+    const typename G::Acc part = load_acc<G>(recv + (size_t)r * stride_words + (size_t)b * G::ACC_WORDS);
+    G::add(acc, part);  // inline: see bucket_finalize_body
+  }
   save_acc<G>(own + (size_t)b * G::ACC_WORDS, acc);
 }
 
@@ -912,8 +924,9 @@ NMSM_HD void reduce1_dense_body(uint32_t id, const uint32_t* buckets, const MsmP
   const uint32_t g0 = w * plan.B + k * plan.K;
   typename G::Acc sum = G::identity(), wsum = G::identity();
   for (int b = plan.K - 1; b >= 0; b--) {
-    nl_add<G>(sum, load_acc<G>(buckets + (size_t)(g0 + (uint32_t)b) * G::ACC_WORDS));
-    nl_add<G>(wsum, sum);
+    const typename G::Acc part = load_acc<G>(buckets + (size_t)(g0 + (uint32_t)b) * G::ACC_WORDS);
+    G::add(sum, part);  // inline: see bucket_finalize_body
+    G::add(wsum, sum);
   }
   save_acc<G>(sums + (size_t)id * G::ACC_WORDS, sum);
   save_acc<G>(wsums + (size_t)id * G::ACC_WORDS, wsum);
@@ -1086,9 +1099,10 @@ NMSM_HD typename Cv::G::Acc scalar_mul_acc(const typename Cv::G::Affine& P, cons
   return acc;
 }
 
+// Validation + scalar multiplication of item i; false (and the index recorded) when the point or scalar is rejected.
 template <class Cv>
-NMSM_HD void mul_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, int allow_zero, uint32_t* out_xy,
-                      uint32_t* out_inf, unsigned int* err) {
+NMSM_HD bool mul_acc_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, int allow_zero,
+                          typename Cv::G::Acc& acc, unsigned int* err) {
   using G = typename Cv::G;
   uint32_t in[G::IN_WORDS];
   load_words<G::IN_WORDS>(in, pts + (size_t)i * G::IN_WORDS);
@@ -1101,8 +1115,19 @@ NMSM_HD void mul_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, 
   if (!allow_zero && nz == 0) bad_sc = true;
   if (bad_pt) atomic_min_u32(&err[0], i);
   if (bad_sc) atomic_min_u32(&err[1], i);
-  if (bad_pt || bad_sc) return;
-  const typename G::Acc acc = scalar_mul_acc<Cv>(G::prepare(in), s);
+  acc = G::identity();
+  if (bad_pt || bad_sc) return false;
+  acc = scalar_mul_acc<Cv>(G::prepare(in), s);
+  return true;
+}
+
+// serial statement (tests/hostemu): one inversion per item; the kernel shares ONE inversion per warp (msm.cuh k_mul_batch)
+template <class Cv>
+NMSM_HD void mul_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, int allow_zero, uint32_t* out_xy,
+                      uint32_t* out_inf, unsigned int* err) {
+  using G = typename Cv::G;
+  typename G::Acc acc;
+  if (!mul_acc_body<Cv>(i, pts, scalars, allow_zero, acc, err)) return;
   uint32_t xy[G::IN_WORDS];
   uint32_t inf;
   nl_to_affine<G>(acc, xy, &inf);

@@ -10,6 +10,10 @@ import ctypes
 import os
 import threading
 
+# The library overlaps kernels on several CUDA streams per MSM; give the device enough hardware work queues that they
+# do not alias (takes effect if the CUDA context has not been created yet; never overrides an explicit setting).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NMSM_LIB") or os.path.join(_HERE, "libnmsm.so")  # NMSM_LIB: build-variant experiments
 
@@ -43,6 +47,7 @@ class PlanInfo(ctypes.Structure):
         ("modmul_equiv", ctypes.c_uint64),
         ("launches", ctypes.c_int),
         ("window_groups", ctypes.c_int),
+        ("bucket_starts", ctypes.c_uint64),
     ]
 
 

@@ -276,8 +276,8 @@ def test_window_groups_give_identical_results(nmsm, name):
 
 
 def test_window_groups_large_bls12_381_g1(nmsm):
-    """2^18 terms: automatic grouping (one group per window) and forced counts agree with (sum k_i s_i)*G; giant
-    buckets (all scalars equal) cross the per-window segment ranges."""
+    """2^18 terms: the default (one group) and forced group counts agree with (sum k_i s_i)*G; giant buckets (all
+    scalars equal) cross the per-window segment ranges."""
     name = "bls12_381_G1"
     P = R.CURVES[name]
     n = 1 << 18
@@ -295,9 +295,8 @@ def test_window_groups_large_bls12_381_g1(nmsm):
                 out, inf = nmsm.msm_packed(cid, pts_b, sb, n)
                 assert (*H.unpack_point(name, out), inf) == exp, (groups, cid)
             _, info = nmsm.last_timing()
-            if groups == 0:
-                assert info.window_groups > 1  # automatic pipelining kicks in at this size
-        nmsm.set_window_groups(0)
+            assert info.window_groups == (groups if groups else 1)
+        nmsm.set_window_groups(8)
         s = 0x1D3F5A7C9B2E4F60718293A4B5C6D7E8F9 % order
         exp2 = H.expected_tuple(name, H.expected_from_total(P, sum(ks) * s % order))
         out, inf = nmsm.msm_packed(4, pts_b, H.pack_scalars([s] * n), n)

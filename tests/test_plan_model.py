@@ -25,7 +25,7 @@ def test_ordinary_plans(name):
         assert p["W"] * p["c"] >= p["T"] > (p["W"] - 1) * p["c"]          # the windows cover bits + 1 exactly once
         assert p["D"] == p["W"] and p["stride"] == 0 and p["wb"] == p["c"] and p["r"] == 0
         assert p["K"] >= 1 and p["K"] * p["chunks"] == p["B"] and p["K"] & (p["K"] - 1) == 0
-        assert 4 <= p["L"] <= 32
+        assert 4 <= p["L"] <= 64  # msm_body.cuh plan_seg_len
     big = plan(name, 1 << 20)
     if name == "secp256k1":  # 130 half-scalar bits: c = 16 would leave a 2-bit top window (two giant buckets)
         assert big["c"] == 13 and big["W"] == 10

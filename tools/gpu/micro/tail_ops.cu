@@ -10,6 +10,9 @@ using G = SwXyzz<F>;
 
 __device__ F mk(uint32_t s) {
   F x;
+  // thread-dependent data: with warp-uniform operands ptxas moves the whole chain to the uniform datapath (UIMAD),
+  // which is not the pipe the kernels use
+  s += (threadIdx.x >> 2) * 7919u + blockIdx.x * 104729u;
   for (int k = 0; k < 12; k++) x.v[k] = FpBls381::R2(k) ^ (s * 2654435761u >> (k & 7));
   x.v[11] &= 0x0fffffffu;
   return x;
@@ -23,6 +26,8 @@ template <int OP>
 __global__ void k(uint32_t* out, long long* cyc, int iters, uint32_t seed) {
   F a = mk(seed + (OP >= 100 ? 0 : 0)), b = mk(seed + 7);
   G::Acc p = mkp(seed + 11), q = mkp(seed + 23);
+  unsigned long long g0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g0));
   long long t0 = clock64();
   for (int i = 0; i < iters; i++) {
     if (OP == 0) a = a * b;
@@ -38,9 +43,11 @@ __global__ void k(uint32_t* out, long long* cyc, int iters, uint32_t seed) {
     if (OP == 10) { F r; mont_mul<FpBls381>(r.v, a.v, b.v); a = r; }
   }
   long long t1 = clock64();
+  unsigned long long g1;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
   uint32_t acc = 0;
   for (int k2 = 0; k2 < 12; k2++) acc ^= a.v[k2] ^ p.X.v[k2] ^ p.Y.v[k2] ^ p.ZZ.v[k2] ^ p.ZZZ.v[k2];
-  if (threadIdx.x == 0 && blockIdx.x == 0) { cyc[0] = t1 - t0; }
+  if (threadIdx.x == 0 && blockIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = (long long)(g1 - g0); }
   if (acc == 0x1234567u) out[threadIdx.x] = acc;
 }
 
@@ -49,7 +56,7 @@ void run(const char* name, int threads, int blocks, int iters) {
   uint32_t* d; long long* c;
   cudaMalloc(&d, 4096 * 4); cudaMalloc(&c, 64);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  float best = 1e9; long long cy = 0;
+  float best = 1e9; long long cy = 0, ns = 0;
   for (int r = 0; r < 3; r++) {
     cudaEventRecord(e0);
     k<OP><<<blocks, threads>>>(d, c, iters, 12345u + r);
@@ -57,15 +64,21 @@ void run(const char* name, int threads, int blocks, int iters) {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (ms < best) best = ms;
     cudaMemcpy(&cy, c, 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&ns, c + 1, 8, cudaMemcpyDeviceToHost);
   }
-  printf("{\"op\": \"%s\", \"threads\": %d, \"blocks\": %d, \"iters\": %d, \"us_per_op\": %.4f, \"cycles_per_op\": %.1f, \"err\": \"%s\"}\n",
-         name, threads, blocks, iters, best * 1e3 / iters, (double)cy / iters, cudaGetErrorString(cudaGetLastError()));
+  printf("{\"op\": \"%s\", \"threads\": %d, \"blocks\": %d, \"iters\": %d, \"us_per_op\": %.4f, \"cycles_per_op\": %.1f, \"sm_mhz\": %.0f, \"gmodmul_s\": %.2f, \"err\": \"%s\"}\n",
+         name, threads, blocks, iters, best * 1e3 / iters, (double)cy / iters, ns ? (double)cy / ns * 1e3 : 0.0,
+         (double)blocks * threads * iters / (best * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
   cudaFree(d); cudaFree(c);
 }
 
 int main() {
+  // burst vs sustained: the same saturating multiply chain for 0.5 ms .. 60 ms
+  for (int it : {256, 1024, 4096, 16384, 32768}) run<0>("mul_sat", 128, 148 * 4, it);
+  for (int it : {256, 4096, 32768}) run<0>("mul_sat8", 128, 148 * 8, it);
+  for (int it : {256, 4096}) run<1>("sqr_sat", 128, 148 * 4, it);
   const int IT = 512;
-  for (int thr : {32, 64, 128}) {
+  for (int thr : {32}) {
     for (int blocks : {1, 148 * 4}) {
       run<0>("mul", thr, blocks, IT);
       run<10>("mul_inline", thr, blocks, IT);
