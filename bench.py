@@ -33,6 +33,8 @@ import threading
 import time
 
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before any CUDA context exists (see nmsm/_lib.py)
+os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")       # before any NCCL communicator exists (see nmsm/_lib.py)
+os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "noble-curves_b200"))
 sys.path.insert(0, ROOT)

@@ -190,6 +190,9 @@ int nmsm_init(int device) {
     for (auto& st : S.acc_stream) CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_lo));
     for (auto& st : S.tail_stream) CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
     CK(cudaStreamCreateWithPriority(&S.horner_stream, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithFlags(&S.prep_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&S.ev_start, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&S.ev_prep, cudaEventDisableTiming));
     CK(cudaMallocHost((void**)&S.h_result, 1024));
     for (auto& ev : S.ev) CK(cudaEventCreate(&ev));
     CK(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
@@ -232,6 +235,7 @@ void nmsm_shutdown(void) {
     for (auto st : S.acc_stream) cudaStreamSynchronize(st);
     for (auto st : S.tail_stream) cudaStreamSynchronize(st);
     cudaStreamSynchronize(S.horner_stream);
+    cudaStreamSynchronize(S.prep_stream);
     for (Buf* b : {&S.in_pts, &S.in_scalars, &S.aff, &S.counts, &S.offsets, &S.cursor, &S.sorted, &S.buckets, &S.heads,
                    &S.tails, &S.chunk_out, &S.window_out, &S.tile_sums, &S.blk, &S.tiles, &S.result, &S.mul_out, &S.hacc,
                    &S.recv, &S.gsend, &S.grecv})
@@ -249,6 +253,9 @@ void nmsm_shutdown(void) {
     for (auto st : S.acc_stream) cudaStreamDestroy(st);
     for (auto st : S.tail_stream) cudaStreamDestroy(st);
     cudaStreamDestroy(S.horner_stream);
+    cudaStreamDestroy(S.prep_stream);
+    cudaEventDestroy(S.ev_start);
+    cudaEventDestroy(S.ev_prep);
     cudaStreamDestroy(S.stream);
     S.pend = Pending();
   }

@@ -63,13 +63,15 @@ struct Pending {
 };
 static constexpr int MAX_GROUPS = 8;       // window groups per single-GPU MSM (engine.cuh submit_msm)
 static constexpr int MAX_WINDOWS = 34;     // sharded MSMs run one group per window: 16-bit windows over <= 256+1 bits, c >= 8
-static constexpr int ACC_STREAMS = 2, TAIL_STREAMS = 4;
+static constexpr int ACC_STREAMS = 8, TAIL_STREAMS = 4;  // 8 accumulate streams: a sharded MSM launches one (small) accumulate kernel per window, all must be able to run at once
 struct Slot {
   cudaStream_t stream = nullptr;
   // Window-group pipelining: the per-group accumulate launches alternate between two low-priority streams (the
   // next group's blocks fill the SMs as the previous group's drain), every finished group's bucket reduction runs
   // on a high-priority tail stream, and the Horner steps on their own high-priority stream.
   cudaStream_t acc_stream[ACC_STREAMS] = {}, tail_stream[TAIL_STREAMS] = {}, horner_stream = nullptr;
+  cudaStream_t prep_stream = nullptr;  // k_prepare (multiplier-bound) runs beside the digit count / scan / scatter (atomics-bound)
+  cudaEvent_t ev_start = nullptr, ev_prep = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_acc[MAX_WINDOWS] = {}, ev_tail[MAX_WINDOWS] = {}, ev_horner = nullptr;
   // multi-GPU bucket exchange (nmsm_msm_sharded_*): NCCL calls are issued on comm_stream
   cudaStream_t comm_stream = nullptr;

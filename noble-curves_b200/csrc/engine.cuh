@@ -60,6 +60,21 @@ static int choose_groups(const MsmPlan& plan, uint64_t max_entries) {
   return ng;
 }
 
+// k_prepare (and, for host inputs, the H2D copy of the points) on the slot's prep_stream, beside the scalar copy and the
+// digit passes on the main stream?  Not while profiling: per-kernel event times need the linear pipeline.
+static bool prepare_on_side_stream(uint64_t n, bool prepared) { return !g_ctx.profiling && !prepared && n >= (1u << 14); }
+
+// H2D of host inputs: scalars first on the main stream (the digit passes only need them), the 3x larger point array on
+// prep_stream where k_prepare follows it — the digit count / scan / scatter overlap the point copy.
+static int stage_host_inputs(Slot& C, const void* pts, const void* scalars, uint64_t n) {
+  CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
+  CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
+  CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
+  CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice,
+                     prepare_on_side_stream(n, false) ? C.prep_stream : C.stream));
+  return NMSM_OK;
+}
+
 // Enqueue the whole pipeline (and the small result D2H); no host sync.
 //
 //   main stream   : prepare, digit count, scan, scatter                                   -> ev_fork
@@ -116,6 +131,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   MsmPlan plan = table_c ? make_table_plan<Cv>(table_points, table_c, g_ctx.sm_count)
                          : make_plan<Cv>(n_plan, g_ctx.forced_c, g_ctx.sm_count, shard ? (n ? n : 1) : 0, shard ? SHARD_MIN_C : 2);
   if (shard && plan.W > MAX_WINDOWS) return fail(NMSM_ERR_ARG, "window count exceeds MAX_WINDOWS");
+  if (shard && g_ctx.forced_groups > 1) plan_one_wave_per_window<Cv>(plan, n, g_ctx.sm_count);  // pipelined sharded form
   const uint64_t max_entries = (n ? n : 1) * (uint64_t)plan.D * (Cv::GLV ? 2 : 1);
   if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
   // bucket reduction levels: every k_reduce2 pass shrinks the per-window chunk count by REDUCE2_CHUNKS_PER_BLOCK
@@ -162,7 +178,14 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   uint32_t* hacc = (uint32_t*)C.hacc.p;
   cudaStream_t st = C.stream;
   const uint32_t n32 = (uint32_t)n;
-  const int NG = shard ? plan.W : choose_groups(plan, max_entries);
+  // sharded: one group per window (the exchange of window w overlaps the accumulation of the rest) or, the default, ONE
+  // group (bulk: one accumulate launch at full efficiency, one exchange step for all windows).  Measured on 2 B200,
+  // 2^20 terms in total: see profiles/r02_trace_sharded_*.txt
+  int NG = choose_groups(plan, max_entries);
+  if (shard) {
+    NG = g_ctx.forced_groups ? (g_ctx.forced_groups >= plan.W ? plan.W : g_ctx.forced_groups) : 1;
+    if (NG > 1) NG = plan.W;  // pipelined form: exactly one window per group
+  }
   static const bool quad_env = getenv("NMSM_QUAD_REDUCE1") ? atoi(getenv("NMSM_QUAD_REDUCE1")) != 0 : false;  // tuning experiment
   const bool quad_reduce1 = quad_env && NG > 1;
   const bool prof = g_ctx.profiling && !shard;
@@ -190,7 +213,18 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   PEV(0);
   CK(cudaMemsetAsync(d_err, 0xff, 8, st));
   CK(cudaMemsetAsync(counts, 0, (size_t)(plan.G + 1) * 4, st));
-  if (!d_prepared && n) { k_prepare<Cv><<<cdiv(n, 128), 128, 0, st>>>(d_pts, n32, aff, d_err); launches++; }
+  // k_prepare only feeds k_accumulate: outside profiling it runs on its own stream beside the digit passes
+  const bool prep_aside = prepare_on_side_stream(n, d_prepared != nullptr);
+  if (!d_prepared && n) {
+    cudaStream_t sp = prep_aside ? C.prep_stream : st;
+    if (prep_aside) {
+      CK(cudaEventRecord(C.ev_start, st));
+      CK(cudaStreamWaitEvent(sp, C.ev_start, 0));
+    }
+    k_prepare<Cv><<<cdiv(n, 128), 128, 0, sp>>>(d_pts, n32, aff, d_err);
+    if (prep_aside) CK(cudaEventRecord(C.ev_prep, sp));
+    launches++;
+  }
   PEV(1);
   if (n) k_digits<Cv, false><<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n32, plan, counts, nullptr, d_err);
   PEV(2);
@@ -210,8 +244,9 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
     cudaEventRecord(C.ev[4], st);  // restart the accumulate interval after the counting kernel
   }
   if (shard) { k_set_identity<Cv><<<1, 32, 0, st>>>(gsend, slots); launches++; }
+  if (prep_aside) CK(cudaStreamWaitEvent(st, C.ev_prep, 0));
   if (NG > 1) CK(cudaEventRecord(C.ev_fork, st));
-  const bool trace = g_ctx.trace && NG > 1 && !shard;
+  const bool trace = g_ctx.trace && (NG > 1 || shard);
   if (trace) cudaEventRecord(C.tr_fork, st);
 
   const int per = (plan.W + NG - 1) / NG;  // windows per group
@@ -229,9 +264,94 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
     if (NG > 1) CK(cudaEventRecord(C.ev_acc[ngroups], sa));
     if (trace) cudaEventRecord(C.tr_acc[ngroups], sa);
   }
-  // Pass 2: per group, the bucket reduction and Horner step (single GPU) or the bucket exchange + owner reduction (sharded)
+  // Pass 2 (sharded): per group — dense buckets, exchange with the window owners, owner fold + reduction + weight
+  if (shard) {
+    const size_t smem2 = (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4;
+    int g = 0;
+    for (int w_hi = plan.W; w_hi > 0; w_hi -= per, g++) {
+      const int w_lo = w_hi > per ? w_hi - per : 0;
+      cudaStream_t stl = NG > 1 ? C.tail_stream[g % TAIL_STREAMS] : st;
+      if (NG > 1) CK(cudaStreamWaitEvent(stl, C.ev_acc[g], 0));
+      {  // tile sums for buckets spanning many accumulate segments (no-ops for ordinary inputs), then the dense bucket arrays
+        const uint32_t a0 = (uint32_t)((uint64_t)w_lo * plan.TPW / STITCH_FAN), a1 = (uint32_t)((uint64_t)w_hi * plan.TPW / STITCH_FAN);
+        k_stitch_tiles<Cv><<<cdiv((uint64_t)(a1 - a0) * 32, 128), 128, 0, stl>>>(offsets, plan, STITCH_FAN, a0, a1, heads, tile1);
+        const uint32_t b0 = a0 / STITCH_FAN, b1 = a1 / STITCH_FAN;
+        k_stitch_tiles<Cv><<<cdiv((uint64_t)(b1 - b0) * 32, 128), 128, 0, stl>>>(offsets, plan, STITCH_FAN * STITCH_FAN, b0, b1,
+                                                                                tile1, tile2);
+        k_bucket_finalize<Cv><<<cdiv((uint64_t)(w_hi - w_lo) * plan.B, 128), 128, 0, stl>>>(
+            offsets, buckets, heads, tails, tile1, tile2, plan, (uint32_t)w_lo * plan.B, (uint32_t)w_hi * plan.B);
+        launches += 3;
+      }
+      if (world > 1) {  // the window owners receive every peer's partial buckets; everybody else sends
+        CK(cudaEventRecord(C.ev_fin[g], stl));
+        CK(cudaStreamWaitEvent(C.comm_stream, C.ev_fin[g], 0));
+        if (nccl_group_start()) return NMSM_ERR_CUDA;
+        for (int w = w_hi - 1; w >= w_lo; w--) {
+          const int own_rank = w % world;
+          if (own_rank == rank) {
+            uint32_t* wrecv = recv + (size_t)(w / world) * (world - 1) * WB;
+            for (int r = 0, k = 0; r < world; r++)
+              if (r != rank && nccl_recv(wrecv + (size_t)(k++) * WB, WB * 4, r, C.comm_stream)) return NMSM_ERR_CUDA;
+          } else if (nccl_send(buckets + (size_t)w * WB, WB * 4, own_rank, C.comm_stream)) {
+            return NMSM_ERR_CUDA;
+          }
+        }
+        if (nccl_group_end()) return NMSM_ERR_CUDA;
+        CK(cudaEventRecord(C.ev_xchg[g], C.comm_stream));
+        if (trace) cudaEventRecord(C.tr_h[g], C.comm_stream);
+      } else {
+        CK(cudaEventRecord(C.ev_xchg[g], stl));
+      }
+      if (trace) cudaEventRecord(C.tr_tail[g], stl);
+      // owned windows of the group: independent chains on the tail streams
+      for (int w = w_hi - 1; w >= w_lo; w--) {
+        if (w % world != rank) continue;
+        const int slot = w / world;
+        cudaStream_t so = C.tail_stream[slot % TAIL_STREAMS];
+        CK(cudaStreamWaitEvent(so, C.ev_xchg[g], 0));
+        uint32_t* wb = buckets + (size_t)w * WB;
+        if (world > 1) {
+          k_bucket_fold<Cv><<<cdiv((uint64_t)plan.B * 4, 128), 128, 0, so>>>(wb, recv + (size_t)slot * (world - 1) * WB, world - 1, WB,
+                                                                          (uint32_t)plan.B);
+          launches++;
+        }
+        const uint32_t id0 = (uint32_t)w * plan.chunks, id1 = id0 + plan.chunks;
+        k_reduce1_dense<Cv><<<cdiv((uint64_t)(id1 - id0) * 4, REDUCE1_THREADS), REDUCE1_THREADS, 0, so>>>(buckets, plan, id0, id1, sums,
+                                                                                                    wsums);
+        launches++;
+        MsmPlan pl = plan;
+        const uint32_t *S = sums, *T = wsums;
+        uint32_t* base = (uint32_t*)C.blk.p;
+        for (;;) {
+          const int R2 = reduce2_r(pl.chunks), per_block = REDUCE2_LOGICAL * R2;
+          const int splits = (pl.chunks + per_block - 1) / per_block;
+          uint32_t* blkP = base;
+          uint32_t* blkQ = base + (size_t)plan.W * splits * G::ACC_WORDS;
+          base = blkQ + (size_t)plan.W * splits * G::ACC_WORDS;
+          k_reduce2<Cv><<<dim3(splits, 1), REDUCE2_THREADS, smem2, so>>>(S, T, pl, R2, (uint32_t)w, blkP, blkQ);
+          launches++;
+          if (splits <= REDUCE2_MAX_SPLITS) {
+            k_reduce3<Cv><<<1, 32, 0, so>>>(blkP, blkQ, pl, splits, R2, (uint32_t)w, window_out);
+            launches++;
+            break;
+          }
+          S = blkQ;
+          T = blkP;
+          pl.chunks = splits;
+          pl.K *= per_block;
+        }
+        // weighted window sum 2^(c w) S_w straight into its gather slot
+        k_horner_step<Cv><<<1, 32, 0, so>>>(window_out, plan, w, w + 1, 1, 1, gsend + (size_t)slot * G::ACC_WORDS);
+        launches++;
+        CK(cudaEventRecord(C.ev_tail[w], so));
+        if (trace && w < 16) cudaEventRecord(C.tr_acc[17 + w], so);
+      }
+    }
+    ngroups = g;
+  }
+  // Pass 2 (single GPU): per group, the bucket reduction and the Horner step
   int g = 0;
-  for (int w_hi = plan.W; w_hi > 0; w_hi -= per, g++) {
+  for (int w_hi = plan.W; w_hi > 0 && !shard; w_hi -= per, g++) {
     const int w_lo = w_hi > per ? w_hi - per : 0;
     const uint32_t nw = (uint32_t)(w_hi - w_lo);
     cudaStream_t stl = NG > 1 ? C.tail_stream[g % TAIL_STREAMS] : st;
@@ -246,39 +366,9 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
                                                                               tile1, tile2);
     }
     PEV(6);
-    bool owner = true;
-    if (shard) {  // one window per group: finalize its dense buckets, exchange with the owner, fold
-      const int w = w_lo, own_rank = w % world, slot = w / world;
-      owner = own_rank == rank;
-      uint32_t* wb = buckets + (size_t)w * WB;
-      uint32_t* wrecv = recv + (size_t)slot * (world - 1) * WB;
-      k_bucket_finalize<Cv><<<cdiv(plan.B, 128), 128, 0, stl>>>(offsets, buckets, heads, tails, tile1, tile2, plan,
-                                                               (uint32_t)w * plan.B, (uint32_t)(w + 1) * plan.B);
-      launches++;
-      if (world > 1) {
-        CK(cudaEventRecord(C.ev_fin[g], stl));
-        CK(cudaStreamWaitEvent(C.comm_stream, C.ev_fin[g], 0));
-        if (nccl_group_start()) return NMSM_ERR_CUDA;
-        if (owner) {
-          for (int r = 0, k = 0; r < world; r++)
-            if (r != rank && nccl_recv(wrecv + (size_t)(k++) * WB, WB * 4, r, C.comm_stream)) return NMSM_ERR_CUDA;
-        } else if (nccl_send(wb, WB * 4, own_rank, C.comm_stream)) {
-          return NMSM_ERR_CUDA;
-        }
-        if (nccl_group_end()) return NMSM_ERR_CUDA;
-        if (owner) {
-          CK(cudaEventRecord(C.ev_xchg[g], C.comm_stream));
-          CK(cudaStreamWaitEvent(stl, C.ev_xchg[g], 0));
-          k_bucket_fold<Cv><<<cdiv(plan.B, 128), 128, 0, stl>>>(wb, wrecv, world - 1, WB, (uint32_t)plan.B);
-          launches++;
-        }
-      }
-    }
-    if (owner) {
+    {
       const uint32_t id0 = (uint32_t)w_lo * plan.chunks, id1 = (uint32_t)w_hi * plan.chunks;
-      if (shard)
-        k_reduce1_dense<Cv><<<cdiv(id1 - id0, REDUCE1_THREADS), REDUCE1_THREADS, 0, stl>>>(buckets, plan, id0, id1, sums, wsums);
-      else if (quad_reduce1 && w_lo == 0)  // last group: its chain is the critical path, run it in the latency form
+      if (quad_reduce1 && w_lo == 0)  // last group: its chain is the critical path, run it in the latency form
         k_reduce1<Cv, true><<<cdiv((uint64_t)(id1 - id0) * 4, REDUCE1_THREADS), REDUCE1_THREADS, 0, stl>>>(
             offsets, buckets, heads, tails, tile1, tile2, plan, id0, id1, sums, wsums);
       else
@@ -287,7 +377,6 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
     }
     PEV(7);
     launches += 4;
-    if (owner)
     {
       // msm.cuh "Bucket reduction": P/Q of one level are the T/S of the next (chunks := splits, K := K * Mb)
       const size_t smem2 = (REDUCE2_THREADS / 32) * G::ACC_WORDS * 4;
@@ -314,14 +403,6 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
       }
     }
     PEV(8);
-    if (shard) {  // owner: weighted window sum 2^(c w) S_w straight into its gather slot
-      if (owner) {
-        k_horner_step<Cv><<<1, 32, 0, stl>>>(window_out, plan, w_lo, w_hi, 1, 1, gsend + (size_t)(w_lo / world) * G::ACC_WORDS);
-        launches++;
-      }
-      if (NG > 1) CK(cudaEventRecord(C.ev_tail[g], stl));
-      continue;
-    }
     if (NG > 1) {
       CK(cudaEventRecord(C.ev_tail[g], stl));
       CK(cudaStreamWaitEvent(sh, C.ev_tail[g], 0));
@@ -331,10 +412,10 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
     if (trace) cudaEventRecord(C.tr_h[g], sh);
     launches++;
   }
+  if (shard) g = ngroups;
   if (shard) {
     cudaStream_t sc = world > 1 ? C.comm_stream : st;
-    if (NG > 1)
-      for (int k = 0; k < g; k++) CK(cudaStreamWaitEvent(sc, C.ev_tail[k], 0));
+    for (int w = rank; w < plan.W; w += world) CK(cudaStreamWaitEvent(sc, C.ev_tail[w], 0));  // every owned window's chain
     k_pack_shard_tail<<<1, 32, 0, sc>>>(gsend + (size_t)slots * G::ACC_WORDS, d_err, shard->offset);
     if (world > 1) {
       if (nccl_all_gather(gsend, grecv, (size_t)gather_words * 4, sc)) return NMSM_ERR_CUDA;
@@ -434,16 +515,23 @@ static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
       if (cudaEventElapsedTime(&C.last_ms[k], C.ev[k], C.ev[k + 1]) != cudaSuccess) C.last_ms[k] = 0;
   if (cudaEventElapsedTime(&C.last_ms[NMSM_T_TOTAL], C.ev_t0, C.ev_t1) != cudaSuccess) C.last_ms[NMSM_T_TOTAL] = 0;
   (void)cudaGetLastError();
-  if (g_ctx.trace && C.pend.groups > 1 && !C.pend.sharded) {
+  if (g_ctx.trace && (C.pend.groups > 1 || C.pend.sharded)) {
     float f = 0, a = 0, t = 0, h = 0, tot = C.last_ms[NMSM_T_TOTAL];
     cudaEventElapsedTime(&f, C.ev_t0, C.tr_fork);
-    fprintf(stderr, "[nmsm trace] fork %.3f total %.3f |", f, tot);
+    fprintf(stderr, "[nmsm trace%s rank %d] fork %.3f total %.3f |", C.pend.sharded ? " sharded" : "", g_dist.rank, f, tot);
     for (int k = 0; k < C.pend.groups; k++) {
+      a = t = h = -1;
       cudaEventElapsedTime(&a, C.ev_t0, C.tr_acc[k]);
       cudaEventElapsedTime(&t, C.ev_t0, C.tr_tail[k]);
-      cudaEventElapsedTime(&h, C.ev_t0, C.tr_h[k]);
-      fprintf(stderr, " g%d acc %.3f tail %.3f horner %.3f |", k, a, t, h);
+      if (!C.pend.sharded || g_dist.world > 1) cudaEventElapsedTime(&h, C.ev_t0, C.tr_h[k]);
+      fprintf(stderr, " g%d acc %.3f %s %.3f %s %.3f |", k, a, C.pend.sharded ? "dense" : "tail", t, C.pend.sharded ? "xchg" : "horner", h);
     }
+    if (C.pend.sharded)
+      for (int w = g_dist.rank; w < C.pend.plan.W && w < 16; w += g_dist.world) {
+        a = -1;
+        cudaEventElapsedTime(&a, C.ev_t0, C.tr_acc[17 + w]);
+        fprintf(stderr, " own w%d done %.3f |", w, a);
+      }
     fprintf(stderr, "\n");
     (void)cudaGetLastError();
   }
@@ -472,10 +560,7 @@ static int submit_any(const void* pts, const void* scalars, uint64_t n, int inpu
   if (d_out_acc && !inputs_on_device) return fail(NMSM_ERR_ARG, "raw-accumulator output needs device-resident inputs");
   if (inputs_on_device || n == 0)
     return submit_msm((const uint32_t*)pts, (const uint32_t*)scalars, n, (uint32_t*)d_out_acc, nullptr, 0, 0, shard);
-  CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
-  CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
-  CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
-  CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
+  if (int r = stage_host_inputs(C, pts, scalars, n)) return r;
   return submit_msm((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p, n, nullptr, nullptr, 0, 0, shard);
 }
 
@@ -676,12 +761,9 @@ static int run_msm_dev(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_
 
 static int run_msm_host(const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t* out_xy, int* out_is_inf) {
   Slot& C = g_ctx.slot[g_ctx.cur];
-  if (n) {
-    CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
-    CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
-    CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
-    CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
-  }
+  if (C.pend.active) return fail(NMSM_ERR_ARG, "slot busy: collect the previous MSM first");
+  if (n)
+    if (int r = stage_host_inputs(C, pts, scalars, n)) return r;
   return run_msm((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p, n, nullptr, out_xy, out_is_inf);
 }
 

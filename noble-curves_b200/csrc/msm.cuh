@@ -212,18 +212,20 @@ k_bucket_finalize(const uint32_t* __restrict__ offsets, uint32_t* __restrict__ b
   const uint32_t g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (g < g1) bucket_finalize_body<Cv>(g, offsets, buckets, heads, tails, tile1, tile2, plan);
 }
+// Both run one logical thread per QUAD of lanes (ec.cuh Par4): an owner's fold and first reduction level sit on the
+// critical path of a sharded MSM (one window = few thousand chains, the GPU is otherwise idle), so the latency form pays.
 template <class Cv>
 __global__ void __launch_bounds__(128)
 k_bucket_fold(uint32_t* __restrict__ own, const uint32_t* __restrict__ recv, int npeers, size_t stride_words, uint32_t B) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) bucket_fold_body<Cv>(b, own, recv, npeers, stride_words);
+  const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  if (b < B) bucket_fold_body<Cv, QuadOps<typename Cv::G>>(b, own, recv, npeers, stride_words);
 }
 template <class Cv>
 __global__ void __launch_bounds__(REDUCE1_THREADS)
 k_reduce1_dense(const uint32_t* __restrict__ buckets, MsmPlan plan, uint32_t id0, uint32_t id1, uint32_t* __restrict__ sums,
                 uint32_t* __restrict__ wsums) {
-  const uint32_t id = id0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (id < id1) reduce1_dense_body<Cv>(id, buckets, plan, sums, wsums);
+  const uint32_t id = id0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 2);
+  if (id < id1) reduce1_dense_body<Cv, QuadOps<typename Cv::G>>(id, buckets, plan, sums, wsums);
 }
 // tail of a rank's gather block: err_pt | err_sc (local indices, 0xffffffff = none) | shard offset (lo, hi)
 static __global__ void k_pack_shard_tail(uint32_t* __restrict__ tail, const unsigned int* __restrict__ err, uint64_t offset) {

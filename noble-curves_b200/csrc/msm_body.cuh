@@ -144,6 +144,17 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_loca
   return p;
 }
 
+// Sharded MSM run as one accumulate launch per window (engine.cuh): size the segments so that ONE window is one wave of
+// short blocks.  The windows then finish one after the other (instead of all together at the end of two long waves) and
+// the bucket exchange / owner reduction of window w overlaps the accumulation of windows w-1..0.
+template <class Cv>
+inline void plan_one_wave_per_window(MsmPlan& p, uint64_t n_local, int sm_count) {
+  const double terms_local = (double)(n_local ? n_local : 1) * (Cv::GLV ? 2 : 1);
+  int L1 = (int)ceil(terms_local / ((double)sm_count * 4.0 * 128.0));
+  p.L = L1 < 4 ? 4 : (L1 > 64 ? 64 : L1);
+  p.TPW = plan_tpw((uint64_t)terms_local, p.L);
+}
+
 // Fixed-base tables (nmsm_points_precompute): level j of the table holds 2^(offset_j) * P_i for every point of the
 // set, so all D digits of a scalar land in ONE bucket window: 1/W of the bucket reduction, no Horner doublings,
 // and c can grow past 16 because the reduce cost no longer multiplies by W.  Same time model as make_plan.
@@ -343,6 +354,12 @@ template <class G>
 struct SerialOps {
   NMSM_HD static void add(typename G::Acc& p, const typename G::Acc& q) { nl_add<G>(p, q); }
   NMSM_HD static void dbl(typename G::Acc& p) { nl_dbl<G>(p); }
+};
+// same, formulas inlined at the call site (bucket_finalize_body explains why the dense kernels avoid nl_add)
+template <class G>
+struct InlineOps {
+  NMSM_HD static void add(typename G::Acc& p, const typename G::Acc& q) { G::add(p, q); }
+  NMSM_HD static void dbl(typename G::Acc& p) { G::dbl(p); }
 };
 
 // c bits of a 256-bit little-endian scalar starting at bit `off`
@@ -905,19 +922,19 @@ NMSM_HD void bucket_finalize_body(uint32_t g, const uint32_t* offsets, uint32_t*
 // bucket b of an owned window: own partial += the partials received from the `npeers` other GPUs (peer arrays are
 // `stride_words` apart).  The EC fold of the "allreduce of bucket accumulators": point addition is not an NCCL
 // reduction operator, so the exchange is send/recv + this kernel.
-template <class Cv>
+template <class Cv, class Ops = InlineOps<typename Cv::G>>
 NMSM_HD void bucket_fold_body(uint32_t b, uint32_t* own, const uint32_t* recv, int npeers, size_t stride_words) {
   using G = typename Cv::G;
   typename G::Acc acc = load_acc<G>(own + (size_t)b * G::ACC_WORDS);
   for (int r = 0; r < npeers; r++) {
     const typename G::Acc part = load_acc<G>(recv + (size_t)r * stride_words + (size_t)b * G::ACC_WORDS);
-    G::add(acc, part);  // inline: see bucket_finalize_body
+    Ops::add(acc, part);
   }
   save_acc<G>(own + (size_t)b * G::ACC_WORDS, acc);
 }
 
 // reduce1 over dense buckets: chunk running sums without any stitching (curve.ts:897-900)
-template <class Cv>
+template <class Cv, class Ops = InlineOps<typename Cv::G>>
 NMSM_HD void reduce1_dense_body(uint32_t id, const uint32_t* buckets, const MsmPlan& plan, uint32_t* sums, uint32_t* wsums) {
   using G = typename Cv::G;
   const uint32_t w = id / plan.chunks, k = id % plan.chunks;
@@ -925,8 +942,8 @@ NMSM_HD void reduce1_dense_body(uint32_t id, const uint32_t* buckets, const MsmP
   typename G::Acc sum = G::identity(), wsum = G::identity();
   for (int b = plan.K - 1; b >= 0; b--) {
     const typename G::Acc part = load_acc<G>(buckets + (size_t)(g0 + (uint32_t)b) * G::ACC_WORDS);
-    G::add(sum, part);  // inline: see bucket_finalize_body
-    G::add(wsum, sum);
+    Ops::add(sum, part);
+    Ops::add(wsum, sum);
   }
   save_acc<G>(sums + (size_t)id * G::ACC_WORDS, sum);
   save_acc<G>(wsums + (size_t)id * G::ACC_WORDS, wsum);

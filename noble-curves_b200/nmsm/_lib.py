@@ -13,6 +13,13 @@ import threading
 # The library overlaps kernels on several CUDA streams per MSM; give the device enough hardware work queues that they
 # do not alias (takes effect if the CUDA context has not been created yet; never overrides an explicit setting).
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# The sharded MSM moves one 6 MB bucket array per window and peer with ncclSend/ncclRecv; NCCL's default of 1-2 channels
+# (CTAs) per peer caps such a transfer near 25 GB/s on NVLink (measured: 0.27 ms per window).  More point-to-point channels
+# = more CTAs copying in parallel.  NCCL caches these parameters at its first communicator, so they must be in the
+# environment before torch.distributed / the library create one; explicit user settings win.
+os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
+os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
+os.environ.setdefault("NCCL_NCHANNELS_PER_NET_PEER", "16")
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NMSM_LIB") or os.path.join(_HERE, "libnmsm.so")  # NMSM_LIB: build-variant experiments

@@ -8,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "noble-curves_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 
+import nmsm  # noqa: F401  (sets CUDA / NCCL environment defaults before torch creates a context)
 import torch
 import torch.distributed as dist
 
@@ -33,6 +34,20 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     nd.init()
     ok = True
+    # both forms of the sharded pipeline: bulk (one group: default) and one group per window (exchange overlapped)
+    for groups in (0, 8):
+      nmsm.set_window_groups(groups)
+      ok = run_cases(rank, world, dev, groups) and ok
+    nmsm.set_window_groups(0)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_WORKER_OK" if int(flag.item()) == 1 else "DIST_WORKER_FAILED", flush=True)
+    dist.destroy_process_group()
+
+
+def run_cases(rank, world, dev, groups):
+    ok = True
     # 1. oracle-sized cases on every curve family; ragged shards incl. an empty one
     for name, n in (("bls12_381_G1", 301), ("secp256k1", 97), ("ed25519", 64), ("bls12_381_G2", 33), ("bn254_G1", 5), ("bls12_381_G1", 1)):
         P, pts, scalars, total = H.soak_inputs(name, n)
@@ -48,7 +63,7 @@ def main():
             got = (*H.unpack_point(name, out), inf)
             if got != exp:
                 ok = False
-                print(f"[rank {rank}] MISMATCH {name} n={n} bounds={bounds}", flush=True)
+                print(f"[rank {rank}] MISMATCH {name} n={n} bounds={bounds} groups={groups}", flush=True)
     # 2. 2^16 BLS12-381 G1 terms (points k_i*G made on the GPU), (sum k_i s_i)*G identity; degenerate: all scalars equal
     name, n = "bls12_381_G1", 1 << 16
     P = R.CURVES[name]
@@ -65,7 +80,7 @@ def main():
             out, inf = nd.msm_sharded(cid, tp, ts, hi - lo)
             if (*H.unpack_point(name, out), inf) != exp:
                 ok = False
-                print(f"[rank {rank}] MISMATCH large cid={cid}", flush=True)
+                print(f"[rank {rank}] MISMATCH large cid={cid} groups={groups}", flush=True)
     # 3. an invalid scalar on the last rank is reported everywhere with its global index
     sc = [rnd.randrange(order) for _ in range(n)]
     sc[n - 5] = order
@@ -79,11 +94,7 @@ def main():
         if f"invalid scalar at index {n - 5}" not in str(e):
             ok = False
             print(f"[rank {rank}] wrong error: {e}", flush=True)
-    flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        print("DIST_WORKER_OK" if int(flag.item()) == 1 else "DIST_WORKER_FAILED", flush=True)
-    dist.destroy_process_group()
+    return ok
 
 
 if __name__ == "__main__":

@@ -41,8 +41,13 @@ def test_sharded_path_world1():
         tp = torch.frombuffer(bytearray(pb), dtype=torch.uint8).to(dev)
         ts = torch.frombuffer(bytearray(sb), dtype=torch.uint8).to(dev)
         torch.cuda.synchronize()
-        out, inf = nd.msm_sharded(H.CURVE_IDS[name], tp, ts, n, layout=(n, 0))
-        assert (*H.unpack_point(name, out), inf) == exp, name
+        try:
+            for groups in (0, 8):  # bulk form (default) and one launch group per window
+                nmsm.set_window_groups(groups)
+                out, inf = nd.msm_sharded(H.CURVE_IDS[name], tp, ts, n, layout=(n, 0))
+                assert (*H.unpack_point(name, out), inf) == exp, (name, groups)
+        finally:
+            nmsm.set_window_groups(0)
     # empty MSM and an invalid point
     out, inf = nd.msm_sharded(4, None, None, 0, layout=(0, 0))
     assert inf == 1

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdint.h>
 #include "ec.cuh"
+#include "field_lat.cuh"
 using namespace nmsm;
 using F = Fp<FpBls381>;
 using G = SwXyzz<F>;
@@ -41,6 +42,9 @@ __global__ void k(uint32_t* out, long long* cyc, int iters, uint32_t seed) {
     if (OP == 8) G::template par_dbl<false>(p);
     if (OP == 9) G::template par_add<false>(p, q);
     if (OP == 10) { F r; mont_mul<FpBls381>(r.v, a.v, b.v); a = r; }
+    if (OP == 11) { F r; mont_mul_c64<FpBls381>(r.v, a.v, b.v); a = r; }
+    if (OP == 12) { F r; mont_mul_sos<FpBls381>(r.v, a.v, b.v); a = r; }
+    if (OP == 13) { F r; mont_mul_lat4<FpBls381>(r.v, a.v, b.v); a = r; }
   }
   long long t1 = clock64();
   unsigned long long g1;
@@ -74,14 +78,20 @@ void run(const char* name, int threads, int blocks, int iters) {
 
 int main() {
   // burst vs sustained: the same saturating multiply chain for 0.5 ms .. 60 ms
-  for (int it : {256, 1024, 4096, 16384, 32768}) run<0>("mul_sat", 128, 148 * 4, it);
-  for (int it : {256, 4096, 32768}) run<0>("mul_sat8", 128, 148 * 8, it);
+  for (int it : {1024}) run<0>("mul_sat", 128, 148 * 4, it);
+  for (int it : {1024}) run<0>("mul_sat8", 128, 148 * 8, it);
   for (int it : {256, 4096}) run<1>("sqr_sat", 128, 148 * 4, it);
+  run<11>("mul_c64_sat", 128, 148 * 4, 1024);
+  run<12>("mul_sos_sat", 128, 148 * 4, 1024);
+  run<13>("mul_lat4_sat", 128, 148 * 4, 1024);
   const int IT = 512;
   for (int thr : {32}) {
     for (int blocks : {1, 148 * 4}) {
       run<0>("mul", thr, blocks, IT);
       run<10>("mul_inline", thr, blocks, IT);
+      run<11>("mul_c64", thr, blocks, IT);
+      run<12>("mul_sos", thr, blocks, IT);
+      run<13>("mul_lat4", thr, blocks, IT);
       run<1>("sqr", thr, blocks, IT);
       run<2>("fadd", thr, blocks, IT * 8);
       run<3>("fsub", thr, blocks, IT * 8);

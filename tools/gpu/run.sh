@@ -35,6 +35,10 @@ case "$task" in
       tests/dist_worker.py > gpurun_out/dist_worker_g$np.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/dist_worker_g$np.log ;;
   sweep)
     timeout 1500 python tools/gpu/sweep_lk.py "$@" > gpurun_out/sweep_lk.jsonl 2> gpurun_out/sweep_lk.err; echo "rc=$?"; cat gpurun_out/sweep_lk.jsonl ;;
+  tracedist)
+    np=${1:-2}
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$np" --master-addr 127.0.0.1 --master-port 29521 \
+      tools/gpu/trace_dist.py > gpurun_out/trace_dist_g$np.log 2>&1; echo "rc=$?"; grep "nmsm trace" gpurun_out/trace_dist_g$np.log | tail -$((2*np)) ;;
   explore)
     timeout 900 python tools/gpu/explore_groups.py "$@" > gpurun_out/explore.jsonl 2> gpurun_out/explore.err; echo "rc=$?"; cat gpurun_out/explore.jsonl ;;
   *) echo "unknown task $task"; exit 2 ;;
