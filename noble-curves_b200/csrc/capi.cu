@@ -146,6 +146,37 @@ static double bench_modmul(int blocks_per_sm, int threads, int iters, int ilp) {
   return (double)blocks * threads * (double)iters * eff_ilp / (best * 1e-3);
 }
 
+// Collective (every rank calls it for the same MSM, because the bucket workspace grows at the same call on every rank: its
+// size depends only on the plan of the whole MSM): publish this rank's bucket array through CUDA IPC and map every peer's.
+int dist_map_peer_buckets(int slot, void* local_base, cudaStream_t st) {
+  DistState& D = g_dist;
+  if (D.world == 1 || !D.p2p) return NMSM_OK;
+  if (D.mapped_local[slot] == local_base) return NMSM_OK;
+  for (int r = 0; r < D.world; r++)
+    if (D.mapped[slot][r]) {
+      cudaIpcCloseMemHandle(D.mapped[slot][r]);
+      D.mapped[slot][r] = nullptr;
+    }
+  cudaIpcMemHandle_t mine;
+  CK(cudaIpcGetMemHandle(&mine, local_base));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t* d_h = nullptr;
+  CK(cudaMalloc((void**)&d_h, sizeof(mine) * (D.world + 1)));
+  CK(cudaMemcpyAsync(d_h + D.world, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  if (int r = nccl_all_gather(d_h + D.world, d_h, sizeof(mine), st)) { cudaFree(d_h); return r; }
+  std::vector<cudaIpcMemHandle_t> all(D.world);
+  CK(cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * D.world, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d_h);
+  for (int r = 0; r < D.world; r++) {
+    if (r == D.rank) continue;
+    cudaError_t e = cudaIpcOpenMemHandle(&D.mapped[slot][r], all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (peer bucket array)");
+  }
+  D.mapped_local[slot] = local_base;
+  return NMSM_OK;
+}
+
 }  // namespace nmsm
 
 using namespace nmsm;
@@ -226,6 +257,9 @@ void nmsm_shutdown(void) {
   if (!C.ready) return;
   if (g_dist.ready) {
     for (Slot& S : C.slot) cudaStreamSynchronize(S.comm_stream);
+    for (int sl = 0; sl < NUM_SLOTS; sl++)
+      for (int r = 0; r < MAX_PEERS; r++)
+        if (g_dist.mapped[sl][r]) cudaIpcCloseMemHandle(g_dist.mapped[sl][r]);
     g_nccl.CommDestroy((ncclComm_t)g_dist.comm);
     g_dist = DistState();
   }
@@ -512,6 +546,22 @@ int nmsm_dist_init(int rank, int world, const uint8_t* id128) {
   g_dist.rank = rank;
   g_dist.world = world;
   g_dist.ready = true;
+  // direct peer access for the bucket exchange: one process per GPU of one NVLink domain.  NMSM_DIST_P2P=0 falls back to
+  // ncclSend / ncclRecv copies (also taken when a peer cannot be mapped).
+  const char* e = getenv("NMSM_DIST_P2P");
+  g_dist.p2p = world > 1 && world <= MAX_PEERS && !(e && atoi(e) == 0);
+  if (g_dist.p2p) {
+    int ndev = 0;
+    cudaGetDeviceCount(&ndev);
+    if (ndev >= world) {  // every rank's device is visible here: check the links
+      for (int d = 0; d < ndev && g_dist.p2p; d++) {
+        if (d == g_ctx.device) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, g_ctx.device, d) != cudaSuccess || !can) g_dist.p2p = false;
+      }
+    }
+    (void)cudaGetLastError();
+  }
   return NMSM_OK;
 }
 

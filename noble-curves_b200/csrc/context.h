@@ -115,16 +115,26 @@ struct Context {
 // NCCL entry points resolved at run time (dlopen "libnccl.so.2": inside a torch process that is the copy torch already
 // loaded), so libnmsm.so has no link-time dependency on NCCL and loads on machines without it.
 struct NcclComm;
+static constexpr int MAX_PEERS = 16;  // ranks of one NVLink domain
+struct PeerPtrs {                      // passed to k_bucket_fold by value: every rank's bucket array (own entry unused)
+  const uint32_t* p[MAX_PEERS];
+};
 struct DistState {
   bool ready = false;
   int rank = 0, world = 1;
   NcclComm* comm = nullptr;
+  // Direct exchange: every rank's `buckets` workspace of a slot is mapped into every other rank through CUDA IPC, so the
+  // window owners PULL the peers' partial buckets over NVLink inside the fold kernel instead of receiving copies.
+  bool p2p = false;                                    // all peers reachable (same NVLink domain, IPC works)
+  void* mapped[NMSM_SLOTS][MAX_PEERS] = {};            // peer r's buckets base in this process (nullptr for self)
+  void* mapped_local[NMSM_SLOTS] = {};                 // the local allocation the mappings were exchanged for
 };
 int nccl_send(const void* buf, size_t bytes, int peer, cudaStream_t st);
 int nccl_recv(void* buf, size_t bytes, int peer, cudaStream_t st);
 int nccl_group_start();
 int nccl_group_end();
 int nccl_all_gather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t st);
+int dist_map_peer_buckets(int slot, void* local_base, cudaStream_t st);  // collective: (re)exchange the IPC mappings
 extern DistState g_dist;
 
 struct ShardArgs {  // sharded MSM: this GPU holds n_local of the n_total terms, starting at global index `offset`

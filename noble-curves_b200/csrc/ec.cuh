@@ -14,6 +14,7 @@
 #pragma once
 #include "curve_consts.cuh"
 #include "field.cuh"
+#include "inv_divsteps.cuh"
 #include "fp2.cuh"
 
 namespace nmsm {

@@ -32,9 +32,16 @@ static int run_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n,
   return collect_msm(out_xy, out_is_inf);
 }
 
-// chunks per logical thread of k_reduce2: 4, or up to 16 when that lets ONE pass leave <= REDUCE2_MAX_SPLITS block results
-// per window (a second pass costs a whole latency-bound launch)
+// chunks per logical thread (quad) of a k_reduce2 pass over `chunks` chunks per window.  A pass that fits one block
+// (the last one) spreads its chunks over as many of the 32 quads as it can: the serial part of the chain is 3 additions
+// per chunk.  A multi-block pass takes 4 chunks per quad, or up to 16 when that leaves <= REDUCE2_MAX_SPLITS block
+// results (one more pass then finishes; every pass is a latency-bound launch).
 static int reduce2_r(uint64_t chunks) {
+  if (chunks <= (uint64_t)REDUCE2_LOGICAL * 4) {  // single block
+    int r = 1;
+    while ((uint64_t)REDUCE2_LOGICAL * r < chunks) r *= 2;
+    return r;
+  }
   int r = REDUCE2_R;
   while (r < 16 && (chunks + (uint64_t)REDUCE2_LOGICAL * r - 1) / ((uint64_t)REDUCE2_LOGICAL * r) > (uint64_t)REDUCE2_MAX_SPLITS &&
          chunks <= (uint64_t)REDUCE2_LOGICAL * 16 * REDUCE2_MAX_SPLITS)
@@ -140,7 +147,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   for (uint64_t m = plan.chunks;;) {
     const uint64_t sp = (m + (uint64_t)REDUCE2_LOGICAL * reduce2_r(m) - 1) / ((uint64_t)REDUCE2_LOGICAL * reduce2_r(m));
     blk_entries += sp;
-    if (sp <= REDUCE2_MAX_SPLITS) break;
+    if (sp <= 1) break;
     m = sp;
   }
   const uint64_t nseg = (uint64_t)plan.W * plan.TPW;  // accumulate segments, TPW per window
@@ -195,13 +202,19 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   const size_t WB = (size_t)plan.B * G::ACC_WORDS;                   // words of one window's dense bucket array
   const int gather_words = slots * G::ACC_WORDS + 4;                 // per rank: weighted window sums | err_pt err_sc off_lo off_hi
   uint32_t *recv = nullptr, *gsend = nullptr, *grecv = nullptr;
+  const bool p2p = shard && g_dist.p2p && world > 1;
+  PeerPtrs peer_ptrs = {};
   if (shard) {
-    CK(C.recv.ensure((size_t)slots * (world - 1) * WB * 4 + 16));
+    if (!p2p) CK(C.recv.ensure((size_t)slots * (world - 1) * WB * 4 + 16));
     CK(C.gsend.ensure((size_t)gather_words * 4));
-    CK(C.grecv.ensure((size_t)gather_words * 4 * world));
+    CK(C.grecv.ensure((size_t)gather_words * 4 * world + 256 + 4 * world));  // + scratch of the 4-byte barrier all-gathers
     recv = (uint32_t*)C.recv.p;
     gsend = (uint32_t*)C.gsend.p;
     grecv = (uint32_t*)C.grecv.p;
+    if (p2p) {  // (re)map the peers' bucket arrays when this slot's own array moved (same call on every rank)
+      if (int r = dist_map_peer_buckets(g_ctx.cur, C.buckets.p, C.comm_stream)) return r;
+      for (int r = 0; r < world; r++) peer_ptrs.p[r] = (const uint32_t*)g_dist.mapped[g_ctx.cur][r];
+    }
   }
   int launches = 0;
 #define PEV(slot)                                   \
@@ -282,7 +295,16 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
             offsets, buckets, heads, tails, tile1, tile2, plan, (uint32_t)w_lo * plan.B, (uint32_t)w_hi * plan.B);
         launches += 3;
       }
-      if (world > 1) {  // the window owners receive every peer's partial buckets; everybody else sends
+      if (world > 1 && p2p) {
+        // direct exchange: the owners pull the peers' partial buckets inside k_bucket_fold_peers.  All that has to cross
+        // the ranks here is "my dense buckets of this group are complete": a 4-byte all-gather as the barrier.
+        CK(cudaEventRecord(C.ev_fin[g], stl));
+        CK(cudaStreamWaitEvent(C.comm_stream, C.ev_fin[g], 0));
+        if (nccl_all_gather(grecv + (size_t)gather_words * world + 16, grecv + (size_t)gather_words * world + 32, 4, C.comm_stream))
+          return NMSM_ERR_CUDA;
+        CK(cudaEventRecord(C.ev_xchg[g], C.comm_stream));
+        if (trace) cudaEventRecord(C.tr_h[g], C.comm_stream);
+      } else if (world > 1) {  // copies: the window owners receive every peer's partial buckets; everybody else sends
         CK(cudaEventRecord(C.ev_fin[g], stl));
         CK(cudaStreamWaitEvent(C.comm_stream, C.ev_fin[g], 0));
         if (nccl_group_start()) return NMSM_ERR_CUDA;
@@ -310,7 +332,11 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
         cudaStream_t so = C.tail_stream[slot % TAIL_STREAMS];
         CK(cudaStreamWaitEvent(so, C.ev_xchg[g], 0));
         uint32_t* wb = buckets + (size_t)w * WB;
-        if (world > 1) {
+        if (world > 1 && p2p) {
+          k_bucket_fold_peers<Cv><<<cdiv((uint64_t)plan.B * 4, 128), 128, 0, so>>>(wb, peer_ptrs, (size_t)w * WB, world, rank,
+                                                                                (uint32_t)plan.B);
+          launches++;
+        } else if (world > 1) {
           k_bucket_fold<Cv><<<cdiv((uint64_t)plan.B * 4, 128), 128, 0, so>>>(wb, recv + (size_t)slot * (world - 1) * WB, world - 1, WB,
                                                                           (uint32_t)plan.B);
           launches++;
@@ -328,13 +354,10 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
           uint32_t* blkP = base;
           uint32_t* blkQ = base + (size_t)plan.W * splits * G::ACC_WORDS;
           base = blkQ + (size_t)plan.W * splits * G::ACC_WORDS;
-          k_reduce2<Cv><<<dim3(splits, 1), REDUCE2_THREADS, smem2, so>>>(S, T, pl, R2, (uint32_t)w, blkP, blkQ);
+          k_reduce2<Cv><<<dim3(splits, 1), REDUCE2_THREADS, smem2, so>>>(S, T, pl, R2, (uint32_t)w, blkP, blkQ,
+                                                                         splits == 1 ? window_out : nullptr);
           launches++;
-          if (splits <= REDUCE2_MAX_SPLITS) {
-            k_reduce3<Cv><<<1, 32, 0, so>>>(blkP, blkQ, pl, splits, R2, (uint32_t)w, window_out);
-            launches++;
-            break;
-          }
+          if (splits == 1) break;
           S = blkQ;
           T = blkP;
           pl.chunks = splits;
@@ -389,13 +412,10 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
         uint32_t* blkP = base;
         uint32_t* blkQ = base + (size_t)plan.W * splits * G::ACC_WORDS;
         base = blkQ + (size_t)plan.W * splits * G::ACC_WORDS;
-        k_reduce2<Cv><<<dim3(splits, nw), REDUCE2_THREADS, smem2, stl>>>(S, T, pl, R2, (uint32_t)w_lo, blkP, blkQ);
+        k_reduce2<Cv><<<dim3(splits, nw), REDUCE2_THREADS, smem2, stl>>>(S, T, pl, R2, (uint32_t)w_lo, blkP, blkQ,
+                                                                         splits == 1 ? window_out : nullptr);
         launches++;
-        if (splits <= REDUCE2_MAX_SPLITS) {
-          k_reduce3<Cv><<<nw, 32, 0, stl>>>(blkP, blkQ, pl, splits, R2, (uint32_t)w_lo, window_out);
-          launches++;
-          break;
-        }
+        if (splits == 1) break;
         S = blkQ;
         T = blkP;
         pl.chunks = splits;

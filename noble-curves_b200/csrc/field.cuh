@@ -304,12 +304,12 @@ NMSM_HD Fp<C> dbl(const Fp<C>& a) {
   return a + a;
 }
 
-// Modular inverse (modular.ts:980 `inv` -> :159-182; the reference runs extended Euclid on BigInt,
-// here a binary extended GCD on the limbs: ~2*BITS shift/subtract steps instead of a BITS-long
-// square-and-multiply chain, which matters because the final to-affine step is single-threaded).
+// Modular inverse by a binary extended GCD on the limbs (modular.ts:980 `inv` -> :159-182; the reference runs extended
+// Euclid on BigInt): ~2*BITS shift/subtract steps.  Since round 2 this is only the FALLBACK of nmsm::inv
+// (inv_divsteps.cuh, batched division steps: 35 us instead of 217 us for a lone warp on B200, 381-bit field).
 // Input and output in Montgomery form; 0 maps to 0.
 template <class C>
-NMSM_HD Fp<C> inv(const Fp<C>& a) {
+NMSM_HD Fp<C> inv_xgcd(const Fp<C>& a) {
   constexpr int N = C::N;
   if (a.is_zero()) return a;
   // invariants: a * x1 == u (mod p), a * x2 == v (mod p), with a taken as the raw limbs

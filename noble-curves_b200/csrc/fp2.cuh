@@ -3,6 +3,7 @@
 //   mul :420-431 (3 base multiplications), sqr :432-438 (2), add/sub/neg :393-418, inv :458-475.
 #pragma once
 #include "field.cuh"
+#include "inv_divsteps.cuh"
 
 namespace nmsm {
 

@@ -16,9 +16,9 @@
 //                  that span > 32 / > 1024 segments (degenerate inputs)                    (T/L/32 warps)
 //   k_reduce1      per-chunk running sums (2 additions per bucket), stitching the partials
 //                  of buckets that straddle accumulate segments on the fly                 (W*B/K threads)
-//   k_reduce2      second level: suffix scan + reduction of chunk sums inside blocks of
-//                  32 quads (registers -> quad/warp shuffles -> shared memory)             (W x splits blocks)
-//   k_reduce3      folds the <= 32 block results of every window                           (W warps)
+//   k_reduce2      upper levels: suffix scan + reduction of chunk sums inside blocks of 32 quads
+//                  (registers -> quad/warp shuffles -> shared memory), re-applied to its own
+//                  block results until one block per window is left                        (W x splits blocks)
 //   k_horner_step  Horner over the windows of one group (c doublings each), one warp whose lanes
 //                  share each formula's independent multiplications; k_combine: inversion to affine (1 warp)
 // The windows form groups that are accumulated top-first as separate launches; the reduction and Horner
@@ -144,9 +144,9 @@ k_accumulate(const uint32_t* __restrict__ aff, const uint32_t* __restrict__ sort
 //   sum_b (b+1) B_b  =  sum_k T_k + K * sum_k k * S_k        k over the M = B/K chunks   (k_reduce1)
 //   per block of Mb chunks:  P_s = sum T_k + K * sum (k - s*Mb) S_k ,  Q_s = sum S_k        (k_reduce2)
 //   window sum = sum_s P_s + K * Mb * sum_s s * Q_s                                          (k_reduce3)
-// The last line has the shape of the first (T := P, S := Q, K := K * Mb): when a window has more than 32 * Mb
-// chunks (fixed-base tables: a single window of up to 2^21 buckets) k_reduce2 is applied again to its own
-// outputs until <= 32 block results per window are left for k_reduce3.
+// The last line has the shape of the first (T := P, S := Q, K := K * Mb): k_reduce2 is applied again to its own outputs
+// (with fewer chunks per quad) until ONE block per window is left, whose P_0 is the window sum.  Ordinary plans: two
+// passes (4096 chunks -> 32 block results -> 1); fixed-base tables (one window of up to 2^21 buckets): three or four.
 // ------------------------------------------------------------------------------------------------
 template <class G>
 __device__ __forceinline__ typename G::Acc shfl_down_acc(const typename G::Acc& a, int delta) {
@@ -220,6 +220,18 @@ k_bucket_fold(uint32_t* __restrict__ own, const uint32_t* __restrict__ recv, int
   const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   if (b < B) bucket_fold_body<Cv, QuadOps<typename Cv::G>>(b, own, recv, npeers, stride_words);
 }
+// Fused exchange + fold: the owner of a window reads every peer's partial bucket b straight from the peer's HBM over
+// NVLink (peer pointers from CUDA IPC, `window_words` = offset of the window inside a bucket array) and adds it.
+template <class Cv>
+__global__ void __launch_bounds__(128)
+k_bucket_fold_peers(uint32_t* __restrict__ own, PeerPtrs peers, size_t window_words, int world, int rank, uint32_t B) {
+  const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  if (b >= B) return;
+  const uint32_t* base[MAX_PEERS];
+#pragma unroll
+  for (int r = 0; r < MAX_PEERS; r++) base[r] = r < world && r != rank ? peers.p[r] + window_words : nullptr;
+  bucket_fold_peers_body<Cv, QuadOps<typename Cv::G>>(b, own, base, world, rank);
+}
 template <class Cv>
 __global__ void __launch_bounds__(REDUCE1_THREADS)
 k_reduce1_dense(const uint32_t* __restrict__ buckets, MsmPlan plan, uint32_t id0, uint32_t id1, uint32_t* __restrict__ sums,
@@ -268,7 +280,7 @@ __device__ __forceinline__ typename G::Acc smem_get(const uint32_t* smem, uint32
 
 static constexpr int REDUCE2_THREADS = 128;                   // 32 logical threads (quads), 4 warps
 static constexpr int REDUCE2_LOGICAL = REDUCE2_THREADS / 4;
-static constexpr int REDUCE2_MAX_SPLITS = 32;                 // k_reduce3: 8 quads x up to 4 splits each
+static constexpr int REDUCE2_MAX_SPLITS = 32;                 // block results per window the LAST pass (one block, R = 1) takes
 static constexpr int REDUCE2_R = 4;                           // chunks per logical thread
 static constexpr int REDUCE2_CHUNKS_PER_BLOCK = REDUCE2_LOGICAL * REDUCE2_R;
 
@@ -276,7 +288,7 @@ static constexpr int REDUCE2_CHUNKS_PER_BLOCK = REDUCE2_LOGICAL * REDUCE2_R;
 template <class Cv>
 __global__ void __launch_bounds__(REDUCE2_THREADS)
 k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums, MsmPlan plan, int R, uint32_t w0,
-          uint32_t* __restrict__ blkP, uint32_t* __restrict__ blkQ) {
+          uint32_t* __restrict__ blkP, uint32_t* __restrict__ blkQ, uint32_t* __restrict__ window_out) {
   using G = typename Cv::G;
   using Acc = typename G::Acc;
   extern __shared__ uint32_t smem[];  // one accumulator per warp
@@ -328,57 +340,13 @@ k_reduce2(const uint32_t* __restrict__ sums, const uint32_t* __restrict__ wsums,
   if (warp == 0 && ql == 0) {
     for (uint32_t q = 1; q < NW; q++) G::template par_add<false>(V, smem_get<G>(smem, q));
     if (lane == 0) {
-      save_acc<G>(blkP + ((size_t)w * splits + s) * G::ACC_WORDS, V);
-      save_acc<G>(blkQ + ((size_t)w * splits + s) * G::ACC_WORDS, SS);  // SS of logical thread 0 = block total
+      if (window_out) {  // last level (one block per window): P_0 is the window sum, the s * Q_s term vanishes
+        save_acc<G>(window_out + (size_t)w * G::ACC_WORDS, V);
+      } else {
+        save_acc<G>(blkP + ((size_t)w * splits + s) * G::ACC_WORDS, V);
+        save_acc<G>(blkQ + ((size_t)w * splits + s) * G::ACC_WORDS, SS);  // SS of logical thread 0 = block total
+      }
     }
-  }
-}
-
-// grid W, one warp: quad q folds splits [q*R3, (q+1)*R3) of the window, then the quads combine.
-//   window = sum_s P_s + K * Mb * sum_s s * Q_s
-template <class Cv>
-__global__ void __launch_bounds__(32)
-k_reduce3(const uint32_t* __restrict__ blkP, const uint32_t* __restrict__ blkQ, MsmPlan plan, int splits, int R,
-          uint32_t w0, uint32_t* __restrict__ window_out) {
-  using G = typename Cv::G;
-  using Acc = typename G::Acc;
-  const uint32_t w = w0 + blockIdx.x, lane = threadIdx.x, ql = lane >> 2;
-  const uint32_t R3 = (uint32_t)(splits + 7) / 8;  // splits is a power of two: R3 in {1, 2, 4}
-  const uint32_t lo = ql * R3;
-  Acc PT = G::identity(), QS = G::identity(), QL = G::identity();
-  for (uint32_t s = lo + R3; s-- > lo;) {
-    if (s < (uint32_t)splits) {
-      G::template par_add<false>(PT, load_acc<G>(blkP + ((size_t)w * splits + s) * G::ACC_WORDS));
-      G::template par_add<false>(QS, load_acc<G>(blkQ + ((size_t)w * splits + s) * G::ACC_WORDS));
-    }
-    if (s > lo) G::template par_add<false>(QL, QS);  // after the loop: sum (s - lo) * Q_s
-  }
-  // suffix scan of the quad totals: sum_s s*Q_s = sum_q [QL_q + R3 * q * QS_q] = sum QL + R3 * sum_{q>=1} SS_q
-  Acc SS = QS;
-  for (int d = 1; d < 8; d <<= 1) {
-    __syncwarp();
-    Acc o = shfl_down_quads<G>(SS, d);
-    if (ql + d < 8) G::template par_add<false>(SS, o);
-  }
-  Acc X = G::identity();
-  if (ql >= 1) {
-    X = SS;
-    for (uint32_t r = 1; r < R3; r <<= 1) G::template par_dbl<false>(X);
-  }
-  G::template par_add<false>(X, QL);
-  for (int d = 4; d >= 1; d >>= 1) {
-    __syncwarp();
-    Acc o = shfl_down_quads<G>(X, d);
-    G::template par_add<false>(X, o);
-    __syncwarp();
-    Acc o2 = shfl_down_quads<G>(PT, d);
-    G::template par_add<false>(PT, o2);
-  }
-  if (ql == 0) {
-    const uint32_t scale = (uint32_t)plan.K * REDUCE2_LOGICAL * (uint32_t)R;  // K * Mb, a power of two
-    for (uint32_t j = 1; j < scale; j <<= 1) G::template par_dbl<false>(X);
-    G::template par_add<false>(PT, X);
-    if (lane == 0) save_acc<G>(window_out + (size_t)w * G::ACC_WORDS, PT);
   }
 }
 
@@ -411,18 +379,27 @@ __global__ void __launch_bounds__(32)
 k_combine(const uint32_t* __restrict__ accs, int count, int per_block, int block_stride, uint32_t* __restrict__ out,
           uint32_t* __restrict__ out_inf) {
   using G = typename Cv::G;
+  // the 8 quads of the warp each sum every 8th accumulator, then a 3-level tree over the quads: 1 + 3 lane-parallel
+  // additions for the 8 weighted window sums of an 8-GPU MSM instead of 8 dependent ones
+  const uint32_t lane = threadIdx.x, ql = lane >> 2;
   typename G::Acc acc = G::identity();
-  for (int i = 0; i < count; i++)
-    G::template par_add<true>(acc, load_acc<G>(accs + (size_t)(i / per_block) * block_stride + (size_t)(i % per_block) * G::ACC_WORDS));
+  for (int i = (int)ql; i < count; i += 8)
+    G::template par_add<false>(acc, load_acc<G>(accs + (size_t)(i / per_block) * block_stride + (size_t)(i % per_block) * G::ACC_WORDS));
+  for (int d = 4; d >= 1; d >>= 1) {
+    __syncwarp();
+    typename G::Acc o = shfl_down_quads<G>(acc, d);
+    G::template par_add<false>(acc, o);
+  }
+  if (ql != 0) return;  // quad 0 holds the total
   if (AFFINE_OUT) {
     uint32_t xy[G::IN_WORDS];
     uint32_t inf;
     nl_to_affine<G>(acc, xy, &inf);
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
       for (int k = 0; k < G::IN_WORDS; k++) out[k] = xy[k];
       *out_inf = inf;
     }
-  } else if (threadIdx.x == 0) {
+  } else if (lane == 0) {
     save_acc<G>(out, acc);
   }
 }

@@ -932,6 +932,19 @@ NMSM_HD void bucket_fold_body(uint32_t b, uint32_t* own, const uint32_t* recv, i
   }
   save_acc<G>(own + (size_t)b * G::ACC_WORDS, acc);
 }
+// Same with the peers' partials read in place from THEIR memory (pointers into the peers' bucket arrays, mapped over
+// NVLink): the exchange is the loads of the fold itself, no copy is made.  peers[r] = window base in rank r's array.
+template <class Cv, class Ops = InlineOps<typename Cv::G>>
+NMSM_HD void bucket_fold_peers_body(uint32_t b, uint32_t* own, const uint32_t* const* peers, int world, int rank) {
+  using G = typename Cv::G;
+  typename G::Acc acc = load_acc<G>(own + (size_t)b * G::ACC_WORDS);
+  for (int r = 0; r < world; r++) {
+    if (r == rank) continue;
+    const typename G::Acc part = load_acc<G>(peers[r] + (size_t)b * G::ACC_WORDS);
+    Ops::add(acc, part);
+  }
+  save_acc<G>(own + (size_t)b * G::ACC_WORDS, acc);
+}
 
 // reduce1 over dense buckets: chunk running sums without any stitching (curve.ts:897-900)
 template <class Cv, class Ops = InlineOps<typename Cv::G>>

@@ -16,6 +16,7 @@
 // fmaheavy pipe is ~62 % active in k_ntt_pass while DRAM throughput stays below 5 % of peak.
 #include "context.h"
 #include "field.cuh"
+#include "inv_divsteps.cuh"
 #include "curve_consts.cuh"
 
 namespace nmsm {

@@ -276,7 +276,8 @@ static void field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) 
     case 0: z = x * y; break;
     case 1: z = x + y; break;
     case 2: z = x - y; break;
-    case 3: z = inv(x); break;
+    case 3: z = inv_xgcd(x); break;                                                  // the fallback path
+    case 10: z = inv(x); break;                                                      // what the kernels call (divsteps)
     case 4: z = Fp<P>::from_canonical(a); break;
     case 5: x.to_canonical(z.v); break;
     case 6: z = sqr(x); break;

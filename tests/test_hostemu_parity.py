@@ -79,7 +79,7 @@ def test_divsteps_inverse(field):
         assert _fop(field, 9, x) == pow(x, -1, p), hex(x)
     for x in vals[:60]:
         xm = x * Rm % p
-        assert _fop(field, 8, xm) == _fop(field, 3, xm) == pow(x, -1, p) * Rm % p
+        assert _fop(field, 8, xm) == _fop(field, 3, xm) == _fop(field, 10, xm) == pow(x, -1, p) * Rm % p
     assert _fop(field, 8, 0) == 0
 
 

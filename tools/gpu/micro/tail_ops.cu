@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include "ec.cuh"
 #include "field_lat.cuh"
+#include "inv_divsteps.cuh"
 using namespace nmsm;
 using F = Fp<FpBls381>;
 using G = SwXyzz<F>;
@@ -45,6 +46,8 @@ __global__ void k(uint32_t* out, long long* cyc, int iters, uint32_t seed) {
     if (OP == 11) { F r; mont_mul_c64<FpBls381>(r.v, a.v, b.v); a = r; }
     if (OP == 12) { F r; mont_mul_sos<FpBls381>(r.v, a.v, b.v); a = r; }
     if (OP == 13) { F r; mont_mul_lat4<FpBls381>(r.v, a.v, b.v); a = r; }
+    if (OP == 14) { a = inv(a) + b; }
+    if (OP == 15) { a = DivstepsInv<FpBls381>::inverse(a) + b; }
   }
   long long t1 = clock64();
   unsigned long long g1;
@@ -92,6 +95,8 @@ int main() {
       run<11>("mul_c64", thr, blocks, IT);
       run<12>("mul_sos", thr, blocks, IT);
       run<13>("mul_lat4", thr, blocks, IT);
+      run<14>("inv_xgcd", thr, blocks, 32);
+      run<15>("inv_divsteps", thr, blocks, 32);
       run<1>("sqr", thr, blocks, IT);
       run<2>("fadd", thr, blocks, IT * 8);
       run<3>("fsub", thr, blocks, IT * 8);

@@ -39,6 +39,9 @@ case "$task" in
     np=${1:-2}
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$np" --master-addr 127.0.0.1 --master-port 29521 \
       tools/gpu/trace_dist.py > gpurun_out/trace_dist_g$np.log 2>&1; echo "rc=$?"; grep "nmsm trace" gpurun_out/trace_dist_g$np.log | tail -$((2*np)) ;;
+  ncu-shard1)
+    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_shard1.csv \
+      python tools/gpu/shard1_profile.py "$@" > gpurun_out/ncu_shard1.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_shard1.log ;;
   explore)
     timeout 900 python tools/gpu/explore_groups.py "$@" > gpurun_out/explore.jsonl 2> gpurun_out/explore.err; echo "rc=$?"; cat gpurun_out/explore.jsonl ;;
   *) echo "unknown task $task"; exit 2 ;;
