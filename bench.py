@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -292,12 +292,15 @@ def main():
         nmsm.set_profiling(False)
 
     # ---- (2) THE TIMED REGION: K serial steps, one complete MSM each (N / wall time of one MSM) -----------
-    for _ in range(W):
-        step_device()
-    check_result()
+    # clocks are sampled (nvidia-smi, 20 ms period) from the warm-up of the device-resident timed region to the end of the
+    # end-to-end timed region: the two regions are a few hundred ms in total, shorter than nvidia-smi's start-up alone
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)
+    for _ in range(W):
+        step_device()
+    check_result()
     dev_ms = []
     barrier()
     t0 = time.perf_counter()
@@ -306,7 +309,6 @@ def main():
         dev_ms.append(nmsm.last_timing()[0]["total"])
     barrier()
     elapsed = max_over_ranks(time.perf_counter() - t0)
-    clocks = sampler.stop() if rank == 0 else None
     check_result()
     main_info = nmsm.last_timing()[1]
     device_ms = max_over_ranks(sum(dev_ms) / len(dev_ms))
@@ -333,6 +335,7 @@ def main():
         step_e2e()
     barrier()
     e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
     check_result()
     e2e_value = n_total * args.steps / e2e_elapsed
 
@@ -462,9 +465,12 @@ def main():
                          "window_groups_timed_region": main_info.window_groups}}
     if world == 1:
         acc_t = sum(acc_ms) / len(acc_ms) * 1e-3
-        # executed mixed additions: every sorted entry except those that START an accumulator (a copy, no multiplications)
-        madds = info.sorted_entries - info.bucket_starts
-        madd_modmuls = madds * 10  # madd-2008-s: 8M + 2S
+        # executed field multiplications of k_accumulate.  Every sorted entry except those that START an accumulator (a copy)
+        # ends in one mixed addition, madd-2008-s 8M + 2S = 10; a same-bucket pair is first added in affine (3 for its share
+        # of the warp's batch inversion + 2M + 1S) and then takes ONE mixed addition: 16 for two entries instead of 20, i.e.
+        # -4 per pair; every thread pays 12 for the prefix / suffix products of the warp-shared inversion.
+        madds = info.sorted_entries - info.bucket_starts - info.bucket_pairs
+        madd_modmuls = 10 * (info.sorted_entries - info.bucket_starts) - 4 * info.bucket_pairs + 12 * info.accumulate_threads
         achieved = madd_modmuls / acc_t
         # whole MSM, executed: mixed additions + bucket reduction (2 additions per bucket of 12M+2S) + Horner doublings (6M+3S)
         W_, B_ = info.windows, info.buckets_per_window
@@ -475,7 +481,8 @@ def main():
         one_ms = 1e3 * elapsed / args.steps
         roofline.update({
             "achieved": achieved / 1e9, "frac": achieved / peak if peak > 0 else None,
-            "mixed_additions_executed": madds, "accumulator_starts": info.bucket_starts,
+            "mixed_additions_executed": madds, "affine_pair_additions_executed": info.bucket_pairs,
+            "accumulator_starts": info.bucket_starts, "accumulate_threads": info.accumulate_threads,
             "modmul_per_launch": madd_modmuls, "kernel_ms": acc_t * 1e3,
             "whole_msm": {"modmul_executed": whole_modmuls, "ms": one_ms,
                           "frac": (whole_modmuls / (one_ms * 1e-3)) / peak if peak > 0 else None,

@@ -233,7 +233,12 @@ typedef struct {
   int launches;                 /* kernels launched by the call                                   */
   int window_groups;            /* window groups the call was pipelined over (1 = linear pipeline) */
   uint64_t bucket_starts;       /* of sorted_entries: copies into an empty accumulator (no multiplications); counted
-                                   while profiling is on, else 0.  executed mixed additions = sorted_entries - this */
+                                   while profiling is on, else 0 */
+  uint64_t bucket_pairs;        /* same-bucket neighbour pairs k_accumulate adds in affine first (3 + 3 multiplications
+                                   each, then ONE mixed addition for the pair); counted while profiling is on, else 0.
+                                   executed multiplications of k_accumulate =
+                                   10 * (sorted_entries - bucket_starts) - 4 * bucket_pairs + 12 * accumulate_threads */
+  uint64_t accumulate_threads;  /* threads with work in k_accumulate (each pays 12 multiplications for the warp-shared inversion) */
 } nmsm_plan_info;
 int nmsm_set_profiling(int enabled);
 int nmsm_last_timing(float* ms, nmsm_plan_info* info);

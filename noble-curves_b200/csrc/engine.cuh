@@ -116,7 +116,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   const uint64_t n_plan = shard ? shard->n_total : n;
   if (shard && (n_plan >= (1ull << 31) || shard->offset + n > n_plan)) return fail(NMSM_ERR_ARG, "sharded MSM: bad shard bounds");
   const int RES_WORDS = G::IN_WORDS + 4;  // xy | inf | err_pt | err_sc | pad   (then 2 words: accumulator starts, profiling)
-  CK(C.result.ensure((RES_WORDS + 2) * 4));
+  CK(C.result.ensure((RES_WORDS + 4) * 4));
   uint32_t* d_res = (uint32_t*)C.result.p;
   unsigned int* d_err = (unsigned int*)(d_res + G::IN_WORDS + 1);
 
@@ -251,7 +251,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   launches += 4;
   PEV(4);
   if (prof) {  // accounting only (not part of the timed kernels: between the scatter and the accumulate events)
-    CK(cudaMemsetAsync(d_res + RES_WORDS, 0, 8, st));
+    CK(cudaMemsetAsync(d_res + RES_WORDS, 0, 16, st));
     const uint64_t items = nseg > (uint64_t)plan.G ? nseg : (uint64_t)plan.G;
     k_count_starts<<<cdiv(items, 256), 256, 0, st>>>(offsets, plan, (unsigned long long*)(d_res + RES_WORDS));
     cudaEventRecord(C.ev[4], st);  // restart the accumulate interval after the counting kernel
@@ -469,7 +469,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   // one small D2H: result + error slots (+ entry count for accounting)
   CK(cudaMemcpyAsync(C.h_result, d_res, RES_WORDS * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(C.h_result + RES_WORDS, offsets + plan.G, 4, cudaMemcpyDeviceToHost, st));
-  if (prof) CK(cudaMemcpyAsync(C.h_result + RES_WORDS + 2, d_res + RES_WORDS, 8, cudaMemcpyDeviceToHost, st));
+  if (prof) CK(cudaMemcpyAsync(C.h_result + RES_WORDS + 2, d_res + RES_WORDS, 16, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(C.done, st));
   C.pend.plan = MsmPlanLite{plan.c, plan.W, plan.B, plan.G, plan.L, plan.K, plan.chunks, plan.D, plan.TPW};
   C.pend.profiled = prof;
@@ -527,6 +527,9 @@ static int collect_msm(uint8_t* out_xy, int* out_is_inf) {
   C.last_info.sorted_entries = entries;
   C.last_info.modmul_equiv = plan_modmuls<Cv>(plan, entries);
   C.last_info.bucket_starts = C.pend.profiled ? ((uint64_t)C.h_result[RES_WORDS + 2] | ((uint64_t)C.h_result[RES_WORDS + 3] << 32)) : 0;
+  C.last_info.bucket_pairs = (C.pend.profiled && NMSM_PAIRED && !G::IS_EDWARDS)
+                                 ? ((uint64_t)C.h_result[RES_WORDS + 4] | ((uint64_t)C.h_result[RES_WORDS + 5] << 32)) : 0;
+  C.last_info.accumulate_threads = C.pend.profiled ? (entries + plan.L - 1) / plan.L : 0;
   C.last_info.launches = C.pend.launches;
   C.last_info.window_groups = C.pend.groups;
   memset(C.last_ms, 0, sizeof(C.last_ms));

@@ -121,6 +121,47 @@ k_scan_apply(const unsigned int* __restrict__ counts, uint32_t G, const uint32_t
   if (base < G && base + SCAN_PER_THREAD >= G) offsets[G] = run;
 }
 
+// One field inversion per warp (Montgomery's trick across the lanes): every lane passes a non-zero z and gets
+// 1/z.  Inclusive prefix and suffix products by shuffles (5 + 5 multiplications per lane), one inversion of the
+// warp total computed redundantly in all lanes (same operand, no divergence), two more multiplications.
+// All 32 lanes must call it.
+template <class F>
+__device__ __forceinline__ F shfl_field(const F& a, int src_lane) {
+  F r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&a);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(F) / 4); k++) d[k] = __shfl_sync(0xffffffffu, s[k], src_lane);
+  return r;
+}
+template <class F>
+__device__ __noinline__ F warp_batch_inverse(const F& z) {
+  const int lane = threadIdx.x & 31;
+  F pre = z, suf = z;
+  for (int d = 1; d < 32; d <<= 1) {
+    F a = shfl_field(pre, lane >= d ? lane - d : lane);
+    F b = shfl_field(suf, lane + d < 32 ? lane + d : lane);
+    if (lane >= d) pre = pre * a;
+    if (lane + d < 32) suf = suf * b;
+  }
+  F r = inv(shfl_field(pre, 31));
+  F left = shfl_field(pre, lane > 0 ? lane - 1 : 0);
+  F right = shfl_field(suf, lane < 31 ? lane + 1 : 31);
+  if (lane > 0) r = r * left;
+  if (lane < 31) r = r * right;
+  return r;
+}
+
+// NMSM_PAIRED=1 builds k_accumulate with paired accumulation (msm_body.cuh accumulate_pairs_pass1/2: same-bucket
+// neighbours added in affine with one warp-shared inversion, 16 instead of 20 multiplications per two entries).  It is
+// bit-exact (hostemu + all GPU parity tests) and executes 20 % fewer multiplications, but on B200 it is SLOWER than the
+// plain loop — 2^20 BLS12-381 G1 terms: 7.09 ms (4 blocks/SM, 704 B of spills) / 6.78 ms (3 blocks/SM) against 6.04 ms —
+// because one 35 us inversion plus 12 scan multiplications per warp amortise over only ~28 pairs per lane, pass 1 is a
+// chain of dependent gathers with one multiplication each, and the extra live state spills.  Kept as a build option
+// (profiles/r02_ab_paired_accumulate.txt); the default is the plain mixed-addition loop.
+#ifndef NMSM_PAIRED
+#define NMSM_PAIRED 0
+#endif
 #ifndef NMSM_ACC_MINBLOCKS_WIDE
 #define NMSM_ACC_MINBLOCKS_WIDE 2  // BLS12-381 G2: a 4-coordinate Fp2 accumulator alone is 96 registers
 #endif
@@ -134,7 +175,20 @@ k_accumulate(const uint32_t* __restrict__ aff, const uint32_t* __restrict__ sort
              uint32_t* __restrict__ heads, uint32_t* __restrict__ tails) {
   // grid = (windows of the group) * TPW threads; TPW is a multiple of the block size, so a block never straddles windows
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-  accumulate_body<Cv>(w0 + gid / plan.TPW, gid % plan.TPW, aff, sorted, offsets, plan, buckets, heads, tails);
+  const uint32_t w = w0 + gid / plan.TPW, t = gid % plan.TPW;
+#if NMSM_PAIRED
+  if constexpr (!Cv::G::IS_EDWARDS) {
+    // paired accumulation (msm_body.cuh): affine sums of same-bucket neighbours, ONE field inversion per warp
+    using F = typename Cv::G::Field;
+    F suf[MAX_PAIRS];
+    int npairs;
+    const F run = accumulate_pairs_pass1<Cv>(w, t, aff, sorted, offsets, plan, suf, npairs);
+    const F inv_all = warp_batch_inverse(run);  // every lane of the warp, also the ones without a pair (run = 1)
+    accumulate_pairs_pass2<Cv>(w, t, aff, sorted, offsets, plan, suf, npairs, inv_all, buckets, heads, tails);
+    return;
+  }
+#endif
+  accumulate_body<Cv>(w, t, aff, sorted, offsets, plan, buckets, heads, tails);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -427,37 +481,6 @@ k_table_level(const uint32_t* __restrict__ prev, uint32_t* __restrict__ next, ui
   if (i < count) table_level_body<Cv>(i, prev, next, c);
 }
 
-// One field inversion per warp (Montgomery's trick across the lanes): every lane passes a non-zero z and gets
-// 1/z.  Inclusive prefix and suffix products by shuffles (5 + 5 multiplications per lane), one inversion of the
-// warp total computed redundantly in all lanes (same operand, no divergence), two more multiplications.
-// All 32 lanes must call it.
-template <class F>
-__device__ __forceinline__ F shfl_field(const F& a, int src_lane) {
-  F r;
-  const uint32_t* s = reinterpret_cast<const uint32_t*>(&a);
-  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-  for (int k = 0; k < (int)(sizeof(F) / 4); k++) d[k] = __shfl_sync(0xffffffffu, s[k], src_lane);
-  return r;
-}
-template <class F>
-__device__ __noinline__ F warp_batch_inverse(const F& z) {
-  const int lane = threadIdx.x & 31;
-  F pre = z, suf = z;
-  for (int d = 1; d < 32; d <<= 1) {
-    F a = shfl_field(pre, lane >= d ? lane - d : lane);
-    F b = shfl_field(suf, lane + d < 32 ? lane + d : lane);
-    if (lane >= d) pre = pre * a;
-    if (lane + d < 32) suf = suf * b;
-  }
-  F r = inv(shfl_field(pre, 31));
-  F left = shfl_field(pre, lane > 0 ? lane - 1 : 0);
-  F right = shfl_field(suf, lane < 31 ? lane + 1 : 31);
-  if (lane > 0) r = r * left;
-  if (lane < 31) r = r * right;
-  return r;
-}
-
 // Fixed-point multiplication tables (nmsm_point_table_*): level 0 = d * P, then k_table_level per level.
 template <class Cv>
 __global__ void __launch_bounds__(128)
@@ -514,24 +537,37 @@ k_torsion(const uint32_t* __restrict__ pts, uint32_t n, uint8_t* __restrict__ ou
 }
 
 // Profiling only: how many of the sorted entries START an accumulator (a copy, no field multiplications) instead of
-// being added to one — one per non-empty bucket plus one per accumulate segment that begins inside a bucket.  The
-// roofline accounting subtracts them from the entry count: executed mixed additions = entries - starts.
+// being added to one — one per non-empty bucket plus one per accumulate segment that begins inside a bucket — and how
+// many same-bucket PAIRS the segments hold (added in affine first).  The roofline accounting counts the executed
+// field multiplications of k_accumulate from them:  10 * (entries - starts) - 4 * pairs + 12 * threads.
 static __global__ void k_count_starts(const uint32_t* __restrict__ offsets, MsmPlan plan, unsigned long long* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned int c = 0;
+  unsigned int c = 0, pairs = 0;
   if (i < (uint32_t)plan.G && offsets[i + 1] > offsets[i]) c++;
   const uint64_t nseg = (uint64_t)plan.W * plan.TPW;
-  if (i < nseg) {  // segment (w, t): does it begin strictly inside a bucket?
+  if (i < nseg) {  // segment (w, t): does it begin strictly inside a bucket?  how many same-bucket pairs does it hold?
     const uint32_t w = i / plan.TPW, t = i % plan.TPW;
     const uint32_t base = offsets[w * (uint32_t)plan.B], T = offsets[(w + 1) * (uint32_t)plan.B];
     const uint64_t seg = (uint64_t)base + (uint64_t)t * (uint32_t)plan.L;
-    if (seg < T && t > 0) {
-      const uint32_t g = bucket_of_entry(offsets, plan, w, (uint32_t)seg);
-      if (offsets[g] < seg) c++;
+    if (seg < T) {
+      uint32_t g = bucket_of_entry(offsets, plan, w, (uint32_t)seg);
+      if (t > 0 && offsets[g] < seg) c++;
+      // pairs (b0 + 2j, b0 + 2j + 1) of every bucket run inside [seg, end): the rule of accumulate_pairs_pass1/2
+      const uint32_t end = (T - (uint32_t)seg > (uint32_t)plan.L) ? (uint32_t)seg + plan.L : T;
+      for (uint32_t pos = (uint32_t)seg; pos < end;) {
+        while (offsets[g + 1] <= pos) g++;
+        const uint32_t b0 = offsets[g], b1 = offsets[g + 1];
+        const uint32_t re = b1 < end ? b1 : end;
+        const uint32_t first = pos + ((pos - b0) & 1u);  // first even offset >= pos
+        if (re > first) pairs += (re - first) / 2;
+        pos = re;
+      }
     }
   }
   c = __reduce_add_sync(0xffffffffu, c);
+  pairs = __reduce_add_sync(0xffffffffu, pairs);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+  if ((threadIdx.x & 31) == 0 && pairs) atomicAdd(out + 1, (unsigned long long)pairs);
 }
 
 // curve-equation check per point (nmsm_points_on_curve)

@@ -762,6 +762,155 @@ NMSM_HD void accumulate_body(uint32_t w, uint32_t t, const uint32_t* aff, const 
   else save_acc<G>(tails + sid * G::ACC_WORDS, acc);
 }
 
+// ---- paired accumulation (short Weierstrass) ---------------------------------------------------------------------
+// Two neighbours of the same bucket are first added in AFFINE coordinates, lambda = (y2 - y1) / (x2 - x1), and only the
+// sum goes through the mixed addition into the XYZZ accumulator.  The division costs one inversion per WARP and segment:
+// every thread multiplies up the denominators of its pairs (pass 1), the 32 running products are inverted together
+// (k_accumulate: warp_batch_inverse — Montgomery's trick, the reference's FpInvertBatch modular.ts:734-760), and pass 2
+// peels the individual inverses off again.  Per pair: 3 multiplications for the shared inversion + 3 for the affine
+// addition (2M + 1S) + 10 for the mixed addition = 16 instead of 20 for two mixed additions.
+// Pairs are fixed by parity relative to the bucket start, (b0 + 2j, b0 + 2j + 1), as far as both entries lie inside the
+// thread's segment; a pair whose x coordinates coincide (P = +-Q: doubling or cancellation) or contain a zero (the
+// affine identity has x = 0) is left to the complete mixed addition, one entry at a time.  Both passes take that
+// decision from the same data, so they agree.
+static constexpr int MAX_PAIRS = 32;  // L <= 64 entries per segment
+
+template <class F>
+NMSM_HD bool pair_usable(const F& x1, const F& x2) {
+  return !x1.is_zero() && !x2.is_zero() && x1 != x2;
+}
+
+// Pass 1, backwards over the segment's pairs: suf[j] = product of the denominators of the pairs AFTER pair (M-1-j) in
+// forward order, i.e. suf is filled in the order the pairs are met walking down.  Returns the product of all of them
+// (one() if the thread has no pair) and the pair count in `npairs`.
+template <class Cv>
+NMSM_HD typename Cv::G::Field accumulate_pairs_pass1(uint32_t w, uint32_t t, const uint32_t* aff, const uint32_t* sorted,
+                                                     const uint32_t* offsets, const MsmPlan& plan,
+                                                     typename Cv::G::Field* suf, int& npairs) {
+  using G = typename Cv::G;
+  using F = typename G::Field;
+  npairs = 0;
+  F run = F::one();
+  const uint32_t g_lo = w * (uint32_t)plan.B, g_hi = g_lo + (uint32_t)plan.B;
+  const uint32_t base = offsets[g_lo], T = offsets[g_hi];
+  const uint64_t seg64 = (uint64_t)base + (uint64_t)t * (uint32_t)plan.L;
+  if (seg64 >= T) return run;
+  const uint32_t seg = (uint32_t)seg64;
+  const uint32_t end = (T - seg > (uint32_t)plan.L) ? seg + plan.L : T;
+  // bucket containing the LAST entry of the segment
+  uint32_t lo = g_lo, hi = g_hi;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= end - 1) lo = mid; else hi = mid;
+  }
+  uint32_t g = lo;
+  uint32_t pos = end;  // walk down: [.., pos) still to do
+  while (pos > seg) {
+    while (offsets[g] >= pos) g--;  // bucket of entry pos - 1 (skips empty buckets)
+    const uint32_t b0 = offsets[g];
+    const uint32_t rs = b0 > seg ? b0 : seg;  // run [rs, pos) of bucket g inside the segment
+    // pair starts p = b0 (mod 2) with rs <= p and p + 1 < pos, from the last one down (signed: p may step below 0)
+    if (pos - rs >= 2) {
+      long long p = (long long)pos - 2;
+      if ((((uint32_t)p - b0) & 1u) != 0) p--;
+      for (; p >= (long long)rs; p -= 2) {
+        const uint32_t e1 = sorted[p], e2 = sorted[p + 1];
+        F x1, x2;
+        load_words<F::LIMBS>(reinterpret_cast<uint32_t*>(&x1), aff + (size_t)(e1 & 0x7fffffffu) * G::AFF_WORDS);
+        load_words<F::LIMBS>(reinterpret_cast<uint32_t*>(&x2), aff + (size_t)(e2 & 0x7fffffffu) * G::AFF_WORDS);
+        if (pair_usable(x1, x2)) {
+          suf[npairs++] = run;
+          run = run * (x2 - x1);
+        }
+      }
+    }
+    pos = rs;
+  }
+  return run;
+}
+
+// Pass 2, forwards: the accumulate loop of accumulate_body with usable pairs replaced by their affine sum.
+// `inv_all` = 1 / (product returned by pass 1).
+template <class Cv>
+NMSM_HD void accumulate_pairs_pass2(uint32_t w, uint32_t t, const uint32_t* aff, const uint32_t* sorted, const uint32_t* offsets,
+                                    const MsmPlan& plan, const typename Cv::G::Field* suf, int npairs,
+                                    typename Cv::G::Field inv_all, uint32_t* buckets, uint32_t* heads, uint32_t* tails) {
+  using G = typename Cv::G;
+  using F = typename G::Field;
+  const uint32_t g_lo = w * (uint32_t)plan.B, g_hi = g_lo + (uint32_t)plan.B;
+  const uint32_t base = offsets[g_lo], T = offsets[g_hi];
+  const uint64_t seg64 = (uint64_t)base + (uint64_t)t * (uint32_t)plan.L;
+  if (seg64 >= T) return;
+  const uint32_t seg = (uint32_t)seg64;
+  const uint32_t end = (T - seg > (uint32_t)plan.L) ? seg + plan.L : T;
+  const size_t sid = (size_t)w * plan.TPW + t;
+  uint32_t lo = g_lo, hi = g_hi;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= seg) lo = mid; else hi = mid;
+  }
+  uint32_t g = lo;
+  uint32_t bstart = offsets[g], bend = offsets[g + 1];
+  typename G::Acc acc = G::identity();
+  int k = 0;  // usable pairs consumed so far (forward order); pass 1 stored pair k at suf[npairs - 1 - k]
+  for (uint32_t pos = seg; pos < end;) {
+    if (pos == bend) {
+      if (bstart >= seg) save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, acc);
+      else save_acc<G>(heads + sid * G::ACC_WORDS, acc);
+      acc = G::identity();
+      do { g++; } while (offsets[g + 1] <= pos);
+      bstart = offsets[g];
+      bend = offsets[g + 1];
+    }
+    const uint32_t e1 = sorted[pos];
+    const uint32_t* p1 = aff + (size_t)(e1 & 0x7fffffffu) * G::AFF_WORDS;
+    const uint32_t rs = bstart > seg ? bstart : seg;
+    const uint32_t re = bend < end ? bend : end;
+    // a pair start: even offset from the bucket start, partner inside the same run (pass 1 enumerated exactly these:
+    // pairs (p, p+1) with p = bstart (mod 2), rs <= p, p + 1 < re)
+    // ONE mixed addition per iteration, of either the affine sum of a usable pair or the single entry at `pos` (an
+    // unusable pair — P = +-Q, or a zero x: the affine identity — is simply taken as two single entries): a single call
+    // site keeps the accumulator in registers; everything live across an out-of-line multiplication is spilled, so the
+    // coordinates are loaded as late and dropped as early as possible.
+    typename G::Affine r;
+    bool paired = false;
+    if (((pos - bstart) & 1u) == 0 && pos >= rs && pos + 1 < re) {
+      const uint32_t e2 = sorted[pos + 1];
+      const uint32_t* p2 = aff + (size_t)(e2 & 0x7fffffffu) * G::AFF_WORDS;
+      F x1, x2;
+      load_words<F::LIMBS>(reinterpret_cast<uint32_t*>(&x1), p1);
+      load_words<F::LIMBS>(reinterpret_cast<uint32_t*>(&x2), p2);
+      if (pair_usable(x1, x2)) {
+        paired = true;
+        const F d = x2 - x1;
+        const F sx = x1 + x2;
+        const F dinv = inv_all * suf[npairs - 1 - k];
+        inv_all = inv_all * d;
+        k++;
+        F y1, y2;
+        load_words<F::LIMBS>(reinterpret_cast<uint32_t*>(&y1), p1 + F::LIMBS);
+        load_words<F::LIMBS>(reinterpret_cast<uint32_t*>(&y2), p2 + F::LIMBS);
+        if ((e1 >> 31) != 0) y1 = -y1;
+        if ((e2 >> 31) != 0) y2 = -y2;
+        const F lam = (y2 - y1) * dinv;
+        r.x = sqr(lam) - sx;
+        r.y = lam * (x1 - r.x) - y1;
+      }
+    }
+    if (!paired) {
+      r = load_aff<G>(p1);
+      r = G::cneg(r, (e1 >> 31) != 0);
+    }
+    G::madd(acc, r);
+    pos += paired ? 2u : 1u;
+  }
+  const bool head_open = bstart < seg;
+  const bool tail_open = bend > end;
+  if (!head_open && !tail_open) save_acc<G>(buckets + (size_t)g * G::ACC_WORDS, acc);
+  else if (head_open) save_acc<G>(heads + sid * G::ACC_WORDS, acc);
+  else save_acc<G>(tails + sid * G::ACC_WORDS, acc);
+}
+
 // Adds the value of bucket g into `sum`.  A bucket wholly inside one accumulate segment was written
 // to `buckets`; one that straddles segments is the sum of tails[ts] and heads[ts+1..te]; an empty
 // bucket contributes nothing.  (This stitching used to be a separate pass; fusing it here costs no

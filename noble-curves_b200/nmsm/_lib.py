@@ -55,6 +55,8 @@ class PlanInfo(ctypes.Structure):
         ("launches", ctypes.c_int),
         ("window_groups", ctypes.c_int),
         ("bucket_starts", ctypes.c_uint64),
+        ("bucket_pairs", ctypes.c_uint64),
+        ("accumulate_threads", ctypes.c_uint64),
     ]
 
 

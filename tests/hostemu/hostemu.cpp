@@ -18,6 +18,29 @@
 
 using namespace nmsm;
 
+// what k_accumulate runs per thread.  g_paired = 0 (the default build, NMSM_PAIRED=0): the plain mixed-addition loop;
+// g_paired = 1: the paired accumulation of the NMSM_PAIRED=1 build for the short-Weierstrass curves (the warp-shared
+// inversion of the kernel becomes a plain inversion of this thread's product) — both are parity-tested.
+static int g_paired = 0;
+extern "C" int emu_set_paired(int on) { int prev = g_paired; g_paired = on; return prev; }
+template <class Cv>
+static void emu_accumulate(uint32_t w, uint32_t t, const uint32_t* aff, const uint32_t* sorted, const uint32_t* offsets,
+                           const MsmPlan& plan, uint32_t* buckets, uint32_t* heads, uint32_t* tails) {
+  if (!g_paired) {
+    accumulate_body<Cv>(w, t, aff, sorted, offsets, plan, buckets, heads, tails);
+    return;
+  }
+  if constexpr (!Cv::G::IS_EDWARDS) {
+    using F = typename Cv::G::Field;
+    F suf[MAX_PAIRS];
+    int npairs;
+    const F run = accumulate_pairs_pass1<Cv>(w, t, aff, sorted, offsets, plan, suf, npairs);
+    accumulate_pairs_pass2<Cv>(w, t, aff, sorted, offsets, plan, suf, npairs, inv(run), buckets, heads, tails);
+  } else {
+    accumulate_body<Cv>(w, t, aff, sorted, offsets, plan, buckets, heads, tails);
+  }
+}
+
 template <class Cv>
 static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, int forced_c, int forced_L,
                      uint32_t* out_xy, uint32_t* out_inf, uint32_t* err_out, uint32_t* plan_out, int table_c = 0,
@@ -69,7 +92,7 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
       for (uint32_t t = 0; t < plan.TPW; t++) {
         // skip the (many) idle segments quickly: same early exit the body takes
         if ((uint64_t)offsets[(size_t)w * plan.B] + (uint64_t)t * plan.L >= offsets[(size_t)(w + 1) * plan.B] && t > 2) break;
-        accumulate_body<Cv>(w, t, aff.data(), sorted.data(), offsets.data(), plan, buckets.data(), heads.data(), tails.data());
+        emu_accumulate<Cv>(w, t, aff.data(), sorted.data(), offsets.data(), plan, buckets.data(), heads.data(), tails.data());
       }
     const uint32_t a0 = (uint32_t)((uint64_t)w_lo * plan.TPW / STITCH_FAN), a1 = (uint32_t)((uint64_t)w_hi * plan.TPW / STITCH_FAN);
     for (uint32_t j = a0; j < a1; j++) stitch_tile_serial<Cv>(j, STITCH_FAN, offsets.data(), plan, heads.data(), tile1.data());
@@ -141,7 +164,7 @@ static int emu_shard_buckets_t(const uint32_t* pts, const uint32_t* scalars, uin
   for (int w = 0; w < plan.W; w++)
     for (uint32_t t = 0; t < plan.TPW; t++) {
       if ((uint64_t)offsets[(size_t)w * plan.B] + (uint64_t)t * plan.L >= offsets[(size_t)(w + 1) * plan.B] && t > 2) break;
-      accumulate_body<Cv>(w, t, aff.data(), sorted.data(), offsets.data(), plan, buckets_out, heads.data(), tails.data());
+      emu_accumulate<Cv>(w, t, aff.data(), sorted.data(), offsets.data(), plan, buckets_out, heads.data(), tails.data());
     }
   for (uint32_t j = 0; j < ntile1; j++) stitch_tile_serial<Cv>(j, STITCH_FAN, offsets.data(), plan, heads.data(), tile1.data());
   for (uint32_t j = 0; j < ntile2; j++) stitch_tile_serial<Cv>(j, STITCH_FAN * STITCH_FAN, offsets.data(), plan, tile1.data(), tile2.data());

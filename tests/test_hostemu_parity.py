@@ -604,3 +604,32 @@ def test_strict_ed25519_decode_and_on_curve_hostemu():
             b[len(b) // 2] ^= 2
             arr = np.frombuffer(bytes(b), dtype=np.uint32).copy()
             assert lib.emu_on_curve(H.CURVE_IDS[name], arr.ctypes.data_as(ctypes.c_void_p)) == 0, name
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "bn254_G2", "bls12_381_G1", "bls12_381_G1_any"])
+def test_paired_accumulation_hostemu(name):
+    """The NMSM_PAIRED=1 build option of k_accumulate (same-bucket neighbours added in affine first, one shared inversion:
+    msm_body.cuh accumulate_pairs_pass1/2) against the oracle, incl. the inputs where a pair is P + P or P + (-P) and must
+    fall back to the complete mixed addition."""
+    cname = "bls12_381_G1" if name.endswith("_any") else name
+    lib = H.hostemu()
+    prev = lib.emu_set_paired(1)
+    try:
+        n = 200
+        P, pts, scalars, _ = H.soak_inputs(cname, n, seed_offset=21)
+        exp = H.expected_tuple(cname, R.pippenger(P, pts, scalars))
+        pb, sb = H.pack_points(cname, pts), H.pack_scalars(scalars)
+        for c, L in ((0, 0), (4, 7), (3, 64), (6, 2)):
+            got, err, plan = H.emu_msm(name, pb, sb, n, forced_c=c, forced_L=L)
+            assert got == exp, (name, c, L, plan)
+        # degenerate: the same point many times with equal scalars (every pair is P + P), P and -P next to each other,
+        # ZERO points inside pairs
+        G = pts[3]
+        deg = [G] * 40 + [pts[5], pts[5].negate()] * 6 + [P.ZERO, pts[7], P.ZERO, P.ZERO]
+        dsc = [9] * 40 + [5] * 12 + [3, 4, 5, 6]
+        exp2 = H.expected_tuple(cname, R.pippenger(P, deg, dsc))
+        for c, L in ((4, 8), (2, 64), (5, 3)):
+            got, _, _ = H.emu_msm(name, H.pack_points(cname, deg), H.pack_scalars(dsc), len(deg), forced_c=c, forced_L=L)
+            assert got == exp2, (name, c, L)
+    finally:
+        lib.emu_set_paired(prev)
