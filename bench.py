@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="N>1: strong (default, the metric's config) = 2^logn terms in total; weak = 2^logn terms PER GPU")
     ap.add_argument("--groups", type=int, default=0, help="force the window-group count of the pipeline (0 = automatic)")
+    ap.add_argument("--configs", action="store_true",
+                    help="instead of the headline line: time every BASELINE.json config on one GPU (one JSON line, key `configs`)")
     return ap.parse_args()
 
 
@@ -201,11 +203,116 @@ def _emit(real_stdout_fd, line: dict):
     os.write(real_stdout_fd, (json.dumps(line) + "\n").encode())
 
 
+# --------------------------------------------------------------------------------------------
+# the five BASELINE.json configs on one GPU (companion table; the parity tests of the same configs are in tests/)
+# --------------------------------------------------------------------------------------------
+def run_configs(args, real_stdout):
+    """Each config is timed through the host-buffer C-ABI entry point a caller of the reference would use (H2D inside) and,
+    for the MSMs, also as device time of the pipeline (library events).  Results are checked on the GPU itself by the
+    scalar-in-the-exponent identity  sum s_i * (k_i G) = (sum k_i s_i) G  (test/slow-curves.test.ts:204-233); the bit-exact
+    comparison against the oracle for these very configs is tests/test_gpu_parity.py::test_config_*."""
+    import nmsm
+
+    nmsm.init(0)
+    rows = []
+
+    def best_of(fn, reps):
+        best = 1e9
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        return best
+
+    def pack(v, nbytes):
+        return v.to_bytes(nbytes, "little") if isinstance(v, int) else b"".join(c.to_bytes(nbytes, "little") for c in v)
+
+    def msm_row(idx, C, logn, seed):
+        n = 1 << logn
+        order, cid, fb = C.Fn.ORDER, C.CURVE_ID, C.FP_BYTES
+        rnd = random.Random(seed)
+        ks = [rnd.randrange(1, order) for _ in range(n)]
+        sc = [rnd.randrange(order) for _ in range(n)]
+        g = pack(C.BASE.x, fb) + pack(C.BASE.y, fb)
+        scb = b"".join(s_.to_bytes(32, "little") for s_ in sc)
+        pts, _ = nmsm.mul_batch_packed(cid, g * n, b"".join(k.to_bytes(32, "little") for k in ks), n, False)
+        total = sum(k * s_ for k, s_ in zip(ks, sc)) % order
+        exp, _ = nmsm.mul_batch_packed(cid, g, total.to_bytes(32, "little"), 1, True)
+        res = {}
+
+        def run():
+            res["o"] = nmsm.msm_packed(cid, pts, scb, n)
+
+        run()
+        run()
+        best = best_of(run, args.steps if args.steps < 8 else 8)
+        ms, info = nmsm.last_timing()
+        rows.append({"config": idx, "what": "%s Pippenger MSM, 2^%d random terms" % (C.NAME, logn), "n": n,
+                     "ms_host_buffers": best * 1e3, "ms_device": ms["total"], "points_per_s_device": n / (ms["total"] * 1e-3),
+                     "plan": {"c": info.c, "windows": info.windows, "sorted_entries": info.sorted_entries},
+                     "check": "ok: equals (sum k_i s_i)*G" if res["o"][0] == exp and res["o"][1] == 0 else "MISMATCH"})
+
+    # config 0: secp256k1 Point.multiply batch of 1024 random scalars (benchmark/point.ts shape: one public key, many scalars)
+    C = nmsm.CURVES["secp256k1"]
+    order = C.Fn.ORDER
+    rnd = random.Random(11)
+    b0 = rnd.randrange(1, order)
+    g = pack(C.BASE.x, 32) + pack(C.BASE.y, 32)
+    pk, _ = nmsm.mul_batch_packed(0, g, b0.to_bytes(32, "little"), 1, False)
+    ks = [rnd.randrange(1, order) for _ in range(1024)]
+    ksb = b"".join(k.to_bytes(32, "little") for k in ks)
+    res = {}
+
+    def run0():
+        res["o"] = nmsm.mul_batch_packed(0, pk * 1024, ksb, 1024, False)
+
+    run0()
+    best = best_of(run0, 5)
+    exp, _ = nmsm.mul_batch_packed(0, g * 1024, b"".join(((k * b0) % order).to_bytes(32, "little") for k in ks), 1024, False)
+    rows.append({"config": 0, "what": "secp256k1 Point.multiply, batch of 1024 random scalars", "n": 1024, "ms_host_buffers": best * 1e3,
+                 "multiplies_per_s": 1024 / best, "check": "ok: k_i*(b*G) == (k_i*b)*G" if res["o"][0] == exp else "MISMATCH"})
+    msm_row(1, nmsm.CURVES["bls12_381_G1"], 16, 101)
+    msm_row(2, nmsm.CURVES["bn254_G1"], 20, 102)
+    msm_row(3, nmsm.CURVES["bls12_381_G2"], 18, 103)
+    # config 4: ed25519 batch verification of 2^16 signatures (1024 fresh signatures tiled x64)
+    try:
+        from cryptography.hazmat.primitives import serialization
+        from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+
+        base = []
+        for i in range(1024):
+            sk = Ed25519PrivateKey.generate()
+            msg = (b"noble-curves_b200 bench %d" % i) * (1 + i % 3)
+            base.append((sk.sign(msg), msg, sk.public_key().public_bytes(serialization.Encoding.Raw, serialization.PublicFormat.Raw)))
+        reps = (1 << 16) // len(base)
+        sigs, msgs, pks = [b[0] for b in base] * reps, [b[1] for b in base] * reps, [b[2] for b in base] * reps
+        z = os.urandom(16 * len(sigs))
+
+        def run4():
+            res["v"] = nmsm.ed25519_verify_batch(sigs, msgs, pks, z)
+
+        run4()
+        best = best_of(run4, 3)
+        bad = list(sigs)
+        bad[777] = bad[777][:40] + bytes([bad[777][40] ^ 1]) + bad[777][41:]
+        rej = nmsm.ed25519_verify_batch(bad, msgs, pks, z)
+        rows.append({"config": 4, "what": "ed25519 batch verification, 2^16 signatures (Edwards MSM of 2^17 + 1 terms)", "n": len(sigs),
+                     "ms_through_python_binding": best * 1e3, "signatures_per_s": len(sigs) / best,
+                     "check": "ok: valid batch accepted, one corrupted signature rejected" if res["v"] == (True, -1) and not rej[0] else "MISMATCH"})
+    except ImportError as e:
+        rows.append({"config": 4, "what": "ed25519 batch verification", "skipped": "no signer available: %r" % (e,)})
+    _emit(real_stdout, {"configs": rows, "n_gpus": 1, "data": "synthetic",
+                        "note": "companion table of bench.py --configs; the headline metric is the default bench.py line"})
+
+
 def main():
     args = parse_args()
     real_stdout = _claim_stdout()
     if args.impl == "reference":
         run_reference(args, real_stdout)
+        return
+    if args.configs:
+        run_configs(args, real_stdout)
         return
 
     import torch

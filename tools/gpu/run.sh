@@ -14,7 +14,7 @@ case "$task" in
   bench)
     timeout 900 python bench.py "$@" > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; cat gpurun_out/bench.json ;;
   configs)
-    timeout 900 python tests/bench_configs.py "$@" > gpurun_out/configs.jsonl 2> gpurun_out/configs.err; echo "rc=$?"; cat gpurun_out/configs.jsonl ;;
+    timeout 900 python bench.py --configs "$@" > gpurun_out/configs.json 2> gpurun_out/configs.err; echo "rc=$?"; cat gpurun_out/configs.json ;;
   ncu-launches)
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-fixed-base "$@" > gpurun_out/ncu_bench.log 2>&1; echo "rc=$?" ;;
