@@ -577,7 +577,8 @@ def main():
         # of the warp's batch inversion + 2M + 1S) and then takes ONE mixed addition: 16 for two entries instead of 20, i.e.
         # -4 per pair; every thread pays 12 for the prefix / suffix products of the warp-shared inversion.
         madds = info.sorted_entries - info.bucket_starts - info.bucket_pairs
-        madd_modmuls = 10 * (info.sorted_entries - info.bucket_starts) - 4 * info.bucket_pairs + 12 * info.accumulate_threads
+        madd_modmuls = 10 * (info.sorted_entries - info.bucket_starts) - 4 * info.bucket_pairs + \
+            (12 * info.accumulate_threads if info.bucket_pairs else 0)  # the warp scan only exists in the paired build
         achieved = madd_modmuls / acc_t
         # whole MSM, executed: mixed additions + bucket reduction (2 additions per bucket of 12M+2S) + Horner doublings (6M+3S)
         W_, B_ = info.windows, info.buckets_per_window

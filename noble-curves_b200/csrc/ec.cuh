@@ -20,7 +20,8 @@
 namespace nmsm {
 
 // ------------------------------------------------------------------------------------------
-// Lane-parallel field multiplications for the single-warp latency tails (k_final / k_fold).
+// Lane-parallel field multiplications for the latency-bound tails (k_horner_step / k_combine / k_fold, k_reduce2, the
+// owner kernels of a sharded MSM).
 // The multiply pipe is occupied per WARP instruction (a lone thread pays ~0.95 us per 381-bit
 // mont_mul, measured), so latency-bound phases run each logical thread on a QUAD of 4 adjacent lanes
 // holding the same replicated state; at each level of a point formula lane (l & 3) computes one of up
@@ -28,8 +29,8 @@ namespace nmsm {
 // (quad-scoped masks, so different quads of a warp may diverge).
 // ------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
-// FULLWARP = true: all 32 lanes hold the same state (k_final / k_fold) and shuffles use the full mask;
-// false: quads are independent logical threads (k_reduce2 / k_reduce3) and shuffles are quad-scoped.
+// FULLWARP = true: all 32 lanes hold the same state (k_horner_step / k_fold) and shuffles use the full mask;
+// false: quads are independent logical threads (k_reduce2, k_combine, the dense kernels) and shuffles are quad-scoped.
 template <class F, bool FULLWARP>
 struct Par4 {
   static constexpr int WORDS = sizeof(F) / 4;

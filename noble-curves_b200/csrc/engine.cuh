@@ -84,27 +84,29 @@ static int stage_host_inputs(Slot& C, const void* pts, const void* scalars, uint
 
 // Enqueue the whole pipeline (and the small result D2H); no host sync.
 //
-//   main stream   : prepare, digit count, scan, scatter                                   -> ev_fork
-//   group g = 0.. : windows [w_lo, w_hi), top windows first
-//       acc_stream[g % 2]  (low priority)  k_accumulate of the group                      -> ev_acc[g]
-//       tail_stream[g % 2] (high priority) stitch tiles, k_reduce1, k_reduce2, k_reduce3  -> ev_tail[g]
+// Single GPU, one window group (the default, see choose_groups): everything on the slot's main stream, except k_prepare
+// (and the point H2D of host inputs) on prep_stream beside the digit passes:
+//   prepare | count, scan, scatter -> k_accumulate -> k_stitch_tiles x2 -> k_reduce1 -> k_reduce2 levels
+//   -> k_horner_step -> k_combine (inversion to affine) -> D2H
+// With NG > 1 groups (nmsm_set_window_groups; windows [w_lo, w_hi), top windows first):
+//       acc_stream[g % 8]  (low priority)  k_accumulate of the group                      -> ev_acc[g]
+//       tail_stream[g % 4] (high priority) stitch tiles, k_reduce1, k_reduce2 levels      -> ev_tail[g]
 //       horner_stream      (high priority) k_horner_step: hacc = 2^(c * windows) * hacc + group sum
-//   main stream   : waits for the last Horner step, k_combine (inversion to affine), D2H   -> done
-// The accumulate launches of consecutive groups sit on alternating streams, so the blocks of group g+1 fill the SMs as
-// the blocks of group g drain (no wave-quantisation gap between launches), while the latency-bound reduction and the
-// doubling chain of every finished group run underneath.  Only the last group's reduction, one Horner step of
-// c * (windows per group) doublings and the inversion remain on the critical path.  With one group (small inputs,
-// profiling) everything is issued on the main stream.
+// all accumulate launches are issued before any tail work (streams may share a hardware queue).
 //
 // Sharded (multi-GPU) MSM, `shard` != nullptr (BASELINE north_star "allreduce of the per-window bucket
 // accumulators"): every GPU accumulates its n_local terms into the full W x B bucket array with the GLOBAL window
-// size; window w is owned by rank w % world.  One group per window, top window first; after a window's accumulate:
-//       tail stream   k_stitch_tiles, k_bucket_finalize (dense bucket array of the window)     -> ev_fin[w]
-//       comm stream   ncclSend of the window's buckets to its owner / ncclRecv from every peer  -> ev_xchg[w]
-//       owner only    k_bucket_fold (EC addition is not an NCCL reduction operator: exchange + fold), k_reduce1_dense,
-//                     k_reduce2, k_reduce3, k_horner_step with the window's weight 2^(c w)      -> ev_tail[w]
-//   comm stream: ncclAllGather of every rank's weighted window sums (+ its validation words); k_combine folds them.
-// The exchange of window w overlaps the accumulation of windows w-1..0; every rank ends with the same affine result.
+// size; window w is owned by rank w % world.  Default (bulk form, one group):
+//   main stream   one k_accumulate over all windows, k_stitch_tiles, k_bucket_finalize (dense buckets)   -> ev_fin
+//   comm stream   direct form: a 4-byte ncclAllGather as the barrier "my dense buckets are complete"     -> ev_xchg
+//                 (copy form, NMSM_DIST_P2P=0: grouped ncclSend / ncclRecv of the dense windows to their owners)
+//   per owned window, on its own tail stream:
+//                 k_bucket_fold_peers — the owner PULLS every peer's partial buckets over NVLink inside the fold kernel
+//                 (EC addition is not an NCCL reduction operator: exchange + fold) — k_reduce1_dense, k_reduce2 levels,
+//                 k_horner_step with the window's weight 2^(c w)                                          -> ev_tail[w]
+//   comm stream   ncclAllGather of every rank's weighted window sums (+ its validation words); k_combine folds them.
+// With nmsm_set_window_groups(> 1): one group per window, top window first, the exchange of window w overlapping the
+// accumulation of windows w-1..0 (measured slower on B200 at 2, 4 and 8 GPUs: DESIGN.md §6).
 static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t n, uint32_t* d_out_acc,
                       const uint32_t* d_prepared, int table_c = 0, uint64_t table_points = 0,
                       const ShardArgs* shard = nullptr) {
@@ -142,7 +144,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   const uint64_t max_entries = (n ? n : 1) * (uint64_t)plan.D * (Cv::GLV ? 2 : 1);
   if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
   // bucket reduction levels: every k_reduce2 pass shrinks the per-window chunk count by REDUCE2_CHUNKS_PER_BLOCK
-  // until <= REDUCE2_MAX_SPLITS block results per window remain for k_reduce3 (one pass for the ordinary plans)
+  // until ONE block per window is left (two passes for the ordinary plans)
   size_t blk_entries = 0;
   for (uint64_t m = plan.chunks;;) {
     const uint64_t sp = (m + (uint64_t)REDUCE2_LOGICAL * reduce2_r(m) - 1) / ((uint64_t)REDUCE2_LOGICAL * reduce2_r(m));

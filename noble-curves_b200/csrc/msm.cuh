@@ -197,7 +197,7 @@ k_accumulate(const uint32_t* __restrict__ aff, const uint32_t* __restrict__ sort
 // (ec.cuh Par4: 4 multiplication levels per addition instead of 14 dependent multiplications).
 //   sum_b (b+1) B_b  =  sum_k T_k + K * sum_k k * S_k        k over the M = B/K chunks   (k_reduce1)
 //   per block of Mb chunks:  P_s = sum T_k + K * sum (k - s*Mb) S_k ,  Q_s = sum S_k        (k_reduce2)
-//   window sum = sum_s P_s + K * Mb * sum_s s * Q_s                                          (k_reduce3)
+//   window sum = sum_s P_s + K * Mb * sum_s s * Q_s                                          (k_reduce2, next level)
 // The last line has the shape of the first (T := P, S := Q, K := K * Mb): k_reduce2 is applied again to its own outputs
 // (with fewer chunks per quad) until ONE block per window is left, whose P_0 is the window sum.  Ordinary plans: two
 // passes (4096 chunks -> 32 block results -> 1); fixed-base tables (one window of up to 2^21 buckets): three or four.

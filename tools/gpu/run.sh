@@ -19,8 +19,8 @@ case "$task" in
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-fixed-base "$@" > gpurun_out/ncu_bench.log 2>&1; echo "rc=$?" ;;
   ncu-full)
-    pat=$1; shift
-    timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$pat" -s 2 -c 2 -f -o gpurun_out/prof_$pat \
+    pat=$1; shift   # one capture of the 2nd launch whose name matches (the first is a cold start)
+    timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$pat" -s 1 -c 1 -f -o gpurun_out/prof_$pat \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-fixed-base "$@" > gpurun_out/ncu_full.log 2>&1; echo "rc=$?" ;;
   sanitizer)
     tool=${1:-memcheck}; shift || true
