@@ -168,10 +168,35 @@ int dist_map_peer_buckets(int slot, void* local_base, cudaStream_t st) {
   CK(cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * D.world, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   cudaFree(d_h);
+  // map every peer; if ANY rank cannot map ANY peer, every rank drops to the copy form together (the owner's fold and the
+  // non-owners' sends must agree on the form): a second tiny all-gather carries the verdicts
+  uint32_t ok = 1;
   for (int r = 0; r < D.world; r++) {
     if (r == D.rank) continue;
     cudaError_t e = cudaIpcOpenMemHandle(&D.mapped[slot][r], all[r], cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (peer bucket array)");
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      D.mapped[slot][r] = nullptr;
+      ok = 0;
+    }
+  }
+  uint32_t* d_ok = nullptr;
+  CK(cudaMalloc((void**)&d_ok, 4 * (D.world + 1)));
+  CK(cudaMemcpyAsync(d_ok + D.world, &ok, 4, cudaMemcpyHostToDevice, st));
+  if (int r = nccl_all_gather(d_ok + D.world, d_ok, 4, st)) { cudaFree(d_ok); return r; }
+  std::vector<uint32_t> oks(D.world);
+  CK(cudaMemcpyAsync(oks.data(), d_ok, 4 * D.world, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d_ok);
+  for (uint32_t v : oks) ok &= v;
+  if (!ok) {
+    for (int r = 0; r < D.world; r++)
+      if (D.mapped[slot][r]) {
+        cudaIpcCloseMemHandle(D.mapped[slot][r]);
+        D.mapped[slot][r] = nullptr;
+      }
+    D.p2p = false;  // for the rest of the process: ncclSend / ncclRecv copies of the dense windows
+    return NMSM_OK;
   }
   D.mapped_local[slot] = local_base;
   return NMSM_OK;

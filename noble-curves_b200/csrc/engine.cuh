@@ -204,19 +204,20 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   const size_t WB = (size_t)plan.B * G::ACC_WORDS;                   // words of one window's dense bucket array
   const int gather_words = slots * G::ACC_WORDS + 4;                 // per rank: weighted window sums | err_pt err_sc off_lo off_hi
   uint32_t *recv = nullptr, *gsend = nullptr, *grecv = nullptr;
-  const bool p2p = shard && g_dist.p2p && world > 1;
+  bool p2p = shard && g_dist.p2p && world > 1;
   PeerPtrs peer_ptrs = {};
   if (shard) {
+    if (p2p) {  // (re)map the peers' bucket arrays when this slot's own array moved (same call on every rank)
+      if (int r = dist_map_peer_buckets(g_ctx.cur, C.buckets.p, C.comm_stream)) return r;
+      p2p = g_dist.p2p;  // a peer that cannot be mapped turns the direct form off on every rank
+      for (int r = 0; r < world && p2p; r++) peer_ptrs.p[r] = (const uint32_t*)g_dist.mapped[g_ctx.cur][r];
+    }
     if (!p2p) CK(C.recv.ensure((size_t)slots * (world - 1) * WB * 4 + 16));
     CK(C.gsend.ensure((size_t)gather_words * 4));
     CK(C.grecv.ensure((size_t)gather_words * 4 * world + 256 + 4 * world));  // + scratch of the 4-byte barrier all-gathers
     recv = (uint32_t*)C.recv.p;
     gsend = (uint32_t*)C.gsend.p;
     grecv = (uint32_t*)C.grecv.p;
-    if (p2p) {  // (re)map the peers' bucket arrays when this slot's own array moved (same call on every rank)
-      if (int r = dist_map_peer_buckets(g_ctx.cur, C.buckets.p, C.comm_stream)) return r;
-      for (int r = 0; r < world; r++) peer_ptrs.p[r] = (const uint32_t*)g_dist.mapped[g_ctx.cur][r];
-    }
   }
   int launches = 0;
 #define PEV(slot)                                   \
