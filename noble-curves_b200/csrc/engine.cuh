@@ -824,8 +824,17 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
   CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(d_err, 0xff, 8, st));
   EV(0);
-  k_mul_batch<Cv><<<cdiv(n, 128), 128, 0, st>>>((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p,
-                                                   (uint32_t)n, allow_zero, d_xy, d_inf, d_err);
+  // one item per quad of lanes while that leaves the multiply pipe under-subscribed (<= 1.5 warps per sub-partition).
+  // Measured on B200 (profiles/r02_sweep_mul_batch.jsonl), kernel ms quad / serial: secp256k1 x 1024 0.81 / 1.19,
+  // x 8192 0.97 / 1.19; BLS12-381 G1 x 1024 2.13 / 3.45, x 16384 5.02 / 3.49 (serial wins once the pipe is full)
+  uint64_t quad_max = (uint64_t)g_ctx.sm_count * 4 * 12;
+  if (const char* e = getenv("NMSM_MUL_QUAD_MAX")) quad_max = strtoull(e, nullptr, 10);  // tuning experiments
+  if (n <= quad_max)
+    k_mul_batch<Cv, true><<<cdiv(n * 4, 128), 128, 0, st>>>((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p,
+                                                            (uint32_t)n, allow_zero, d_xy, d_inf, d_err);
+  else
+    k_mul_batch<Cv, false><<<cdiv(n, 128), 128, 0, st>>>((const uint32_t*)C.in_pts.p, (const uint32_t*)C.in_scalars.p,
+                                                          (uint32_t)n, allow_zero, d_xy, d_inf, d_err);
   EV(1);
   CK(cudaGetLastError());
   std::vector<uint32_t> inf(n);

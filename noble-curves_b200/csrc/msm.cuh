@@ -241,6 +241,7 @@ template <class G>
 struct QuadOps {
   __device__ static void add(typename G::Acc& p, const typename G::Acc& q) { G::template par_add<false>(p, q); }
   __device__ static void dbl(typename G::Acc& p) { G::template par_dbl<false>(p); }
+  __device__ static void madd(typename G::Acc& p, const typename G::Affine& q) { G::template par_add<false>(p, G::from_affine(q)); }
 };
 #endif
 template <class Cv, bool QUAD>
@@ -510,17 +511,23 @@ k_table_mul(const uint32_t* __restrict__ tbl, const uint32_t* __restrict__ scala
 // out[i] = scalars[i] * pts[i].  The to-affine step is the reference's normalizeZ (curve.ts:311-326: one inversion for
 // a whole batch by Montgomery's trick, FpInvertBatch modular.ts:734-760): here ONE inversion per warp shared through
 // prefix / suffix products over the lanes (warp_batch_inverse), instead of a ~770-step binary xgcd in every thread.
-template <class Cv>
+// QUAD: one item per quad of lanes (ec.cuh Par4) — a batch of a few thousand multiplications is a pure latency chain of
+// ~130 doublings + ~70 additions per item, and the lane-parallel formulas cut each link from 9 / 14 dependent field
+// multiplications to 3 / 4 levels.  The engine picks it while the batch leaves multiply-pipe slots idle (engine.cuh).
+template <class Cv, bool QUAD>
 __global__ void __launch_bounds__(128)
 k_mul_batch(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars, uint32_t n,
             int allow_zero, uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_inf,
             unsigned int* err) {
   using G = typename Cv::G;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = QUAD ? gt >> 2 : gt;
   typename G::Acc acc = G::identity();
-  const bool ok = i < n && mul_acc_body<Cv>(i, pts, scalars, allow_zero, acc, err);
+  bool ok;
+  if (QUAD) ok = i < n && mul_acc_body<Cv, QuadOps<G>>(i, pts, scalars, allow_zero, acc, err);  // whole quads leave together
+  else ok = i < n && mul_acc_body<Cv>(i, pts, scalars, allow_zero, acc, err);
   const typename G::Field iz = warp_batch_inverse(G::inv_target(acc));  // whole warp, also the idle lanes
-  if (!ok) return;
+  if (!ok || (QUAD && (gt & 3u))) return;
   uint32_t xy[G::IN_WORDS];
   uint32_t inf;
   G::to_affine_canonical_with_inv(acc, iz, xy, &inf);

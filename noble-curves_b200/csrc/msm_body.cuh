@@ -354,6 +354,7 @@ template <class G>
 struct SerialOps {
   NMSM_HD static void add(typename G::Acc& p, const typename G::Acc& q) { nl_add<G>(p, q); }
   NMSM_HD static void dbl(typename G::Acc& p) { nl_dbl<G>(p); }
+  NMSM_HD static void madd(typename G::Acc& p, const typename G::Affine& q) { nl_madd<G>(p, q); }
 };
 // same, formulas inlined at the call site (bucket_finalize_body explains why the dense kernels avoid nl_add)
 template <class G>
@@ -1211,7 +1212,8 @@ NMSM_HD int mul_window_digit(const uint32_t* m, int nwords, int w, uint32_t& car
 }
 
 // s * P as an un-normalised accumulator (the core of mul_body / torsion_body); s < n, 8 words
-template <class Cv>
+// Ops: SerialOps (one thread per item) or msm.cuh QuadOps (one item per quad of lanes, k_mul_batch for small batches).
+template <class Cv, class Ops = SerialOps<typename Cv::G>>
 NMSM_HD typename Cv::G::Acc scalar_mul_acc(const typename Cv::G::Affine& P, const uint32_t* s) {
   using G = typename Cv::G;
   using Acc = typename G::Acc;
@@ -1219,10 +1221,10 @@ NMSM_HD typename Cv::G::Acc scalar_mul_acc(const typename Cv::G::Affine& P, cons
   Acc table[MUL_TABLE];
   table[0] = G::from_affine(P);
   table[1] = table[0];
-  nl_dbl<G>(table[1]);
+  Ops::dbl(table[1]);
   for (int d = 2; d < MUL_TABLE; d++) {
     table[d] = table[d - 1];
-    nl_madd<G>(table[d], P);
+    Ops::madd(table[d], P);
   }
   Acc acc = G::identity();
   if constexpr (Cv::GLV && Cv::COFACTOR_ONE) {  // multiply() must be right for every on-curve point (subgroup checks, cofactor clearing)
@@ -1244,19 +1246,19 @@ NMSM_HD typename Cv::G::Acc scalar_mul_acc(const typename Cv::G::Affine& P, cons
     }
     for (int w = NW - 1; w >= 0; w--) {
       if (w != NW - 1)
-        for (int j = 0; j < MUL_WBITS; j++) nl_dbl<G>(acc);
+        for (int j = 0; j < MUL_WBITS; j++) Ops::dbl(acc);
       if (d1[w] != 0) {
         const int a = d1[w] < 0 ? -d1[w] : d1[w];
         Acc t = table[a - 1];
         if ((d1[w] < 0) != neg1) t = G::neg(t);
-        nl_add<G>(acc, t);
+        Ops::add(acc, t);
       }
       if (d2[w] != 0) {
         const int a = d2[w] < 0 ? -d2[w] : d2[w];
         Acc t = table[a - 1];
         t.X = t.X * beta;  // phi on XYZZ coordinates: x = X / ZZ
         if ((d2[w] < 0) != neg2) t = G::neg(t);
-        nl_add<G>(acc, t);
+        Ops::add(acc, t);
       }
     }
   } else {
@@ -1266,12 +1268,12 @@ NMSM_HD typename Cv::G::Acc scalar_mul_acc(const typename Cv::G::Affine& P, cons
     for (int w = 0; w < NW; w++) dg[w] = (signed char)mul_window_digit(s, SCALAR_WORDS, w, c);
     for (int w = NW - 1; w >= 0; w--) {
       if (w != NW - 1)
-        for (int j = 0; j < MUL_WBITS; j++) nl_dbl<G>(acc);
+        for (int j = 0; j < MUL_WBITS; j++) Ops::dbl(acc);
       if (dg[w] != 0) {
         const int a = dg[w] < 0 ? -dg[w] : dg[w];
         Acc t = table[a - 1];
         if (dg[w] < 0) t = G::neg(t);
-        nl_add<G>(acc, t);
+        Ops::add(acc, t);
       }
     }
   }
@@ -1279,7 +1281,7 @@ NMSM_HD typename Cv::G::Acc scalar_mul_acc(const typename Cv::G::Affine& P, cons
 }
 
 // Validation + scalar multiplication of item i; false (and the index recorded) when the point or scalar is rejected.
-template <class Cv>
+template <class Cv, class Ops = SerialOps<typename Cv::G>>
 NMSM_HD bool mul_acc_body(uint32_t i, const uint32_t* pts, const uint32_t* scalars, int allow_zero,
                           typename Cv::G::Acc& acc, unsigned int* err) {
   using G = typename Cv::G;
@@ -1296,7 +1298,7 @@ NMSM_HD bool mul_acc_body(uint32_t i, const uint32_t* pts, const uint32_t* scala
   if (bad_sc) atomic_min_u32(&err[1], i);
   acc = G::identity();
   if (bad_pt || bad_sc) return false;
-  acc = scalar_mul_acc<Cv>(G::prepare(in), s);
+  acc = scalar_mul_acc<Cv, Ops>(G::prepare(in), s);
   return true;
 }
 

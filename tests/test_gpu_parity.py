@@ -151,8 +151,12 @@ def test_object_api_matches_reference_semantics(nmsm, name):
     assert G.multiply(a).multiply(b).equals(G.multiply(a * b % C.Fn.ORDER))
 
 
+@pytest.mark.parametrize("form", ["quad", "serial"])
 @pytest.mark.parametrize("name", ALL)
-def test_mul_batch_vs_oracle(nmsm, name):
+def test_mul_batch_vs_oracle(nmsm, name, form, monkeypatch):
+    """Both forms of k_mul_batch: one item per quad of lanes (small batches, the default here) and one item per thread."""
+    if form == "serial":
+        monkeypatch.setenv("NMSM_MUL_QUAD_MAX", "0")
     P = R.CURVES[name]
     n_order = P.Fn.ORDER
     rng = R.Xorshift64(0xDEADBEEF)

@@ -42,6 +42,8 @@ case "$task" in
   ncu-shard1)
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_shard1.csv \
       python tools/gpu/shard1_profile.py "$@" > gpurun_out/ncu_shard1.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_shard1.log ;;
+  sweepc)
+    timeout 1500 python tools/gpu/sweep_c.py "$@" > gpurun_out/sweep_c.jsonl 2> gpurun_out/sweep_c.err; echo "rc=$?"; cat gpurun_out/sweep_c.jsonl ;;
   explore)
     timeout 900 python tools/gpu/explore_groups.py "$@" > gpurun_out/explore.jsonl 2> gpurun_out/explore.err; echo "rc=$?"; cat gpurun_out/explore.jsonl ;;
   *) echo "unknown task $task"; exit 2 ;;
