@@ -47,15 +47,18 @@ enum {
   NMSM_BN254_G1 = 2,
   NMSM_BN254_G2 = 3,
   NMSM_BLS12_381_G1 = 4,      /* points in the prime-order subgroup (what assertValidity / fromBytes accept): GLV schedule */
-  NMSM_BLS12_381_G2 = 5,
-  NMSM_BLS12_381_G1_ANY = 6   /* any point of E(Fp), e.g. before a subgroup check or cofactor clearing: plain windows */
+  NMSM_BLS12_381_G2 = 5,      /* points in the prime-order subgroup: psi-GLS schedule (4 windows instead of 16) */
+  NMSM_BLS12_381_G1_ANY = 6,  /* any point of E(Fp), e.g. before a subgroup check or cofactor clearing: plain windows */
+  NMSM_BLS12_381_G2_ANY = 7   /* any point of the twist E'(Fp2): plain windows */
 };
 /* Why two ids for BLS12-381 G1: the reference's pippenger is the plain group law and accepts every Point instance.
  * The GLV endomorphism phi(P) = lambda * P this engine uses for MSMs only holds on the prime-order subgroup; the
  * curve's cofactor is 0x396c8c005555e1568c00aaab0000aaab.  With id 4 the MSM equals the reference on every input the
  * reference itself considers a valid G1 point (on curve and torsion-free, weierstrass.ts:690-707); with id 6 on every
  * on-curve point, at 16 windows instead of 8.  nmsm_mul_batch (Point.multiply) never relies on the subgroup: it is
- * what isTorsionFree / clearCofactor run.  secp256k1 and bn254 G1 have cofactor 1: no distinction needed. */
+ * what isTorsionFree / clearCofactor run.  secp256k1 and bn254 G1 have cofactor 1: no distinction needed.
+ * BLS12-381 G2 likewise: id 5 splits every term four ways along psi, which is multiplication by the curve parameter
+ * only on the prime-order subgroup of the twist (bls12-381.ts:600); id 7 is the plain schedule for every on-curve point. */
 
 enum {
   NMSM_OK = 0,

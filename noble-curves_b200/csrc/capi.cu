@@ -83,6 +83,7 @@ static const EngineVTable* engine_for(int curve) {
     case NMSM_BLS12_381_G1: return engine_bls381g1();
     case NMSM_BLS12_381_G2: return engine_bls381g2();
     case NMSM_BLS12_381_G1_ANY: return engine_bls381g1_any();
+    case NMSM_BLS12_381_G2_ANY: return engine_bls381g2_any();
     default: return nullptr;
   }
 }

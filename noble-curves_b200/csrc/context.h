@@ -204,5 +204,6 @@ const EngineVTable* engine_bn254g2();
 const EngineVTable* engine_bls381g1();
 const EngineVTable* engine_bls381g1_any();
 const EngineVTable* engine_bls381g2();
+const EngineVTable* engine_bls381g2_any();
 
 }  // namespace nmsm

@@ -141,7 +141,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
                          : make_plan<Cv>(n_plan, g_ctx.forced_c, g_ctx.sm_count, shard ? (n ? n : 1) : 0, shard ? SHARD_MIN_C : 2);
   if (shard && plan.W > MAX_WINDOWS) return fail(NMSM_ERR_ARG, "window count exceeds MAX_WINDOWS");
   if (shard && g_ctx.forced_groups > 1) plan_one_wave_per_window<Cv>(plan, n, g_ctx.sm_count);  // pipelined sharded form
-  const uint64_t max_entries = (n ? n : 1) * (uint64_t)plan.D * (Cv::GLV ? 2 : 1);
+  const uint64_t max_entries = (n ? n : 1) * (uint64_t)plan.D * split_of<Cv>();
   if (max_entries >= (1ull << 32)) return fail(NMSM_ERR_ARG, "n * windows must be < 2^32");
   // bucket reduction levels: every k_reduce2 pass shrinks the per-window chunk count by REDUCE2_CHUNKS_PER_BLOCK
   // until ONE block per window is left (two passes for the ordinary plans)
@@ -154,7 +154,7 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
   }
   const uint64_t nseg = (uint64_t)plan.W * plan.TPW;  // accumulate segments, TPW per window
 
-  if (!d_prepared) CK(C.aff.ensure((n ? n : 1) * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
+  if (!d_prepared) CK(C.aff.ensure((n ? n : 1) * split_of<Cv>() * G::AFF_WORDS * 4));
   CK(C.counts.ensure((size_t)(plan.G + 1) * 4));
   CK(C.offsets.ensure((size_t)(plan.G + 1) * 4));
   CK(C.cursor.ensure((size_t)(plan.G + 1) * 4));
@@ -596,7 +596,7 @@ static int prepare_points(const uint8_t* pts, uint64_t n, uint32_t** out_dev) {
   Slot& C = g_ctx.slot[g_ctx.cur];
   if (n == 0 || n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be in [1, 2^31)");
   uint32_t* d_aff = nullptr;
-  CK(cudaMalloc((void**)&d_aff, n * (Cv::GLV ? 2 : 1) * G::AFF_WORDS * 4));
+  CK(cudaMalloc((void**)&d_aff, n * split_of<Cv>() * G::AFF_WORDS * 4));
   cudaError_t e1 = C.in_pts.ensure(n * G::IN_WORDS * 4);
   cudaError_t e2 = C.result.ensure((G::IN_WORDS + 4) * 4);
   if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFree(d_aff); return cuda_fail(e1 != cudaSuccess ? e1 : e2, "workspace"); }
@@ -648,7 +648,7 @@ static int submit_prepared(const uint32_t* d_prepared, uint64_t n_points, int ta
 // every later MSM over the set needs one bucket window instead of W and no Horner doublings.
 static int precompute_table(uint32_t** d_prepared, uint64_t n_points, int c_req, int* out_c, int* out_levels) {
   Slot& C = g_ctx.slot[g_ctx.cur];
-  const uint64_t terms = n_points * (Cv::GLV ? 2 : 1);
+  const uint64_t terms = n_points * split_of<Cv>();
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   if (c_req != 0 && (c_req < 4 || c_req > MAX_TABLE_BITS))
@@ -684,7 +684,7 @@ static int build_point_table(const uint8_t* point_xy, uint32_t** out_tbl, int* o
   memcpy(in, point_xy, sizeof(in));
   if (!G::input_in_range(in)) return fail(NMSM_ERR_POINT, "invalid point at index 0", 0);
   CK(C.in_pts.ensure(G::IN_WORDS * 4));
-  CK(C.aff.ensure(2 * G::AFF_WORDS * 4));
+  CK(C.aff.ensure((size_t)split_of<Cv>() * G::AFF_WORDS * 4));
   CK(C.result.ensure((G::IN_WORDS + 4) * 4));
   unsigned int* d_err = (unsigned int*)C.result.p;
   uint32_t* tbl = nullptr;

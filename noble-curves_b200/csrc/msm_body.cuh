@@ -69,6 +69,9 @@ constexpr int glv_bits() {
   if constexpr (Cv::GLV) return Cv::Glv::BITS;
   else return Cv::Fn::BITS;
 }
+// sub-terms per input term: k*P = sum_j k_j * E_j(P) with short k_j; sub-term j of term i lives at index j*n + i
+template <class Cv>
+constexpr int split_of() { return Cv::GLV_KIND == 3 ? 4 : (Cv::GLV ? 2 : 1); }
 
 // ---------------------------------------------------------------------------------------------
 // plan selection: pick the window size c that minimises a TIME model of the pipeline, with constants
@@ -89,7 +92,7 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_loca
   using F = typename G::Field;
   // with GLV every scalar becomes two signed halves of at most 127 bits, each attached to its own point
   const int bits = glv_bits<Cv>();
-  const double terms = (double)n * (Cv::GLV ? 2 : 1);
+  const double terms = (double)n * split_of<Cv>();
   const double limb_ratio = (double)(F::LIMBS / F::BASE_MULS == 12 ? 1.0 : (8.0 * 8.0) / (12.0 * 12.0));
   const double fscale = limb_ratio * F::BASE_MULS;                       // field multiplication cost vs 381-bit Fp
   const double t_madd = 0.352e-6 * fscale * G::COST_MADD / 10.0;         // ms
@@ -126,7 +129,7 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_loca
   p.W = (bits + 1 + c - 1) / c;
   p.B = 1 << (c - 1);
   p.G = p.W * p.B;
-  const double terms_local = n_local ? (double)n_local * (Cv::GLV ? 2 : 1) : terms;
+  const double terms_local = n_local ? (double)n_local * split_of<Cv>() : terms;
   p.L = seg_len(terms_local * p.W);
   // reduce chunk: 8 buckets per thread keeps >= 1 warp per SM sub-partition busy down to ~150k buckets
   int Kc = K;
@@ -149,7 +152,7 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_loca
 // the bucket exchange / owner reduction of window w overlaps the accumulation of windows w-1..0.
 template <class Cv>
 inline void plan_one_wave_per_window(MsmPlan& p, uint64_t n_local, int sm_count) {
-  const double terms_local = (double)(n_local ? n_local : 1) * (Cv::GLV ? 2 : 1);
+  const double terms_local = (double)(n_local ? n_local : 1) * split_of<Cv>();
   int L1 = (int)ceil(terms_local / ((double)sm_count * 4.0 * 128.0));
   p.L = L1 < 4 ? 4 : (L1 > 64 ? 64 : L1);
   p.TPW = plan_tpw((uint64_t)terms_local, p.L);
@@ -182,7 +185,7 @@ inline int choose_table_bits(uint64_t n_points, int sm_count, double mem_budget_
   using G = typename Cv::G;
   using F = typename G::Field;
   const int T = glv_bits<Cv>() + 1;
-  const double terms = (double)n_points * (Cv::GLV ? 2 : 1);
+  const double terms = (double)n_points * split_of<Cv>();
   const double limb_ratio = (double)(F::LIMBS / F::BASE_MULS == 12 ? 1.0 : (8.0 * 8.0) / (12.0 * 12.0));
   const double fscale = limb_ratio * F::BASE_MULS;
   const double t_madd = 0.352e-6 * fscale * G::COST_MADD / 10.0;
@@ -222,7 +225,7 @@ template <class Cv>
 inline MsmPlan make_table_plan(uint64_t n_points, int c, int sm_count) {
   MsmPlan p;
   const int T = glv_bits<Cv>() + 1;
-  const double terms = (double)n_points * (Cv::GLV ? 2 : 1);
+  const double terms = (double)n_points * split_of<Cv>();
   p.D = table_digits<Cv>(c);
   p.wb = T / p.D;
   p.r = T % p.D;
@@ -230,7 +233,7 @@ inline MsmPlan make_table_plan(uint64_t n_points, int c, int sm_count) {
   p.W = 1;
   p.B = 1 << (p.c - 1);
   p.G = p.B;
-  p.stride = (uint32_t)(n_points * (Cv::GLV ? 2 : 1));
+  p.stride = (uint32_t)(n_points * split_of<Cv>());
   p.L = plan_seg_len(terms * p.D, sm_count);
   int Kc = TABLE_REDUCE_CHUNK;
 #if !defined(__CUDA_ARCH__)
@@ -566,6 +569,83 @@ NMSM_HD void glv_split_lattice(const uint32_t* k, uint32_t* m1, bool& neg1, uint
 }
 
 // ---------------------------------------------------------------------------------------------
+// psi-GLS split (BLS12-381 G2, GLV_KIND 3): balanced digits of k in base z = |x| (the 64-bit curve parameter),
+//   k = k0 + k1 z + k2 z^2 + k3 z^3 (mod r),  |k_i| <= z/2 + 1 < 2^63,
+// attached to P, -psi(P), psi^2(P), -psi^3(P) (psi(P) = [x]P = -[z]P on the prime-order subgroup, bls12-381.ts:600).
+// Three schoolbook divisions by the normalised two-word z (Knuth D with a one-word quotient estimate), then the digits
+// are centred; a carry out of the top digit is folded back with z^4 = z^2 - 1 (mod r = z^4 - z^2 + 1).
+// ---------------------------------------------------------------------------------------------
+// u (nw words, little-endian) := floor(u / z); returns u mod z.  z = z1 * 2^32 + z0 with bit 31 of z1 set.
+NMSM_HD uint64_t divmod_2w(uint32_t* u, int nw, uint32_t z1, uint32_t z0) {
+  uint64_t rem = 0;  // < z
+  for (int i = nw - 1; i >= 0; i--) {
+    // cur = rem * 2^32 + u[i] (96 bits, held as hi = bits 32.., lo = bits 0..31); the quotient word is < 2^32
+    const uint64_t cur_hi = rem;
+    const uint32_t cur_lo = u[i];
+    uint64_t q = cur_hi / z1;
+    if (q > 0xffffffffull) q = 0xffffffffull;
+    uint64_t p0 = q * z0, p1 = q * z1;
+    uint64_t prod_hi = p1 + (p0 >> 32);
+    uint32_t prod_lo = (uint32_t)p0;
+    // the estimate exceeds the true quotient word by at most 2
+    for (int it = 0; it < 3 && (prod_hi > cur_hi || (prod_hi == cur_hi && prod_lo > cur_lo)); it++) {
+      q--;
+      const uint32_t br = prod_lo < z0 ? 1u : 0u;
+      prod_lo -= z0;
+      prod_hi -= (uint64_t)z1 + br;
+    }
+    const uint32_t br = cur_lo < prod_lo ? 1u : 0u;
+    const uint32_t d_lo = cur_lo - prod_lo;
+    const uint64_t d_hi = cur_hi - prod_hi - br;  // < 2^32
+    rem = (d_hi << 32) | d_lo;
+    u[i] = (uint32_t)q;
+  }
+  return rem;
+}
+// (mag, neg) += delta for delta = +-1
+NMSM_HD void signed_adjust(uint64_t& mag, bool& neg, int delta) {
+  const bool dneg = delta < 0;
+  if (mag == 0) {
+    mag = 1;
+    neg = dneg;
+  } else if (neg == dneg) {
+    mag += 1;
+  } else {
+    mag -= 1;
+    if (mag == 0) neg = false;
+  }
+}
+template <class Gls>
+NMSM_HD void gls_split(const uint32_t* s, uint64_t* mag, bool* neg) {
+  const uint32_t z0 = Gls::Z(0), z1 = Gls::Z(1);
+  const uint64_t z = ((uint64_t)z1 << 32) | z0, half = ((uint64_t)Gls::HALF(1) << 32) | Gls::HALF(0);
+  uint32_t q[SCALAR_WORDS];
+  for (int k = 0; k < SCALAR_WORDS; k++) q[k] = s[k];
+  uint64_t d[4];
+  d[0] = divmod_2w(q, 8, z1, z0);
+  d[1] = divmod_2w(q, 6, z1, z0);
+  d[2] = divmod_2w(q, 4, z1, z0);
+  d[3] = ((uint64_t)q[1] << 32) | q[0];  // k < r < z^4
+  uint32_t carry = 0;
+  for (int i = 0; i < 4; i++) {
+    const uint64_t u = d[i] + carry;  // <= z
+    if (u > half) {
+      mag[i] = z - u;
+      neg[i] = true;
+      carry = 1;
+    } else {
+      mag[i] = u;
+      neg[i] = false;
+      carry = 0;
+    }
+  }
+  if (carry) {  // + z^4 = z^2 - 1
+    signed_adjust(mag[2], neg[2], +1);
+    signed_adjust(mag[0], neg[0], -1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // bodies
 // ---------------------------------------------------------------------------------------------
 // err[0] = min index of an out-of-range point coordinate, err[1] = min index of an invalid scalar
@@ -580,7 +660,35 @@ NMSM_HD void prepare_body(uint32_t i, uint32_t n, const uint32_t* pts, uint32_t*
   }
   typename G::Affine a = G::prepare(in);
   store_words<G::AFF_WORDS>(aff + (size_t)i * G::AFF_WORDS, reinterpret_cast<const uint32_t*>(&a));
-  if constexpr (Cv::GLV) {  // phi(P) = (beta * x, y) at index n + i; (0,0) stays the identity
+  if constexpr (Cv::GLV_KIND == 3) {  // psi^j(P) at index j*n + i, j = 1..3; (0,0) stays the identity
+    using F2 = typename G::Field;
+    using B = typename F2::Base;
+    using Gls = typename Cv::Glv;
+    F2 px, py, p3x, p3y;
+    B p2x;
+    for (int k = 0; k < B::LIMBS; k++) {
+      px.c0.v[k] = Gls::PSI_X_C0_MONT(k);
+      px.c1.v[k] = Gls::PSI_X_C1_MONT(k);
+      py.c0.v[k] = Gls::PSI_Y_C0_MONT(k);
+      py.c1.v[k] = Gls::PSI_Y_C1_MONT(k);
+      p3x.c0.v[k] = Gls::PSI3_X_C0_MONT(k);
+      p3x.c1.v[k] = Gls::PSI3_X_C1_MONT(k);
+      p3y.c0.v[k] = Gls::PSI3_Y_C0_MONT(k);
+      p3y.c1.v[k] = Gls::PSI3_Y_C1_MONT(k);
+      p2x.v[k] = Gls::PSI2_X_MONT(k);
+    }
+    const F2 cx{a.x.c0, -a.x.c1}, cy{a.y.c0, -a.y.c1};  // Frobenius = conjugation
+    typename G::Affine t;
+    t.x = cx * px;
+    t.y = cy * py;
+    store_words<G::AFF_WORDS>(aff + (size_t)(n + i) * G::AFF_WORDS, reinterpret_cast<const uint32_t*>(&t));
+    t.x = F2{a.x.c0 * p2x, a.x.c1 * p2x};
+    t.y = -a.y;
+    store_words<G::AFF_WORDS>(aff + (size_t)(2 * (size_t)n + i) * G::AFF_WORDS, reinterpret_cast<const uint32_t*>(&t));
+    t.x = cx * p3x;
+    t.y = cy * p3y;
+    store_words<G::AFF_WORDS>(aff + (size_t)(3 * (size_t)n + i) * G::AFF_WORDS, reinterpret_cast<const uint32_t*>(&t));
+  } else if constexpr (Cv::GLV) {  // phi(P) = (beta * x, y) at index n + i; (0,0) stays the identity
     typename G::Field beta;
     for (int k = 0; k < G::Field::LIMBS; k++) beta.v[k] = Cv::Glv::BETA_MONT(k);
     a.x = a.x * beta;
@@ -712,6 +820,14 @@ NMSM_HD void digits_body(uint32_t i, uint32_t n, const uint32_t* scalars, const 
     glv_split_lattice<typename Cv::Glv>(s, m1, neg1, m2, neg2);
     emit_digits<SCATTER>(m1, 5, i, neg1 ? 1u : 0u, plan, counts_or_cursor, sorted);
     emit_digits<SCATTER>(m2, 5, n + i, neg2 ? 1u : 0u, plan, counts_or_cursor, sorted);
+  } else if constexpr (Cv::GLV_KIND == 3) {
+    uint64_t mag[4];
+    bool neg[4];
+    gls_split<typename Cv::Glv>(s, mag, neg);
+    for (int j = 0; j < 4; j++) {  // k_j against (-1)^j psi^j(P)
+      const uint32_t m[2] = {(uint32_t)mag[j], (uint32_t)(mag[j] >> 32)};
+      emit_digits<SCATTER>(m, 2, (uint32_t)j * n + i, (neg[j] ? 1u : 0u) ^ (uint32_t)(j & 1), plan, counts_or_cursor, sorted);
+    }
   } else {
     emit_digits<SCATTER>(s, SCALAR_WORDS, i, 0u, plan, counts_or_cursor, sorted);
   }

@@ -22,7 +22,7 @@ NMSM_HD typename Cv::G::Field curve_b() {
   if constexpr (Cv::ID == 0) return field_from_small<F>(7);
   else if constexpr (Cv::ID == 2) return field_from_small<F>(3);
   else if constexpr (Cv::ID == 4 || Cv::ID == 6) return field_from_small<F>(4);
-  else if constexpr (Cv::ID == 5) {  // 4 * (1 + u)
+  else if constexpr (Cv::ID == 5 || Cv::ID == 7) {  // 4 * (1 + u)
     using B = typename F::Base;
     return F{field_from_small<B>(4), field_from_small<B>(4)};
   } else {  // bn254 G2: 3 / (9 + u)

@@ -396,7 +396,8 @@ def _raise_mapped(e: NmsmError):
 
 
 # include/nmsm.h: NMSM_BLS12_381_G1 (4) assumes torsion-free points (GLV); NMSM_BLS12_381_G1_ANY (6) does not
-_ANY_POINT_ID = {4: 6}
+# likewise NMSM_BLS12_381_G2 (5, psi split) / NMSM_BLS12_381_G2_ANY (7)
+_ANY_POINT_ID = {4: 6, 5: 7}
 
 
 def _all_valid(points) -> bool:

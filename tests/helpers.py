@@ -12,13 +12,14 @@ from oracle import noble_ref as R
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# "bls12_381_G1_any" = NMSM_BLS12_381_G1_ANY: the same curve without the subgroup assumption (no GLV)
+# "bls12_381_G1_any" / "bls12_381_G2_any" = NMSM_BLS12_381_G{1,2}_ANY: the same curve without the subgroup assumption
+# (no endomorphism split)
 CURVE_IDS = {"secp256k1": 0, "ed25519": 1, "bn254_G1": 2, "bn254_G2": 3, "bls12_381_G1": 4, "bls12_381_G2": 5,
-             "bls12_381_G1_any": 6}
+             "bls12_381_G1_any": 6, "bls12_381_G2_any": 7}
 FP_BYTES = {"secp256k1": 32, "ed25519": 32, "bn254_G1": 32, "bn254_G2": 32, "bls12_381_G1": 48, "bls12_381_G2": 48,
-            "bls12_381_G1_any": 48}
+            "bls12_381_G1_any": 48, "bls12_381_G2_any": 48}
 PARTS = {"secp256k1": 1, "ed25519": 1, "bn254_G1": 1, "bn254_G2": 2, "bls12_381_G1": 1, "bls12_381_G2": 2,
-         "bls12_381_G1_any": 1}
+         "bls12_381_G1_any": 1, "bls12_381_G2_any": 2}
 
 
 def bls_g1_non_subgroup_points(count, seed=3):
@@ -41,6 +42,31 @@ def bls_g1_non_subgroup_points(count, seed=3):
             continue  # happens with probability 1/h
         out.append(cand)
     return out
+
+
+def bls_g2_non_subgroup_points(count, seed=5):
+    """On-curve points of the BLS12-381 twist E'(Fp2): y^2 = x^3 + 4(1 + u) outside the prime-order subgroup G2."""
+    import random
+
+    P = R.CURVES["bls12_381_G2"]
+    Fp2 = P.Fp
+    p, r = Fp2.Fp.ORDER, P.Fn.ORDER
+    rnd = random.Random(seed)
+    out = []
+    while len(out) < count:
+        x = (rnd.randrange(p), rnd.randrange(p))
+        y2 = Fp2.add(Fp2.mul(Fp2.sqr(x), x), (4, 4))
+        try:
+            y = Fp2.sqrt(y2)
+        except ValueError:
+            continue
+        cand = P.fromAffine({"x": x, "y": y})
+        if cand.multiplyUnsafe(r - 1).add(cand).is0():
+            continue
+        out.append(cand)
+    return out
+
+
 # curve index in test/slow-curves.test.ts:186-194
 SOAK_INDEX = {"secp256k1": 0, "ed25519": 2, "bls12_381_G1": 3, "bls12_381_G2": 4, "bn254_G1": 5, "bn254_G2": 6}
 

@@ -50,10 +50,10 @@ static int emu_msm_t(const uint32_t* pts, const uint32_t* scalars, uint32_t n, i
   MsmPlan plan = table_c ? make_table_plan<Cv>(n, canonical_table_bits<Cv>(table_c), 148) : make_plan<Cv>(n, forced_c, 148);
   if (forced_L > 0) {
     plan.L = forced_L;
-    plan.TPW = plan_tpw((uint64_t)n * (Cv::GLV ? 2 : 1) * (table_c ? plan.D : 1), plan.L);
+    plan.TPW = plan_tpw((uint64_t)n * split_of<Cv>() * (table_c ? plan.D : 1), plan.L);
   }
   plan_out[0] = plan.c; plan_out[1] = plan.W; plan_out[2] = plan.B; plan_out[3] = plan.L;
-  const size_t terms = (size_t)n * (Cv::GLV ? 2 : 1);
+  const size_t terms = (size_t)n * split_of<Cv>();
   std::vector<uint32_t> aff(terms * G::AFF_WORDS * (table_c ? plan.D : 1));
   std::vector<unsigned int> counts(plan.G + 1, 0), cursor(plan.G + 1, 0);
   std::vector<uint32_t> offsets(plan.G + 1, 0);
@@ -144,7 +144,7 @@ static int emu_shard_buckets_t(const uint32_t* pts, const uint32_t* scalars, uin
   MsmPlan plan = make_plan<Cv>(n_total, 0, 148, n_local ? n_local : 1);
   plan_out[0] = plan.c; plan_out[1] = plan.W; plan_out[2] = plan.B; plan_out[3] = G::ACC_WORDS;
   if (!buckets_out) return 0;  // plan query
-  const size_t terms = (size_t)(n_local ? n_local : 1) * (Cv::GLV ? 2 : 1);
+  const size_t terms = (size_t)(n_local ? n_local : 1) * split_of<Cv>();
   std::vector<uint32_t> aff(terms * G::AFF_WORDS);
   std::vector<unsigned int> counts(plan.G + 1, 0), cursor(plan.G + 1, 0);
   std::vector<uint32_t> offsets(plan.G + 1, 0);
@@ -240,7 +240,7 @@ static int emu_point_table_t(const uint32_t* point_xy, const uint32_t* scalars, 
   constexpr int LV = point_table_levels<Cv, TB>();
   constexpr uint32_t HALF = 1u << (TB - 1);
   unsigned int err[2] = {0xffffffffu, 0xffffffffu};
-  std::vector<uint32_t> aff(2 * G::AFF_WORDS);
+  std::vector<uint32_t> aff((size_t)split_of<Cv>() * G::AFF_WORDS);
   prepare_body<Cv>(0, 1, point_xy, aff.data(), err);
   const size_t level_words = (size_t)HALF * G::AFF_WORDS;
   std::vector<uint32_t> tbl(level_words * LV);
@@ -288,6 +288,7 @@ static int emu_plan_t(uint32_t n, int table_c_req, uint32_t* out) {
     case 4: { using Cv = CurveBls381G1; return EXPR; }               \
     case 5: { using Cv = CurveBls381G2; return EXPR; }               \
     case 6: { using Cv = CurveBls381G1Any; return EXPR; }            \
+    case 7: { using Cv = CurveBls381G2Any; return EXPR; }            \
     default: return -1;                                              \
   }
 
@@ -363,6 +364,18 @@ int emu_glv_split(const uint32_t* k, uint32_t* out) {
   glv_split<Bls381G1Glv>(k, out, n1, out + 4, n2);
   out[8] = n1;
   out[9] = n2;
+  return 0;
+}
+// psi-GLS split of one scalar (BLS12-381 G2): out = mag[4] as (lo, hi) word pairs, then neg[4]
+int emu_gls_split(const uint32_t* k, uint32_t* out) {
+  uint64_t mag[4];
+  bool neg[4];
+  gls_split<Bls381G2Gls>(k, mag, neg);
+  for (int j = 0; j < 4; j++) {
+    out[2 * j] = (uint32_t)mag[j];
+    out[2 * j + 1] = (uint32_t)(mag[j] >> 32);
+    out[8 + j] = neg[j];
+  }
   return 0;
 }
 // lattice GLV split (curve 0 = secp256k1, 2 = bn254 G1): out = m1[5], m2[5], neg1, neg2

@@ -80,6 +80,68 @@ def test_pippenger_default_arguments_on_non_subgroup_points(nmsm):
         off.assertValidity()
 
 
+def test_bls12_381_g2_psi_split_and_default_arguments(nmsm):
+    """BLS12-381 G2: id 5 splits every term four ways along psi (valid on the prime-order subgroup), id 7 is the plain
+    schedule.  Both against the oracle on subgroup points incl. scalars that isolate each psi power; twist points outside
+    G2 through id 7 and through nmsm.pippenger with DEFAULT arguments (unvalidated handles -> id 7, validated -> id 5)."""
+    name = "bls12_381_G2"
+    P = R.CURVES[name]
+    C = nmsm.CURVES[name]
+    r = P.Fn.ORDER
+    z = 0xD201000000010000
+    half = z // 2
+    rnd = random.Random(77)
+    n = 300
+    ks = [rnd.randrange(1, r) for _ in range(n)]
+    pts_b, _ = nmsm.mul_batch_packed(5, H.point_bytes(name, P.BASE) * n, H.pack_scalars(ks), n, False)
+    edge = [0, 1, z, z * z, z**3, r - 1, r - z, half, half + 1, (half + 1) * z**3 % r, z**3 + z * z + z + 1, z**3 * (z - 1)]
+    scalars = edge + [rnd.randrange(r) for _ in range(n - len(edge))]
+    total = sum(k * s for k, s in zip(ks, scalars)) % r
+    exp = H.expected_tuple(name, P.BASE.multiplyUnsafe(total))
+    for cid in (5, 7):
+        for c in (0, 7, 13):
+            nmsm.set_window_bits(c)
+            try:
+                out, inf = nmsm.msm_packed(cid, pts_b, H.pack_scalars(scalars), n)
+            finally:
+                nmsm.set_window_bits(0)
+            x, y = H.unpack_point(name, out)
+            assert (x, y, inf) == exp, (cid, c)
+    # one term at a time: k * P for the scalars that use a single psi power
+    one = pts_b[:192]
+    p0 = P.BASE.multiplyUnsafe(ks[0])
+    for k in edge[1:]:
+        out, inf = nmsm.msm_packed(5, one, H.pack_scalars([k]), 1)
+        assert (*H.unpack_point(name, out), inf) == H.expected_tuple(name, p0.multiplyUnsafe(k)), hex(k)
+    # fixed-base table over the split set
+    ps = nmsm.PointSet(5, pts_b, n)
+    ps.precompute(0)
+    out, inf = ps.msm(H.pack_scalars(scalars), n)
+    assert (*H.unpack_point(name, out), inf) == exp
+    # outside the subgroup
+    bad = H.bls_g2_non_subgroup_points(6)
+    good = [P.BASE.multiplyUnsafe(rnd.randrange(1, r)) for _ in range(6)]
+    pts = R.normalizeZ(P, bad + good)
+    rnd.shuffle(pts)
+    sc = [rnd.randrange(r) for _ in pts]
+    exp_bad = H.expected_tuple(name, R.pippenger(P, pts, sc))
+    out, inf = nmsm.msm_packed(7, H.pack_points(name, pts), H.pack_scalars(sc), len(pts))
+    assert (*H.unpack_point(name, out), inf) == exp_bad
+    cpts = [C.fromAffine(p.toAffine()) for p in pts]
+    assert not any(p._valid for p in cpts)
+    got = nmsm.pippenger(C, cpts, sc)  # DEFAULT arguments
+    assert as_tuple(got) == exp_bad and not got._valid
+    assert as_tuple(nmsm.interleavedMSMUnsafe(C, cpts, 4)(sc)) == exp_bad
+    gpts = R.normalizeZ(P, good)
+    vpts = [C.fromAffine(p.toAffine()) for p in gpts]
+    for v in vpts:
+        v.assertValidity()
+    res = nmsm.pippenger(C, vpts, sc[: len(vpts)])
+    assert as_tuple(res) == H.expected_tuple(name, R.pippenger(P, gpts, sc[: len(vpts)])) and res._valid
+    with pytest.raises(ValueError, match="not in prime-order subgroup"):
+        C.fromAffine(bad[0].toAffine()).assertValidity()
+
+
 @pytest.mark.parametrize("name", ALL)
 def test_points_on_curve(nmsm, name):
     P, pts, scalars, _ = H.soak_inputs(name, 40)

@@ -257,6 +257,70 @@ def test_bls12_381_g1_points_outside_the_subgroup():
             assert got == H.expected_tuple("bls12_381_G1", pt.multiplyUnsafe(k)), (name, k)
 
 
+def test_bls12_381_g2_psi_split():
+    """BLS12-381 G2 (id 5) splits k four ways along psi (msm_body.cuh gls_split): the device digits against a Python
+    statement of the same rule, k = sum (+-mag_i) z^i (mod r) with mag_i < 2^63; single-term MSMs whose scalars select
+    each of P, -psi(P), psi^2(P), -psi^3(P) on their own (the constants of curve_consts.cuh Bls381G2Gls) against the
+    oracle; and twist points OUTSIDE the prime-order subgroup, where psi is not [x]: NMSM_BLS12_381_G2_ANY (plain
+    windows) matches the oracle's pippenger, and nmsm_mul_batch of either id does (multiply never uses psi)."""
+    import ctypes
+    import random as _r
+
+    import numpy as np
+
+    name = "bls12_381_G2"
+    P = R.CURVES[name]
+    r = P.Fn.ORDER
+    z = 0xD201000000010000
+    assert r == z**4 - z**2 + 1
+    half = z // 2
+    lib = H.hostemu()
+    rnd = _r.Random(11)
+    cases = [0, 1, 2, r - 1, r - 2, z - 1, z, z + 1, z * z, z**3, z**3 - 1, half, half + 1, half * z, (half + 1) * z**3,
+             (half + 1) * (1 + z + z * z + z**3) % r, r // 2, z**3 * (z - 1)]
+    cases += [rnd.randrange(r) for _ in range(3000)]
+    for k in cases:
+        kw = np.frombuffer(k.to_bytes(32, "little"), dtype=np.uint32).copy()
+        out = np.zeros(12, np.uint32)
+        assert lib.emu_gls_split(kw.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == 0
+        mags = [int(out[2 * j]) | (int(out[2 * j + 1]) << 32) for j in range(4)]
+        negs = [int(out[8 + j]) for j in range(4)]
+        assert all(m < (1 << 63) for m in mags), hex(k)
+        assert sum((-m if s else m) * z**j for j, (m, s) in enumerate(zip(mags, negs))) % r == k, hex(k)
+    # one term, scalars that isolate the sub-terms (and mixtures with carries)
+    base = P.BASE.multiplyUnsafe(0xA5A5F00D1234567)
+    for k in [1, z, z * z, z**3, r - 1, r - z, half + 1, (half + 1) * z**3 % r, z**3 + z * z + z + 1] + cases[-6:]:
+        for c, L in ((0, 0), (7, 2)):
+            got, err, plan = H.emu_msm(name, H.pack_points(name, R.normalizeZ(P, [base])), H.pack_scalars([k]), 1, c, L)
+            assert err == (0xFFFFFFFF, 0xFFFFFFFF)
+            assert got == H.expected_tuple(name, base.multiplyUnsafe(k) if k else P.ZERO), (hex(k), c)
+    assert plan[1] == (64 + 6) // 7  # 63-bit digits + sign: ceil(64 / c) windows
+    # fixed-base table over the four-way split set
+    pts = R.normalizeZ(P, [P.BASE.multiplyUnsafe(rnd.randrange(1, r)) for _ in range(9)] + [P.ZERO])
+    scalars = [rnd.randrange(r) for _ in pts]
+    exp = H.expected_tuple(name, R.pippenger(P, pts, scalars))
+    pb, sb = H.pack_points(name, pts), H.pack_scalars(scalars)
+    assert H.emu_msm(name, pb, sb, len(pts), table_c=9)[0] == exp
+    assert H.emu_msm(name, pb, sb, len(pts), 11, 3)[0] == exp == H.emu_msm(name + "_any", pb, sb, len(pts), 11, 3)[0]
+    # points outside the subgroup
+    bad = R.normalizeZ(P, H.bls_g2_non_subgroup_points(3) + [pts[0]])
+    bs = [rnd.randrange(r) for _ in bad]
+    exp_bad = H.expected_tuple(name, R.pippenger(P, bad, bs))
+    bpb, bsb = H.pack_points(name, bad), H.pack_scalars(bs)
+    for c, L in ((0, 0), (6, 3)):
+        assert H.emu_msm(name + "_any", bpb, bsb, len(bad), c, L)[0] == exp_bad
+    assert H.emu_msm(name + "_any", bpb, bsb, len(bad), table_c=8)[0] == exp_bad
+    assert H.emu_msm(name, bpb, bsb, len(bad))[0] != exp_bad  # psi is not [x] off the subgroup: id 5 is not specified there
+    ks = [r - 1, 5, rnd.randrange(r)]
+    for nm in (name, name + "_any"):
+        res, err = H.emu_mul_batch(nm, H.pack_points(name, bad[:3]), H.pack_scalars(ks), 3, False)
+        assert err == (0xFFFFFFFF, 0xFFFFFFFF)
+        for pt, k, got in zip(bad[:3], ks, res):
+            assert got == H.expected_tuple(name, pt.multiplyUnsafe(k)), (nm, k)
+    got, _ = H.emu_torsion(name, H.pack_points(name, bad), len(bad))
+    assert got == [0, 0, 0, 1]
+
+
 def test_torsion_free_batch():
     """nmsm_points_torsion_free body (isTorsionFree, weierstrass.ts:971-975 / edwards.ts:584-586) against the oracle's
     n*P == O on subgroup points, points outside the subgroup, small-order points and the identity."""

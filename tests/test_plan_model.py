@@ -7,7 +7,9 @@ import pytest
 
 import helpers as H
 
-NAMES = ["secp256k1", "ed25519", "bn254_G1", "bn254_G2", "bls12_381_G1", "bls12_381_G2", "bls12_381_G1_any"]
+NAMES = ["secp256k1", "ed25519", "bn254_G1", "bn254_G2", "bls12_381_G1", "bls12_381_G2", "bls12_381_G1_any", "bls12_381_G2_any"]
+# sub-terms per term (msm_body.cuh split_of): endomorphism halves, or the four psi digits of BLS12-381 G2
+SPLIT = {"secp256k1": 2, "bn254_G1": 2, "bls12_381_G1": 2, "bls12_381_G2": 4}
 
 
 def plan(name, n, table_c=0):
@@ -29,7 +31,7 @@ def test_ordinary_plans(name):
     big = plan(name, 1 << 20)
     if name == "secp256k1":  # 130 half-scalar bits: c = 16 would leave a 2-bit top window (two giant buckets)
         assert big["c"] == 13 and big["W"] == 10
-    elif name in ("bls12_381_G1", "bn254_G1", "bls12_381_G2", "bls12_381_G1_any"):
+    elif name in ("bls12_381_G1", "bn254_G1", "bls12_381_G2", "bls12_381_G1_any", "bls12_381_G2_any"):
         assert big["c"] == 16  # the measured configurations at the BASELINE sizes (profiles/)
     else:
         assert 13 <= big["c"] <= 16
@@ -37,12 +39,11 @@ def test_ordinary_plans(name):
 
 @pytest.mark.parametrize("name", NAMES)
 def test_table_plans_spread_the_digits_evenly(name):
-    glv = name in ("secp256k1", "bn254_G1", "bls12_381_G1")
     for n in (5, 1 << 10, 1 << 20):
         for c_req in range(4, 23):
             p = plan(name, n, c_req)
             T = p["T"]
-            assert p["W"] == 1 and p["stride"] == n * (2 if glv else 1)
+            assert p["W"] == 1 and p["stride"] == n * SPLIT.get(name, 1)
             assert p["c"] <= c_req and p["B"] == 1 << (p["c"] - 1)
             widths = [p["wb"] + (1 if w < p["r"] else 0) for w in range(p["D"])]
             assert sum(widths) == T and max(widths) == p["c"] and max(widths) - min(widths) <= 1
