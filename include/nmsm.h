@@ -83,7 +83,11 @@ int nmsm_acc_bytes(int curve);
 int nmsm_msm(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, uint8_t* out_xy,
              int* out_is_inf);
 
-/* Same with inputs already resident in device memory (16-byte aligned device pointers). */
+/* Same with inputs already resident in device memory (16-byte aligned device pointers).
+ * Stream ordering: every *_device / *_submit entry point launches on the library's own non-blocking streams, which are
+ * NOT ordered against the caller's streams.  The producer of d_pts / d_scalars must have completed (event / stream /
+ * device synchronize on the caller's side) before the call; the buffers must stay untouched until the call (or the
+ * matching *_collect) returns.  nmsm/dist.py and bench.py synchronize the torch stream before they hand pointers over. */
 int nmsm_msm_device(int curve, const void* d_pts, const void* d_scalars, uint64_t n, uint8_t* out_xy,
                     int* out_is_inf);
 

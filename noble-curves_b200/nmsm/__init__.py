@@ -765,17 +765,25 @@ def ed25519_verify_batch(signatures, messages, public_keys, z: bytes | None = No
         z = os.urandom(16 * n)
     if len(z) != 16 * n:
         raise ValueError("z must hold 16 bytes per signature")
-    _lib.ensure_init()
-    lib = _lib.load()
     offs = [0]
     for m in messages:
         offs.append(offs[-1] + len(m))
     blob = b"".join(bytes(m) for m in messages)
+    return ed25519_verify_batch_packed(b"".join(signatures), b"".join(public_keys), blob,
+                                       struct.pack("<%dQ" % (n + 1), *offs), n, bytes(z))
+
+
+def ed25519_verify_batch_packed(sigs: bytes, pks: bytes, msgs: bytes, msg_off: bytes, n: int, z: bytes):
+    """The C-ABI call itself (nmsm_ed25519_verify_batch) on caller-packed arrays: n*64 signature bytes, n*32 key bytes,
+    the concatenated messages with n+1 little-endian u64 offsets, n*16 bytes of randomness."""
+    if len(sigs) != 64 * n or len(pks) != 32 * n or len(msg_off) != 8 * (n + 1) or len(z) != 16 * n:
+        raise ValueError("packed arrays do not match n")
+    _lib.ensure_init()
+    lib = _lib.load()
     ok = ctypes.c_int(0)
     bad = ctypes.c_longlong(-1)
     cp = lambda b: ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p)  # noqa: E731
-    rc = lib.nmsm_ed25519_verify_batch(cp(b"".join(signatures)), cp(b"".join(public_keys)), cp(blob or b"\0"),
-                                       cp(struct.pack("<%dQ" % (n + 1), *offs)), n, cp(bytes(z)), ctypes.byref(ok),
+    rc = lib.nmsm_ed25519_verify_batch(cp(sigs), cp(pks), cp(msgs or b"\0"), cp(msg_off), n, cp(z), ctypes.byref(ok),
                                        ctypes.byref(bad))
     try:
         _lib.check(rc)

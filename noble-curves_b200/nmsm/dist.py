@@ -85,6 +85,12 @@ def msm_sharded(curve_id: int, local_pts, local_scalars, n_local: int, group=Non
     pb = lib.nmsm_point_bytes(curve_id)
     out = ctypes.create_string_buffer(pb)
     inf = ctypes.c_int(0)
+    if n_local:
+        # the library's streams are not ordered against torch's: whatever produced the shard must have finished
+        # (include/nmsm.h "Stream ordering")
+        import torch
+
+        torch.cuda.current_stream(local_pts.device).synchronize()
     rc = lib.nmsm_msm_sharded(curve_id, local_pts.data_ptr() if n_local else None,
                               local_scalars.data_ptr() if n_local else None, n_local, n_total, offset, 1,
                               ctypes.cast(out, ctypes.c_void_p), ctypes.byref(inf))
