@@ -108,6 +108,12 @@ int nmsm_msm_submit_partial(int curve, const void* d_pts, const void* d_scalars,
 int nmsm_msm_partial_device(int curve, const void* d_pts, const void* d_scalars, uint64_t n, void* d_out_acc);
 int nmsm_fold_partials_device(int curve, const void* d_accs, int count, uint8_t* out_xy, int* out_is_inf);
 
+/* normalizeZ (/root/reference/src/abstract/curve.ts:311-326) for raw accumulators: n un-normalised results (host buffer
+ * or, with on_device != 0, device pointer; nmsm_acc_bytes each, the layout nmsm_msm_partial_device writes) -> canonical
+ * affine x||y per point + one infinity flag byte each, with ONE field inversion per 32 points (Montgomery's trick,
+ * modular.ts:734-760 FpInvertBatch).  The identity comes back as (0,0) / Edwards (0,1) with flag 1. */
+int nmsm_accs_normalize(int curve, const void* accs, int on_device, uint64_t n, uint8_t* out_xy, uint8_t* out_is_inf);
+
 /* Multi-GPU MSM with a bucket exchange (BASELINE north_star: "a single NCCL allreduce over NVLink of the
  * per-window bucket accumulators").  One process per GPU.  The (point, scalar) array is split across the ranks; every
  * rank accumulates its shard into the full W x B bucket array with the window size of the WHOLE MSM (n_total), window w

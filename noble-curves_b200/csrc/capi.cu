@@ -388,6 +388,16 @@ int nmsm_fold_partials_device(int curve, const void* d_accs, int count, uint8_t*
   return E->fold((const uint32_t*)d_accs, count, out_xy, out_is_inf);
 }
 
+int nmsm_accs_normalize(int curve, const void* accs, int on_device, uint64_t n, uint8_t* out_xy, uint8_t* out_is_inf) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (int r = ensure_init()) return r;
+  g_ctx.cur = 0;
+  SLOT0_FREE();
+  if (n && (!accs || !out_xy || !out_is_inf)) return fail(NMSM_ERR_ARG, "null pointer");
+  ENGINE(curve);
+  return E->normalize(accs, on_device, n, out_xy, out_is_inf);
+}
+
 int nmsm_mul_batch(int curve, const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero,
                    uint8_t* out_xy, uint8_t* out_is_inf) {
   std::lock_guard<std::mutex> lk(g_mu);

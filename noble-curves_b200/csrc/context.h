@@ -191,6 +191,7 @@ struct EngineVTable {
                          int scalars_on_device);
   int (*torsion_free)(const uint8_t* pts, uint64_t n, uint8_t* out_ok);
   int (*on_curve)(const uint8_t* pts, uint64_t n, uint8_t* out_ok);
+  int (*normalize)(const void* accs, int on_device, uint64_t n, uint8_t* out_xy, uint8_t* out_is_inf);
 };
 int ed25519_verify_batch_impl(const uint8_t* sigs, const uint8_t* pks, const uint8_t* msgs, const uint64_t* msg_off,
                               uint64_t n, const uint8_t* z16, int* out_ok, long long* out_bad_index);

@@ -807,6 +807,31 @@ static int run_fold(const uint32_t* d_accs, int count, uint8_t* out_xy, int* out
   return NMSM_OK;
 }
 
+// nmsm_accs_normalize: raw accumulators (host or device) -> canonical affine + infinity flags on the host
+static int run_normalize(const void* accs, int on_device, uint64_t n, uint8_t* out_xy, uint8_t* out_is_inf) {
+  Slot& C = g_ctx.slot[g_ctx.cur];
+  if (n == 0) return NMSM_OK;
+  if (n >= (1ull << 31)) return fail(NMSM_ERR_ARG, "n must be < 2^31");
+  CK(C.mul_out.ensure(n * (G::IN_WORDS + 1) * 4 + 16));
+  uint32_t* d_xy = (uint32_t*)C.mul_out.p;
+  uint32_t* d_inf = d_xy + n * G::IN_WORDS;
+  cudaStream_t st = C.stream;
+  const uint32_t* d_accs = (const uint32_t*)accs;
+  if (!on_device) {
+    CK(C.in_pts.ensure(n * G::ACC_WORDS * 4));
+    CK(cudaMemcpyAsync(C.in_pts.p, accs, n * G::ACC_WORDS * 4, cudaMemcpyHostToDevice, st));
+    d_accs = (const uint32_t*)C.in_pts.p;
+  }
+  k_normalize_batch<Cv><<<cdiv(n, 128), 128, 0, st>>>(d_accs, (uint32_t)n, d_xy, d_inf);
+  CK(cudaGetLastError());
+  std::vector<uint32_t> inf(n);
+  CK(cudaMemcpyAsync(out_xy, d_xy, n * G::IN_WORDS * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(inf.data(), d_inf, n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (uint64_t i = 0; i < n; i++) out_is_inf[i] = (uint8_t)inf[i];
+  return NMSM_OK;
+}
+
 static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n, int allow_zero, uint8_t* out_xy,
                          uint8_t* out_is_inf) {
   Slot& C = g_ctx.slot[g_ctx.cur];
@@ -863,7 +888,7 @@ static int run_mul_batch(const uint8_t* pts, const uint8_t* scalars, uint64_t n,
                                     &Engine<CURVE>::build_point_table, &Engine<CURVE>::table_mul_batch, \
                                     &Engine<CURVE>::submit_any,     &Engine<CURVE>::collect_msm,    \
                                     &Engine<CURVE>::submit_prepared, &Engine<CURVE>::run_torsion,  \
-                                    &Engine<CURVE>::run_on_curve};  \
+                                    &Engine<CURVE>::run_on_curve,   &Engine<CURVE>::run_normalize};  \
     return &vt;                                                                                \
   }
 

@@ -535,6 +535,25 @@ k_mul_batch(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scala
   out_inf[i] = inf;
 }
 
+// Batch normalisation of raw accumulators to canonical affine: the device form of normalizeZ (curve.ts:311-326) — one
+// field inversion per warp shared through prefix / suffix products (FpInvertBatch, modular.ts:734-760), identities pass
+// through as (0,0) / (0,1) with the infinity flag like toAffine(ZERO).
+template <class Cv>
+__global__ void __launch_bounds__(128)
+k_normalize_batch(const uint32_t* __restrict__ accs, uint32_t n, uint32_t* __restrict__ out_xy, uint32_t* __restrict__ out_inf) {
+  using G = typename Cv::G;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  typename G::Acc acc = G::identity();
+  if (i < n) acc = load_acc<G>(accs + (size_t)i * G::ACC_WORDS);
+  const typename G::Field iz = warp_batch_inverse(G::inv_target(acc));  // whole warp, also the idle lanes
+  if (i >= n) return;
+  uint32_t xy[G::IN_WORDS];
+  uint32_t inf;
+  G::to_affine_canonical_with_inv(acc, iz, xy, &inf);
+  store_words<G::IN_WORDS>(out_xy + (size_t)i * G::IN_WORDS, xy);
+  out_inf[i] = inf;
+}
+
 // n * P == O per point (nmsm_points_torsion_free)
 template <class Cv>
 __global__ void __launch_bounds__(128)

@@ -186,8 +186,9 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
             GPU picks its own 16-bit windows, `windowSize` is only validated).  Like the reference's WeakMap cache
             (curve.ts:412,532) the table is built at the first multiply (isLazy) or now, and multiply_many /
             multiply / multiplyUnsafe of this point then take the table route."""
-            if not (isinstance(windowSize, int) and 1 <= windowSize <= Fn.BITS):
-                raise ValueError("invalid window size, expected [1..%d], got W=%s" % (Fn.BITS, windowSize))
+            _validate_w(windowSize, Fn.BITS)
+            # curve.ts:776-781 setWindowSize sizes against the blinded path: ceil((bits + BLIND_BITS) / W) + 1 windows
+            _validate_table_bytes((-(-(Fn.BITS + 128) // windowSize) + 1) * 2 ** (windowSize - 1), Fp.BYTES)
             _TABLE_MARKS.add((Point.CURVE_ID, self.x, self.y))
             if not isLazy:
                 _table_for(Point, self)
@@ -258,6 +259,20 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
             if not edwards:
                 P_._valid = True  # decodePoint checks the equation, assertValidity the subgroup (weierstrass.ts:720-724)
             return P_
+
+        @staticmethod
+        def fromHex(hex_: str, zip215: bool = False):
+            """weierstrass.ts:726-728 / edwards.ts:438-440: fromBytes(hexToBytes(hex))"""
+            if not isinstance(hex_, str):
+                raise TypeError("hex string expected, got " + type(hex_).__name__)
+            try:
+                raw = bytes.fromhex(hex_)
+            except ValueError as e:
+                raise ValueError("hex string expected, got non-hex character") from e
+            return Point.fromBytes(raw, zip215) if edwards else Point.fromBytes(raw)
+
+        def toHex(self, *args) -> str:
+            return self.toBytes(*args).hex()
 
         def to_packed(self) -> bytes:
             return _coord_to_bytes(self.x, fp_bytes, parts) + _coord_to_bytes(self.y, fp_bytes, parts)
@@ -366,6 +381,41 @@ CURVES = {
 # ----------------------------------------------------------------------------------------------
 # validation (exact messages of curve.ts:390-404, :875)
 # ----------------------------------------------------------------------------------------------
+TABLE_BYTES_MAX = 2 ** 31  # curve.ts:37
+
+
+def validatePointCons(c) -> None:
+    """curve.ts:259-272: the generic helpers dereference fromAffine / fromBytes / fromHex / BASE / ZERO / Fp / Fn of the
+    point constructor; fail with a typed error up front instead of an attribute error later."""
+    if not isinstance(c, type):
+        raise TypeError('"Point" expected constructor, got type=' + type(c).__name__)
+    for fn_name in ("fromAffine", "fromBytes", "fromHex"):
+        if not callable(getattr(c, fn_name, None)):
+            raise TypeError('"Point.%s" expected function' % fn_name)
+    for obj_name in ("BASE", "ZERO"):
+        if getattr(c, obj_name, None) is None:
+            raise TypeError('"Point.%s" expected object' % obj_name)
+    for f_name in ("Fp", "Fn"):
+        f = getattr(c, f_name, None)
+        if f is None or not isinstance(getattr(f, "ORDER", None), int) or not isinstance(getattr(f, "BITS", None), int):
+            raise TypeError('"Point.%s" expected a field' % f_name)
+
+
+def _validate_w(W, bits: int, lo: int = 1) -> None:
+    """curve.ts:328-331 validateW"""
+    if not (isinstance(W, int) and not isinstance(W, bool) and lo <= W <= bits):
+        raise ValueError("invalid window size, expected [%d..%d], got W=%s" % (lo, bits, W))
+
+
+def _validate_table_bytes(num_points: int, fp_bytes: int) -> None:
+    """curve.ts:336-346 validateTableBytes: the reference refuses window sizes whose tables would need more than ~2 GiB
+    of heap (4 coordinates of Fp.BYTES + 128 bytes of object overhead per point); same rule, same message."""
+    nbytes = num_points * (4 * fp_bytes + 128)
+    if nbytes > TABLE_BYTES_MAX:
+        raise ValueError("invalid window size: table would need ~%d MiB, max %d MiB"
+                         % (-(-nbytes // 2 ** 20), TABLE_BYTES_MAX // 2 ** 20))
+
+
 def _validate_msm_points(points, c) -> None:
     if not isinstance(points, (list, tuple)):
         raise TypeError('"points" expected Array, got type=' + type(points).__name__)
@@ -487,6 +537,7 @@ def pippenger(c, points, scalars, assume_torsion_free=None):
     `_valid` bit: assertValidity / fromBytes / BASE / arithmetic on valid points), otherwise plain windows (id 6).
     `assume_torsion_free=True` lets a caller who knows its fromAffine-built points are subgroup members (e.g. an
     SRS) opt into the fast schedule; False forces the plain one."""
+    validatePointCons(c)
     _validate_msm_points(points, c)
     _validate_msm_scalars(scalars, c.Fn)
     if len(points) != len(scalars):
@@ -499,7 +550,10 @@ def pippenger(c, points, scalars, assume_torsion_free=None):
 def normalizeZ(c, points):
     """curve.ts:311-326: batch projective -> affine.  Host handles are already canonical affine (every
     GPU result is normalised on the device — k_mul_batch / k_table_mul share ONE inversion per warp, the device form
-    of FpInvertBatch modular.ts:734-760), so this validates and returns fresh equal points."""
+    of FpInvertBatch modular.ts:734-760), so this validates and returns fresh equal points.  Un-normalised values only
+    exist as raw accumulators on the device side of the C ABI; their batch normalisation is normalize_accs
+    (nmsm_accs_normalize)."""
+    validatePointCons(c)
     _validate_msm_points(points, c)
     return [c.from_packed(p.to_packed(), 1 if p.is0() else 0, p._valid) for p in points]
 
@@ -520,6 +574,7 @@ def mulAddUnsafe(c, points, scalars, allowOversized: bool = False):
     must NOT be reduced mod ORDER (the reference uses them for torsion checks `ORDER*P == O` on points that may lie
     outside the prime-order subgroup), so s is cut into digits of Fn.BITS-1 bits, s = sum_j d_j 2^(b j), and the term
     becomes sum_j d_j * (2^(b j) * P) with every d_j and 2^b in the accelerated range — exact for any point."""
+    validatePointCons(c)
     _validate_msm_points(points, c)
     if not isinstance(allowOversized, bool):
         raise TypeError('"allowOversized" expected boolean')
@@ -653,6 +708,25 @@ def multiply_many(c, points, scalars, unsafe: bool = False) -> List:
     return [c.from_packed(out_xy[i * pb:(i + 1) * pb], infs[i], points[i]._valid) for i in range(n)]
 
 
+def normalize_accs(curve_id: int, accs, n: int, on_device: bool = False):
+    """nmsm_accs_normalize — the device form of normalizeZ (curve.ts:311-326): n raw accumulators (bytes, or a device
+    pointer with on_device=True; nmsm_acc_bytes each) -> (packed canonical affine points, infinity flags), one field
+    inversion per 32 points."""
+    _lib.ensure_init()
+    lib = _lib.load()
+    pb, ab = lib.nmsm_point_bytes(curve_id), lib.nmsm_acc_bytes(curve_id)
+    if pb <= 0:
+        raise ValueError("unknown curve id")
+    if not on_device and len(accs) != n * ab:
+        raise ValueError("expected %d bytes per accumulator" % ab)
+    out = ctypes.create_string_buffer(max(1, n * pb))
+    infs = ctypes.create_string_buffer(max(1, n))
+    src = ctypes.c_void_p(accs) if on_device else ctypes.cast(ctypes.c_char_p(bytes(accs)), ctypes.c_void_p)
+    _lib.check(lib.nmsm_accs_normalize(curve_id, src, 1 if on_device else 0, n, ctypes.cast(out, ctypes.c_void_p),
+                                       ctypes.cast(infs, ctypes.c_void_p)))
+    return out.raw[: n * pb], infs.raw[:n]
+
+
 def mul_batch_packed(curve_id: int, pts: bytes, scalars: bytes, n: int, allow_zero: bool):
     _lib.ensure_init()
     lib = _lib.load()
@@ -725,9 +799,10 @@ def interleavedMSMUnsafe(c, points, windowSize: int = 4, precompute: bool = True
     tables built at capture time) the fixed-base table of nmsm_points_precompute; `windowSize` is accepted for
     signature compatibility (the GPU schedule picks its own window).  Fewer scalars than points are zero-padded.
     BLS12-381 G1: the endomorphism id is used only for sets of known-valid points (see pippenger)."""
-    if not (isinstance(windowSize, int) and 2 <= windowSize <= c.Fn.BITS):
-        raise ValueError("invalid window size, expected [2..%d], got W=%s" % (c.Fn.BITS, windowSize))
+    validatePointCons(c)
+    _validate_w(windowSize, c.Fn.BITS, 2)
     _validate_msm_points(points, c)
+    _validate_table_bytes(len(points) * 2 ** (windowSize - 2), c.Fp.BYTES)  # curve.ts:947
     n = len(points)
     valid = _all_valid(points)
     ps = PointSet(_curve_id_for(c, points, assume_torsion_free), _pack_points(points), n) if n else None

@@ -38,7 +38,7 @@ EXPORTS = [
     "nmsm_host_alloc", "nmsm_host_free", "nmsm_points_upload", "nmsm_points_free", "nmsm_msm_points", "nmsm_points_precompute", "nmsm_msm_points_submit", "nmsm_point_table_create", "nmsm_point_table_free",
     "nmsm_point_table_mul_batch", "nmsm_ntt", "nmsm_ntt_device", "nmsm_points_torsion_free",
     "nmsm_ed25519_verify_batch", "nmsm_msm_submit", "nmsm_msm_collect", "nmsm_points_decode", "nmsm_msm_submit_partial",
-    "nmsm_points_decode_ex", "nmsm_points_on_curve", "nmsm_set_window_groups",
+    "nmsm_points_decode_ex", "nmsm_points_on_curve", "nmsm_set_window_groups", "nmsm_accs_normalize",
     "nmsm_dist_unique_id", "nmsm_dist_init", "nmsm_dist_info", "nmsm_msm_sharded", "nmsm_msm_sharded_submit",
 ]
 
@@ -107,6 +107,8 @@ def load() -> ctypes.CDLL:
         lib.nmsm_msm_partial_device.restype = ctypes.c_int
         lib.nmsm_fold_partials_device.argtypes = [ctypes.c_int, u8p, ctypes.c_int, u8p, ctypes.POINTER(ctypes.c_int)]
         lib.nmsm_fold_partials_device.restype = ctypes.c_int
+        lib.nmsm_accs_normalize.argtypes = [ctypes.c_int, u8p, ctypes.c_int, ctypes.c_uint64, u8p, u8p]
+        lib.nmsm_accs_normalize.restype = ctypes.c_int
         lib.nmsm_mul_batch.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_uint64, ctypes.c_int, u8p, u8p]
         lib.nmsm_mul_batch.restype = ctypes.c_int
         lib.nmsm_set_window_bits.argtypes = [ctypes.c_int]

@@ -289,6 +289,40 @@ def test_shard_fold_path_matches_oracle(nmsm, name):
             assert _shard_fold(nmsm, name, pb, sb, n, cuts, use_slots) == exp, (name, cuts, use_slots)
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_normalize_accs_matches_oracle(nmsm, name):
+    """nmsm_accs_normalize, the device form of normalizeZ (curve.ts:311-326): raw accumulators of 70 one-term MSMs (among
+    them zero scalars and the identity point, which normalise to ZERO) -> canonical affine, from a device pointer and
+    from a host copy; compared with the oracle's s_i * P_i."""
+    import torch
+
+    from nmsm import _lib
+
+    lib = _lib.load()
+    cid = H.CURVE_IDS[name]
+    pbytes, ab = lib.nmsm_point_bytes(cid), lib.nmsm_acc_bytes(cid)
+    n = 70 if "G2" not in name else 36
+    P, pts, scalars, _ = H.soak_inputs(name, n)
+    pts[5] = P.ZERO
+    dev = torch.device("cuda", 0)
+    accs = torch.zeros(n * ab, dtype=torch.uint8, device=dev)
+    pb, sb = H.pack_points(name, pts), H.pack_scalars(scalars)
+    keep = []
+    for i in range(n):
+        dp = torch.frombuffer(bytearray(pb[i * pbytes:(i + 1) * pbytes]), dtype=torch.uint8).to(dev)
+        ds = torch.frombuffer(bytearray(sb[i * 32:(i + 1) * 32]), dtype=torch.uint8).to(dev)
+        keep.append((dp, ds))
+        torch.cuda.synchronize()
+        _lib.check(lib.nmsm_msm_partial_device(cid, dp.data_ptr(), ds.data_ptr(), 1, accs.data_ptr() + i * ab))
+    want = [H.expected_tuple(name, p.multiplyUnsafe(s) if s else P.ZERO) for p, s in zip(pts, scalars)]
+    assert sum(w[2] for w in want) >= 5  # every 17th scalar is zero, point 5 is the identity
+    for src, on_dev in ((accs.data_ptr(), True), (bytes(accs.cpu().numpy()), False)):
+        out, infs = nmsm.normalize_accs(cid, src, n, on_device=on_dev)
+        got = [(*H.unpack_point(name, out[i * pbytes:(i + 1) * pbytes]), infs[i]) for i in range(n)]
+        assert got == want, (name, on_dev)
+    assert nmsm.normalize_accs(cid, b"", 0) == (b"", b"")
+
+
 def test_shard_fold_large_bls12_381_g1(nmsm):
     """2^17 terms in 8 uneven shards: sum s_i*(k_i*G) = (sum k_i s_i)*G (test/slow-curves.test.ts:204-233)."""
     name = "bls12_381_G1"

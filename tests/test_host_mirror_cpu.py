@@ -141,3 +141,48 @@ def test_round2_host_validation_without_device():
     assert nmsm._curve_id_for(B, [B.BASE, unv]) == 6
     assert nmsm._curve_id_for(B, [unv], True) == 4 and nmsm._curve_id_for(B, [B.BASE], False) == 6
     assert nmsm._curve_id_for(C, [C(1, 1)]) == 0
+    # same rule for BLS12-381 G2 (id 5 = psi split, id 7 = plain windows)
+    unv2 = G2.fromAffine({"x": G2.BASE.x, "y": G2.BASE.y})
+    assert nmsm._curve_id_for(G2, [G2.BASE]) == 5 and nmsm._curve_id_for(G2, [G2.BASE, unv2]) == 7
+
+
+def test_cold_path_validators():
+    """validatePointCons / validateW / validateTableBytes (curve.ts:259-272, :328-346, :947, :776-781): typed errors and
+    the reference's messages, all before anything reaches the GPU."""
+    import nmsm
+
+    C = nmsm.CURVES["secp256k1"]
+    nmsm.validatePointCons(C)
+    for bad in (None, 5, "Point", C.BASE):
+        with pytest.raises(TypeError, match="expected constructor"):
+            nmsm.validatePointCons(bad)
+
+    class Fake:
+        pass
+
+    with pytest.raises(TypeError, match="Point.fromAffine"):
+        nmsm.validatePointCons(Fake)
+    with pytest.raises(TypeError, match="expected constructor"):
+        nmsm.pippenger(None, [], [])
+    with pytest.raises(TypeError, match="Point.fromAffine"):
+        nmsm.mulAddUnsafe(Fake, [], [])
+    with pytest.raises(TypeError, match="Point.fromAffine"):
+        nmsm.interleavedMSMUnsafe(Fake, [], 4)
+    bits = C.Fn.BITS
+    for w in (1, 0, -3, bits + 1, 2.5, True):
+        with pytest.raises(ValueError, match=r"invalid window size, expected \[2\.\.%d\]" % bits):
+            nmsm.interleavedMSMUnsafe(C, [], w)
+    # 2^20 points at W = 16: 2^34 table entries of (4 * 32 + 128) bytes -> the reference refuses
+    pts = [C.BASE] * 8
+    with pytest.raises(ValueError, match=r"invalid window size: table would need ~\d+ MiB, max 2048 MiB"):
+        nmsm.interleavedMSMUnsafe(C, pts, 24)
+    with pytest.raises(ValueError, match=r"invalid window size, expected \[1\.\.%d\]" % bits):
+        C.BASE.precompute(0)
+    with pytest.raises(ValueError, match="table would need"):
+        C.BASE.precompute(30)
+    assert nmsm.interleavedMSMUnsafe(C, [], 4)([]).is0()  # empty set: nothing to upload
+    assert C.fromHex is not None and C.BASE.toHex() == C.BASE.toBytes().hex()
+    with pytest.raises(TypeError):
+        C.fromHex(b"02")
+    with pytest.raises(ValueError):
+        C.fromHex("zz")
