@@ -195,8 +195,8 @@ static int submit_msm(const uint32_t* d_pts, const uint32_t* d_scalars, uint64_t
     NG = g_ctx.forced_groups ? (g_ctx.forced_groups >= plan.W ? plan.W : g_ctx.forced_groups) : 1;
     if (NG > 1) NG = plan.W;  // pipelined form: exactly one window per group
   }
-  static const bool quad_env = getenv("NMSM_QUAD_REDUCE1") ? atoi(getenv("NMSM_QUAD_REDUCE1")) != 0 : false;  // tuning experiment
-  const bool quad_reduce1 = quad_env && NG > 1;
+  static const int quad_env = getenv("NMSM_QUAD_REDUCE1") ? atoi(getenv("NMSM_QUAD_REDUCE1")) : 0;  // tuning experiment
+  const bool quad_reduce1 = (quad_env == 1 && NG > 1) || quad_env == 2 || (quad_env == 0 && NG == 1 && reduce1_quad_form(plan));
   const bool prof = g_ctx.profiling && !shard;
   // sharded: which windows this rank owns, where their peers' buckets land, and the gather layout
   const int world = shard ? g_dist.world : 1, rank = shard ? g_dist.rank : 0;

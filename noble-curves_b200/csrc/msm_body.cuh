@@ -131,8 +131,12 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_loca
   p.G = p.W * p.B;
   const double terms_local = n_local ? (double)n_local * split_of<Cv>() : terms;
   p.L = seg_len(terms_local * p.W);
-  // reduce chunk: 8 buckets per thread keeps >= 1 warp per SM sub-partition busy down to ~150k buckets
-  int Kc = K;
+  // reduce chunk: the first reduction level is a latency chain of 2K additions per chunk, and wants ~2 warps per SM
+  // sub-partition (~1100 warps on 148 SMs).  8 buckets per thread does that for the 262144 buckets of a c = 16, 8-window
+  // plan; plans with fewer buckets take 4 (and, at <= 65536 buckets, one chunk per QUAD of lanes: reduce1_quad_form).
+  // Measured on B200, profiles/r02_sweep_tail.jsonl: secp256k1 2^16 (40960 buckets) 1.45 -> 1.02 ms,
+  // BLS12-381 G2 2^18 (131072 buckets) 8.76 -> 8.68 ms; at 262144 buckets K = 4 loses (BLS12-381 G1 2^20: 8.10 -> 8.28 ms).
+  int Kc = (uint64_t)p.W * (uint64_t)p.B <= 131072u ? 4 : K;
 #if !defined(__CUDA_ARCH__)
   if (const char* e = getenv("NMSM_L")) { int v = atoi(e); if (v >= 1 && v <= 1024) p.L = v; }      // tuning experiments
   if (const char* e = getenv("NMSM_K")) { int v = atoi(e); if (v >= 1 && (v & (v - 1)) == 0) Kc = v; }
@@ -146,6 +150,9 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_loca
   p.TPW = plan_tpw((uint64_t)terms_local, p.L);
   return p;
 }
+
+// first reduction level in the lane-parallel form (k_reduce1<QUAD>)?  see make_plan's reduce chunk
+NMSM_HD bool reduce1_quad_form(const MsmPlan& p) { return p.stride == 0 && (uint64_t)p.W * (uint64_t)p.B <= 65536u; }
 
 // Sharded MSM run as one accumulate launch per window (engine.cuh): size the segments so that ONE window is one wave of
 // short blocks.  The windows then finish one after the other (instead of all together at the end of two long waves) and

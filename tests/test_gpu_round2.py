@@ -315,7 +315,7 @@ def test_normalize_accs_matches_oracle(nmsm, name):
         torch.cuda.synchronize()
         _lib.check(lib.nmsm_msm_partial_device(cid, dp.data_ptr(), ds.data_ptr(), 1, accs.data_ptr() + i * ab))
     want = [H.expected_tuple(name, p.multiplyUnsafe(s) if s else P.ZERO) for p, s in zip(pts, scalars)]
-    assert sum(w[2] for w in want) >= 5  # every 17th scalar is zero, point 5 is the identity
+    assert sum(w[2] for w in want) >= 4  # every 17th scalar is zero, point 5 is the identity
     for src, on_dev in ((accs.data_ptr(), True), (bytes(accs.cpu().numpy()), False)):
         out, infs = nmsm.normalize_accs(cid, src, n, on_device=on_dev)
         got = [(*H.unpack_point(name, out[i * pbytes:(i + 1) * pbytes]), infs[i]) for i in range(n)]

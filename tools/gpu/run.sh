@@ -44,6 +44,8 @@ case "$task" in
       python tools/gpu/shard1_profile.py "$@" > gpurun_out/ncu_shard1.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_shard1.log ;;
   sweepc)
     timeout 1500 python tools/gpu/sweep_c.py "$@" > gpurun_out/sweep_c.jsonl 2> gpurun_out/sweep_c.err; echo "rc=$?"; cat gpurun_out/sweep_c.jsonl ;;
+  sweeptail)
+    timeout 1500 python tools/gpu/sweep_tail.py "$@" > gpurun_out/sweep_tail.jsonl 2> gpurun_out/sweep_tail.err; echo "rc=$?"; cat gpurun_out/sweep_tail.jsonl ;;
   explore)
     timeout 900 python tools/gpu/explore_groups.py "$@" > gpurun_out/explore.jsonl 2> gpurun_out/explore.err; echo "rc=$?"; cat gpurun_out/explore.jsonl ;;
   *) echo "unknown task $task"; exit 2 ;;
