@@ -171,6 +171,100 @@ NMSM_HD void mont_sqr(uint32_t* r, const uint32_t* a) {
   reduce_once<C>(r, top);
 }
 
+// ---- building blocks of the lazily reduced Fp2 multiplication (fp2.cuh) ----------------------------------------
+// T = a * b as a plain 2N-limb integer (operands need not be reduced: any N-limb values).  Products are placed by the
+// parity of their absolute position (i + j), so every row is one carry chain per column array, as in mont_sqr.
+template <class C>
+NMSM_HD void mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = C::N;
+  uint32_t E[2 * N + 2], O[2 * N + 2];
+#pragma unroll
+  for (int k = 0; k < 2 * N + 2; k++) {
+    E[k] = 0;
+    O[k] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const uint32_t w = b[i];
+    const int j0e = i & 1, j0o = 1 - (i & 1);  // first j with (i + j) even / odd
+#pragma unroll
+    for (int j = j0e; j < N; j += 2) {
+      E[i + j] = (j == j0e) ? mad_lo_cc(a[j], w, E[i + j]) : madc_lo_cc(a[j], w, E[i + j]);
+      E[i + j + 1] = madc_hi_cc(a[j], w, E[i + j + 1]);
+    }
+    {
+      const int last = j0e + 2 * ((N - 1 - j0e) / 2);
+      E[i + last + 2] = addc(E[i + last + 2], 0);
+    }
+#pragma unroll
+    for (int j = j0o; j < N; j += 2) {
+      O[i + j] = (j == j0o) ? mad_lo_cc(a[j], w, O[i + j]) : madc_lo_cc(a[j], w, O[i + j]);
+      O[i + j + 1] = madc_hi_cc(a[j], w, O[i + j + 1]);
+    }
+    {
+      const int last = j0o + 2 * ((N - 1 - j0o) / 2);
+      O[i + last + 2] = addc(O[i + last + 2], 0);
+    }
+  }
+  T[0] = add_cc(E[0], O[0]);
+#pragma unroll
+  for (int k = 1; k < 2 * N; k++) T[k] = addc_cc(E[k], O[k]);
+}
+
+// r = T / R mod p, fully reduced, for a plain 2N-limb T < p * R / 2 (so that the result before the final conditional
+// subtraction is below 2p): the N reduction rows of mont_sqr on E = T, O = 0.
+template <class C>
+NMSM_HD void mont_reduce_wide(uint32_t* r, const uint32_t* T) {
+  constexpr int N = C::N;
+  uint32_t E[2 * N + 2], O[2 * N + 2], Cw[2 * N + 2];
+#pragma unroll
+  for (int k = 0; k < 2 * N + 2; k++) {
+    E[k] = k < 2 * N ? T[k] : 0u;
+    O[k] = 0;
+    Cw[k] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t* P1 = (i & 1) ? O : E;
+    uint32_t* P2 = (i & 1) ? E : O;
+    if (i > 0) P1[i] = add_cc(P1[i], P2[i]);  // carry continues into P2's chain at position i+1
+    const uint32_t m = P1[i] * C::INV;
+#pragma unroll
+    for (int j = 1; j < N; j += 2) {
+      P2[i + j] = (i == 0 && j == 1) ? mad_lo_cc(m, C::P(j), P2[i + j]) : madc_lo_cc(m, C::P(j), P2[i + j]);
+      P2[i + j + 1] = madc_hi_cc(m, C::P(j), P2[i + j + 1]);
+    }
+    Cw[i + N + 1] = addc(Cw[i + N + 1], 0);
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      P1[i + j] = (j == 0) ? mad_lo_cc(m, C::P(j), P1[i + j]) : madc_lo_cc(m, C::P(j), P1[i + j]);
+      P1[i + j + 1] = madc_hi_cc(m, C::P(j), P1[i + j + 1]);
+    }
+    Cw[i + N] = addc(Cw[i + N], 0);
+  }
+  r[0] = add_cc(E[N], O[N]);
+#pragma unroll
+  for (int k = 1; k < N; k++) r[k] = addc_cc(E[N + k], O[N + k]);
+  uint32_t top = addc(E[2 * N], O[2 * N]);
+  r[0] = add_cc(r[0], Cw[N]);
+#pragma unroll
+  for (int k = 1; k < N; k++) r[k] = addc_cc(r[k], Cw[N + k]);
+  top = addc(top, Cw[2 * N]);
+  reduce_once<C>(r, top);
+}
+
+// limb k of p * R / 4 = p << (32 N - 2) as a 2N-limb integer: the multiple of p added before a double-width
+// subtraction so that the difference stays non-negative (p < R / 4 for every field here, hence p^2 <= p R / 4)
+template <class C>
+NMSM_HD constexpr uint32_t p_times_quarter_r(int k) {
+  constexpr int N = C::N;
+  const int w = k - (N - 1);  // p << 30 placed at word N - 1
+  if (w < 0 || w > N) return 0u;
+  const uint32_t lo = w >= 1 ? (C::P(w - 1) >> 2) : 0u;
+  const uint32_t hi = w < N ? (C::P(w) << 30) : 0u;
+  return lo | hi;
+}
+
 template <class C>
 struct Fp;
 #if defined(__CUDACC__)

@@ -334,6 +334,23 @@ static int emu_ed_verify(const uint8_t* sigs, const uint8_t* pks, const uint8_t*
   return 0;
 }
 
+// Fp2 product of Montgomery-form operands (a, b, r: c0 limbs then c1 limbs), both statements of the multiplication:
+// form 0 = three reduced base multiplications (tower.ts:420-431 order), form 1 = Karatsuba with lazy reduction
+template <class P>
+static void fp2_mul_forms(int form, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  Fp2<P> x, y, z;
+  for (int i = 0; i < P::N; i++) {
+    x.c0.v[i] = a[i]; x.c1.v[i] = a[P::N + i];
+    y.c0.v[i] = b[i]; y.c1.v[i] = b[P::N + i];
+  }
+  if (form == 1) {
+    z = Fp2<P>::mul_lazy(x, y);
+  } else {
+    Fp<P> t1 = x.c0 * y.c0, t2 = x.c1 * y.c1;
+    z = Fp2<P>{t1 - t2, (x.c0 + x.c1) * (y.c0 + y.c1) - (t1 + t2)};
+  }
+  for (int i = 0; i < P::N; i++) { r[i] = z.c0.v[i]; r[P::N + i] = z.c1.v[i]; }
+}
 extern "C" {
 int emu_ed25519_decompress(const uint8_t* enc, uint32_t* out_xy) { return ed_decompress(enc, out_xy) ? 1 : 0; }
 int emu_sha512_rAM(const uint8_t* r, const uint8_t* a, const uint8_t* msg, uint64_t mlen, uint8_t* digest) {
@@ -428,6 +445,11 @@ int emu_owner_window(int curve, uint32_t n_total, int w, uint32_t* own, const ui
 }
 int emu_fold(int curve, const uint32_t* accs, int count, uint32_t* out_xy, uint32_t* out_inf) {
   DISPATCH(curve, emu_fold_t<Cv>(accs, count, out_xy, out_inf));
+}
+int emu_fp2_mul(int field, int form, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  if (field == 2) { fp2_mul_forms<FpBn254>(form, a, b, r); return 0; }
+  if (field == 3) { fp2_mul_forms<FpBls381>(form, a, b, r); return 0; }
+  return -1;
 }
 // field: 0 secp256k1, 1 ed25519, 2 bn254, 3 bls12-381
 int emu_field(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {

@@ -83,6 +83,39 @@ def test_divsteps_inverse(field):
     assert _fop(field, 8, 0) == 0
 
 
+@pytest.mark.parametrize("field", [2, 3])
+def test_fp2_lazy_reduction_multiplication(field):
+    """fp2.cuh mul_lazy (Karatsuba on plain double-width products, two Montgomery reductions) against Python integers and
+    against the three-multiplication form, on the extreme residues (0, 1, p - 1 in every slot: the operand sums reach
+    2p - 2 and the double-width differences their bounds) and random ones."""
+    import ctypes
+    import random as _r
+
+    import numpy as np
+
+    p = FIELDS[field]
+    n = 12 if field == 3 else 8
+    Rm = 1 << (32 * n)
+    rinv = pow(Rm, -1, p)
+    lib = H.hostemu()
+    rnd = _r.Random(field)
+    ext = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (1 << (32 * n - 34)) - 1 if field == 3 else p // 3]
+    cases = [(a0, a1, b0, b1) for a0 in ext[:5] for a1 in ext[:5] for b0 in (0, p - 1, 1) for b1 in (0, p - 1, 2)]
+    cases += [tuple(rnd.choice(ext) for _ in range(4)) for _ in range(200)]
+    cases += [tuple(rnd.randrange(p) for _ in range(4)) for _ in range(1500)]
+    cp = lambda x: x.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    for a0, a1, b0, b1 in cases:
+        a = H.u32(a0.to_bytes(4 * n, "little") + a1.to_bytes(4 * n, "little"))
+        b = H.u32(b0.to_bytes(4 * n, "little") + b1.to_bytes(4 * n, "little"))
+        want = ((a0 * b0 - a1 * b1) * rinv % p, (a0 * b1 + a1 * b0) * rinv % p)
+        for form in (1, 0):
+            out = np.zeros(2 * n, np.uint32)
+            assert lib.emu_fp2_mul(field, form, cp(a), cp(b), cp(out)) == 0
+            raw = out.tobytes()
+            got = (int.from_bytes(raw[: 4 * n], "little"), int.from_bytes(raw[4 * n:], "little"))
+            assert got == want, (form, hex(a0), hex(a1), hex(b0), hex(b1))
+
+
 @pytest.mark.parametrize("name", ALL)
 def test_msm_soak(name):
     """test/slow-curves.test.ts:185-252 construction (every 17th scalar zero), several window sizes."""

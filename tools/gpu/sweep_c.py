@@ -82,6 +82,11 @@ def main():
         sweep_mul("secp256k1", [1024, 8192, 65536])
         sweep_mul("bls12_381_G1", [1024, 16384, 65536])
         sweep_mul("bls12_381_G2", [1024])
+    if what == "g2quick":
+        sweep_msm("bls12_381_G2", 18, [0], ids=[5, 7])
+        sweep_msm("bls12_381_G2", 14, [0], ids=[5])
+        sweep_msm("bn254_G2", 18, [0])
+        sweep_mul("bls12_381_G2", [1024, 32768])
     if what == "g2":
         sweep_msm("bls12_381_G2", 18, [0, 13, 14, 15, 16], ids=[5, 7])
         sweep_msm("bls12_381_G2", 14, [0, 11, 13, 16], ids=[5])
