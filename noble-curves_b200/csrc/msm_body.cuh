@@ -133,10 +133,12 @@ inline MsmPlan make_plan(uint64_t n, int forced_c, int sm_count, uint64_t n_loca
   p.L = seg_len(terms_local * p.W);
   // reduce chunk: the first reduction level is a latency chain of 2K additions per chunk, and wants ~2 warps per SM
   // sub-partition (~1100 warps on 148 SMs).  8 buckets per thread does that for the 262144 buckets of a c = 16, 8-window
-  // plan; plans with fewer buckets take 4 (and, at <= 65536 buckets, one chunk per QUAD of lanes: reduce1_quad_form).
-  // Measured on B200, profiles/r02_sweep_tail.jsonl: secp256k1 2^16 (40960 buckets) 1.45 -> 1.02 ms,
-  // BLS12-381 G2 2^18 (131072 buckets) 8.76 -> 8.68 ms; at 262144 buckets K = 4 loses (BLS12-381 G1 2^20: 8.10 -> 8.28 ms).
-  int Kc = (uint64_t)p.W * (uint64_t)p.B <= 131072u ? 4 : K;
+  // plan; plans with fewer buckets take 4, and at <= 65536 buckets 2 with one chunk per QUAD of lanes (reduce1_quad_form).
+  // Measured on B200, profiles/r02_sweep_tail.jsonl: secp256k1 2^16 (40960 buckets) 1.45 -> 1.02 ms (K = 4) -> 0.97 ms
+  // (K = 2), 2^20 5.63 -> 5.32 ms; BLS12-381 G2 2^18 (131072 buckets) 8.76 -> 8.68 ms; at 262144 buckets K = 4 loses
+  // (BLS12-381 G1 2^20: 8.10 -> 8.28 ms) and so does K = 2 on ed25519's 278528 (1.26 -> 1.35 ms).
+  const uint64_t nbuckets = (uint64_t)p.W * (uint64_t)p.B;
+  int Kc = nbuckets <= 65536u ? 2 : (nbuckets <= 131072u ? 4 : K);
 #if !defined(__CUDA_ARCH__)
   if (const char* e = getenv("NMSM_L")) { int v = atoi(e); if (v >= 1 && v <= 1024) p.L = v; }      // tuning experiments
   if (const char* e = getenv("NMSM_K")) { int v = atoi(e); if (v >= 1 && (v & (v - 1)) == 0) Kc = v; }

@@ -82,6 +82,10 @@ def main():
         sweep_mul("secp256k1", [1024, 8192, 65536])
         sweep_mul("bls12_381_G1", [1024, 16384, 65536])
         sweep_mul("bls12_381_G2", [1024])
+    if what == "secp":
+        sweep_msm("secp256k1", 16, [0])
+        sweep_msm("secp256k1", 20, [0])
+        sweep_msm("ed25519", 17, [0])
     if what == "g2quick":
         sweep_msm("bls12_381_G2", 18, [0], ids=[5, 7])
         sweep_msm("bls12_381_G2", 14, [0], ids=[5])
