@@ -652,8 +652,10 @@ def main():
                    ("BLS12-381 G1 Pippenger MSM, 2^%d terms per GPU: one MSM of %d*2^%d terms" % (args.logn, world, args.logn)),
                    "terms": n_total, "terms_per_gpu": n_local,
                    "parallelism": "1 GPU" if world == 1 else
-                   ("term-sharded x%d; per-window bucket exchange (NCCL send/recv to the window owner w %% N, issued by the "
-                    "library on its own stream), owner fold + reduce, all-gather of %d-byte weighted window sums" % (world, 192)),
+                   ("term-sharded x%d; per-window bucket exchange to the window owner w %% N inside the library (%s), owner "
+                    "fold + reduce, ncclAllGather of %d-byte weighted window sums"
+                    % (world, "owners read the peers' buckets in place over NVLink peer memory, fused into the fold kernel"
+                       if lib.nmsm_dist_exchange_mode() == 2 else "grouped ncclSend / ncclRecv on the library's own stream", 192)),
                    "steps_are": "serial: one complete MSM per step, result on the host before the next step starts",
                    "l2": "inputs + workspace (>= 450 MB at 2^20 terms) exceed the 126 MB L2; no flush needed",
                    "nccl_version": nccl_ver},

@@ -133,6 +133,10 @@ int nmsm_accs_normalize(int curve, const void* accs, int on_device, uint64_t n, 
 int nmsm_dist_unique_id(uint8_t* out128);
 int nmsm_dist_init(int rank, int world, const uint8_t* id128);
 int nmsm_dist_info(int* out_rank, int* out_world, int* out_nccl_version);
+/* How the partial buckets travel to their window owners: 0 = nmsm_dist_init not called, 1 = grouped ncclSend / ncclRecv
+ * copies, 2 = the owners read the peers' buckets in place over NVLink (CUDA-IPC mappings; every rank falls back to 1
+ * together when a mapping cannot be opened or NMSM_DIST_P2P=0).  Final after the first sharded MSM. */
+int nmsm_dist_exchange_mode(void);
 int nmsm_msm_sharded(int curve, const void* pts, const void* scalars, uint64_t n_local, uint64_t n_total,
                      uint64_t shard_offset, int inputs_on_device, uint8_t* out_xy, int* out_is_inf);
 int nmsm_msm_sharded_submit(int curve, const void* pts, const void* scalars, uint64_t n_local, uint64_t n_total,

@@ -3,6 +3,7 @@
 // process-wide context, the Montgomery-multiplication microbenchmark and the extern "C" surface.
 // There is deliberately no CPU path: every entry point needs a CUDA device.
 #include <dlfcn.h>
+#include <thread>
 #include <nccl.h>  // types only: the entry points are resolved with dlsym (no link-time dependency)
 
 #include "context.h"
@@ -72,6 +73,103 @@ int nccl_group_start() { return nccl_check(g_nccl.GroupStart(), "ncclGroupStart"
 int nccl_group_end() { return nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd"); }
 int nccl_all_gather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t st) {
   return nccl_check(g_nccl.AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t)g_dist.comm, st), "ncclAllGather");
+}
+
+// ---------------------------------------------------------------------------------------------
+// staged upload of pageable host memory (context.h h2d_any)
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int STAGE_THREADS_MAX = 8;
+constexpr int STAGE_SLOTS_PER_THREAD = 2;
+constexpr size_t STAGE_CHUNK = 4u << 20;      // bytes per staging buffer
+constexpr size_t STAGE_MIN_BYTES = 2u << 20;  // below this the plain copy is as fast
+struct StageState {
+  bool ready = false;
+  int threads = 0;
+  uint8_t* buf[STAGE_THREADS_MAX][STAGE_SLOTS_PER_THREAD] = {};
+  cudaEvent_t ev[STAGE_THREADS_MAX][STAGE_SLOTS_PER_THREAD] = {};
+  cudaStream_t st[STAGE_THREADS_MAX] = {};
+  cudaEvent_t done[STAGE_THREADS_MAX] = {};
+};
+StageState g_stage;
+
+bool stage_init() {
+  StageState& S = g_stage;
+  if (S.ready) return S.threads > 0;
+  S.ready = true;
+  int want = 4;
+  if (const char* e = getenv("NMSM_STAGE_THREADS")) want = atoi(e);  // 0 disables the staged path
+  const int hw = (int)std::thread::hardware_concurrency();
+  if (hw > 0 && want > hw / 2) want = hw / 2;
+  if (want > STAGE_THREADS_MAX) want = STAGE_THREADS_MAX;
+  if (want < 1) return false;
+  for (int t = 0; t < want; t++) {
+    bool ok = cudaStreamCreateWithFlags(&S.st[t], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&S.done[t], cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; ok && k < STAGE_SLOTS_PER_THREAD; k++)
+      ok = cudaHostAlloc((void**)&S.buf[t][k], STAGE_CHUNK, cudaHostAllocDefault) == cudaSuccess &&
+           cudaEventCreateWithFlags(&S.ev[t][k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {  // keep what was fully set up
+      (void)cudaGetLastError();
+      break;
+    }
+    S.threads = t + 1;
+  }
+  return S.threads > 0;
+}
+}  // namespace
+
+void h2d_release() {
+  StageState& S = g_stage;
+  for (int t = 0; t < STAGE_THREADS_MAX; t++) {
+    for (int k = 0; k < STAGE_SLOTS_PER_THREAD; k++) {
+      if (S.buf[t][k]) cudaFreeHost(S.buf[t][k]);
+      if (S.ev[t][k]) cudaEventDestroy(S.ev[t][k]);
+    }
+    if (S.st[t]) cudaStreamDestroy(S.st[t]);
+    if (S.done[t]) cudaEventDestroy(S.done[t]);
+  }
+  S = StageState();
+}
+
+int h2d_any(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return NMSM_OK;
+  bool pageable = false;
+  if (bytes >= STAGE_MIN_BYTES) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+    else (void)cudaGetLastError();
+  }
+  if (!pageable || !stage_init()) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    return NMSM_OK;
+  }
+  StageState& S = g_stage;
+  const size_t nchunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+  const int T = (size_t)S.threads < nchunks ? S.threads : (int)nchunks;
+  const int device = g_ctx.device;
+  cudaError_t errs[STAGE_THREADS_MAX];
+  auto work = [&](int t) {
+    cudaError_t e = cudaSetDevice(device);
+    int k = 0;
+    for (size_t c = (size_t)t; e == cudaSuccess && c < nchunks; c += (size_t)T, k ^= 1) {
+      const size_t off = c * STAGE_CHUNK, len = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+      e = cudaEventSynchronize(S.ev[t][k]);  // the DMA that last read this staging buffer (no-op the first time)
+      if (e != cudaSuccess) break;
+      memcpy(S.buf[t][k], (const uint8_t*)src + off, len);
+      e = cudaMemcpyAsync((uint8_t*)dst + off, S.buf[t][k], len, cudaMemcpyHostToDevice, S.st[t]);
+      if (e == cudaSuccess) e = cudaEventRecord(S.ev[t][k], S.st[t]);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(S.done[t], S.st[t]);
+    errs[t] = e;
+  };
+  std::thread th[STAGE_THREADS_MAX];
+  for (int t = 1; t < T; t++) th[t] = std::thread(work, t);
+  work(0);
+  for (int t = 1; t < T; t++) th[t].join();
+  for (int t = 0; t < T; t++) CK(errs[t]);
+  for (int t = 0; t < T; t++) CK(cudaStreamWaitEvent(stream, S.done[t], 0));
+  return NMSM_OK;
 }
 
 static const EngineVTable* engine_for(int curve) {
@@ -319,6 +417,7 @@ void nmsm_shutdown(void) {
     cudaStreamDestroy(S.stream);
     S.pend = Pending();
   }
+  h2d_release();
   C.ed_scratch.release();
   for (Buf* b : {&C.ntt_data, &C.ntt_work, &C.ntt_tmp, &C.ntt_roots, &C.ntt_aux}) b->release();
   C.ntt_key_field = -1;
@@ -608,6 +707,12 @@ int nmsm_dist_info(int* out_rank, int* out_world, int* out_nccl_version) {
   if (out_world) *out_world = g_dist.world;
   if (out_nccl_version) g_nccl.GetVersion(out_nccl_version);
   return NMSM_OK;
+}
+
+int nmsm_dist_exchange_mode(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_dist.ready) return 0;
+  return g_dist.p2p ? 2 : 1;
 }
 
 int nmsm_msm_sharded_submit(int curve, const void* pts, const void* scalars, uint64_t n_local, uint64_t n_total,

@@ -112,6 +112,14 @@ struct Context {
   long long last_error_index = -1;
 };
 
+// H2D copy of a caller's host array, ordered before later work on `stream`.  Pinned (cudaHostAlloc / cudaHostRegister /
+// nmsm_host_alloc) sources go out as one cudaMemcpyAsync.  Large PAGEABLE sources — what a JS typed array or a Python
+// bytes object is — would be staged by the driver on ONE thread at ~12 GB/s (measured: 100 MB of bn254 points and
+// scalars 8.6 ms, twice the MSM itself); instead a few worker threads copy chunks into a ring of pinned staging buffers
+// and issue the chunk DMAs themselves, which keeps PCIe near its pinned rate.  capi.cu.
+int h2d_any(void* dst, const void* src, size_t bytes, cudaStream_t stream);
+void h2d_release();
+
 // NCCL entry points resolved at run time (dlopen "libnccl.so.2": inside a torch process that is the copy torch already
 // loaded), so libnmsm.so has no link-time dependency on NCCL and loads on machines without it.
 struct NcclComm;

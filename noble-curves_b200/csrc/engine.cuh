@@ -76,10 +76,9 @@ static bool prepare_on_side_stream(uint64_t n, bool prepared) { return !g_ctx.pr
 static int stage_host_inputs(Slot& C, const void* pts, const void* scalars, uint64_t n) {
   CK(C.in_pts.ensure(n * G::IN_WORDS * 4));
   CK(C.in_scalars.ensure(n * SCALAR_WORDS * 4));
-  CK(cudaMemcpyAsync(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, cudaMemcpyHostToDevice, C.stream));
-  CK(cudaMemcpyAsync(C.in_pts.p, pts, n * G::IN_WORDS * 4, cudaMemcpyHostToDevice,
-                     prepare_on_side_stream(n, false) ? C.prep_stream : C.stream));
-  return NMSM_OK;
+  // h2d_any: pinned sources are one DMA each; large pageable ones are staged through pinned chunks by worker threads
+  if (int r = h2d_any(C.in_scalars.p, scalars, n * SCALAR_WORDS * 4, C.stream)) return r;
+  return h2d_any(C.in_pts.p, pts, n * G::IN_WORDS * 4, prepare_on_side_stream(n, false) ? C.prep_stream : C.stream);
 }
 
 // Enqueue the whole pipeline (and the small result D2H); no host sync.

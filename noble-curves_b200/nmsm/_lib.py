@@ -39,7 +39,7 @@ EXPORTS = [
     "nmsm_point_table_mul_batch", "nmsm_ntt", "nmsm_ntt_device", "nmsm_points_torsion_free",
     "nmsm_ed25519_verify_batch", "nmsm_msm_submit", "nmsm_msm_collect", "nmsm_points_decode", "nmsm_msm_submit_partial",
     "nmsm_points_decode_ex", "nmsm_points_on_curve", "nmsm_set_window_groups", "nmsm_accs_normalize",
-    "nmsm_dist_unique_id", "nmsm_dist_init", "nmsm_dist_info", "nmsm_msm_sharded", "nmsm_msm_sharded_submit",
+    "nmsm_dist_unique_id", "nmsm_dist_init", "nmsm_dist_info", "nmsm_dist_exchange_mode", "nmsm_msm_sharded", "nmsm_msm_sharded_submit",
 ]
 
 
@@ -119,6 +119,8 @@ def load() -> ctypes.CDLL:
         lib.nmsm_dist_init.restype = ctypes.c_int
         lib.nmsm_dist_info.argtypes = [ctypes.POINTER(ctypes.c_int)] * 3
         lib.nmsm_dist_info.restype = ctypes.c_int
+        lib.nmsm_dist_exchange_mode.argtypes = []
+        lib.nmsm_dist_exchange_mode.restype = ctypes.c_int
         lib.nmsm_msm_sharded.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int,
                                          u8p, ctypes.POINTER(ctypes.c_int)]
         lib.nmsm_msm_sharded.restype = ctypes.c_int

@@ -24,7 +24,7 @@ case "$task" in
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-fixed-base "$@" > gpurun_out/ncu_full.log 2>&1; echo "rc=$?" ;;
   sanitizer)
     tool=${1:-memcheck}; shift || true
-    timeout 1500 compute-sanitizer --tool "$tool" python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "${1:-boundary_soak or degenerate}" > gpurun_out/sanitizer_$tool.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/sanitizer_$tool.log ;;
+    timeout 1500 compute-sanitizer --tool "$tool" python -m pytest tests -m gpu -x -q -k "${1:-boundary_soak or degenerate}" > gpurun_out/sanitizer_$tool.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/sanitizer_$tool.log ;;
   dist)
     np=$1; shift
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$np" --master-addr 127.0.0.1 --master-port 29517 \
