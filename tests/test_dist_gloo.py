@@ -117,7 +117,8 @@ def _run(world, name, n, bad_scalar_at=None):
     assert sorted(res) == [(r, True) for r in range(world)]
 
 
-@pytest.mark.parametrize("world,name,n", [(2, "bls12_381_G1", 37), (2, "ed25519", 24), (2, "bls12_381_G1", 1), (3, "secp256k1", 50)])
+@pytest.mark.parametrize("world,name,n", [(2, "bls12_381_G1", 37), (2, "ed25519", 24), (2, "bls12_381_G1", 1), (3, "secp256k1", 50),
+                                          (2, "bls12_381_G2", 9)])  # G2: four sub-terms per term (psi split)
 def test_bucket_exchange_msm_gloo(world, name, n):
     _run(world, name, n)
 
