@@ -9,6 +9,10 @@
  *                                                                 src/abstract/edwards.ts:555-577
  *   nmsm_msm_partial_device / nmsm_fold_partials_device           (multi-GPU split of the same MSM; MSM is
  *                                                                 linear in its term set, curve.ts:863)
+ *   nmsm_dist_init / nmsm_msm_sharded                             the same MSM sharded over the GPUs of one box with the
+ *                                                                 per-window bucket exchange inside the library
+ *   nmsm_accs_normalize <- normalizeZ(c, points)                  curve.ts:311-326 (batch normalisation, one inversion per 32)
+ *   nmsm_points_on_curve <- the equation half of assertValidity   weierstrass.ts:617-624,752-771
  *   nmsm_last_error     <- the thrown Error messages              curve.ts:390-404,875
  * and, for the callers and data formats either side of that path:
  *   nmsm_msm_submit / _collect / nmsm_msm_points_submit           asynchronous halves (several MSMs in flight)
