@@ -149,6 +149,12 @@ def _make_point_class(name: str, curve_id: int, p: int, n: int, h: int, Gx, Gy, 
         def double(self):
             return _msm_points(Point, [self], [2])
 
+        def hasEvenY(self) -> bool:
+            """weierstrass.ts:768-772 (prime base fields only: Fp2 has no isOdd)"""
+            if edwards or parts != 1:
+                raise ValueError("Field doesn't support isOdd")
+            return (self.toAffine()["y"] & 1) == 0
+
         def assertValidity(self) -> None:
             """weierstrass.ts:752-771 / edwards.ts:461-480: on-curve + prime-order-subgroup check (both on the GPU:
             the curve equation through nmsm_points_on_curve, n*P == O through nmsm_points_torsion_free)."""

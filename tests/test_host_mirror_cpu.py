@@ -186,3 +186,6 @@ def test_cold_path_validators():
         C.fromHex(b"02")
     with pytest.raises(ValueError):
         C.fromHex("zz")
+    assert C.BASE.hasEvenY() == (C.BASE.y % 2 == 0) and C.BASE.negate().hasEvenY() != C.BASE.hasEvenY()
+    with pytest.raises(ValueError, match="isOdd"):
+        nmsm.CURVES["bls12_381_G2"].BASE.hasEvenY()
