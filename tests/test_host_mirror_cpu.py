@@ -189,3 +189,16 @@ def test_cold_path_validators():
     assert C.BASE.hasEvenY() == (C.BASE.y % 2 == 0) and C.BASE.negate().hasEvenY() != C.BASE.hasEvenY()
     with pytest.raises(ValueError, match="isOdd"):
         nmsm.CURVES["bls12_381_G2"].BASE.hasEvenY()
+
+
+def test_packed_entry_points_validate_lengths_before_the_gpu():
+    import nmsm
+
+    with pytest.raises(ValueError, match="packed arrays do not match n"):
+        nmsm.ed25519_verify_batch_packed(bytes(64), bytes(32), b"", bytes(8), 1, bytes(16))  # n + 1 offsets expected
+    with pytest.raises(ValueError, match="packed arrays do not match n"):
+        nmsm.ed25519_verify_batch_packed(bytes(63), bytes(32), b"", bytes(16), 1, bytes(16))
+    with pytest.raises(ValueError, match="z must hold 16 bytes per signature"):
+        nmsm.ed25519_verify_batch([bytes(64)], [b"m"], [bytes(32)], bytes(15))
+    with pytest.raises(ValueError, match="signature expected 64 bytes"):
+        nmsm.ed25519_verify_batch([bytes(63)], [b"m"], [bytes(32)])
